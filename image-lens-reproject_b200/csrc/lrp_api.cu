@@ -1,0 +1,909 @@
+// lrp_api.cu — the C ABI (include/lrp.h): argument validation, kernel dispatch, per-GPU
+// contexts, the synchronous host drop-ins and the asynchronous job / multi-GPU scheduler.
+//
+// There is no CPU compute path in this library: everything that produces pixels launches
+// a CUDA kernel, and every entry point fails loudly (LRP_E_NO_DEVICE / LRP_E_CUDA)
+// without a GPU.  The only host arithmetic is what the reference's *host* also computes
+// outside reproject(): the rotation matrix, the lens structs, and the two 256-entry
+// gamma tables built with the host's own powf.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/lrp.h"
+#include "lrp_params.h"
+
+namespace lrp {
+// instantiation TUs (lrp_inst.cu compiled per coordinate mode x sampler)
+#define LRP_DECL(c, i) LaunchFn get_launcher_c##c##_i##i(int fc);
+LRP_DECL(0, 0) LRP_DECL(0, 1) LRP_DECL(0, 2) LRP_DECL(1, 0) LRP_DECL(1, 1) LRP_DECL(1, 2)
+LRP_DECL(2, 0) LRP_DECL(2, 1) LRP_DECL(2, 2) LRP_DECL(3, 0) LRP_DECL(3, 1) LRP_DECL(3, 2)
+LRP_DECL(4, 0) LRP_DECL(4, 1) LRP_DECL(4, 2) LRP_DECL(5, 0) LRP_DECL(5, 1) LRP_DECL(5, 2)
+#undef LRP_DECL
+int launch_coords(const KParams &P, int coord, void *stream);
+int launch_post_process(float *data, size_t n_pixels, int channels, float exposure, float reinhard, void *stream);
+int launch_libm(int fn, const float *a, const float *b, float *out, size_t n, int use_fma, void *stream);
+
+static LaunchFn get_launcher(int coord, int interp, int fc) {
+  typedef LaunchFn (*Getter)(int);
+  static const Getter table[COORD_COUNT][3] = {
+      {get_launcher_c0_i0, get_launcher_c0_i1, get_launcher_c0_i2},
+      {get_launcher_c1_i0, get_launcher_c1_i1, get_launcher_c1_i2},
+      {get_launcher_c2_i0, get_launcher_c2_i1, get_launcher_c2_i2},
+      {get_launcher_c3_i0, get_launcher_c3_i1, get_launcher_c3_i2},
+      {get_launcher_c4_i0, get_launcher_c4_i1, get_launcher_c4_i2},
+      {get_launcher_c5_i0, get_launcher_c5_i1, get_launcher_c5_i2},
+  };
+  return table[coord][interp](fc);
+}
+} // namespace lrp
+
+using namespace lrp;
+
+// ---- host tables ---------------------------------------------------------------------------
+
+namespace {
+
+struct HostTables {
+  float lut[256]; // powf(p / 255, 2.2)                         reference src/image_formats.cpp:195-197
+  float thr[256]; // thr[k] = min{ s in [0,1] : q(s) >= k }     reference src/image_formats.cpp:156-158
+  int libm_fma;   // 1 / 0, -1 = the host libm matches neither known variant
+};
+
+inline uint8_t gamma_q(float s) {
+  volatile float e = 1.0f / 2.2f;
+  float g = powf(s, e);
+  return (uint8_t)(255.9f * g);
+}
+inline float bits_to_float(uint32_t u) {
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+inline uint32_t float_to_bits(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+
+// glibc dispatches sinf/cosf per CPU (IFUNC) to an FMA or a non-FMA build; the two differ
+// on 12 + 22 arguments with |x| < 120.  Probe the host's own libm
+// on a few of them so that the device code reproduces THIS host's reference output.
+int probe_libm_fma() {
+  static const uint32_t probes[][4] = {
+      // fn (0 cos / 1 sin), argument bits, FMA-variant result, non-FMA result
+      {0, 0x418a3adbu, 0xb7b4f770u, 0xb7b4f76fu}, {0, 0x418a3adcu, 0xb7a4f770u, 0xb7a4f76fu},
+      {1, 0x4255b0a9u, 0xbc7d08a9u, 0xbc7d08a8u}, {1, 0x42a35c07u, 0xbadaa3b4u, 0xbadaa3b5u},
+      {1, 0x42a97360u, 0x3dc7b08au, 0x3dc7b089u},
+  };
+  int fma = 0, nofma = 0;
+  for (auto &p : probes) {
+    volatile float x = bits_to_float(p[1]);
+    float r = p[0] ? sinf(x) : cosf(x);
+    uint32_t b = float_to_bits(r);
+    fma += (b == p[2]);
+    nofma += (b == p[3]);
+  }
+  const int n = (int)(sizeof(probes) / sizeof(probes[0]));
+  if (fma == n) return 1;
+  if (nofma == n) return 0;
+  return -1;
+}
+
+const HostTables &host_tables() {
+  static HostTables t;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    volatile float g = 2.2f;
+    for (int p = 0; p < 256; ++p) t.lut[p] = powf((float)p / 255.0f, g);
+    t.thr[0] = 0.0f;
+    const uint32_t one = float_to_bits(1.0f);
+    for (int k = 1; k < 256; ++k) { // bisection over float bit patterns (q is monotone)
+      uint32_t lo = 0, hi = one;    // q(lo) < k <= q(hi)
+      while (hi - lo > 1) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (gamma_q(bits_to_float(mid)) >= k) hi = mid;
+        else lo = mid;
+      }
+      t.thr[k] = bits_to_float(hi);
+    }
+    const char *env = getenv("LRP_LIBM_FMA");
+    t.libm_fma = env ? atoi(env) : probe_libm_fma();
+  });
+  return t;
+}
+
+int map_cuda(cudaError_t e) {
+  if (e == cudaSuccess) return LRP_OK;
+  if (e == cudaErrorMemoryAllocation) return LRP_E_OOM;
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return LRP_E_NO_DEVICE;
+  return LRP_E_CUDA;
+}
+#define LRP_CUDA(call)                          \
+  do {                                          \
+    cudaError_t e__ = (call);                   \
+    if (e__ != cudaSuccess) {                   \
+      cudaGetLastError();                       \
+      return map_cuda(e__);                     \
+    }                                           \
+  } while (0)
+
+bool lens_supported(int t) { return t == LENS_RECT || t == LENS_EQUIDISTANT || t == LENS_ERECT; }
+
+LensP to_lensp(const lrp_lens &l) {
+  LensP r;
+  r.type = l.type;
+  r.p0 = l.u.raw[0];
+  r.p1 = l.u.raw[1];
+  r.p2 = l.u.raw[2];
+  r.p3 = l.u.raw[3];
+  r.sw = l.sensor_width;
+  r.sh = l.sensor_height;
+  return r;
+}
+
+// reference src/reproject.cpp:386-388 — wrap only for a full-2*pi equirectangular input
+bool loops_horizontally(const lrp_lens &l) {
+  if (l.type != LENS_ERECT) return false;
+  float long_range = l.u.equirectangular.longitude_max - l.u.equirectangular.longitude_min;
+  return std::abs(long_range - (2 * M_PI)) < 1e-5f;
+}
+
+size_t format_bytes(int fmt, int w, int h, int c) {
+  size_t n = (size_t)w * (size_t)h;
+  switch (fmt) {
+  case LRP_FMT_F32: return n * c * 4;
+  case LRP_FMT_U8_RGBA: return n * 4;
+  case LRP_FMT_F16_PLANAR: return n * c * 2;
+  default: return 0;
+  }
+}
+
+} // namespace
+
+// ---- context ---------------------------------------------------------------------------------
+
+struct Slot { // one stream with grow-only device staging buffers
+  cudaStream_t stream = nullptr;
+  void *d_in = nullptr, *d_out = nullptr;
+  size_t cap_in = 0, cap_out = 0;
+  bool busy = false;
+};
+
+struct lrp_ctx {
+  int device = 0;       // logical device index
+  int phys_device = 0;  // CUDA ordinal (differs only under LRP_FAKE_GPUS)
+  float *d_lut = nullptr, *d_thr = nullptr;
+  std::vector<cudaStream_t> streams;
+  std::vector<Slot> slots; // for the synchronous host drop-ins
+  std::mutex mu;
+  std::condition_variable cv;
+  struct Pool *pool = nullptr; // lazily created by lrp_submit
+};
+
+namespace {
+
+int physical_device(int logical, int *phys) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return LRP_E_NO_DEVICE;
+  }
+  const char *fake = getenv("LRP_FAKE_GPUS"); // map N logical GPUs onto the physical ones (tests)
+  int logical_n = fake ? atoi(fake) : n;
+  if (logical < 0 || logical >= logical_n) return LRP_E_BAD_ARG;
+  *phys = logical % n;
+  return LRP_OK;
+}
+
+int slot_reserve(Slot &s, size_t in_bytes, size_t out_bytes) {
+  if (in_bytes > s.cap_in) {
+    LRP_CUDA(cudaStreamSynchronize(s.stream));
+    if (s.d_in) cudaFree(s.d_in);
+    s.d_in = nullptr;
+    s.cap_in = 0;
+    LRP_CUDA(cudaMalloc(&s.d_in, in_bytes));
+    s.cap_in = in_bytes;
+  }
+  if (out_bytes > s.cap_out) {
+    LRP_CUDA(cudaStreamSynchronize(s.stream));
+    if (s.d_out) cudaFree(s.d_out);
+    s.d_out = nullptr;
+    s.cap_out = 0;
+    LRP_CUDA(cudaMalloc(&s.d_out, out_bytes));
+    s.cap_out = out_bytes;
+  }
+  return LRP_OK;
+}
+
+void slot_destroy(Slot &s) {
+  if (s.d_in) cudaFree(s.d_in);
+  if (s.d_out) cudaFree(s.d_out);
+  if (s.stream) cudaStreamDestroy(s.stream);
+  s = Slot();
+}
+
+// Validates a reproject call and fills the kernel parameter block + dispatch keys.
+int prepare(const lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const lrp_params *p,
+            bool need_data, KParams &K, int &coord, int &fc) {
+  if (!ctx || !in || !out || !p) return LRP_E_BAD_ARG;
+  if (in->width <= 0 || in->height <= 0 || out->width <= 0 || out->height <= 0) return LRP_E_BAD_ARG;
+  if (p->num_samples < 1 || p->num_samples > 64) return LRP_E_BAD_ARG;
+  if (!lens_supported(out->lens.type)) return LRP_E_UNSUPPORTED_OUTPUT_LENS; // reference :415-417
+  if (!lens_supported(in->lens.type)) return LRP_E_UNSUPPORTED_INPUT_LENS;   // reference :395-397
+  if (p->interpolation < 0 || p->interpolation > 2) return LRP_E_UNSUPPORTED_INTERP; // :364-366
+  if (need_data) {
+    if (!in->data || !out->data) return LRP_E_BAD_ARG;
+    if (in->channels != out->channels) return LRP_E_BAD_ARG; // reference: output.channels = input.channels
+    const int c = in->channels;
+    switch (in->format) {
+    case LRP_FMT_F32: fc = c == 3 ? FC_F32_3 : c == 4 ? FC_F32_4 : c == 5 ? FC_F32_5 : -1; break;
+    case LRP_FMT_U8_RGBA: fc = c == 3 ? FC_U8_3 : -1; break; // read_png always yields 3 channels
+    case LRP_FMT_F16_PLANAR: fc = c == 3 ? FC_F16_3 : c == 4 ? FC_F16_4 : c == 5 ? FC_F16_5 : -1; break;
+    default: return LRP_E_UNSUPPORTED_FORMAT;
+    }
+    if (fc < 0) return LRP_E_UNSUPPORTED_FORMAT;
+    if (out->format < LRP_FMT_F32 || out->format > LRP_FMT_F16_PLANAR) return LRP_E_UNSUPPORTED_FORMAT;
+    // save_png with 5 channels overruns its buffer in the reference (UB): refused here
+    if (out->format == LRP_FMT_U8_RGBA && c > 4) return LRP_E_UNSUPPORTED_FORMAT;
+  }
+  const HostTables &T = host_tables();
+  memset(&K, 0, sizeof(K));
+  K.ol = to_lensp(out->lens);
+  K.il = to_lensp(in->lens);
+  K.W = out->width;
+  K.H = out->height;
+  K.w = in->width;
+  K.h = in->height;
+  K.ns = p->num_samples;
+  K.ss_den = (float)p->num_samples + 1.0f;
+  K.normalize = (1.0f / (p->num_samples * p->num_samples)); // reference :280
+  K.has_rot = p->has_rotation ? 1 : 0;
+  memcpy(K.R, p->rotation, sizeof(K.R));
+  K.post = p->apply_post ? 1 : 0;
+  K.exposure = p->exposure;
+  K.r2 = p->reinhard * p->reinhard;
+  K.use_fma = T.libm_fma != 0; // -1 (unknown host variant) falls back to the FMA build
+  K.dst_fmt = out->format;
+  K.src = in->data;
+  K.dst = out->data;
+  K.src_plane = (long long)in->width * in->height;
+  K.dst_plane = (long long)out->width * out->height;
+  K.lut = ctx->d_lut;
+  K.thr = ctx->d_thr;
+  K.neg_zero2 = 0x8000000080000000ull;
+  switch (in->lens.type) {
+  case LENS_RECT: coord = COORD_RECT; break;
+  case LENS_EQUIDISTANT: coord = COORD_EQUIDISTANT; break;
+  default: coord = loops_horizontally(in->lens) ? COORD_ERECT_WRAP : COORD_ERECT_CLAMP; break;
+  }
+  return LRP_OK;
+}
+
+// The *_device entry points may be called with any current device (e.g. under torch):
+// switch to the context's device for the launch and restore the caller's afterwards.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int want) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != want) cudaSetDevice(want);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const lrp_params *p,
+                 const void *remap, cudaStream_t stream) {
+  if (!ctx) return LRP_E_BAD_ARG;
+  DeviceGuard guard(ctx->phys_device);
+  KParams K;
+  int coord = 0, fc = 0;
+  int rc = prepare(ctx, in, out, p, true, K, coord, fc);
+  if (rc != LRP_OK) return rc;
+  if (remap) {
+    K.remap = (const float2 *)remap;
+    coord = (coord == COORD_ERECT_WRAP) ? COORD_TABLE_WRAP : COORD_TABLE_CLAMP;
+  }
+  LaunchFn fn = get_launcher(coord, p->interpolation, fc);
+  if (!fn) return LRP_E_UNSUPPORTED_FORMAT;
+  return map_cuda((cudaError_t)fn(K, stream));
+}
+
+} // namespace
+
+// ---- asynchronous worker pool (also the multi-GPU scheduler) ---------------------------------
+
+struct Pool {
+  struct Item {
+    lrp_job job;
+    uint64_t ticket;
+  };
+  struct Worker {
+    lrp_ctx *ctx;
+    Slot slot;
+    std::thread th;
+    int dev_index; // index into the pool's ctx list
+  };
+  std::vector<lrp_ctx *> ctxs;
+  std::vector<Worker *> workers;
+  std::deque<Item> queue;
+  std::map<uint64_t, int> done; // ticket -> status
+  std::vector<int64_t> per_device;
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done;
+  uint64_t next_ticket = 1;
+  uint64_t in_flight = 0;
+  int first_error = LRP_OK;
+  bool stopping = false;
+
+  static int run_job(Worker *w, const lrp_job &job) {
+    lrp_ctx *ctx = w->ctx;
+    LRP_CUDA(cudaSetDevice(ctx->phys_device));
+    const size_t in_bytes = lrp_image_bytes(&job.in), out_bytes = lrp_image_bytes(&job.out);
+    if (!in_bytes || !out_bytes || !job.in.data || !job.out.data) return LRP_E_BAD_ARG;
+    int rc = slot_reserve(w->slot, in_bytes, out_bytes);
+    if (rc != LRP_OK) return rc;
+    lrp_image din = job.in, dout = job.out;
+    din.data = w->slot.d_in;
+    dout.data = w->slot.d_out;
+    LRP_CUDA(cudaMemcpyAsync(w->slot.d_in, job.in.data, in_bytes, cudaMemcpyHostToDevice, w->slot.stream));
+    rc = launch_fused(ctx, &din, &dout, &job.params, nullptr, w->slot.stream);
+    if (rc != LRP_OK) return rc;
+    LRP_CUDA(cudaMemcpyAsync(job.out.data, w->slot.d_out, out_bytes, cudaMemcpyDeviceToHost, w->slot.stream));
+    LRP_CUDA(cudaStreamSynchronize(w->slot.stream));
+    return LRP_OK;
+  }
+
+  void worker_main(Worker *w) {
+    cudaSetDevice(w->ctx->phys_device);
+    for (;;) {
+      Item it;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_work.wait(lk, [&] { return stopping || !queue.empty(); });
+        if (queue.empty()) return; // stopping and drained
+        it = queue.front();
+        queue.pop_front();
+      }
+      int rc = run_job(w, it.job);
+      if (it.job.on_done) it.job.on_done(it.job.user, rc);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        done[it.ticket] = rc;
+        per_device[w->dev_index]++;
+        if (rc != LRP_OK && first_error == LRP_OK) first_error = rc;
+        in_flight--;
+      }
+      cv_done.notify_all();
+    }
+  }
+
+  int start(const std::vector<lrp_ctx *> &cs, int workers_per_ctx) {
+    ctxs = cs;
+    per_device.assign(cs.size(), 0);
+    for (size_t d = 0; d < cs.size(); ++d)
+      for (int k = 0; k < workers_per_ctx; ++k) {
+        Worker *w = new Worker();
+        w->ctx = cs[d];
+        w->dev_index = (int)d;
+        LRP_CUDA(cudaSetDevice(cs[d]->phys_device));
+        LRP_CUDA(cudaStreamCreateWithFlags(&w->slot.stream, cudaStreamNonBlocking));
+        workers.push_back(w);
+      }
+    for (Worker *w : workers) w->th = std::thread([this, w] { worker_main(w); });
+    return LRP_OK;
+  }
+
+  uint64_t submit(const lrp_job &job) {
+    std::lock_guard<std::mutex> lk(mu);
+    uint64_t t = next_ticket++;
+    queue.push_back(Item{job, t});
+    in_flight++;
+    cv_work.notify_one();
+    return t;
+  }
+
+  int wait(uint64_t ticket) {
+    std::unique_lock<std::mutex> lk(mu);
+    if (ticket == 0 || ticket >= next_ticket) return LRP_E_BAD_ARG;
+    cv_done.wait(lk, [&] { return done.count(ticket) != 0; });
+    int rc = done[ticket];
+    done.erase(ticket);
+    return rc;
+  }
+
+  int wait_all() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv_done.wait(lk, [&] { return in_flight == 0; });
+    int rc = first_error;
+    first_error = LRP_OK;
+    done.clear();
+    return rc;
+  }
+
+  void stop() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stopping = true;
+    }
+    cv_work.notify_all();
+    for (Worker *w : workers) {
+      if (w->th.joinable()) w->th.join();
+      cudaSetDevice(w->ctx->phys_device);
+      slot_destroy(w->slot);
+      delete w;
+    }
+    workers.clear();
+  }
+};
+
+struct lrp_sched {
+  std::vector<lrp_ctx *> ctxs;
+  Pool pool;
+};
+
+// ---- C ABI -----------------------------------------------------------------------------------
+
+extern "C" {
+
+const char *lrp_version(void) { return "lrp-b200 0.1 (sm_100a)"; }
+
+const char *lrp_strerror(int s) {
+  switch (s) {
+  case LRP_OK: return "ok";
+  case LRP_E_BAD_ARG: return "bad argument";
+  case LRP_E_UNSUPPORTED_OUTPUT_LENS: return "Output lens type not supported.";
+  case LRP_E_UNSUPPORTED_INPUT_LENS: return "Input lens type not supported.";
+  case LRP_E_UNSUPPORTED_INTERP: return "Interpolation method not supported.";
+  case LRP_E_UNSUPPORTED_FORMAT: return "sample format / channel count not supported";
+  case LRP_E_CUDA: return "CUDA error";
+  case LRP_E_OOM: return "out of device memory";
+  case LRP_E_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+  default: return "unknown status";
+  }
+}
+
+int lrp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  const char *fake = getenv("LRP_FAKE_GPUS");
+  if (fake && n > 0) return atoi(fake);
+  return n;
+}
+
+size_t lrp_image_bytes(const lrp_image *img) {
+  if (!img) return 0;
+  return format_bytes(img->format, img->width, img->height, img->channels);
+}
+
+int lrp_host_libm_uses_fma(void) { return host_tables().libm_fma; }
+
+// reference src/main.cpp:98-142
+void lrp_rotation_matrix(float pan, float pitch, float roll, float m[9]) {
+  const float rx = pitch, ry = pan, rz = roll;
+  const float Rx[9] = {1, 0, 0, 0, std::cos(rx), -std::sin(rx), 0, std::sin(rx), std::cos(rx)};
+  const float Ry[9] = {std::cos(ry), 0, std::sin(ry), 0, 1, 0, -std::sin(ry), 0, std::cos(ry)};
+  const float Rz[9] = {std::cos(rz), -std::sin(rz), 0, std::sin(rz), std::cos(rz), 0, 0, 0, 1};
+  auto mul = [](const float *a, const float *b, float *r) {
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        float acc = 0;
+        for (int k = 0; k < 3; ++k) acc += a[i * 3 + k] * b[k * 3 + j];
+        r[i * 3 + j] = acc;
+      }
+  };
+  float tmp[9];
+  mul(Rx, Rz, tmp); // R = R_y * (R_x * R_z)
+  mul(Ry, tmp, m);
+}
+
+// reference src/main.cpp:316-321: degrees -> radians in double, narrowed to float
+void lrp_rotation_from_degrees(double pan_deg, double pitch_deg, double roll_deg, float m[9]) {
+  float pan = pan_deg / 180.0 * M_PI;
+  float pitch = pitch_deg / 180.0 * M_PI;
+  float roll = roll_deg / 180.0 * M_PI;
+  lrp_rotation_matrix(pan, pitch, roll, m);
+}
+
+// reference src/main.cpp:15-29
+void lrp_lens_rectilinear(float focal_length, float sensor_width, int res_x, int res_y, lrp_lens *o) {
+  memset(o, 0, sizeof(*o));
+  o->type = LRP_RECTILINEAR;
+  o->u.rectilinear.focal_length = focal_length;
+  o->sensor_width = sensor_width;
+  o->sensor_height = (float)res_y / (float)res_x * o->sensor_width;
+}
+// reference src/main.cpp:49-56
+void lrp_lens_equidistant(float fov, lrp_lens *o) {
+  memset(o, 0, sizeof(*o));
+  o->type = LRP_FISHEYE_EQUIDISTANT;
+  o->u.fisheye_equidistant.fov = fov;
+  o->sensor_width = 36.0f;
+  o->sensor_height = 36.0f;
+}
+// reference src/main.cpp:31-47
+void lrp_lens_equisolid(float focal_length, float sensor_width, float fov, int res_x, int res_y, lrp_lens *o) {
+  memset(o, 0, sizeof(*o));
+  o->type = LRP_FISHEYE_EQUISOLID;
+  o->u.fisheye_equisolid.focal_length = focal_length;
+  o->u.fisheye_equisolid.fov = fov;
+  o->sensor_width = sensor_width;
+  o->sensor_height = (float)res_y / (float)res_x * o->sensor_width;
+}
+// reference src/main.cpp:62-66
+void lrp_lens_equirectangular_full(lrp_lens *o) {
+  memset(o, 0, sizeof(*o));
+  o->type = LRP_EQUIRECTANGULAR;
+  o->u.equirectangular.longitude_min = -M_PI;
+  o->u.equirectangular.longitude_max = M_PI;
+  o->u.equirectangular.latitude_min = -M_PI * 0.5f;
+  o->u.equirectangular.latitude_max = M_PI * 0.5f;
+}
+// reference src/main.cpp:68-93
+void lrp_lens_equirectangular(float lon_min, float lon_max, float lat_min, float lat_max, lrp_lens *o) {
+  memset(o, 0, sizeof(*o));
+  o->type = LRP_EQUIRECTANGULAR;
+  o->u.equirectangular.longitude_min = lon_min;
+  o->u.equirectangular.longitude_max = lon_max;
+  o->u.equirectangular.latitude_min = lat_min;
+  o->u.equirectangular.latitude_max = lat_max;
+}
+
+// ---- context ----
+
+int lrp_ctx_create(int device, int n_streams, lrp_ctx **out) {
+  if (!out || n_streams < 1 || n_streams > 64) return LRP_E_BAD_ARG;
+  *out = nullptr;
+  int phys = 0;
+  int rc = physical_device(device, &phys);
+  if (rc != LRP_OK) return rc;
+  LRP_CUDA(cudaSetDevice(phys));
+  lrp_ctx *c = new lrp_ctx();
+  c->device = device;
+  c->phys_device = phys;
+  const HostTables &T = host_tables();
+  cudaError_t e = cudaMalloc(&c->d_lut, sizeof(T.lut));
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_thr, sizeof(T.thr));
+  if (e == cudaSuccess) e = cudaMemcpy(c->d_lut, T.lut, sizeof(T.lut), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(c->d_thr, T.thr, sizeof(T.thr), cudaMemcpyHostToDevice);
+  for (int i = 0; i < n_streams && e == cudaSuccess; ++i) {
+    cudaStream_t s;
+    e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (e == cudaSuccess) c->streams.push_back(s);
+  }
+  c->slots.resize(n_streams);
+  for (int i = 0; i < n_streams && e == cudaSuccess; ++i)
+    e = cudaStreamCreateWithFlags(&c->slots[i].stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    lrp_ctx_destroy(c);
+    return map_cuda(e);
+  }
+  *out = c;
+  return LRP_OK;
+}
+
+int lrp_ctx_destroy(lrp_ctx *c) {
+  if (!c) return LRP_E_BAD_ARG;
+  if (c->pool) {
+    c->pool->wait_all();
+    c->pool->stop();
+    delete c->pool;
+  }
+  cudaSetDevice(c->phys_device);
+  for (auto s : c->streams) cudaStreamDestroy(s);
+  for (auto &s : c->slots) slot_destroy(s);
+  if (c->d_lut) cudaFree(c->d_lut);
+  if (c->d_thr) cudaFree(c->d_thr);
+  delete c;
+  return LRP_OK;
+}
+
+int lrp_ctx_device(const lrp_ctx *c) { return c ? c->device : -1; }
+int lrp_ctx_num_streams(const lrp_ctx *c) { return c ? (int)c->streams.size() : 0; }
+void *lrp_ctx_stream(lrp_ctx *c, int idx) {
+  if (!c || idx < 0 || idx >= (int)c->streams.size()) return nullptr;
+  return (void *)c->streams[idx];
+}
+
+int lrp_reproject_device(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const lrp_params *p,
+                         void *stream) {
+  if (!ctx) return LRP_E_BAD_ARG;
+  return launch_fused(ctx, in, out, p, nullptr, (cudaStream_t)stream);
+}
+
+int lrp_post_process_device(lrp_ctx *ctx, const lrp_image *img, float exposure, float reinhard, void *stream) {
+  if (!ctx || !img || !img->data || img->width <= 0 || img->height <= 0 || img->channels < 1) return LRP_E_BAD_ARG;
+  if (img->format != LRP_FMT_F32) return LRP_E_UNSUPPORTED_FORMAT;
+  DeviceGuard guard(ctx->phys_device);
+  return map_cuda((cudaError_t)launch_post_process((float *)img->data, (size_t)img->width * img->height,
+                                                   img->channels, exposure, reinhard, stream));
+}
+
+size_t lrp_remap_bytes(int W, int H, int ns) {
+  if (W <= 0 || H <= 0 || ns < 1) return 0;
+  return (size_t)W * H * ns * ns * sizeof(float) * 2;
+}
+
+int lrp_build_remap(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const lrp_params *p,
+                    void *remap_dev, void *stream) {
+  if (!remap_dev) return LRP_E_BAD_ARG;
+  KParams K;
+  int coord = 0, fc = 0;
+  int rc = prepare(ctx, in, out, p, false, K, coord, fc);
+  if (rc != LRP_OK) return rc;
+  DeviceGuard guard(ctx->phys_device);
+  K.coords_out = (float2 *)remap_dev;
+  K.coords_planes = K.ns * K.ns;
+  if (coord == COORD_ERECT_WRAP) coord = COORD_ERECT_CLAMP; // wrap only affects the sampler
+  return map_cuda((cudaError_t)launch_coords(K, coord, stream));
+}
+
+int lrp_reproject_device_remap(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const lrp_params *p,
+                               const void *remap_dev, void *stream) {
+  if (!ctx || !remap_dev) return LRP_E_BAD_ARG;
+  return launch_fused(ctx, in, out, p, remap_dev, (cudaStream_t)stream);
+}
+
+int lrp_debug_coords(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const lrp_params *p,
+                     float *out_sxy_dev, void *stream) {
+  if (!out_sxy_dev) return LRP_E_BAD_ARG;
+  KParams K;
+  int coord = 0, fc = 0;
+  int rc = prepare(ctx, in, out, p, false, K, coord, fc);
+  if (rc != LRP_OK) return rc;
+  DeviceGuard guard(ctx->phys_device);
+  K.coords_out = (float2 *)out_sxy_dev;
+  K.coords_planes = 1;
+  if (coord == COORD_ERECT_WRAP) coord = COORD_ERECT_CLAMP;
+  return map_cuda((cudaError_t)launch_coords(K, coord, stream));
+}
+
+int lrp_debug_libm(lrp_ctx *ctx, int fn, const float *a, const float *b, float *out, size_t n, void *stream) {
+  if (!ctx || !a || !out || fn < 0 || fn > 4 || (fn == 4 && !b)) return LRP_E_BAD_ARG;
+  DeviceGuard guard(ctx->phys_device);
+  return map_cuda((cudaError_t)launch_libm(fn, a, b, out, n, host_tables().libm_fma != 0, stream));
+}
+
+// ---- memory ----
+
+int lrp_alloc_pinned(size_t bytes, void **out) {
+  if (!out) return LRP_E_BAD_ARG;
+  LRP_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+  return LRP_OK;
+}
+int lrp_free_pinned(void *p) {
+  LRP_CUDA(cudaFreeHost(p));
+  return LRP_OK;
+}
+int lrp_alloc_device(lrp_ctx *ctx, size_t bytes, void **out) {
+  if (!ctx || !out) return LRP_E_BAD_ARG;
+  LRP_CUDA(cudaSetDevice(ctx->phys_device));
+  LRP_CUDA(cudaMalloc(out, bytes));
+  return LRP_OK;
+}
+int lrp_free_device(lrp_ctx *ctx, void *p) {
+  if (!ctx) return LRP_E_BAD_ARG;
+  LRP_CUDA(cudaSetDevice(ctx->phys_device));
+  LRP_CUDA(cudaFree(p));
+  return LRP_OK;
+}
+int lrp_memcpy_h2d(lrp_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream) {
+  if (!ctx) return LRP_E_BAD_ARG;
+  LRP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return LRP_OK;
+}
+int lrp_memcpy_d2h(lrp_ctx *ctx, void *dst, const void *src, size_t bytes, void *stream) {
+  if (!ctx) return LRP_E_BAD_ARG;
+  LRP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return LRP_OK;
+}
+int lrp_stream_sync(lrp_ctx *ctx, void *stream) {
+  if (!ctx) return LRP_E_BAD_ARG;
+  LRP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return LRP_OK;
+}
+
+// ---- synchronous host drop-ins ----
+
+static std::mutex g_default_mu;
+static std::map<int, lrp_ctx *> g_default_ctx;
+
+static int default_ctx(int device, lrp_ctx **out) {
+  std::lock_guard<std::mutex> lk(g_default_mu);
+  auto it = g_default_ctx.find(device);
+  if (it != g_default_ctx.end()) {
+    *out = it->second;
+    return LRP_OK;
+  }
+  lrp_ctx *c = nullptr;
+  int rc = lrp_ctx_create(device, 4, &c);
+  if (rc != LRP_OK) return rc;
+  g_default_ctx[device] = c;
+  *out = c;
+  return LRP_OK;
+}
+
+namespace {
+struct SlotLease { // re-entrant use from many host threads: each call leases one stream + buffers
+  lrp_ctx *c;
+  Slot *s = nullptr;
+  explicit SlotLease(lrp_ctx *ctx) : c(ctx) {
+    std::unique_lock<std::mutex> lk(c->mu);
+    c->cv.wait(lk, [&] {
+      for (auto &x : c->slots)
+        if (!x.busy) return true;
+      return false;
+    });
+    for (auto &x : c->slots)
+      if (!x.busy) {
+        x.busy = true;
+        s = &x;
+        break;
+      }
+  }
+  ~SlotLease() {
+    {
+      std::lock_guard<std::mutex> lk(c->mu);
+      s->busy = false;
+    }
+    c->cv.notify_one();
+  }
+};
+} // namespace
+
+int lrp_reproject_host(const lrp_image *in, lrp_image *out, const lrp_params *p, int device) {
+  if (!in || !out || !p) return LRP_E_BAD_ARG;
+  lrp_ctx *ctx = nullptr;
+  int rc = default_ctx(device, &ctx);
+  if (rc != LRP_OK) return rc;
+  { // validate before touching the device so that errors mirror the reference's early exits
+    KParams K;
+    int coord, fc;
+    rc = prepare(ctx, in, out, p, true, K, coord, fc);
+    if (rc != LRP_OK) return rc;
+  }
+  LRP_CUDA(cudaSetDevice(ctx->phys_device));
+  SlotLease lease(ctx);
+  const size_t in_bytes = lrp_image_bytes(in), out_bytes = lrp_image_bytes(out);
+  rc = slot_reserve(*lease.s, in_bytes, out_bytes);
+  if (rc != LRP_OK) return rc;
+  cudaStream_t st = lease.s->stream;
+  lrp_image din = *in, dout = *out;
+  din.data = lease.s->d_in;
+  dout.data = lease.s->d_out;
+  LRP_CUDA(cudaMemcpyAsync(lease.s->d_in, in->data, in_bytes, cudaMemcpyHostToDevice, st));
+  rc = launch_fused(ctx, &din, &dout, p, nullptr, st);
+  if (rc != LRP_OK) return rc;
+  LRP_CUDA(cudaMemcpyAsync(out->data, lease.s->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+  LRP_CUDA(cudaStreamSynchronize(st));
+  return LRP_OK;
+}
+
+int lrp_post_process_host(lrp_image *img, float exposure, float reinhard, int device) {
+  if (!img || !img->data || img->width <= 0 || img->height <= 0 || img->channels < 1) return LRP_E_BAD_ARG;
+  if (img->format != LRP_FMT_F32) return LRP_E_UNSUPPORTED_FORMAT;
+  lrp_ctx *ctx = nullptr;
+  int rc = default_ctx(device, &ctx);
+  if (rc != LRP_OK) return rc;
+  LRP_CUDA(cudaSetDevice(ctx->phys_device));
+  SlotLease lease(ctx);
+  const size_t bytes = lrp_image_bytes(img);
+  rc = slot_reserve(*lease.s, bytes, 0);
+  if (rc != LRP_OK) return rc;
+  cudaStream_t st = lease.s->stream;
+  LRP_CUDA(cudaMemcpyAsync(lease.s->d_in, img->data, bytes, cudaMemcpyHostToDevice, st));
+  lrp_image d = *img;
+  d.data = lease.s->d_in;
+  rc = lrp_post_process_device(ctx, &d, exposure, reinhard, st);
+  if (rc != LRP_OK) return rc;
+  LRP_CUDA(cudaMemcpyAsync(img->data, lease.s->d_in, bytes, cudaMemcpyDeviceToHost, st));
+  LRP_CUDA(cudaStreamSynchronize(st));
+  return LRP_OK;
+}
+
+// ---- asynchronous jobs on one context ----
+
+int lrp_submit(lrp_ctx *ctx, const lrp_job *job, uint64_t *ticket) {
+  if (!ctx || !job) return LRP_E_BAD_ARG;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->pool) {
+      Pool *p = new Pool();
+      int rc = p->start({ctx}, (int)ctx->streams.size());
+      if (rc != LRP_OK) {
+        p->stop();
+        delete p;
+        return rc;
+      }
+      ctx->pool = p;
+    }
+  }
+  uint64_t t = ctx->pool->submit(*job);
+  if (ticket) *ticket = t;
+  return LRP_OK;
+}
+
+int lrp_wait(lrp_ctx *ctx, uint64_t ticket) {
+  if (!ctx || !ctx->pool) return LRP_E_BAD_ARG;
+  return ctx->pool->wait(ticket);
+}
+
+int lrp_wait_all(lrp_ctx *ctx) {
+  if (!ctx) return LRP_E_BAD_ARG;
+  if (!ctx->pool) return LRP_OK;
+  return ctx->pool->wait_all();
+}
+
+// ---- multi-GPU scheduler ----
+
+int lrp_sched_create(const int *devices, int n_devices, int streams_per_device, lrp_sched **out) {
+  if (!out || n_devices < 1 || streams_per_device < 1 || streams_per_device > 16) return LRP_E_BAD_ARG;
+  *out = nullptr;
+  lrp_sched *s = new lrp_sched();
+  for (int i = 0; i < n_devices; ++i) {
+    lrp_ctx *c = nullptr;
+    int rc = lrp_ctx_create(devices ? devices[i] : i, 1, &c);
+    if (rc != LRP_OK) {
+      for (auto x : s->ctxs) lrp_ctx_destroy(x);
+      delete s;
+      return rc;
+    }
+    s->ctxs.push_back(c);
+  }
+  int rc = s->pool.start(s->ctxs, streams_per_device);
+  if (rc != LRP_OK) {
+    lrp_sched_destroy(s);
+    return rc;
+  }
+  *out = s;
+  return LRP_OK;
+}
+
+int lrp_sched_submit(lrp_sched *s, const lrp_job *job) {
+  if (!s || !job) return LRP_E_BAD_ARG;
+  s->pool.submit(*job);
+  return LRP_OK;
+}
+
+int lrp_sched_wait_all(lrp_sched *s) {
+  if (!s) return LRP_E_BAD_ARG;
+  return s->pool.wait_all();
+}
+
+int lrp_sched_num_devices(const lrp_sched *s) { return s ? (int)s->ctxs.size() : 0; }
+
+int lrp_sched_stats(const lrp_sched *s, int64_t *jobs_per_device) {
+  if (!s || !jobs_per_device) return LRP_E_BAD_ARG;
+  lrp_sched *m = const_cast<lrp_sched *>(s);
+  std::lock_guard<std::mutex> lk(m->pool.mu);
+  for (size_t i = 0; i < m->pool.per_device.size(); ++i) jobs_per_device[i] = m->pool.per_device[i];
+  return LRP_OK;
+}
+
+int lrp_sched_destroy(lrp_sched *s) {
+  if (!s) return LRP_E_BAD_ARG;
+  s->pool.wait_all();
+  s->pool.stop();
+  for (auto c : s->ctxs) lrp_ctx_destroy(c);
+  delete s;
+  return LRP_OK;
+}
+
+} // extern "C"

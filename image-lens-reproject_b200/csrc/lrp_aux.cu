@@ -1,0 +1,75 @@
+// lrp_aux.cu — small kernels around the main one: the remap-table / coordinate dump
+// kernel, the stand-alone post_process kernel and the libm test hook.
+#include "lrp_kernel.cuh"
+
+namespace lrp {
+
+// Writes (sx, sy) of every output pixel for the first `coords_planes` sub-samples
+// ([ssx*ns + ssy][H][W] float2).  Serves lrp_build_remap (all ns*ns planes) and
+// lrp_debug_coords (plane 0).  Same device functions as the fused kernel, so a remap
+// table is bit-identical to on-the-fly coordinates by construction.
+__global__ void __launch_bounds__(TILE_X *TILE_Y) coords_kernel(const __grid_constant__ KParams P, int coord) {
+  const int x = blockIdx.x * TILE_X + threadIdx.x;
+  const int y = blockIdx.y * TILE_Y + threadIdx.y;
+  if (x >= P.W || y >= P.H) return;
+  const float cx = fsub(fadd((float)x, 0.5f), fmul((float)P.W, 0.5f));
+  const float cy = fsub(fadd((float)y, 0.5f), fmul((float)P.H, 0.5f));
+  for (int plane = 0; plane < P.coords_planes; ++plane) {
+    const int ssx = plane / P.ns, ssy = plane % P.ns;
+    const float scx = fsub(fadd(cx, fdiv(fadd((float)ssx, 1.0f), P.ss_den)), 0.5f);
+    const float scy = fsub(fadd(cy, fdiv(fadd((float)ssy, 1.0f), P.ss_den)), 0.5f);
+    float sx, sy;
+    if (coord == COORD_RECT) source_coord<COORD_RECT>(P, scx, scy, sx, sy);
+    else if (coord == COORD_EQUIDISTANT) source_coord<COORD_EQUIDISTANT>(P, scx, scy, sx, sy);
+    else source_coord<COORD_ERECT_CLAMP>(P, scx, scy, sx, sy);
+    P.coords_out[((size_t)plane * (size_t)P.H + (size_t)y) * (size_t)P.W + (size_t)x] = make_float2(sx, sy);
+  }
+}
+
+int launch_coords(const KParams &P, int coord, void *stream) {
+  dim3 block(TILE_X, TILE_Y);
+  dim3 grid((P.W + TILE_X - 1) / TILE_X, (P.H + TILE_Y - 1) / TILE_Y);
+  coords_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(P, coord);
+  return (int)cudaGetLastError();
+}
+
+// reproject::post_process (reference src/reproject.cpp:421-437) on an interleaved float32
+// image, in place: first min(C,3) channels of every pixel.
+__global__ void post_process_kernel(float *data, size_t n_pixels, int channels, float exposure, float r2) {
+  const int ch = channels < 3 ? channels : 3;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += (size_t)gridDim.x * blockDim.x) {
+    float *p = data + i * channels;
+    for (int c = 0; c < ch; ++c) p[c] = canon_nan(post_process_value(p[c], exposure, r2));
+  }
+}
+
+int launch_post_process(float *data, size_t n_pixels, int channels, float exposure, float reinhard, void *stream) {
+  const float r2 = reinhard * reinhard; // host float product == the reference's per-pixel (reinhard * reinhard)
+  int block = 256;
+  size_t want = (n_pixels + block - 1) / block;
+  int grid = (int)(want < 148 * 16 ? (want ? want : 1) : 148 * 16);
+  post_process_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(data, n_pixels, channels, exposure, r2);
+  return (int)cudaGetLastError();
+}
+
+// test hook: the device libm restatement, element-wise
+__global__ void libm_kernel(int fn, const float *a, const float *b, float *out, size_t n, int use_fma) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float x = a[i], r;
+    switch (fn) {
+    case 0: r = dev_atanf(x); break;
+    case 1: r = dev_asinf(x); break;
+    case 2: dev_sincosf(x, use_fma != 0, &r, nullptr); break;
+    case 3: dev_sincosf(x, use_fma != 0, nullptr, &r); break;
+    default: r = dev_atan2f(x, b[i]); break;
+    }
+    out[i] = r;
+  }
+}
+
+int launch_libm(int fn, const float *a, const float *b, float *out, size_t n, int use_fma, void *stream) {
+  libm_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(fn, a, b, out, n, use_fma);
+  return (int)cudaGetLastError();
+}
+
+} // namespace lrp

@@ -1,0 +1,60 @@
+// lrp_params.h — kernel parameter block shared by the host API and the kernels.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+namespace lrp {
+
+enum : int { LENS_RECT = 0, LENS_EQUIDISTANT = 1, LENS_EQUISOLID = 2, LENS_STEREO = 3, LENS_ERECT = 4 };
+enum : int { INTERP_NN = 0, INTERP_BL = 1, INTERP_BC = 2 };
+enum : int { FMT_F32 = 0, FMT_U8 = 1, FMT_F16 = 2 };
+
+// How a kernel obtains the source coordinate of a sub-sample.  The four on-the-fly modes
+// are the reference's four `vec2src x LoopHorizontally` instantiations
+// (src/reproject.cpp:378-394); the two table modes read a precomputed remap table.
+enum : int {
+  COORD_RECT = 0,
+  COORD_EQUIDISTANT = 1,
+  COORD_ERECT_CLAMP = 2,
+  COORD_ERECT_WRAP = 3,
+  COORD_TABLE_CLAMP = 4,
+  COORD_TABLE_WRAP = 5,
+  COORD_COUNT = 6
+};
+
+// (source format, channels) combinations that are instantiated
+enum : int { FC_F32_3 = 0, FC_F32_4, FC_F32_5, FC_U8_3, FC_F16_3, FC_F16_4, FC_F16_5, FC_COUNT };
+
+struct LensP {
+  int type;
+  float p0, p1, p2, p3; // union payload of reproject::LensInfo
+  float sw, sh;
+};
+
+struct KParams {
+  LensP ol, il;          // output / input lens
+  int W, H, w, h;        // output / input size
+  int ns;                // sub-samples per axis
+  float ss_den;          // float(ns) + 1.0f        (src/reproject.cpp:295)
+  float normalize;       // 1.0f / float(ns * ns)   (src/reproject.cpp:280)
+  int has_rot;
+  float R[9];
+  int post;              // fused post_process
+  float exposure, r2;    // r2 = reinhard * reinhard (float product, src/reproject.cpp:430)
+  int use_fma;           // host libm sinf/cosf variant
+  int dst_fmt;           // FMT_*
+  const void *src;
+  void *dst;
+  long long src_plane;   // elements between planes (F16 planar)
+  long long dst_plane;
+  const float *lut;      // [256] gamma decode table            (host powf, image_formats.cpp:195)
+  const float *thr;      // [256] gamma encode threshold table  (host powf, image_formats.cpp:156-158)
+  const float2 *remap;   // COORD_TABLE_*: [ns*ns][H][W] (sx, sy)
+  float2 *coords_out;    // coords kernel output
+  int coords_planes;     // how many sub-sample planes the coords kernel writes
+  unsigned long long neg_zero2; // packed (-0.0f, -0.0f); opaque to ptxas (see lrp_math.cuh)
+};
+
+typedef int (*LaunchFn)(const KParams &P, void *stream);
+
+} // namespace lrp

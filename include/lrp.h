@@ -1,0 +1,226 @@
+/* lrp.h — C ABI of the B200-native lens-reprojection hot path (liblrp.so).
+ *
+ * This is the drop-in boundary for the per-pixel reprojection path of
+ * IDLabMedia/image-lens-reproject.  The reference has no plugin system; its
+ * seam is the C++ header src/reproject.hpp:22-25, called from one place, the
+ * thread-pool worker in src/main.cpp:597-603.  Every entry point below cites
+ * the reference interface it replaces.  Plain C: POD structs, raw pointers and
+ * sizes, int status codes; nothing throws or exit()s across this boundary
+ * (the reference printf()+exit(1)s on unsupported lenses, src/reproject.cpp:
+ * 365-366, 396-397, 416-417 — here that is LRP_E_UNSUPPORTED_*).
+ *
+ * There is NO CPU fallback: every compute entry point needs a CUDA device and
+ * returns LRP_E_NO_DEVICE / LRP_E_CUDA otherwise.
+ */
+#ifndef LRP_H
+#define LRP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRP_VERSION_MAJOR 0
+#define LRP_VERSION_MINOR 1
+
+/* ---- status codes ------------------------------------------------------- */
+typedef enum lrp_status {
+  LRP_OK = 0,
+  LRP_E_BAD_ARG = 1,
+  LRP_E_UNSUPPORTED_OUTPUT_LENS = 2, /* reference: "Output lens type not supported." + exit(1) */
+  LRP_E_UNSUPPORTED_INPUT_LENS = 3,  /* reference: "Input lens type not supported." + exit(1)  */
+  LRP_E_UNSUPPORTED_INTERP = 4,      /* reference: "Interpolation method not supported."       */
+  LRP_E_UNSUPPORTED_FORMAT = 5,
+  LRP_E_CUDA = 6,
+  LRP_E_OOM = 7,
+  LRP_E_NO_DEVICE = 8
+} lrp_status;
+
+/* ---- payload types (reference src/config.hpp:7-37, src/reproject.hpp:7-20) */
+
+/* same values as reproject::LensType, src/config.hpp:7-13 */
+typedef enum lrp_lens_type {
+  LRP_RECTILINEAR = 0,
+  LRP_FISHEYE_EQUIDISTANT = 1,
+  LRP_FISHEYE_EQUISOLID = 2,     /* parsed by the reference CLI, NOT implemented by its kernel   */
+  LRP_FISHEYE_STEREOGRAPHIC = 3, /* idem                                                          */
+  LRP_EQUIRECTANGULAR = 4
+} lrp_lens_type;
+
+/* Byte-for-byte the layout of reproject::LensInfo (28 bytes), so a reference
+ * LensInfo* can be reinterpret_cast to lrp_lens*. */
+typedef struct lrp_lens {
+  int32_t type;
+  union {
+    struct { float focal_length; } rectilinear;
+    struct { float fov; } fisheye_equidistant;
+    struct { float focal_length; float fov; } fisheye_equisolid;
+    struct { float latitude_min, latitude_max, longitude_min, longitude_max; } equirectangular;
+    float raw[4];
+  } u;
+  float sensor_width;
+  float sensor_height;
+} lrp_lens;
+
+/* reproject::DataLayout, src/reproject.hpp:7 */
+typedef enum lrp_layout { LRP_RGB = 0, LRP_RGBA = 1, LRP_RGBZ = 2, LRP_RGBAZ = 3 } lrp_layout;
+
+/* reproject::Interpolation, src/reproject.hpp:16-20 */
+typedef enum lrp_interp { LRP_NEAREST = 0, LRP_BILINEAR = 1, LRP_BICUBIC = 2 } lrp_interp;
+
+/* How the samples of an image are stored.  F32 is the reference's in-memory
+ * layout; the other two are the codec-native layouts, with the codec-edge
+ * arithmetic of src/image_formats.cpp fused into the kernel's load / store:
+ *   U8_RGBA    4 bytes/pixel as lodepng produces/consumes.  As a source:
+ *              powf(p/255, 2.2) on R,G,B, alpha dropped, 3 channels
+ *              (read_png, :191-199).  As a sink: clamp, powf(s, 1/2.2),
+ *              uint8(255.9*s) on every channel, alpha = 255 unless channels==4
+ *              (save_png, :150-165).
+ *   F16_PLANAR `channels` planes of IEEE half, plane stride = width*height
+ *              (the HALF slices of read_exr :252-261 / save_exr :319-329);
+ *              half->float exact, float->half RNE with overflow to inf. */
+typedef enum lrp_format { LRP_FMT_F32 = 0, LRP_FMT_U8_RGBA = 1, LRP_FMT_F16_PLANAR = 2 } lrp_format;
+
+/* reproject::Image, src/reproject.hpp:9-14, plus the storage format.  `data`
+ * is a HOST pointer for the *_host entry points and a DEVICE pointer for the
+ * *_device ones.  Caller-owned; the library never retains it past completion. */
+typedef struct lrp_image {
+  lrp_lens lens;
+  int32_t width, height, channels;
+  int32_t layout; /* lrp_layout: carried, not interpreted (as in the reference) */
+  int32_t format; /* lrp_format */
+  void *data;
+} lrp_image;
+
+/* The remaining arguments of reproject() + post_process() (src/reproject.hpp:22-25)
+ * and the condition under which main() calls post_process (src/main.cpp:601). */
+typedef struct lrp_params {
+  int32_t num_samples;   /* N x N sub-samples per output pixel (>= 1)                       */
+  int32_t interpolation; /* lrp_interp                                                      */
+  int32_t has_rotation;  /* 0: rotation_matrix == nullptr in the reference                  */
+  float rotation[9];     /* row-major 3x3                                                   */
+  int32_t apply_post;    /* run post_process (exposure, Reinhard) fused into the same pass  */
+  float exposure;        /* linear multiplier (2^EV)                                        */
+  float reinhard;        /* extended-Reinhard white point                                   */
+  int32_t variant;       /* lrp_variant: source-access strategy; 0 = library default        */
+} lrp_params;
+
+/* Source-access strategies (north-star item 3); results are bit-identical. */
+typedef enum lrp_variant {
+  LRP_VARIANT_AUTO = 0,
+  LRP_VARIANT_GATHER = 1, /* on-the-fly coordinates, L1/L2 gather of the taps              */
+  LRP_VARIANT_REMAP = 2   /* coordinates read from a precomputed remap table (lrp_build_remap) */
+} lrp_variant;
+
+typedef struct lrp_ctx lrp_ctx;     /* one per GPU; thread-safe                          */
+typedef struct lrp_sched lrp_sched; /* multi-GPU image scheduler (replaces ctpl pool)    */
+
+/* ---- library ------------------------------------------------------------ */
+const char *lrp_version(void);
+const char *lrp_strerror(int status);
+/* Number of CUDA devices visible (0 when there is no driver / no GPU). */
+int lrp_device_count(void);
+/* Bytes of an image's sample buffer for its format. */
+size_t lrp_image_bytes(const lrp_image *img);
+/* Which sinf/cosf variant of the host libm the device code reproduces: 1 = FMA
+ * IFUNC variant, 0 = non-FMA.  Probed from the host's own libm at load time
+ * (the reference's coordinates depend on it). */
+int lrp_host_libm_uses_fma(void);
+
+/* ---- host helpers that feed the kernel (bit-exact host arithmetic) ------- */
+/* computeRotationMatrix(pan, pitch, roll), radians — src/main.cpp:110-142 */
+void lrp_rotation_matrix(float pan, float pitch, float roll, float out9[9]);
+/* the `--rotation pan,pitch,roll` degree parsing — src/main.cpp:312-325 */
+void lrp_rotation_from_degrees(double pan_deg, double pitch_deg, double roll_deg, float out9[9]);
+/* lens constructors mirroring the CLI parsers — src/main.cpp:15-95 */
+void lrp_lens_rectilinear(float focal_length, float sensor_width, int res_x, int res_y, lrp_lens *out);
+void lrp_lens_equidistant(float fov, lrp_lens *out);
+void lrp_lens_equisolid(float focal_length, float sensor_width, float fov, int res_x, int res_y,
+                        lrp_lens *out);
+void lrp_lens_equirectangular_full(lrp_lens *out);
+void lrp_lens_equirectangular(float lon_min, float lon_max, float lat_min, float lat_max, lrp_lens *out);
+
+/* ---- synchronous drop-ins (HOST buffers) -------------------------------- */
+/* reproject::reproject(in, out, num_samples, interpolation, rotation_matrix)
+ * [src/reproject.cpp:405-419] followed, when p->apply_post, by
+ * reproject::post_process(out, exposure, reinhard) [src/reproject.cpp:421-437],
+ * as the worker does in src/main.cpp:597-603.  H2D copy, one fused kernel, D2H
+ * copy on device `device` (use 0). */
+int lrp_reproject_host(const lrp_image *in, lrp_image *out, const lrp_params *p, int device);
+/* reproject::post_process(img, exposure, reinhard) stand-alone, in place. */
+int lrp_post_process_host(lrp_image *img, float exposure, float reinhard, int device);
+
+/* ---- per-GPU context (device-resident / pipelined use) ------------------- */
+int lrp_ctx_create(int device, int n_streams, lrp_ctx **out);
+int lrp_ctx_destroy(lrp_ctx *ctx);
+int lrp_ctx_device(const lrp_ctx *ctx);
+int lrp_ctx_num_streams(const lrp_ctx *ctx);
+/* cudaStream_t of the ctx's stream `idx` (as void*), for event timing by the caller */
+void *lrp_ctx_stream(lrp_ctx *ctx, int idx);
+
+/* Fused reproject(+post_process) on DEVICE buffers, asynchronous on `cuda_stream`
+ * (a cudaStream_t passed as void*; NULL = the legacy default stream). */
+int lrp_reproject_device(lrp_ctx *ctx, const lrp_image *in_dev, const lrp_image *out_dev,
+                         const lrp_params *p, void *cuda_stream);
+int lrp_post_process_device(lrp_ctx *ctx, const lrp_image *img_dev, float exposure, float reinhard,
+                            void *cuda_stream);
+
+/* Remap table: the (sx, sy) source coordinate of every output pixel (sub-sample
+ * major: [ssx][ssy][H][W] float2), computed once per (lens pair, sizes, rotation)
+ * and reused across the frames of a batch (LRP_VARIANT_REMAP). */
+size_t lrp_remap_bytes(int out_width, int out_height, int num_samples);
+int lrp_build_remap(lrp_ctx *ctx, const lrp_image *in_geom, const lrp_image *out_geom,
+                    const lrp_params *p, void *remap_dev, void *cuda_stream);
+int lrp_reproject_device_remap(lrp_ctx *ctx, const lrp_image *in_dev, const lrp_image *out_dev,
+                               const lrp_params *p, const void *remap_dev, void *cuda_stream);
+
+/* memory helpers (pinned host buffers for the pipeline; device buffers) */
+int lrp_alloc_pinned(size_t bytes, void **out);
+int lrp_free_pinned(void *p);
+int lrp_alloc_device(lrp_ctx *ctx, size_t bytes, void **out);
+int lrp_free_device(lrp_ctx *ctx, void *p);
+int lrp_memcpy_h2d(lrp_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, void *cuda_stream);
+int lrp_memcpy_d2h(lrp_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes, void *cuda_stream);
+int lrp_stream_sync(lrp_ctx *ctx, void *cuda_stream);
+
+/* ---- asynchronous job API: H2D -> kernel -> D2H on one of the ctx's streams
+ * (replaces one iteration of the worker lambda, src/main.cpp:565-613, minus the
+ * codecs).  Host buffers should be pinned (lrp_alloc_pinned) to overlap. */
+typedef void (*lrp_done_fn)(void *user, int status);
+typedef struct lrp_job {
+  lrp_image in;  /* host buffer */
+  lrp_image out; /* host buffer */
+  lrp_params params;
+  lrp_done_fn on_done; /* may be NULL; called from a library thread */
+  void *user;
+} lrp_job;
+int lrp_submit(lrp_ctx *ctx, const lrp_job *job, uint64_t *ticket);
+int lrp_wait(lrp_ctx *ctx, uint64_t ticket); /* returns the job's status */
+int lrp_wait_all(lrp_ctx *ctx);
+
+/* ---- multi-GPU scheduler: replaces `ctpl::thread_pool pool(num_threads)` +
+ * pool.push(job) + pool.stop(true) (src/main.cpp:538-541, 657).  Images are
+ * independent, so jobs are handed to whichever GPU stream frees up first; no
+ * collective is involved. */
+int lrp_sched_create(const int *devices, int n_devices, int streams_per_device, lrp_sched **out);
+int lrp_sched_submit(lrp_sched *s, const lrp_job *job);
+int lrp_sched_wait_all(lrp_sched *s); /* returns first non-OK job status, else LRP_OK */
+int lrp_sched_destroy(lrp_sched *s);
+int lrp_sched_num_devices(const lrp_sched *s);
+/* jobs completed per device so far (array of n_devices) — for tests / stats */
+int lrp_sched_stats(const lrp_sched *s, int64_t *jobs_per_device);
+
+/* ---- test hooks (Level-0 parity) -------------------------- */
+/* per-pixel (sx, sy) of sub-sample (0,0): out_sxy_dev = float[H*W*2] on device */
+int lrp_debug_coords(lrp_ctx *ctx, const lrp_image *in_geom, const lrp_image *out_geom,
+                     const lrp_params *p, float *out_sxy_dev, void *cuda_stream);
+/* device libm restatement: fn 0 atanf, 1 asinf, 2 sinf, 3 cosf, 4 atan2f(a,b) */
+int lrp_debug_libm(lrp_ctx *ctx, int fn, const float *a_dev, const float *b_dev, float *out_dev,
+                   size_t n, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRP_H */

@@ -1,0 +1,151 @@
+"""CPU-side (`-m "not gpu"`) checks of the drop-in boundary: the C-ABI library loads, exports
+every symbol include/lrp.h declares, the header is valid C, the host helpers reproduce the
+reference's host arithmetic, and — with no GPU here — the compute entry points fail loudly
+instead of falling back to a CPU path."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import kat_data as K
+import oracle_lib as ol
+
+ROOT = ol.ROOT
+HDR = os.path.join(ROOT, "include", "lrp.h")
+PKG = os.path.join(ROOT, "image-lens-reproject_b200")
+ORC = ol.oracle()
+
+
+@pytest.fixture(scope="module")
+def lrp():
+    if not os.path.exists(os.path.join(PKG, "liblrp.so")):
+        import __graft_entry__ as g
+        g.build()
+    import lrp as m
+    m.lib()
+    return m
+
+
+def declared_symbols():
+    src = open(HDR).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lrp_[a-z0-9_]+)\s*\(", src)) - {"lrp_done_fn"})
+
+
+def test_header_is_valid_c(tmp_path):
+    c = tmp_path / "t.c"
+    c.write_text('#include "lrp.h"\nint main(void){ lrp_lens l; lrp_image i; lrp_params p; lrp_job j; '
+                 '(void)l;(void)i;(void)p;(void)j; return sizeof(lrp_lens) == 28 ? 0 : 1; }\n')
+    exe = tmp_path / "t"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.dirname(HDR), str(c), "-o", str(exe)],
+                   check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_library_exports_every_declared_symbol(lrp):
+    names = declared_symbols()
+    assert len(names) >= 35, names
+    L = C.CDLL(os.path.join(PKG, "liblrp.so"))
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_struct_layouts_match_header(lrp):
+    assert C.sizeof(lrp.Lens) == 28  # == sizeof(reproject::LensInfo), reference src/config.hpp:15-37
+    assert C.sizeof(ol.Lens) == 28
+    assert lrp.Image.data.offset == 48 and C.sizeof(lrp.Image) == 56
+    assert C.sizeof(lrp.Params) == 12 + 36 + 16
+
+
+def test_rotation_matrix_matches_reference_kat(lrp):
+    m = lrp.rotation_from_degrees(30, 20, 10)
+    assert ol.same_bits(m, np.array(K.ROT_30_20_10, np.float32))
+    for ang in ((0, 0, 0), (180, 0, 0), (-75.5, -33.25, 140), (90, 90, 90), (0.001, 359.9, -0.5)):
+        assert ol.same_bits(lrp.rotation_from_degrees(*ang), ORC.rotation_from_degrees(*ang)), ang
+    assert ol.same_bits(lrp.rotation_matrix(0.1, 0.2, 0.3), ORC.rotation_matrix(0.1, 0.2, 0.3))
+
+
+def test_lens_constructors_match_cli_parsers(lrp):
+    def same(a, b):
+        return bytes(a) == bytes(b)
+    assert same(lrp.lens_rectilinear(18.0, 36.0, 3840, 2160), ol.rect(18.0, 36.0, 3840, 2160))
+    assert same(lrp.lens_rectilinear(36.0, 36.0, 1920, 1080), ol.rect(36.0, 36.0, 1920, 1080))
+    assert same(lrp.lens_equidistant(3.14159), ol.equidistant(3.14159))
+    assert same(lrp.lens_equirectangular(), ol.erect())
+    assert same(lrp.lens_equirectangular(-1.0, 2.0, -0.7, 0.9), ol.erect(-1.0, 2.0, -0.7, 0.9))
+    assert same(lrp.lens_equisolid(12.5, 36.0, 3.14159, 1920, 1080), ol.equisolid(12.5, 36.0, 3.14159, 1920, 1080))
+
+
+def test_host_libm_probe(lrp):
+    assert lrp.host_libm_uses_fma() in (0, 1)
+
+
+def test_image_bytes(lrp):
+    L = lrp.lib()
+    im = lrp.make_image(lrp.Lens(), 10, 7, 4, lrp.FMT_F32, None)
+    assert L.lrp_image_bytes(C.byref(im)) == 10 * 7 * 4 * 4
+    im.format = lrp.FMT_U8_RGBA
+    assert L.lrp_image_bytes(C.byref(im)) == 10 * 7 * 4
+    im.format = lrp.FMT_F16_PLANAR
+    assert L.lrp_image_bytes(C.byref(im)) == 10 * 7 * 4 * 2
+    assert L.lrp_remap_bytes(10, 7, 2) == 10 * 7 * 4 * 8
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="this check is for the GPU-less build container")
+def test_no_cpu_fallback_without_a_gpu(lrp):
+    """The product path must fail loudly when there is no device: no oracle, no CPU path behind it."""
+    assert lrp.device_count() == 0
+    src = ol.noise(8, 8, 3)
+    with pytest.raises(lrp.LrpError) as e:
+        lrp.reproject_host(src, lrp.lens_equirectangular(), lrp.lens_rectilinear(18, 36, 8, 8), 8, 8)
+    assert e.value.status == lrp.E_NO_DEVICE
+    with pytest.raises(lrp.LrpError) as e:
+        lrp.Context(0, 1)
+    assert e.value.status == lrp.E_NO_DEVICE
+    with pytest.raises(lrp.LrpError):
+        lrp.post_process_host(src, 1.5, 4.0)
+    with pytest.raises(lrp.LrpError):
+        lrp.Scheduler([0, 1])
+
+
+def test_product_does_not_link_or_import_the_oracle(lrp):
+    out = subprocess.run(["ldd", os.path.join(PKG, "liblrp.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+    for dirpath, _, files in os.walk(PKG):
+        if os.sep + "build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".h", ".hpp", ".cpp", ".py")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                for pat in (r'#\s*include\s*[<"][^>"]*oracle', r'\bimport\s+oracle', r'\bfrom\s+oracle',
+                            r'liblrp_oracle', r'libref_oracle', r'\borc_[a-z]', r'\bref_reproject'):
+                    assert not re.search(pat, txt), (dirpath, f, pat)
+
+
+def test_packed_arithmetic_is_never_contracted(lrp):
+    """ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false.  Every FFMA2
+    in the library must therefore have the opaque -0.0 pair as its addend (one and the same register
+    per kernel) — anything else is a contracted multiply-add that would break bit parity."""
+    sass = subprocess.run(["cuobjdump", "-sass", os.path.join(PKG, "liblrp.so")], capture_output=True,
+                          text=True).stdout
+    kernels = sass.split("Function : ")[1:]
+    n_ffma2 = 0
+    for k in kernels:
+        name = k.split("\n", 1)[0]
+        addends = set()
+        for m in re.finditer(r"FFMA2\s+[^;]*,\s*([^,;]+?)\s*;", k):
+            n_ffma2 += 1
+            addends.add(re.sub(r"\.reuse|\.F32x2\.\w+|\.F32", "", m.group(1)).strip())
+        assert len(addends) <= 1, (name, addends)
+    assert n_ffma2 > 1000  # the packed bicubic kernels are really in there

@@ -1,0 +1,413 @@
+"""GPU parity tests (`-m gpu`): the CUDA path, called through the C ABI (liblrp.so), against the
+CPU oracle on the same seeded inputs, against the golden fixtures produced by the reference
+itself, and — when oracle/_ref travelled to the box — against the compiled reference directly.
+
+Tolerances (BASELINE.json north_star): <= 1 LSB for 8-bit PNG, <= 1e-5 relative for float EXR
+colour + depth, out-of-FOV / clamped pixels bit-identical.  What is actually asserted is
+STRICTER: float32 and half outputs must be bit-identical to the oracle (NaNs compared as the
+canonical x86 NaN), 8-bit outputs must be identical (0 LSB).
+"""
+import itertools
+import math
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+ORC = ol.oracle()
+
+
+@pytest.fixture(scope="module")
+def lrp():
+    import lrp as m
+    m.lib()
+    assert m.device_count() >= 1
+    return m
+
+
+@pytest.fixture(scope="module")
+def ctx(lrp):
+    c = lrp.Context(0, 2)
+    yield c
+    c.close()
+
+
+def L(lrp, lens):
+    return lrp.lens_from(lens)
+
+
+LENS = {
+    "rect": lambda W, H: ol.rect(18.0, 36.0, W, H),
+    "rect_tele": lambda W, H: ol.rect(50.0, 36.0, W, H),
+    "equidistant": lambda W, H: ol.equidistant(math.pi),
+    "equidistant_120": lambda W, H: ol.equidistant(2.0943951),
+    "erect": lambda W, H: ol.erect(),
+    "erect_part": lambda W, H: ol.erect(-1.0, 2.0, -0.7, 0.9),
+}
+ROTS = {"none": None, "ident": (0, 0, 0), "r30_20_10": (30, 20, 10), "pitch90": (0, 90, 0),
+        "pan180": (180, 0, 0), "neg": (-75.5, -33.25, 140)}
+
+
+def rot(name):
+    r = ROTS[name]
+    return None if r is None else ORC.rotation_from_degrees(*r)
+
+
+def assert_same(a, b, what):
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    eq = (ol.bits(a) == ol.bits(b)) | (np.isnan(a) & np.isnan(b))
+    if not eq.all():
+        idx = np.argwhere(~eq)[0]
+        raise AssertionError("%s: %d / %d values differ; first at %s: gpu %r (0x%08x) oracle %r (0x%08x)" % (
+            what, (~eq).sum(), eq.size, tuple(idx), a[tuple(idx)], ol.bits(a)[tuple(idx)], b[tuple(idx)],
+            ol.bits(b)[tuple(idx)]))
+
+
+# ---- host helpers of the C ABI ----------------------------------------------------------------
+
+def test_host_libm_variant_detected(lrp):
+    assert lrp.host_libm_uses_fma() in (0, 1), "host libm matches neither known sinf/cosf variant"
+
+
+# ---- Level 0: device libm + coordinates --------------------------------------------------------
+
+def test_device_libm_matches_host_libm(lrp, ctx):
+    import ctypes as C
+    import torch
+    libm = C.CDLL("libm.so.6")
+    rng = np.random.default_rng(0)
+    n = 1 << 21
+    fma = lrp.host_libm_uses_fma()
+    sets = {
+        0: np.concatenate([rng.standard_normal(n).astype(np.float32) * 3, rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32).view(np.float32)]),
+        1: np.concatenate([rng.uniform(-1, 1, n).astype(np.float32), rng.integers(0, 2**32, n // 4, dtype=np.uint64).astype(np.uint32).view(np.float32)]),
+        2: rng.uniform(-100, 100, 2 * n).astype(np.float32),
+        3: rng.uniform(-100, 100, 2 * n).astype(np.float32),
+    }
+    names = {0: "atanf", 1: "asinf", 2: "sinf", 3: "cosf"}
+    for fn, xs in sets.items():
+        got = ctx.debug_libm(fn, torch.from_numpy(xs).cuda()).cpu().numpy()
+        # the oracle's restated functions are proven == host libm by the CPU suite; use the host libm itself here
+        f = getattr(libm, names[fn])
+        f.restype, f.argtypes = C.c_float, [C.c_float]
+        sub = rng.choice(len(xs), 200000, replace=False)
+        want = np.array([f(float(x)) for x in xs[sub]], np.float32)
+        assert_same(got[sub], want, names[fn])
+    y = np.concatenate([rng.uniform(-1, 1, n).astype(np.float32), rng.standard_normal(n).astype(np.float32) * 1e3])
+    x = np.concatenate([rng.uniform(-1, 1, n).astype(np.float32), rng.standard_normal(n).astype(np.float32)])
+    got = ctx.debug_libm(4, torch.from_numpy(y).cuda(), torch.from_numpy(x).cuda()).cpu().numpy()
+    libm.atan2f.restype, libm.atan2f.argtypes = C.c_float, [C.c_float, C.c_float]
+    sub = rng.choice(len(x), 200000, replace=False)
+    want = np.array([libm.atan2f(float(a), float(b)) for a, b in zip(y[sub], x[sub])], np.float32)
+    assert_same(got[sub], want, "atan2f")
+    assert fma in (0, 1)
+
+
+@pytest.mark.parametrize("o,i", list(itertools.product(["rect", "equidistant", "erect"], repeat=2)))
+def test_coordinates_bit_exact(lrp, ctx, o, i):
+    W, H, w, h = 640, 480, 1000, 500
+    for rn in ("r30_20_10", "ident", "pitch90", "neg", "none"):
+        p = lrp.make_params(1, lrp.BICUBIC, rot(rn))
+        got = ctx.debug_coords(L(lrp, LENS[i](w, h)), w, h, L(lrp, LENS[o](W, H)), W, H, p).cpu().numpy()
+        want = ORC.coords_image(LENS[o](W, H), W, H, LENS[i](w, h), w, h, rot(rn))
+        assert_same(got, want, "coords %s<-%s %s" % (o, i, rn))
+
+
+def test_coordinates_kats(lrp, ctx):
+    import kat_data as K
+    r = np.array(K.ROT_30_20_10, np.float32)
+    for (o, i), rows in K.SXY.items():
+        p = lrp.make_params(1, lrp.BICUBIC, r)
+        got = ctx.debug_coords(L(lrp, K.in_lens(i)), K.w, K.h, L(lrp, K.out_lens(o)), K.W, K.H, p).cpu().numpy()
+        for (x, y), (sx, sy) in zip(K.PIXELS, rows):
+            want = np.array([float.fromhex(sx), float.fromhex(sy)], np.float32)
+            assert_same(got[y, x], want, "KAT %s<-%s (%d,%d)" % (o, i, x, y))
+
+
+# ---- Level 1: float32 pixels -------------------------------------------------------------------
+
+@pytest.mark.parametrize("o,i", list(itertools.product(LENS, LENS)))
+def test_pixels_lens_matrix(lrp, o, i):
+    W, H, w, h = 53, 38, 61, 47
+    src = ol.noise(h, w, 3, seed=7)
+    for interp in (ol.NEAREST, ol.BILINEAR, ol.BICUBIC):
+        for rn in ("r30_20_10", "pitch90"):
+            want = ORC.reproject(src, LENS[i](w, h), LENS[o](W, H), W, H, 1, interp, rot(rn))
+            got = lrp.reproject_host(src, L(lrp, LENS[i](w, h)), L(lrp, LENS[o](W, H)), W, H, 1, interp, rot(rn))
+            assert_same(got, want, "%s<-%s interp %d %s" % (o, i, interp, rn))
+
+
+@pytest.mark.parametrize("rn", sorted(ROTS))
+@pytest.mark.parametrize("c", [3, 4, 5])
+def test_pixels_channels_rotations(lrp, rn, c):
+    W, H, w, h = 64, 33, 128, 64
+    src = ol.noise(h, w, c, seed=11 + c)
+    for o, i in (("rect", "erect"), ("erect", "equidistant"), ("equidistant", "rect")):
+        for interp in (ol.NEAREST, ol.BILINEAR, ol.BICUBIC):
+            want = ORC.reproject(src, LENS[i](w, h), LENS[o](W, H), W, H, 1, interp, rot(rn))
+            got = lrp.reproject_host(src, L(lrp, LENS[i](w, h)), L(lrp, LENS[o](W, H)), W, H, 1, interp, rot(rn))
+            assert_same(got, want, "%s<-%s interp %d %s c%d" % (o, i, interp, rn, c))
+
+
+@pytest.mark.parametrize("ns", [1, 2, 3, 4])
+def test_pixels_supersampling(lrp, ns):
+    W, H, w, h = 40, 30, 96, 48
+    src = ol.smooth(h, w, 4) + 0.1 * ol.noise(h, w, 4, seed=5)
+    for o, i in (("rect", "erect"), ("erect", "rect"), ("equidistant", "equidistant")):
+        for interp in (ol.NEAREST, ol.BILINEAR, ol.BICUBIC):
+            want = ORC.reproject(src, LENS[i](w, h), LENS[o](W, H), W, H, ns, interp, rot("r30_20_10"))
+            got = lrp.reproject_host(src, L(lrp, LENS[i](w, h)), L(lrp, LENS[o](W, H)), W, H, ns, interp,
+                                     rot("r30_20_10"))
+            assert_same(got, want, "%s<-%s interp %d ns %d" % (o, i, interp, ns))
+
+
+def test_pixels_special_values_and_nan_rays(lrp):
+    # +inf / 1e10 depth, NaN texel; odd output size with identity rotation (on-axis NaN ray)
+    w = h = 64
+    src = ol.noise(h, w, 4, seed=2)
+    src[::7, ::5, 3] = np.inf
+    src[3::11, 2::9, 3] = 1e10
+    src[5, 5, 0] = np.nan
+    for interp in (ol.NEAREST, ol.BILINEAR, ol.BICUBIC):
+        want = ORC.reproject(src, ol.equidistant(math.pi), ol.erect(), 48, 48, 1, interp, rot("ident"))
+        got = lrp.reproject_host(src, L(lrp, ol.equidistant(math.pi)), L(lrp, ol.erect()), 48, 48, 1, interp,
+                                 rot("ident"))
+        assert_same(got, want, "special interp %d" % interp)
+        # generated NaNs are stored as the x86 default NaN
+        gen = np.isnan(got) & ~np.isnan(want) if False else np.isnan(got)
+        if gen.any() and interp != ol.NEAREST:
+            assert (ol.bits(got)[gen] == 0xFFC00000).all()
+    src = ol.noise(128, 128, 3, seed=9)
+    for o, i in (("rect", "equidistant"), ("equidistant", "rect"), ("equidistant", "equidistant")):
+        for interp in (ol.NEAREST, ol.BILINEAR, ol.BICUBIC):
+            want = ORC.reproject(src, LENS[i](128, 128), LENS[o](65, 65), 65, 65, 1, interp, rot("ident"))
+            got = lrp.reproject_host(src, L(lrp, LENS[i](128, 128)), L(lrp, LENS[o](65, 65)), 65, 65, 1, interp,
+                                     rot("ident"))
+            assert_same(got, want, "nan-ray %s<-%s %d" % (o, i, interp))
+
+
+def test_pixels_ragged_and_tiny_sizes(lrp):
+    for (W, H, w, h) in ((1, 1, 1, 1), (2, 3, 5, 1), (33, 9, 2, 2), (31, 7, 4, 300), (257, 5, 1024, 3)):
+        src = ol.noise(h, w, 3, seed=W + H)
+        for interp in (ol.NEAREST, ol.BILINEAR, ol.BICUBIC):
+            want = ORC.reproject(src, ol.erect(), ol.rect(18, 36, W, H), W, H, 1, interp, rot("r30_20_10"))
+            got = lrp.reproject_host(src, L(lrp, ol.erect()), L(lrp, ol.rect(18, 36, W, H)), W, H, 1, interp,
+                                     rot("r30_20_10"))
+            assert_same(got, want, "ragged %r interp %d" % ((W, H, w, h), interp))
+
+
+def test_golden_fixtures_from_the_reference(lrp):
+    import golden.make_golden as mg
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.npz"))
+    n = 0
+    for case in mg.cases():
+        src = mg.source(case)
+        got = lrp.reproject_host(src, L(lrp, case["in_lens"]), L(lrp, case["out_lens"]), case["W"], case["H"],
+                                 case["ns"], case["interp"], case["rot"], post=case["post"])
+        assert_same(got, g[case["name"]], "golden " + case["name"])
+        n += 1
+    assert n >= 20
+
+
+def test_against_compiled_reference_when_present(lrp):
+    ref = ol.reference()
+    if ref is None:
+        pytest.skip("oracle/_ref did not travel to this box")
+    W, H, w, h = 160, 90, 256, 128
+    src = ol.noise(h, w, 4, seed=21)
+    for o, i in itertools.product(["rect", "equidistant", "erect"], repeat=2):
+        want = ref.reproject(src, LENS[i](w, h), LENS[o](W, H), W, H, 2, ol.BICUBIC, rot("neg"))
+        want = ref.post_process(want, 1.5, 4.0)
+        got = lrp.reproject_host(src, L(lrp, LENS[i](w, h)), L(lrp, LENS[o](W, H)), W, H, 2, ol.BICUBIC, rot("neg"),
+                                 post=(1.5, 4.0))
+        assert_same(got, want, "ref %s<-%s" % (o, i))
+
+
+# ---- post_process --------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("c", [3, 4, 5])
+def test_post_process_standalone_and_fused(lrp, c):
+    img = (ol.noise(37, 29, c, seed=4) * 3.0).astype(np.float32)
+    for ex, rh in ((1.5, 4.0), (2.0 ** 0.5, 1.0), (1.0, 2.0), (0.25, 0.5)):
+        assert_same(lrp.post_process_host(img, ex, rh), ORC.post_process(img, ex, rh), "post c%d" % c)
+    src = ol.noise(40, 80, c, seed=6) * 2.0
+    want = ORC.post_process(ORC.reproject(src, ol.erect(), ol.rect(18, 36, 50, 30), 50, 30, 1, ol.BICUBIC,
+                                          rot("r30_20_10")), 1.5, 4.0)
+    got = lrp.reproject_host(src, L(lrp, ol.erect()), L(lrp, ol.rect(18, 36, 50, 30)), 50, 30, 1, ol.BICUBIC,
+                             rot("r30_20_10"), post=(1.5, 4.0))
+    assert_same(got, want, "fused post c%d" % c)
+
+
+# ---- Level 2: codec-native formats -----------------------------------------------------------------
+
+def _png_source(h, w, seed):
+    rng = np.random.default_rng(seed)
+    rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    return rgba
+
+
+@pytest.mark.parametrize("interp", [ol.NEAREST, ol.BILINEAR, ol.BICUBIC])
+def test_png_path_u8_to_u8(lrp, interp):
+    """read_png -> reproject -> post_process -> save_png, fused; tolerance <= 1 LSB, asserted 0 LSB."""
+    W, H, w, h = 96, 54, 256, 128
+    rgba = _png_source(h, w, 3)
+    src_f = ORC.png_decode(rgba)
+    for post in (None, (1.5, 4.0)):
+        for o, i in (("rect", "erect"), ("equidistant", "rect"), ("erect", "equidistant")):
+            want = ORC.reproject(src_f, LENS[i](w, h), LENS[o](W, H), W, H, 1, interp, rot("r30_20_10"))
+            if post:
+                want = ORC.post_process(want, *post)
+            want8 = ORC.png_encode(want)
+            got8 = lrp.reproject_host(rgba, L(lrp, LENS[i](w, h)), L(lrp, LENS[o](W, H)), W, H, 1, interp,
+                                      rot("r30_20_10"), post=post, in_fmt=lrp.FMT_U8_RGBA, out_fmt=lrp.FMT_U8_RGBA)
+            diff = np.abs(got8.astype(np.int32) - want8.astype(np.int32))
+            assert diff.max() <= 1, "PNG tolerance (<= 1 LSB) violated"
+            assert diff.max() == 0, "PNG path not bit-identical: %d values differ" % (diff > 0).sum()
+            assert (got8[..., 3] == 255).all()
+
+
+def test_png_encode_every_threshold(lrp):
+    """f32 -> u8 sink on values straddling every quantisation threshold (+-2 ulp) and specials."""
+    one = np.array([1.0], np.float32).view(np.uint32)[0]
+    vals = []
+    # thresholds by bisection with the HOST powf (oracle encode)
+    def q(bits):
+        s = np.array([bits], np.uint32).view(np.float32).reshape(1, 1, 1)
+        return int(ORC.png_encode(np.repeat(s, 3, axis=2))[0, 0, 0])
+    for k in range(1, 256):
+        lo, hi = 0, int(one)
+        while hi - lo > 1:
+            mid = (lo + hi) // 2
+            if q(mid) >= k:
+                hi = mid
+            else:
+                lo = mid
+        vals += [hi - 2, hi - 1, hi, hi + 1, hi + 2]
+    v = np.array(vals, np.uint32).view(np.float32)
+    v = np.concatenate([v, np.array([0.0, -0.0, 1.0, 1.5, -3.0, np.inf, -np.inf, np.nan, 1e-30, 0.999999], np.float32)])
+    n = len(v)
+    W = 64
+    H = (n + W - 1) // W
+    img = np.zeros((H * W,), np.float32)
+    img[:n] = v
+    img = np.repeat(img.reshape(H, W, 1), 3, axis=2)
+    img[..., 1] = img[::-1, ::-1, 0]
+    # identity geometry: nearest, same lens, no rotation -> pure format conversion
+    lens = ol.rect(18, 36, W, H)
+    want = ORC.png_encode(ORC.reproject(img, lens, lens, W, H, 1, ol.NEAREST, None))
+    got = lrp.reproject_host(img, L(lrp, lens), L(lrp, lens), W, H, 1, ol.NEAREST, None, out_fmt=lrp.FMT_U8_RGBA)
+    assert (got == want).all(), "%d encode mismatches" % (got != want).sum()
+
+
+@pytest.mark.parametrize("c", [3, 4, 5])
+def test_exr_path_f16_planar(lrp, c):
+    """read_exr (half planes) -> reproject -> post -> save_exr (half planes); bit-identical halves,
+    including the inf depth samples that bicubic turns into NaN."""
+    W, H, w, h = 80, 40, 96, 96
+    f = ol.noise(h, w, c, seed=30 + c) * 2.0
+    if c >= 4:
+        f[..., c - 1] = 1.0 + 0.001 * np.arange(w, dtype=np.float32)[None, :]
+        f[::9, ::7, c - 1] = 1e10  # -> +inf in half
+    planes = ORC.f32_to_half_planar(f)
+    src_f = ORC.half_planar_to_f32(planes)
+    for interp in (ol.NEAREST, ol.BICUBIC):
+        for post in (None, (1.5, 4.0)):
+            want = ORC.reproject(src_f, ol.equidistant(math.pi), ol.erect(), W, H, 1, interp, rot("r30_20_10"))
+            if post:
+                want = ORC.post_process(want, *post)
+            want16 = ORC.f32_to_half_planar(want)
+            got16 = lrp.reproject_host(planes, L(lrp, ol.equidistant(math.pi)), L(lrp, ol.erect()), W, H, 1, interp,
+                                       rot("r30_20_10"), post=post, in_fmt=lrp.FMT_F16_PLANAR,
+                                       out_fmt=lrp.FMT_F16_PLANAR)
+            same = (got16 == want16) | (((got16 & 0x7fff) > 0x7c00) & ((want16 & 0x7fff) > 0x7c00))
+            assert same.all(), "half planes differ in %d samples" % (~same).sum()
+            # float tolerance of the north star, on the finite samples
+            g = got16.view(np.float16).astype(np.float64)
+            wv = want16.view(np.float16).astype(np.float64)
+            fin = np.isfinite(g) & np.isfinite(wv)
+            assert np.all(np.abs(g[fin] - wv[fin]) <= 1e-5 * np.abs(wv[fin]))
+
+
+def test_mixed_formats(lrp):
+    # EXR source -> PNG sink with 4 channels (4th channel gamma-encoded into alpha, as save_png does)
+    W, H, w, h = 64, 48, 100, 50
+    f = ol.noise(h, w, 4, seed=77)
+    planes = ORC.f32_to_half_planar(f)
+    src_f = ORC.half_planar_to_f32(planes)
+    want = ORC.png_encode(ORC.reproject(src_f, ol.erect(), ol.rect(18, 36, W, H), W, H, 1, ol.BILINEAR, rot("neg")))
+    got = lrp.reproject_host(planes, L(lrp, ol.erect()), L(lrp, ol.rect(18, 36, W, H)), W, H, 1, ol.BILINEAR,
+                             rot("neg"), in_fmt=lrp.FMT_F16_PLANAR, out_fmt=lrp.FMT_U8_RGBA)
+    assert (got == want).all()
+    # PNG source -> float32 sink
+    rgba = _png_source(h, w, 5)
+    want = ORC.reproject(ORC.png_decode(rgba), ol.erect(), ol.rect(18, 36, W, H), W, H, 1, ol.BICUBIC, rot("neg"))
+    got = lrp.reproject_host(rgba, L(lrp, ol.erect()), L(lrp, ol.rect(18, 36, W, H)), W, H, 1, ol.BICUBIC, rot("neg"),
+                             in_fmt=lrp.FMT_U8_RGBA, out_fmt=lrp.FMT_F32)
+    assert_same(got, want, "u8 -> f32")
+
+
+# ---- source-access variants ---------------------------------------------------------------------------
+
+def test_remap_table_variant_is_bit_identical(lrp, ctx):
+    import torch
+    W, H, w, h = 120, 70, 256, 128
+    src = ol.noise(h, w, 3, seed=13)
+    src_t = torch.from_numpy(src).cuda()
+    for (o, i) in (("rect", "erect"), ("erect", "rect"), ("equidistant", "erect_part")):
+        for ns in (1, 2):
+            for interp in (ol.NEAREST, ol.BILINEAR, ol.BICUBIC):
+                p = lrp.make_params(ns, interp, rot("r30_20_10"), (1.5, 4.0))
+                a = torch.empty((H, W, 3), dtype=torch.float32, device="cuda")
+                b = torch.empty_like(a)
+                il, olens = L(lrp, LENS[i](w, h)), L(lrp, LENS[o](W, H))
+                ctx.reproject(src_t, il, lrp.FMT_F32, a, olens, lrp.FMT_F32, p)
+                table = ctx.build_remap(il, w, h, olens, W, H, p)
+                ctx.reproject(src_t, il, lrp.FMT_F32, b, olens, lrp.FMT_F32, p, remap=table)
+                torch.cuda.synchronize()
+                assert_same(b.cpu().numpy(), a.cpu().numpy(), "remap %s<-%s" % (o, i))
+                want = ORC.post_process(ORC.reproject(src, LENS[i](w, h), LENS[o](W, H), W, H, ns, interp,
+                                                      rot("r30_20_10")), 1.5, 4.0)
+                assert_same(a.cpu().numpy(), want, "device path %s<-%s" % (o, i))
+
+
+# ---- error behaviour (reference: message + exit(1)) ------------------------------------------------------
+
+def test_unsupported_lenses_and_interp(lrp):
+    src = ol.noise(8, 8, 3)
+    eq = ol.equisolid(12.5, 36, math.pi, 8, 8)
+    with pytest.raises(lrp.LrpError) as e:
+        lrp.reproject_host(src, L(lrp, ol.rect(18, 36, 8, 8)), L(lrp, eq), 8, 8)
+    assert e.value.status == lrp.E_UNSUPPORTED_OUTPUT_LENS
+    assert "Output lens type not supported." in str(e.value)
+    with pytest.raises(lrp.LrpError) as e:
+        lrp.reproject_host(src, L(lrp, eq), L(lrp, ol.rect(18, 36, 8, 8)), 8, 8)
+    assert e.value.status == lrp.E_UNSUPPORTED_INPUT_LENS
+    with pytest.raises(lrp.LrpError) as e:
+        lrp.reproject_host(src, L(lrp, ol.erect()), L(lrp, ol.rect(18, 36, 8, 8)), 8, 8, interp=7)
+    assert e.value.status == lrp.E_UNSUPPORTED_INTERP
+    with pytest.raises(lrp.LrpError) as e:  # 5 channels into a PNG sink overruns in the reference: refused
+        lrp.reproject_host(ol.noise(8, 8, 5), L(lrp, ol.erect()), L(lrp, ol.rect(18, 36, 8, 8)), 8, 8,
+                           out_fmt=lrp.FMT_U8_RGBA)
+    assert e.value.status == lrp.E_UNSUPPORTED_FORMAT
+
+
+# ---- headline configuration at full size ------------------------------------------------------------------
+
+def test_c2_full_size_png_path(lrp):
+    """BASELINE config #2 at full size: 8192x4096 equirectangular PNG -> rectilinear 3840x2160, rotation
+    30,20,10, bicubic.  The oracle needs a few seconds for it; bit-identical RGBA8 is asserted."""
+    w, h, W, H = 8192, 4096, 3840, 2160
+    rng = np.random.default_rng(1)
+    rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    il, olens = ol.erect(), ol.rect(18.0, 36.0, W, H)
+    r = ORC.rotation_from_degrees(30, 20, 10)
+    got = lrp.reproject_host(rgba, L(lrp, il), L(lrp, olens), W, H, 1, ol.BICUBIC, r, in_fmt=lrp.FMT_U8_RGBA,
+                             out_fmt=lrp.FMT_U8_RGBA)
+    want = ORC.png_encode(ORC.reproject(ORC.png_decode(rgba), il, olens, W, H, 1, ol.BICUBIC, r))
+    diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    assert diff.max() == 0, "%d of %d samples differ (max %d LSB)" % ((diff > 0).sum(), diff.size, diff.max())

@@ -1,0 +1,94 @@
+"""GPU tests of the asynchronous job API and the multi-GPU image scheduler (the replacement of the
+reference's ctpl thread pool, src/main.cpp:536-657).  The N-GPU result set must equal the 1-GPU
+result set bit for bit in any order; LRP_FAKE_GPUS maps several logical devices onto the GPUs that
+exist so the sharding logic is exercised on a one-GPU box."""
+import threading
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+ORC = ol.oracle()
+
+
+@pytest.fixture(scope="module")
+def lrp():
+    import lrp as m
+    m.lib()
+    return m
+
+
+def _jobs(lrp, n, W=96, H=54, w=160, h=80):
+    il, olens = lrp.lens_from(ol.erect()), lrp.lens_from(ol.rect(18, 36, W, H))
+    r = ORC.rotation_from_degrees(30, 20, 10)
+    srcs = [ol.noise(h, w, 3, seed=100 + k) for k in range(n)]
+    outs = [np.zeros((H, W, 3), np.float32) for _ in range(n)]
+    p = lrp.make_params(1, lrp.BICUBIC, r, (1.5, 4.0))
+    jobs = [lrp.make_job(s.ctypes.data, il, w, h, 3, lrp.FMT_F32, o.ctypes.data, olens, W, H, lrp.FMT_F32, p)
+            for s, o in zip(srcs, outs)]
+    want = [ORC.post_process(ORC.reproject(s, ol.erect(), ol.rect(18, 36, W, H), W, H, 1, ol.BICUBIC, r), 1.5, 4.0)
+            for s in srcs]
+    return srcs, outs, jobs, want
+
+
+def test_async_submit_wait(lrp):
+    ctx = lrp.Context(0, 3)
+    srcs, outs, jobs, want = _jobs(lrp, 12)
+    tickets = [ctx.submit(j) for j in jobs]
+    for t in reversed(tickets):
+        ctx.wait(t)
+    for o, wv in zip(outs, want):
+        assert ol.same_bits(o, wv)
+    ctx.close()
+
+
+def test_scheduler_fake_multi_gpu_equals_oracle(lrp, monkeypatch):
+    monkeypatch.setenv("LRP_FAKE_GPUS", "4")
+    assert lrp.device_count() == 4
+    s = lrp.Scheduler([0, 1, 2, 3], streams_per_device=2)
+    srcs, outs, jobs, want = _jobs(lrp, 40)
+    for j in jobs:
+        s.submit(j)
+    s.wait_all()
+    st = s.stats()
+    assert sum(st) == 40 and len(st) == 4
+    for o, wv in zip(outs, want):
+        assert ol.same_bits(o, wv)
+    s.close()
+
+
+def test_scheduler_error_isolation(lrp):
+    """an unsupported lens fails that image only (reference: per-image try/catch, src/main.cpp:617-619)"""
+    s = lrp.Scheduler([0], streams_per_device=2)
+    srcs, outs, jobs, want = _jobs(lrp, 6)
+    jobs[2].out.lens.type = lrp.FISHEYE_EQUISOLID
+    for j in jobs:
+        s.submit(j)
+    with pytest.raises(lrp.LrpError) as e:
+        s.wait_all()
+    assert e.value.status == lrp.E_UNSUPPORTED_OUTPUT_LENS
+    for k, (o, wv) in enumerate(zip(outs, want)):
+        if k != 2:
+            assert ol.same_bits(o, wv)
+    s.close()
+
+
+def test_sync_dropin_is_reentrant(lrp):
+    """lrp_reproject_host is called concurrently from `-j N` pool threads in the reference's structure"""
+    W, H, w, h = 64, 36, 128, 64
+    il, olens = lrp.lens_from(ol.erect()), lrp.lens_from(ol.rect(18, 36, W, H))
+    r = ORC.rotation_from_degrees(10, 20, 30)
+    srcs = [ol.noise(h, w, 4, seed=k) for k in range(16)]
+    want = [ORC.reproject(s, ol.erect(), ol.rect(18, 36, W, H), W, H, 1, ol.BILINEAR, r) for s in srcs]
+    got = [None] * 16
+
+    def work(k):
+        got[k] = lrp.reproject_host(srcs[k], il, olens, W, H, 1, lrp.BILINEAR, r)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(16)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for g, wv in zip(got, want):
+        assert ol.same_bits(g, wv)
