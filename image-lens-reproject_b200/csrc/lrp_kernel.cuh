@@ -180,8 +180,8 @@ LRP_DEV void sample_bilinear(const KParams &P, const float *lut, float sx, float
   int ux = index_x<WRAP>(f2i_x86(fadd(sx, 1.0f)), P.w);
   int ly = index_y(f2i_x86(sy), P.h);
   int uy = index_y(f2i_x86(fadd(sy, 1.0f)), P.h);
-  float fx = std_max(0.0f, std_min(1.0f, fsub(sx, (float)lx))); // post-wrap/clamp lx, :70
-  float fy = std_max(0.0f, std_min(1.0f, fsub(sy, (float)ly)));
+  float fx = clamp01_std(fsub(sx, (float)lx)); // post-wrap/clamp lx, :70
+  float fy = clamp01_std(fsub(sy, (float)ly));
   float cfx = fsub(1.0f, fx), cfy = fsub(1.0f, fy);
   float ll[C], lu[C], ul[C], uu[C];
   Texel<FMT, C>::load(P, lut, lx, ly, ll);
@@ -229,8 +229,8 @@ LRP_DEV void sample_bicubic(const KParams &P, const float *lut, float sx, float 
   ys[1] = index_y(f2i_x86(sy), P.h);
   ys[2] = index_y(f2i_x86(fadd(sy, 1.0f)), P.h);
   ys[3] = index_y(f2i_x86(fadd(sy, 2.0f)), P.h);
-  float fx = std_max(0.0f, std_min(1.0f, fsub(sx, (float)xs[1]))); // :130
-  float fy = std_max(0.0f, std_min(1.0f, fsub(sy, (float)ys[1]))); // :131
+  float fx = clamp01_std(fsub(sx, (float)xs[1])); // :130
+  float fy = clamp01_std(fsub(sy, (float)ys[1])); // :131
 
   float p[4][4][C]; // [xi][yi][c] — all 16 taps are issued before any arithmetic (MLP)
 #pragma unroll
@@ -290,7 +290,7 @@ LRP_DEV float post_process_value(float v, float exposure, float r2) {
 // [0,1] by the test-suite), so d = max{k : thr[k] <= s} with thr built on the host from
 // the host's own powf.  A fast approximate pow lands within +-1 of d; two table probes fix it.
 LRP_DEV unsigned encode_u8(float s, const float *thr) {
-  s = std_max(0.0f, std_min(1.0f, s)); // NaN -> 1.0 by operand order, as std::min/max
+  s = clamp01_std(s); // NaN -> 1.0 by operand order of std::min/max
   float a = exp2f(fmul(__log2f(s), 0.45454545f));
   int k = __float2int_rz(fmul(255.9f, a));
   k = max(0, min(255, k));

@@ -26,6 +26,13 @@ LRP_DEV float fsqrt(float a) { return __fsqrt_rn(a); }
 LRP_DEV float std_min(float a, float b) { return (b < a) ? b : a; }
 LRP_DEV float std_max(float a, float b) { return (a < b) ? b : a; }
 
+// std::max(0.0f, std::min(1.0f, v)) — the reference's fraction / gamma clamps (src/reproject.cpp:70-71,
+// 130-131, src/image_formats.cpp:156): in-range values pass, v < 0 and -0 give +0, v > 1 gives 1 and a
+// NaN gives 1.0 (operand order of std::min).  Written with the saturating convert + an explicit NaN
+// patch on purpose: ptxas 12.9 pattern-matches a select/min/max clamp into FADD.SAT, which flushes NaN
+// to 0 and silently changes the NaN-coordinate pixels (measured on B200; DESIGN.md "toolchain traps").
+LRP_DEV float clamp01_std(float v) { return (v != v) ? 1.0f : __saturatef(v); }
+
 // int(float) as x86-64 `cvttss2si` performs it: NaN / out-of-range -> INT_MIN
 // (CUDA's cvt.rzi saturates instead).
 LRP_DEV int f2i_x86(float v) {
