@@ -33,6 +33,7 @@ LRP_DECL(4, 0) LRP_DECL(4, 1) LRP_DECL(4, 2) LRP_DECL(5, 0) LRP_DECL(5, 1) LRP_D
 int launch_coords(const KParams &P, int coord, void *stream);
 int launch_post_process(float *data, size_t n_pixels, int channels, float exposure, float reinhard, void *stream);
 int launch_libm(int fn, const float *a, const float *b, float *out, size_t n, int use_fma, void *stream);
+int launch_encode_u8(const float *in, unsigned char *out, size_t n, const float *thr, void *stream);
 
 static LaunchFn get_launcher(int coord, int interp, int fc) {
   typedef LaunchFn (*Getter)(int);
@@ -183,6 +184,7 @@ struct Slot { // one stream with grow-only device staging buffers
 struct lrp_ctx {
   int device = 0;       // logical device index
   int phys_device = 0;  // CUDA ordinal (differs only under LRP_FAKE_GPUS)
+  int num_sms = 148;
   float *d_lut = nullptr, *d_thr = nullptr;
   std::vector<cudaStream_t> streams;
   std::vector<Slot> slots; // for the synchronous host drop-ins
@@ -283,6 +285,7 @@ int prepare(const lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const
   K.lut = ctx->d_lut;
   K.thr = ctx->d_thr;
   K.neg_zero2 = 0x8000000080000000ull;
+  K.num_sms = ctx->num_sms;
   switch (in->lens.type) {
   case LENS_RECT: coord = COORD_RECT; break;
   case LENS_EQUIDISTANT: coord = COORD_EQUIDISTANT; break;
@@ -578,6 +581,8 @@ int lrp_ctx_create(int device, int n_streams, lrp_ctx **out) {
   c->device = device;
   c->phys_device = phys;
   const HostTables &T = host_tables();
+  cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, phys);
+  if (c->num_sms <= 0) c->num_sms = 148;
   cudaError_t e = cudaMalloc(&c->d_lut, sizeof(T.lut));
   if (e == cudaSuccess) e = cudaMalloc(&c->d_thr, sizeof(T.thr));
   if (e == cudaSuccess) e = cudaMemcpy(c->d_lut, T.lut, sizeof(T.lut), cudaMemcpyHostToDevice);
@@ -679,6 +684,12 @@ int lrp_debug_libm(lrp_ctx *ctx, int fn, const float *a, const float *b, float *
   if (!ctx || !a || !out || fn < 0 || fn > 4 || (fn == 4 && !b)) return LRP_E_BAD_ARG;
   DeviceGuard guard(ctx->phys_device);
   return map_cuda((cudaError_t)launch_libm(fn, a, b, out, n, host_tables().libm_fma != 0, stream));
+}
+
+int lrp_debug_encode_u8(lrp_ctx *ctx, const float *in, uint8_t *out, size_t n, void *stream) {
+  if (!ctx || !in || !out) return LRP_E_BAD_ARG;
+  DeviceGuard guard(ctx->phys_device);
+  return map_cuda((cudaError_t)launch_encode_u8(in, out, n, ctx->d_thr, stream));
 }
 
 // ---- memory ----

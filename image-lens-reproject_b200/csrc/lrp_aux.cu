@@ -8,9 +8,9 @@ namespace lrp {
 // ([ssx*ns + ssy][H][W] float2).  Serves lrp_build_remap (all ns*ns planes) and
 // lrp_debug_coords (plane 0).  Same device functions as the fused kernel, so a remap
 // table is bit-identical to on-the-fly coordinates by construction.
-__global__ void __launch_bounds__(TILE_X *TILE_Y) coords_kernel(const __grid_constant__ KParams P, int coord) {
-  const int x = blockIdx.x * TILE_X + threadIdx.x;
-  const int y = blockIdx.y * TILE_Y + threadIdx.y;
+__global__ void __launch_bounds__(256) coords_kernel(const __grid_constant__ KParams P, int coord) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
   if (x >= P.W || y >= P.H) return;
   const float cx = fsub(fadd((float)x, 0.5f), fmul((float)P.W, 0.5f));
   const float cy = fsub(fadd((float)y, 0.5f), fmul((float)P.H, 0.5f));
@@ -27,8 +27,8 @@ __global__ void __launch_bounds__(TILE_X *TILE_Y) coords_kernel(const __grid_con
 }
 
 int launch_coords(const KParams &P, int coord, void *stream) {
-  dim3 block(TILE_X, TILE_Y);
-  dim3 grid((P.W + TILE_X - 1) / TILE_X, (P.H + TILE_Y - 1) / TILE_Y);
+  dim3 block(32, 8);
+  dim3 grid((P.W + 31) / 32, (P.H + 7) / 8);
   coords_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(P, coord);
   return (int)cudaGetLastError();
 }
@@ -69,6 +69,20 @@ __global__ void libm_kernel(int fn, const float *a, const float *b, float *out, 
 
 int launch_libm(int fn, const float *a, const float *b, float *out, size_t n, int use_fma, void *stream) {
   libm_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(fn, a, b, out, n, use_fma);
+  return (int)cudaGetLastError();
+}
+
+// test hook: the 8-bit sink quantiser, element-wise
+__global__ void encode_u8_kernel(const float *in, unsigned char *out, size_t n, const float *thr_g) {
+  __shared__ float s_thr[THR_FLOATS];
+  for (int i = threadIdx.x; i <= 256; i += blockDim.x) s_thr[i] = (i < 256) ? thr_g[i] : __int_as_float(0x7f800000);
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = (unsigned char)encode_u8(in[i], s_thr);
+}
+
+int launch_encode_u8(const float *in, unsigned char *out, size_t n, const float *thr, void *stream) {
+  encode_u8_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(in, out, n, thr);
   return (int)cudaGetLastError();
 }
 

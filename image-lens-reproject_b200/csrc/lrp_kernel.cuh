@@ -19,8 +19,8 @@
 
 namespace lrp {
 
-constexpr int TILE_X = 32; // one warp = 32 consecutive output pixels of a row: coalesced stores
-constexpr int TILE_Y = 8;
+constexpr int TILE = 32;        // 32x32 output pixels per tile; one warp = 32 consecutive pixels of a row
+constexpr int NTHREADS = 1024;  // one persistent CTA per SM
 
 // ---- lens functions -----------------------------------------------------------------------
 
@@ -90,11 +90,9 @@ LRP_DEV void vec_to_source(const KParams &P, float x, float y, float z, float &c
   }
 }
 
-// One sub-sample's coordinate chain: reference :301-324.
+// Rotation + input-lens projection + re-centring of one ray: reference :303-324.
 template <int COORD>
-LRP_DEV void source_coord(const KParams &P, float scx, float scy, float &sx, float &sy) {
-  float vx, vy, vz;
-  target_to_vec(P, scx, scy, vx, vy, vz);
+LRP_DEV void ray_to_source(const KParams &P, float vx, float vy, float vz, float &sx, float &sy) {
   if (P.has_rot) { // :303-311
     const float *R = P.R;
     float nx = fadd(fadd(fmul(R[0], vx), fmul(R[1], vy)), fmul(R[2], vz));
@@ -110,30 +108,80 @@ LRP_DEV void source_coord(const KParams &P, float scx, float scy, float &sx, flo
   sy = fadd(fsub(cy, 0.5f), fmul((float)P.h, 0.5f)); // :324
 }
 
+// One sub-sample's whole coordinate chain: reference :301-324.
+template <int COORD>
+LRP_DEV void source_coord(const KParams &P, float scx, float scy, float &sx, float &sy) {
+  float vx, vy, vz;
+  target_to_vec(P, scx, scy, vx, vy, vz);
+  ray_to_source<COORD>(P, vx, vy, vz, sx, sy);
+}
+
 // ---- source texel access -------------------------------------------------------------------
 
-template <bool WRAP> LRP_DEV int index_x(int i, int w) {
-  if (WRAP) {
-    // (i + w) % w with C remainder semantics (:43, 60-61, 114-117) without a division on
-    // the common paths; a negative remainder (NaN coordinate only) is defined as column 0.
-    int s = (int)((unsigned)i + (unsigned)w);
-    if ((unsigned)s < (unsigned)w) return s;
-    unsigned t = (unsigned)s - (unsigned)w;
-    if (t < (unsigned)w) return (int)t;
-    int r = s % w;
-    return r < 0 ? 0 : r;
-  } else {
-    return max(0, min(w - 1, i));
-  }
+// Per-thread view of the source: parameters + this lane's base address into the
+// lane-replicated gamma table (FMT_U8 only).
+struct SrcView {
+  const KParams &P;
+  uint32_t lut_lane; // shared-window address of  LUT[0][lane]  (64 KB-aligned table | lane*4)
+};
+
+// (i + w) % w with C remainder semantics (:43, 60-61, 114-117); a negative remainder (NaN
+// coordinate only, where the reference reads out of bounds) is defined as column 0.
+LRP_DEV int wrap_slow(int i, int w) {
+  int s = (int)((unsigned)i + (unsigned)w);
+  int r = s % w;
+  return r < 0 ? 0 : r;
 }
-LRP_DEV int index_y(int i, int h) { return max(0, min(h - 1, i)); }
+// branch-free wrap for -w <= i < 2w (every finite coordinate of a full panorama)
+LRP_DEV int wrap_fast(int i, int w) {
+  int r = i + ((i < 0) ? w : 0);
+  return r - ((r >= w) ? w : 0);
+}
+LRP_DEV int clampi(int i, int n) { return max(0, min(n - 1, i)); }
+
+// Integer tap positions of one sample: N consecutive truncations int(s + off[k]) with x86
+// semantics, wrapped / clamped.  One range test covers all of them on the common path.
+template <bool WRAP, int N>
+LRP_DEV void tap_indices(float sx, float sy, const float (&off)[N], int w, int h, int (&xs)[N], int (&ys)[N]) {
+  // |s| < 2^30 (and not NaN): plain cvt.rzi equals cvttss2si for s + off
+  const bool safe = (fabsf(sx) < 1073741824.0f) && (fabsf(sy) < 1073741824.0f);
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    xs[k] = __float2int_rz(off[k] == 0.0f ? sx : fadd(sx, off[k]));
+    ys[k] = __float2int_rz(off[k] == 0.0f ? sy : fadd(sy, off[k]));
+  }
+  if (!safe) { // NaN / inf / |s| >= 2^30: the x86 conversion yields INT_MIN where CUDA saturates
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      xs[k] = f2i_x86(off[k] == 0.0f ? sx : fadd(sx, off[k]));
+      ys[k] = f2i_x86(off[k] == 0.0f ? sy : fadd(sy, off[k]));
+    }
+  }
+  if (WRAP) {
+    const bool in_range = safe && (xs[0] >= -w) && (xs[N - 1] < 2 * w);
+    if (in_range) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) xs[k] = wrap_fast(xs[k], w);
+    } else {
+#pragma unroll
+      for (int k = 0; k < N; ++k) xs[k] = wrap_slow(xs[k], w);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < N; ++k) xs[k] = clampi(xs[k], w);
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) ys[k] = clampi(ys[k], h);
+}
 
 template <int FMT, int C> struct Texel;
 
 // float32 interleaved — the reference's in-memory layout (src/reproject.cpp:49-51)
 template <int C> struct Texel<FMT_F32, C> {
-  static LRP_DEV void load(const KParams &P, const float *, int x, int y, float (&v)[C]) {
-    const float *p = (const float *)P.src + ((size_t)y * (size_t)P.w + (size_t)x) * C;
+  typedef const float *Row;
+  static LRP_DEV Row row(const SrcView &S, int y) { return (const float *)S.P.src + (size_t)((unsigned)y * (unsigned)S.P.w) * C; }
+  static LRP_DEV void load(const SrcView &, Row r, int x, float (&v)[C]) {
+    const float *p = r + (unsigned)x * C;
     if (C == 4) {
       float4 t = __ldg((const float4 *)p);
       v[0] = t.x; v[1] = t.y; v[2] = t.z; v[C - 1] = t.w;
@@ -144,50 +192,62 @@ template <int C> struct Texel<FMT_F32, C> {
   }
 };
 
-// RGBA8 as lodepng decodes it; gamma decode through the host-built 256-entry table
-// (== powf(p/255, 2.2) of src/image_formats.cpp:195-197, bit-exact by construction)
+// RGBA8 as lodepng decodes it.  Gamma decode == powf(p/255, 2.2) of src/image_formats.cpp:195-197
+// through the host-built 256-entry table, replicated per lane in shared memory:
+//   address = table (64 KB aligned) | value << 8 | lane << 2
+// so that ONE byte-permute forms the address and every lane hits its own bank (no conflicts).
 template <int C> struct Texel<FMT_U8, C> {
-  static LRP_DEV void load(const KParams &P, const float *lut, int x, int y, float (&v)[C]) {
+  typedef const uchar4 *Row;
+  static LRP_DEV Row row(const SrcView &S, int y) { return (const uchar4 *)S.P.src + (size_t)((unsigned)y * (unsigned)S.P.w); }
+  static LRP_DEV float lut(uint32_t addr) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+    return r;
+  }
+  static LRP_DEV void load(const SrcView &S, Row r, int x, float (&v)[C]) {
     static_assert(C == 3, "PNG sources decode to 3 channels");
-    uchar4 t = __ldg((const uchar4 *)P.src + (size_t)y * (size_t)P.w + (size_t)x);
-    v[0] = lut[t.x];
-    v[1] = lut[t.y];
-    v[2] = lut[t.z];
+    const uint32_t t = __ldg((const unsigned int *)(r + (unsigned)x));
+    v[0] = lut(__byte_perm(t, S.lut_lane, 0x7604));
+    v[1] = lut(__byte_perm(t, S.lut_lane, 0x7614));
+    v[2] = lut(__byte_perm(t, S.lut_lane, 0x7624));
   }
 };
 
 // planar IEEE half (the HALF slices of read_exr); half -> float is exact
 template <int C> struct Texel<FMT_F16, C> {
-  static LRP_DEV void load(const KParams &P, const float *, int x, int y, float (&v)[C]) {
-    const __half *p = (const __half *)P.src + (size_t)y * (size_t)P.w + (size_t)x;
+  typedef const __half *Row;
+  static LRP_DEV Row row(const SrcView &S, int y) { return (const __half *)S.P.src + (size_t)((unsigned)y * (unsigned)S.P.w); }
+  static LRP_DEV void load(const SrcView &S, Row r, int x, float (&v)[C]) {
+    const __half *p = r + (unsigned)x;
 #pragma unroll
-    for (int c = 0; c < C; ++c) v[c] = __half2float(__ldg(p + (size_t)c * (size_t)P.src_plane));
+    for (int c = 0; c < C; ++c) v[c] = __half2float(__ldg(p + (size_t)c * (size_t)S.P.src_plane));
   }
 };
 
 // ---- samplers (reference :39-148) ----------------------------------------------------------
 
 template <bool WRAP, int FMT, int C>
-LRP_DEV void sample_nearest(const KParams &P, const float *lut, float sx, float sy, float (&out)[C]) {
-  int lx = index_x<WRAP>(f2i_x86(fadd(sx, 0.5f)), P.w);
-  int ly = index_y(f2i_x86(fadd(sy, 0.5f)), P.h);
-  Texel<FMT, C>::load(P, lut, lx, ly, out);
+LRP_DEV void sample_nearest(const SrcView &S, float sx, float sy, float (&out)[C]) {
+  const float off[1] = {0.5f};
+  int xs[1], ys[1];
+  tap_indices<WRAP, 1>(sx, sy, off, S.P.w, S.P.h, xs, ys); // :43-47
+  Texel<FMT, C>::load(S, Texel<FMT, C>::row(S, ys[0]), xs[0], out);
 }
 
 template <bool WRAP, int FMT, int C>
-LRP_DEV void sample_bilinear(const KParams &P, const float *lut, float sx, float sy, float (&out)[C]) {
-  int lx = index_x<WRAP>(f2i_x86(sx), P.w);
-  int ux = index_x<WRAP>(f2i_x86(fadd(sx, 1.0f)), P.w);
-  int ly = index_y(f2i_x86(sy), P.h);
-  int uy = index_y(f2i_x86(fadd(sy, 1.0f)), P.h);
-  float fx = clamp01_std(fsub(sx, (float)lx)); // post-wrap/clamp lx, :70
-  float fy = clamp01_std(fsub(sy, (float)ly));
+LRP_DEV void sample_bilinear(const SrcView &S, float sx, float sy, float (&out)[C]) {
+  const float off[2] = {0.0f, 1.0f};
+  int xs[2], ys[2];
+  tap_indices<WRAP, 2>(sx, sy, off, S.P.w, S.P.h, xs, ys); // :60-67  (s + 0.0f == s bit for bit, -0 -> index 0 either way)
+  float fx = clamp01_std(fsub(sx, (float)xs[0])); // post-wrap/clamp lx, :70
+  float fy = clamp01_std(fsub(sy, (float)ys[0]));
   float cfx = fsub(1.0f, fx), cfy = fsub(1.0f, fy);
   float ll[C], lu[C], ul[C], uu[C];
-  Texel<FMT, C>::load(P, lut, lx, ly, ll);
-  Texel<FMT, C>::load(P, lut, ux, ly, lu);
-  Texel<FMT, C>::load(P, lut, lx, uy, ul);
-  Texel<FMT, C>::load(P, lut, ux, uy, uu);
+  typename Texel<FMT, C>::Row r0 = Texel<FMT, C>::row(S, ys[0]), r1 = Texel<FMT, C>::row(S, ys[1]);
+  Texel<FMT, C>::load(S, r0, xs[0], ll);
+  Texel<FMT, C>::load(S, r0, xs[1], lu);
+  Texel<FMT, C>::load(S, r1, xs[0], ul);
+  Texel<FMT, C>::load(S, r1, xs[1], uu);
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     float l = fadd(fmul(fx, lu[c]), fmul(cfx, ll[c])); // :83
@@ -219,24 +279,20 @@ LRP_DEV f2 cubic2(f2 p0, f2 p1, f2 p2, f2 p3, f2 t, f2 h, const Cubic2Consts &k)
 }
 
 template <bool WRAP, int FMT, int C, bool PACKED>
-LRP_DEV void sample_bicubic(const KParams &P, const float *lut, float sx, float sy, float (&out)[C]) {
+LRP_DEV void sample_bicubic(const SrcView &S, float sx, float sy, float (&out)[C]) {
+  const float off[4] = {-1.0f, 0.0f, 1.0f, 2.0f}; // s + (-1.0f) == s - 1.0f bit for bit
   int xs[4], ys[4];
-  xs[0] = index_x<WRAP>(f2i_x86(fsub(sx, 1.0f)), P.w); // :114-122
-  xs[1] = index_x<WRAP>(f2i_x86(sx), P.w);
-  xs[2] = index_x<WRAP>(f2i_x86(fadd(sx, 1.0f)), P.w);
-  xs[3] = index_x<WRAP>(f2i_x86(fadd(sx, 2.0f)), P.w);
-  ys[0] = index_y(f2i_x86(fsub(sy, 1.0f)), P.h); // :124-127
-  ys[1] = index_y(f2i_x86(sy), P.h);
-  ys[2] = index_y(f2i_x86(fadd(sy, 1.0f)), P.h);
-  ys[3] = index_y(f2i_x86(fadd(sy, 2.0f)), P.h);
-  float fx = clamp01_std(fsub(sx, (float)xs[1])); // :130
-  float fy = clamp01_std(fsub(sy, (float)ys[1])); // :131
+  tap_indices<WRAP, 4>(sx, sy, off, S.P.w, S.P.h, xs, ys);  // :114-127
+  float fx = clamp01_std(fsub(sx, (float)xs[1]));            // :130
+  float fy = clamp01_std(fsub(sy, (float)ys[1]));            // :131
 
-  float p[4][4][C]; // [xi][yi][c] — all 16 taps are issued before any arithmetic (MLP)
+  float p[4][4][C]; // [xi][yi][c]
 #pragma unroll
-  for (int yi = 0; yi < 4; ++yi)
+  for (int yi = 0; yi < 4; ++yi) {
+    typename Texel<FMT, C>::Row r = Texel<FMT, C>::row(S, ys[yi]);
 #pragma unroll
-    for (int xi = 0; xi < 4; ++xi) Texel<FMT, C>::load(P, lut, xs[xi], ys[yi], p[xi][yi]);
+    for (int xi = 0; xi < 4; ++xi) Texel<FMT, C>::load(S, r, xs[xi], p[xi][yi]);
+  }
 
   const float hy = fmul(0.5f, fy), hx = fmul(0.5f, fx);
   if (!PACKED) {
@@ -254,7 +310,7 @@ LRP_DEV void sample_bicubic(const KParams &P, const float *lut, float sx, float 
     k.three = pack2(3.0f, 3.0f);
     k.four = pack2(4.0f, 4.0f);
     k.five = pack2(5.0f, 5.0f);
-    k.nz = P.neg_zero2;
+    k.nz = S.P.neg_zero2;
     const f2 ty = pack2(fy, fy), hy2 = pack2(hy, hy), tx = pack2(fx, fx), hx2 = pack2(hx, hx);
     float arr[4][C]; // [xi][c]
     // phase 1: 4*C column interpolations, two per instruction.  Item j = xi*C + c.
@@ -286,16 +342,20 @@ LRP_DEV float post_process_value(float v, float exposure, float r2) {
 
 // save_png's per-sample arithmetic (src/image_formats.cpp:156-158):
 //   s = max(0, min(1, s)); s = powf(s, 1/2.2f); d = uint8(255.9f * s)
-// evaluated exactly without a device powf: q(s) is monotone (proved over all floats in
-// [0,1] by the test-suite), so d = max{k : thr[k] <= s} with thr built on the host from
-// the host's own powf.  A fast approximate pow lands within +-1 of d; two table probes fix it.
+// evaluated exactly without a device powf: q(s) is monotone (proved over all floats in [0,1] by the
+// test-suite), so d = max{k : thr[k] <= s} with thr[1..255] built on the host from the host's own
+// powf, thr[0] = 0 and thr[256] = +inf.  Two MUFU approximations land within +-1 of d (proved
+// exhaustively on the device by tests/test_gpu_parity.py::test_png_encode_exhaustive); two table
+// probes correct it without a branch.
 LRP_DEV unsigned encode_u8(float s, const float *thr) {
   s = clamp01_std(s); // NaN -> 1.0 by operand order of std::min/max
-  float a = exp2f(fmul(__log2f(s), 0.45454545f));
-  int k = __float2int_rz(fmul(255.9f, a));
-  k = max(0, min(255, k));
-  while (k < 255 && s >= thr[k + 1]) ++k;
-  while (k > 0 && s < thr[k]) --k;
+  float lg, a;
+  asm("lg2.approx.f32 %0, %1;" : "=f"(lg) : "f"(s));
+  asm("ex2.approx.f32 %0, %1;" : "=f"(a) : "f"(fmul(lg, 0.45454545f)));
+  int k = min(255, __float2int_rz(fmul(255.9f, a)));
+  const float t0 = thr[k], t1 = thr[k + 1];
+  k += (s >= t1) ? 1 : 0;
+  k -= (s < t0) ? 1 : 0;
   return (unsigned)k;
 }
 
@@ -307,7 +367,7 @@ LRP_DEV unsigned short encode_half(float v) {
 
 template <int C>
 LRP_DEV void store_pixel(const KParams &P, const float *thr, int x, int y, float (&v)[C]) {
-  const size_t pix = (size_t)y * (size_t)P.W + (size_t)x;
+  const size_t pix = (size_t)((unsigned)y * (unsigned)P.W + (unsigned)x);
   if (P.dst_fmt == FMT_F32) {
     float *d = (float *)P.dst + pix * C;
     if (C == 4) {
@@ -317,12 +377,11 @@ LRP_DEV void store_pixel(const KParams &P, const float *thr, int x, int y, float
       for (int c = 0; c < C; ++c) d[c] = canon_nan(v[c]);
     }
   } else if (P.dst_fmt == FMT_U8) {
-    uchar4 o;
-    o.x = (unsigned char)encode_u8(v[0], thr);
-    o.y = (unsigned char)encode_u8(v[1 < C ? 1 : 0], thr);
-    o.z = (unsigned char)encode_u8(v[2 < C ? 2 : 0], thr);
-    o.w = (C == 4) ? (unsigned char)encode_u8(v[C - 1], thr) : (unsigned char)255;
-    ((uchar4 *)P.dst)[pix] = o;
+    unsigned o = encode_u8(v[0], thr);
+    o |= encode_u8(v[1 < C ? 1 : 0], thr) << 8;
+    o |= encode_u8(v[2 < C ? 2 : 0], thr) << 16;
+    o |= ((C == 4) ? encode_u8(v[C - 1], thr) : 255u) << 24;
+    ((unsigned *)P.dst)[pix] = o;
   } else {
     unsigned short *d = (unsigned short *)P.dst + pix;
 #pragma unroll
@@ -331,69 +390,163 @@ LRP_DEV void store_pixel(const KParams &P, const float *thr, int x, int y, float
 }
 
 // ---- the kernel ------------------------------------------------------------------------------
+//
+// Persistent, warp-granular scheduling: one 1024-thread CTA per SM; every WARP walks its own
+// sequence of 32 x TILE_ROWS output tiles (lane = column, rows in sequence), so warps never wait for
+// each other after the one-off table setup — a CTA-wide barrier per tile phase-locks all 32 warps
+// of an SM onto the same pipe (measured: issue utilisation 82 % -> 68 %, profiles/r1_c2_bc_v2).
+// A lane keeps the column part of its output ray (rect / equirect output lenses are separable:
+// reference :155-157, :249-256) in registers for all rows of the tile; the row part is computed by
+// lane r for row r and broadcast with a shuffle.
+//
+// Per launch a CTA sets up its shared-memory tables once: the lane-replicated gamma LUT (64 KB,
+// FMT_U8) and the 8-bit threshold table.
+//
+// Dynamic shared memory map (bytes from the start of the dynamic window):
+//   [0, 1088)                                       thr[257] (+ padding)
+//   next 64 KB-aligned shared address .. +64 KB     gamma LUT, FMT_U8 only
+constexpr int THR_FLOATS = 272;
+constexpr int TILE_ROWS = 8;
+
+LRP_DEV uint32_t shared_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int COORD, int INTERP, int FMT, int C, bool PACKED>
-__global__ void __launch_bounds__(TILE_X *TILE_Y)
-    reproject_kernel(const __grid_constant__ KParams P) {
-  __shared__ float s_lut[256];
-  __shared__ float s_thr[256];
-  const int tid = threadIdx.y * TILE_X + threadIdx.x;
-  if (FMT == FMT_U8) s_lut[tid] = P.lut[tid];
-  if (P.dst_fmt == FMT_U8) s_thr[tid] = P.thr[tid];
-  if (FMT == FMT_U8 || P.dst_fmt == FMT_U8) __syncthreads();
-
-  const int x = blockIdx.x * TILE_X + threadIdx.x;
-  const int y = blockIdx.y * TILE_Y + threadIdx.y;
-  if (x >= P.W || y >= P.H) return;
-
+__global__ void __launch_bounds__(NTHREADS, 1) reproject_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool WRAP = (COORD == COORD_ERECT_WRAP || COORD == COORD_TABLE_WRAP);
   constexpr bool TABLE = (COORD == COORD_TABLE_CLAMP || COORD == COORD_TABLE_WRAP);
 
-  // pixel centre, image centred on (0,0): :287-288
-  const float cx = fsub(fadd((float)x, 0.5f), fmul((float)P.W, 0.5f));
-  const float cy = fsub(fadd((float)y, 0.5f), fmul((float)P.H, 0.5f));
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  float *s_thr = (float *)smem_raw;
 
-  float acc[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) acc[c] = 0.0f;
+  // ---- once per CTA: tables ----
+  if (P.dst_fmt == FMT_U8 && tid <= 256) s_thr[tid] = (tid < 256) ? P.thr[tid] : __int_as_float(0x7f800000);
+  uint32_t lut_lane = 0;
+  if (FMT == FMT_U8) {
+    const uint32_t low_end = shared_addr(s_thr + THR_FLOATS);
+    const uint32_t lut_base = (low_end + 0xFFFFu) & ~0xFFFFu;
+    for (int i = tid; i < 256 * 32; i += NTHREADS) {
+      const float g = __ldg(P.lut + (i >> 5));
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(lut_base + ((uint32_t)(i >> 5) << 8) + ((uint32_t)(i & 31) << 2)), "f"(g));
+    }
+    lut_lane = lut_base | ((uint32_t)lane << 2);
+  }
+  __syncthreads(); // the only CTA-wide barrier
 
-  for (int ssx = 0; ssx < P.ns; ++ssx) {
-    const float scx = fsub(fadd(cx, fdiv(fadd((float)ssx, 1.0f), P.ss_den)), 0.5f); // :295
-    for (int ssy = 0; ssy < P.ns; ++ssy) {
-      const float scy = fsub(fadd(cy, fdiv(fadd((float)ssy, 1.0f), P.ss_den)), 0.5f); // :298
-      float sx, sy;
-      if (TABLE) {
-        const size_t plane = (size_t)(ssx * P.ns + ssy) * (size_t)P.H;
-        float2 s = __ldg(P.remap + (plane + (size_t)y) * (size_t)P.W + (size_t)x);
-        sx = s.x;
-        sy = s.y;
+  const SrcView S{P, lut_lane};
+  // separable output rays from registers need one value per sub-sample column: ns == 1 only;
+  // supersampled launches recompute the ray per sub-sample (its cost is amortised over ns^2 taps sets)
+  const bool separable = !TABLE && (P.ol.type != LENS_EQUIDISTANT) && (P.ns == 1);
+  const bool out_rect = (P.ol.type == LENS_RECT);
+  const float Wf = (float)P.W, Hf = (float)P.H;
+  const float half_W = fmul(Wf, 0.5f), half_H = fmul(Hf, 0.5f);
+
+  const int tiles_x = (P.W + TILE - 1) / TILE, tiles_y = (P.H + TILE_ROWS - 1) / TILE_ROWS;
+  const int n_tiles = tiles_x * tiles_y;
+  const int warps_total = gridDim.x * (NTHREADS / 32);
+
+  for (int tile = blockIdx.x * (NTHREADS / 32) + wrp; tile < n_tiles; tile += warps_total) {
+    const int x0 = (tile % tiles_x) * TILE, y0 = (tile / tiles_x) * TILE_ROWS;
+    const int x = x0 + lane;
+    const float cx = fsub(fadd((float)x, 0.5f), half_W); // pixel centre, image centred on (0,0): :287
+
+    // ---- per tile: the separable parts of the output rays (ns == 1: scx == cx exactly, :295) ----
+    float col_vx = 0.0f, col_vz = -1.0f, row_vy = 0.0f;
+    if (separable) {
+      const float q = fdiv(fadd(0.0f, 1.0f), P.ss_den);
+      const float scx = fsub(fadd(cx, q), 0.5f);
+      const float cyl = fsub(fadd((float)(y0 + lane), 0.5f), half_H);
+      const float scyl = fsub(fadd(cyl, q), 0.5f);
+      if (out_rect) {
+        col_vx = fdiv(fmul(fdiv(scx, Wf), P.ol.sw), P.ol.p0);
+        row_vy = fdiv(fmul(fdiv(scyl, Hf), P.ol.sh), P.ol.p0);
       } else {
-        source_coord<COORD>(P, scx, scy, sx, sy);
+        const float lon = fadd(fmul(fadd(fdiv(scx, Wf), 0.5f), fsub(P.ol.p3, P.ol.p2)), P.ol.p2);
+        const float lat = fadd(fmul(fadd(fdiv(scyl, Hf), 0.5f), fsub(P.ol.p1, P.ol.p0)), P.ol.p0);
+        float sn, cs;
+        dev_sincosf(lon, P.use_fma != 0, &sn, &cs);
+        col_vx = sn;
+        col_vz = -cs;
+        dev_sincosf(lat, P.use_fma != 0, &row_vy, nullptr); // not scaled by cos(lat): reference quirk
       }
-      float smp[C];
-      if (INTERP == INTERP_NN) sample_nearest<WRAP, FMT, C>(P, s_lut, sx, sy, smp);
-      else if (INTERP == INTERP_BL) sample_bilinear<WRAP, FMT, C>(P, s_lut, sx, sy, smp);
-      else sample_bicubic<WRAP, FMT, C, PACKED>(P, s_lut, sx, sy, smp);
+    }
+
+    for (int r = 0; r < TILE_ROWS; ++r) {
+      const int y = y0 + r;
+      if (y >= P.H) break; // warp-uniform
+      const float vy_row = __shfl_sync(0xffffffffu, row_vy, r);
+      if (x >= P.W) continue;
+      const float cy = fsub(fadd((float)y, 0.5f), half_H); // :288
+      float acc[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) acc[c] = fadd(acc[c], smp[c]); // :334-336
+      for (int c = 0; c < C; ++c) acc[c] = 0.0f;
+
+      for (int ssx = 0; ssx < P.ns; ++ssx) {
+        for (int ssy = 0; ssy < P.ns; ++ssy) {
+          float sx, sy;
+          if (TABLE) {
+            const size_t plane = (size_t)(ssx * P.ns + ssy) * (size_t)P.H;
+            float2 s = __ldg(P.remap + (plane + (size_t)y) * (size_t)P.W + (size_t)x);
+            sx = s.x;
+            sy = s.y;
+          } else {
+            float vx, vy, vz;
+            if (separable) {
+              vx = col_vx;
+              vz = col_vz;
+              vy = vy_row;
+            } else {
+              const float scx = fsub(fadd(cx, fdiv(fadd((float)ssx, 1.0f), P.ss_den)), 0.5f); // :295
+              const float scy = fsub(fadd(cy, fdiv(fadd((float)ssy, 1.0f), P.ss_den)), 0.5f); // :298
+              target_to_vec(P, scx, scy, vx, vy, vz);
+            }
+            ray_to_source<COORD>(P, vx, vy, vz, sx, sy);
+          }
+          float smp[C];
+          if (INTERP == INTERP_NN) sample_nearest<WRAP, FMT, C>(S, sx, sy, smp);
+          else if (INTERP == INTERP_BL) sample_bilinear<WRAP, FMT, C>(S, sx, sy, smp);
+          else sample_bicubic<WRAP, FMT, C, PACKED>(S, sx, sy, smp);
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[c] = fadd(acc[c], smp[c]); // :334-336
+        }
+      }
+
+      float v[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) v[c] = fmul(acc[c], P.normalize); // :338-341
+      if (P.post) {                                                  // fused post_process, :421-437
+#pragma unroll
+        for (int c = 0; c < (C < 3 ? C : 3); ++c) v[c] = post_process_value(v[c], P.exposure, P.r2);
+      }
+      store_pixel<C>(P, s_thr, x, y, v);
     }
   }
+}
 
-  float v[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) v[c] = fmul(acc[c], P.normalize); // :338-341
-  if (P.post) {                                                  // fused post_process, :421-437
-#pragma unroll
-    for (int c = 0; c < (C < 3 ? C : 3); ++c) v[c] = post_process_value(v[c], P.exposure, P.r2);
-  }
-  store_pixel<C>(P, s_thr, x, y, v);
+// dynamic shared memory a launch needs (see the map above)
+inline size_t reproject_smem_bytes(int fmt) {
+  if (fmt != FMT_U8) return (size_t)THR_FLOATS * 4;
+  // the LUT must start at a 64 KB-aligned SHARED-WINDOW address; the dynamic window starts a little
+  // above 0 (driver-reserved + static shared memory), so reserve up to the second 64 KB boundary.
+  return (size_t)2 * 65536;
 }
 
 template <int COORD, int INTERP, int FMT, int C, bool PACKED>
 int launch_reproject(const KParams &P, void *stream) {
-  dim3 block(TILE_X, TILE_Y);
-  dim3 grid((P.W + TILE_X - 1) / TILE_X, (P.H + TILE_Y - 1) / TILE_Y);
-  reproject_kernel<COORD, INTERP, FMT, C, PACKED><<<grid, block, 0, (cudaStream_t)stream>>>(P);
+  auto kern = reproject_kernel<COORD, INTERP, FMT, C, PACKED>;
+  const size_t smem = reproject_smem_bytes(FMT);
+  static thread_local int configured_device = -1; // opt-in to > 48 KB dynamic shared memory, once per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > 48 * 1024 && configured_device != dev) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured_device = dev;
+  }
+  const int tiles = ((P.W + TILE - 1) / TILE) * ((P.H + TILE_ROWS - 1) / TILE_ROWS);
+  const int ctas_needed = (tiles + NTHREADS / 32 - 1) / (NTHREADS / 32);
+  const int grid = ctas_needed < P.num_sms ? ctas_needed : P.num_sms;
+  kern<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(P);
   return (int)cudaGetLastError();
 }
 

@@ -114,6 +114,7 @@ def lib():
         L.lrp_sched_stats.argtypes = [vp, C.POINTER(C.c_int64)]
         L.lrp_debug_coords.argtypes = [vp, ip, ip, pp, vp, vp]
         L.lrp_debug_libm.argtypes = [vp, C.c_int, vp, vp, vp, C.c_size_t, vp]
+        L.lrp_debug_encode_u8.argtypes = [vp, vp, vp, C.c_size_t, vp]
         _lib = L
     return _lib
 
@@ -340,6 +341,13 @@ class Context:
                                    C.c_void_p(b_t.data_ptr()) if b_t is not None else None,
                                    C.c_void_p(out.data_ptr()), a_t.numel(), self._stream(stream)),
               "lrp_debug_libm")
+        return out
+
+    def debug_encode_u8(self, a_t, stream=None):
+        import torch
+        out = torch.empty(a_t.shape, dtype=torch.uint8, device=a_t.device)
+        check(lib().lrp_debug_encode_u8(self.h, C.c_void_p(a_t.data_ptr()), C.c_void_p(out.data_ptr()), a_t.numel(),
+                                        self._stream(stream)), "lrp_debug_encode_u8")
         return out
 
     # -- asynchronous host-buffer jobs on this context's worker streams --

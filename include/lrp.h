@@ -220,6 +220,9 @@ int lrp_debug_coords(lrp_ctx *ctx, const lrp_image *in_geom, const lrp_image *ou
 int lrp_debug_libm(lrp_ctx *ctx, int fn, const float *a_dev, const float *b_dev, float *out_dev,
                    size_t n, void *cuda_stream);
 
+/* the fused 8-bit sink quantiser (save_png arithmetic, src/image_formats.cpp:156-158) element-wise */
+int lrp_debug_encode_u8(lrp_ctx *ctx, const float *in_dev, uint8_t *out_dev, size_t n, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,8 @@ float orc_cosf(float x, int use_fma);
 int64_t orc_libm_sweep(int fn, uint32_t first, uint64_t count, uint32_t step, int use_fma,
                        uint32_t *first_bad);
 int64_t orc_atan2_sweep(uint64_t seed, uint64_t count, uint32_t *first_bad_y, uint32_t *first_bad_x);
+void orc_host_libm_eval(int fn, const float *a, const float *b, float *out, uint64_t n);
+void orc_gamma_encode_eval(const float *s, uint8_t *out, uint64_t n);
 /* monotonicity of q(s)=uint8(255.9f*powf(s,1/2.2f)) over float bit patterns [first,last] */
 int64_t orc_gamma_monotone_violations(uint32_t first, uint32_t last);
 

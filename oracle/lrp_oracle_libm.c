@@ -320,3 +320,26 @@ int64_t orc_gamma_monotone_violations(uint32_t first, uint32_t last) {
   for (int t = 0; t < T; ++t) { pthread_join(th[t], NULL); bad += jobs[t].bad; }
   return bad;
 }
+
+/* host libm over arrays (the GPU suite compares the device restatement against these) */
+void orc_host_libm_eval(int fn, const float *a, const float *b, float *out, uint64_t n) {
+  for (uint64_t i = 0; i < n; ++i) {
+    switch (fn) {
+    case 0: out[i] = atanf(a[i]); break;
+    case 1: out[i] = asinf(a[i]); break;
+    case 2: out[i] = sinf(a[i]); break;
+    case 3: out[i] = cosf(a[i]); break;
+    default: out[i] = atan2f(a[i], b[i]); break;
+    }
+  }
+}
+
+/* the reference's 8-bit quantiser over arrays: uint8(255.9f * powf(max(0, min(1, s)), 1/2.2f)) */
+void orc_gamma_encode_eval(const float *s, uint8_t *out, uint64_t n) {
+  for (uint64_t i = 0; i < n; ++i) {
+    float v = s[i];
+    v = (v < 1.0f) ? v : 1.0f;      /* std::min(1.0f, v) */
+    v = (0.0f < v) ? v : 0.0f;      /* std::max(0.0f, .) */
+    out[i] = gamma_q(v);
+  }
+}

@@ -211,8 +211,26 @@ class _Oracle(_Checker):
         L.orc_atan2_sweep.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32),
                                       C.POINTER(C.c_uint32)]
         L.orc_atan2_sweep.restype = C.c_int64
+        L.orc_host_libm_eval.argtypes = [C.c_int, _fp, _fp, _fp, C.c_uint64]
+        L.orc_host_libm_eval.restype = None
+        L.orc_gamma_encode_eval.argtypes = [_fp, u8p, C.c_uint64]
+        L.orc_gamma_encode_eval.restype = None
         L.orc_gamma_monotone_violations.argtypes = [C.c_uint32, C.c_uint32]
         L.orc_gamma_monotone_violations.restype = C.c_int64
+
+    def host_libm(self, fn, a, b=None):
+        """host glibc atanf/asinf/sinf/cosf/atan2f (fn 0..4) over arrays"""
+        a = np.ascontiguousarray(a, np.float32)
+        bb = None if b is None else np.ascontiguousarray(b, np.float32)
+        out = np.empty_like(a)
+        self.lib.orc_host_libm_eval(fn, self._ptr(a), self._ptr(bb), self._ptr(out), a.size)
+        return out
+
+    def gamma_encode(self, s):
+        s = np.ascontiguousarray(s, np.float32)
+        out = np.empty(s.shape, np.uint8)
+        self.lib.orc_gamma_encode_eval(self._ptr(s), out.ctypes.data_as(C.POINTER(C.c_uint8)), s.size)
+        return out
 
     def coords_image(self, out_lens, W, H, in_lens, w, h, rot):
         s = np.zeros((H, W, 2), np.float32)
