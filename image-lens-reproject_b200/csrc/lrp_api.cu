@@ -242,6 +242,9 @@ int prepare(const lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const
   if (!ctx || !in || !out || !p) return LRP_E_BAD_ARG;
   if (in->width <= 0 || in->height <= 0 || out->width <= 0 || out->height <= 0) return LRP_E_BAD_ARG;
   if (p->num_samples < 1 || p->num_samples > 64) return LRP_E_BAD_ARG;
+  // pixel indices are 32-bit on the device (the reference's own index arithmetic is `int`)
+  if ((uint64_t)in->width * (uint64_t)in->height >= (1ull << 31)) return LRP_E_BAD_ARG;
+  if ((uint64_t)out->width * (uint64_t)out->height >= (1ull << 31)) return LRP_E_BAD_ARG;
   if (!lens_supported(out->lens.type)) return LRP_E_UNSUPPORTED_OUTPUT_LENS; // reference :415-417
   if (!lens_supported(in->lens.type)) return LRP_E_UNSUPPORTED_INPUT_LENS;   // reference :395-397
   if (p->interpolation < 0 || p->interpolation > 2) return LRP_E_UNSUPPORTED_INTERP; // :364-366
@@ -286,6 +289,7 @@ int prepare(const lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const
   K.thr = ctx->d_thr;
   K.neg_zero2 = 0x8000000080000000ull;
   K.num_sms = ctx->num_sms;
+  K.src_px_bytes = in->format == LRP_FMT_F32 ? 4u * (unsigned)in->channels : in->format == LRP_FMT_U8_RGBA ? 4u : 2u;
   switch (in->lens.type) {
   case LENS_RECT: coord = COORD_RECT; break;
   case LENS_EQUIDISTANT: coord = COORD_EQUIDISTANT; break;

@@ -174,14 +174,24 @@ LRP_DEV void tap_indices(float sx, float sy, const float (&off)[N], int w, int h
   for (int k = 0; k < N; ++k) ys[k] = clampi(ys[k], h);
 }
 
+// base + idx * scale with a 32-bit unsigned index as exactly one IMAD.WIDE.U32.  The scale comes from
+// a kernel parameter on purpose: with a literal power of two ptxas strength-reduces the multiply into
+// shift + IMAD.HI + 64-bit add pairs.  (ptxas still hoists x*scale out of the four tap rows and adds
+// a 64-bit pair per tap: 2 instructions per tap instead of the 4 the plain C++ indexing compiles to.)
+LRP_DEV const char *byte_offset_rt(const void *base, uint32_t idx, uint32_t scale) {
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(idx), "r"(scale), "l"(base));
+  return (const char *)r;
+}
+
 template <int FMT, int C> struct Texel;
 
 // float32 interleaved — the reference's in-memory layout (src/reproject.cpp:49-51)
 template <int C> struct Texel<FMT_F32, C> {
-  typedef const float *Row;
-  static LRP_DEV Row row(const SrcView &S, int y) { return (const float *)S.P.src + (size_t)((unsigned)y * (unsigned)S.P.w) * C; }
-  static LRP_DEV void load(const SrcView &, Row r, int x, float (&v)[C]) {
-    const float *p = r + (unsigned)x * C;
+  typedef const char *Row;
+  static LRP_DEV Row row(const SrcView &S, int y) { return byte_offset_rt(S.P.src, (unsigned)y * (unsigned)S.P.w, S.P.src_px_bytes); }
+  static LRP_DEV void load(const SrcView &S, Row r, int x, float (&v)[C]) {
+    const float *p = (const float *)byte_offset_rt(r, (unsigned)x, S.P.src_px_bytes);
     if (C == 4) {
       float4 t = __ldg((const float4 *)p);
       v[0] = t.x; v[1] = t.y; v[2] = t.z; v[C - 1] = t.w;
@@ -197,8 +207,8 @@ template <int C> struct Texel<FMT_F32, C> {
 //   address = table (64 KB aligned) | value << 8 | lane << 2
 // so that ONE byte-permute forms the address and every lane hits its own bank (no conflicts).
 template <int C> struct Texel<FMT_U8, C> {
-  typedef const uchar4 *Row;
-  static LRP_DEV Row row(const SrcView &S, int y) { return (const uchar4 *)S.P.src + (size_t)((unsigned)y * (unsigned)S.P.w); }
+  typedef const char *Row;
+  static LRP_DEV Row row(const SrcView &S, int y) { return byte_offset_rt(S.P.src, (unsigned)y * (unsigned)S.P.w, S.P.src_px_bytes); }
   static LRP_DEV float lut(uint32_t addr) {
     float r;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
@@ -206,7 +216,7 @@ template <int C> struct Texel<FMT_U8, C> {
   }
   static LRP_DEV void load(const SrcView &S, Row r, int x, float (&v)[C]) {
     static_assert(C == 3, "PNG sources decode to 3 channels");
-    const uint32_t t = __ldg((const unsigned int *)(r + (unsigned)x));
+    const uint32_t t = __ldg((const unsigned int *)byte_offset_rt(r, (unsigned)x, S.P.src_px_bytes));
     v[0] = lut(__byte_perm(t, S.lut_lane, 0x7604));
     v[1] = lut(__byte_perm(t, S.lut_lane, 0x7614));
     v[2] = lut(__byte_perm(t, S.lut_lane, 0x7624));
@@ -215,12 +225,14 @@ template <int C> struct Texel<FMT_U8, C> {
 
 // planar IEEE half (the HALF slices of read_exr); half -> float is exact
 template <int C> struct Texel<FMT_F16, C> {
-  typedef const __half *Row;
-  static LRP_DEV Row row(const SrcView &S, int y) { return (const __half *)S.P.src + (size_t)((unsigned)y * (unsigned)S.P.w); }
+  typedef const char *Row;
+  static LRP_DEV Row row(const SrcView &S, int y) { return byte_offset_rt(S.P.src, (unsigned)y * (unsigned)S.P.w, S.P.src_px_bytes); }
   static LRP_DEV void load(const SrcView &S, Row r, int x, float (&v)[C]) {
-    const __half *p = r + (unsigned)x;
+    const char *p = byte_offset_rt(r, (unsigned)x, S.P.src_px_bytes);
+    const uint32_t plane_bytes = (uint32_t)S.P.src_plane * 2u; // w*h*2 < 2^32 (checked on the host)
 #pragma unroll
-    for (int c = 0; c < C; ++c) v[c] = __half2float(__ldg(p + (size_t)c * (size_t)S.P.src_plane));
+    for (int c = 0; c < C; ++c)
+      v[c] = __half2float(__ldg((const __half *)(c == 0 ? p : byte_offset_rt(p, (uint32_t)c, plane_bytes))));
   }
 };
 
@@ -350,8 +362,8 @@ LRP_DEV float post_process_value(float v, float exposure, float r2) {
 LRP_DEV unsigned encode_u8(float s, const float *thr) {
   s = clamp01_std(s); // NaN -> 1.0 by operand order of std::min/max
   float lg, a;
-  asm("lg2.approx.f32 %0, %1;" : "=f"(lg) : "f"(s));
-  asm("ex2.approx.f32 %0, %1;" : "=f"(a) : "f"(fmul(lg, 0.45454545f)));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(s)); // one MUFU each; a flushed denormal lands on k = 0, which is exact
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(fmul(lg, 0.45454545f)));
   int k = min(255, __float2int_rz(fmul(255.9f, a)));
   const float t0 = thr[k], t1 = thr[k + 1];
   k += (s >= t1) ? 1 : 0;

@@ -53,6 +53,7 @@ struct KParams {
   float2 *coords_out;    // coords kernel output
   int coords_planes;     // how many sub-sample planes the coords kernel writes
   unsigned long long neg_zero2; // packed (-0.0f, -0.0f); opaque to ptxas (see lrp_math.cuh)
+  unsigned src_px_bytes;        // bytes between horizontally adjacent source texels (4*C, 4 or 2)
   int num_sms;                  // persistent grid size (SM count of the context's device)
 };
 
