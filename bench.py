@@ -202,14 +202,15 @@ def run_gpu_arm(args, rank, world, local_rank):
     in_lens = lrp.lens_equirectangular()
     out_lens = lrp.lens_rectilinear(18.0, 36.0, OUT_W, OUT_H)
     rot = lrp.rotation_from_degrees(*ROTATION_DEG)
-    params = lrp.make_params(1, interp, rot, None)
+    variant = {"auto": lrp.VARIANT_AUTO, "gather": lrp.VARIANT_GATHER, "staged": lrp.VARIANT_STAGED}[args.variant]
+    params = lrp.make_params(1, interp, rot, None, variant=variant)
 
     B = FRAMES_PER_STEP
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + rank)
     srcs = [torch.randint(0, 256, (SRC_H, SRC_W, 4), dtype=torch.uint8, device=dev, generator=g) for _ in range(B)]
     dsts = [torch.empty((OUT_H, OUT_W, 4), dtype=torch.uint8, device=dev) for _ in range(B)]
-    remap = ctx.build_remap(in_lens, SRC_W, SRC_H, out_lens, OUT_W, OUT_H, params) if args.variant == "remap" else None
+    remap = ctx.build_remap(in_lens, SRC_W, SRC_H, out_lens, OUT_W, OUT_H, params) if args.coords == "table" else None
 
     def step():
         for s, d in zip(srcs, dsts):
@@ -276,7 +277,7 @@ def run_gpu_arm(args, rank, world, local_rank):
             "metric": "output_gpix_per_s", "value": value, "unit": "Gpix/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "interp": args.interp, "variant": args.variant,
+            "config": {"workload": WORKLOAD, "interp": args.interp, "variant": args.variant, "coords": args.coords,
                        "frames_per_step": B, "frames_per_gpu": B,
                        "l2": "inputs larger than L2: each step walks %d distinct 134 MB sources (%.2f GB) and "
                              "%d distinct 33 MB sinks per GPU" % (B, B * in_bytes / 1e9, B),
@@ -284,8 +285,10 @@ def run_gpu_arm(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(args.interp), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": balg, "us_per_launch": per_launch_s * 1e6,
-                         "kernel": "lrp::reproject_kernel<COORD_ERECT_WRAP, BICUBIC, U8, 3>" if args.variant == "gather"
-                         else "lrp::reproject_kernel<COORD_TABLE_WRAP, ...>"},
+                         "kernel": "lrp::%s<%s, %s, U8, 3>" % (
+                             "reproject_kernel" if args.variant == "gather" else "reproject_staged_kernel",
+                             "COORD_TABLE_WRAP" if args.coords == "table" else "COORD_ERECT_WRAP",
+                             {"nn": "NEAREST", "bl": "BILINEAR", "bc": "BICUBIC"}[args.interp])},
             "e2e": {"value": e2e_value, "unit": "Gpix/s", "h2d_bytes_per_step": B * in_bytes,
                     "d2h_bytes_per_step": B * out_bytes, "steps": e2e_steps, "matches_device_path": e2e_ok,
                     "api": "lrp_submit/lrp_wait_all (C ABI, pinned host buffers, 4 streams)"},
@@ -316,7 +319,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lrp", choices=["lrp", "reference"])
     ap.add_argument("--interp", default="bc", choices=["nn", "bl", "bc"])
-    ap.add_argument("--variant", default="gather", choices=["gather", "remap"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "gather", "staged"],
+                    help="source access: footprint staging in shared memory (auto = the library default) or per-tap gather")
+    ap.add_argument("--coords", default="fly", choices=["fly", "table"],
+                    help="source coordinates computed on the fly, or read from a per-batch remap table")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -30,13 +30,27 @@ LRP_DECL(0, 0) LRP_DECL(0, 1) LRP_DECL(0, 2) LRP_DECL(1, 0) LRP_DECL(1, 1) LRP_D
 LRP_DECL(2, 0) LRP_DECL(2, 1) LRP_DECL(2, 2) LRP_DECL(3, 0) LRP_DECL(3, 1) LRP_DECL(3, 2)
 LRP_DECL(4, 0) LRP_DECL(4, 1) LRP_DECL(4, 2) LRP_DECL(5, 0) LRP_DECL(5, 1) LRP_DECL(5, 2)
 #undef LRP_DECL
+#define LRP_DECL(c, i) LaunchFn get_staged_launcher_c##c##_i##i(int fc);
+LRP_DECL(0, 0) LRP_DECL(0, 1) LRP_DECL(0, 2) LRP_DECL(1, 0) LRP_DECL(1, 1) LRP_DECL(1, 2)
+LRP_DECL(2, 0) LRP_DECL(2, 1) LRP_DECL(2, 2) LRP_DECL(3, 0) LRP_DECL(3, 1) LRP_DECL(3, 2)
+LRP_DECL(4, 0) LRP_DECL(4, 1) LRP_DECL(4, 2) LRP_DECL(5, 0) LRP_DECL(5, 1) LRP_DECL(5, 2)
+#undef LRP_DECL
 int launch_coords(const KParams &P, int coord, void *stream);
 int launch_post_process(float *data, size_t n_pixels, int channels, float exposure, float reinhard, void *stream);
 int launch_libm(int fn, const float *a, const float *b, float *out, size_t n, int use_fma, void *stream);
 int launch_encode_u8(const float *in, unsigned char *out, size_t n, const float *thr, void *stream);
 
-static LaunchFn get_launcher(int coord, int interp, int fc) {
+static LaunchFn get_launcher(int coord, int interp, int fc, bool staged) {
   typedef LaunchFn (*Getter)(int);
+  static const Getter staged_table[COORD_COUNT][3] = {
+      {get_staged_launcher_c0_i0, get_staged_launcher_c0_i1, get_staged_launcher_c0_i2},
+      {get_staged_launcher_c1_i0, get_staged_launcher_c1_i1, get_staged_launcher_c1_i2},
+      {get_staged_launcher_c2_i0, get_staged_launcher_c2_i1, get_staged_launcher_c2_i2},
+      {get_staged_launcher_c3_i0, get_staged_launcher_c3_i1, get_staged_launcher_c3_i2},
+      {get_staged_launcher_c4_i0, get_staged_launcher_c4_i1, get_staged_launcher_c4_i2},
+      {get_staged_launcher_c5_i0, get_staged_launcher_c5_i1, get_staged_launcher_c5_i2},
+  };
+  if (staged) return staged_table[coord][interp](fc);
   static const Getter table[COORD_COUNT][3] = {
       {get_launcher_c0_i0, get_launcher_c0_i1, get_launcher_c0_i2},
       {get_launcher_c1_i0, get_launcher_c1_i1, get_launcher_c1_i2},
@@ -248,6 +262,7 @@ int prepare(const lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const
   if (!lens_supported(out->lens.type)) return LRP_E_UNSUPPORTED_OUTPUT_LENS; // reference :415-417
   if (!lens_supported(in->lens.type)) return LRP_E_UNSUPPORTED_INPUT_LENS;   // reference :395-397
   if (p->interpolation < 0 || p->interpolation > 2) return LRP_E_UNSUPPORTED_INTERP; // :364-366
+  if (p->variant < LRP_VARIANT_AUTO || p->variant > LRP_VARIANT_STAGED) return LRP_E_BAD_ARG;
   if (need_data) {
     if (!in->data || !out->data) return LRP_E_BAD_ARG;
     if (in->channels != out->channels) return LRP_E_BAD_ARG; // reference: output.channels = input.channels
@@ -324,7 +339,12 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
     K.remap = (const float2 *)remap;
     coord = (coord == COORD_ERECT_WRAP) ? COORD_TABLE_WRAP : COORD_TABLE_CLAMP;
   }
-  LaunchFn fn = get_launcher(coord, p->interpolation, fc);
+  // source access: the staged kernel handles one sample per pixel; supersampled launches gather
+  const char *force = getenv("LRP_FORCE_VARIANT"); // A/B runs of unmodified callers: "gather" | "staged"
+  int variant = p->variant;
+  if (force && variant == LRP_VARIANT_AUTO) variant = force[0] == 'g' ? LRP_VARIANT_GATHER : LRP_VARIANT_STAGED;
+  const bool staged = (variant != LRP_VARIANT_GATHER) && p->num_samples == 1;
+  LaunchFn fn = get_launcher(coord, p->interpolation, fc, staged);
   if (!fn) return LRP_E_UNSUPPORTED_FORMAT;
   return map_cuda((cudaError_t)fn(K, stream));
 }

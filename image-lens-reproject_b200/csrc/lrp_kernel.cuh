@@ -90,6 +90,15 @@ LRP_DEV void vec_to_source(const KParams &P, float x, float y, float z, float &c
   }
 }
 
+// Input-lens projection + re-centring of an already rotated ray: reference :313-324.
+template <int COORD>
+LRP_DEV void rotated_to_source(const KParams &P, float vx, float vy, float vz, float &sx, float &sy) {
+  float cx, cy;
+  vec_to_source<COORD>(P, vx, vy, vz, cx, cy);
+  sx = fadd(fsub(cx, 0.5f), fmul((float)P.w, 0.5f)); // :323
+  sy = fadd(fsub(cy, 0.5f), fmul((float)P.h, 0.5f)); // :324
+}
+
 // Rotation + input-lens projection + re-centring of one ray: reference :303-324.
 template <int COORD>
 LRP_DEV void ray_to_source(const KParams &P, float vx, float vy, float vz, float &sx, float &sy) {
@@ -120,10 +129,15 @@ LRP_DEV void source_coord(const KParams &P, float scx, float scy, float &sx, flo
 
 // Per-thread view of the source: parameters + this lane's base address into the
 // lane-replicated gamma table (FMT_U8 only).
-struct SrcView {
+// REPL: the gamma table is lane-replicated (64 KB, conflict-free, one PRMT forms the address); otherwise it
+// is the plain 256-entry table (1 KB-aligned; lut_lane = its shared-window address) — the staged kernel's
+// rare fall-back path, where the 64 KB are better spent on staging space.
+template <bool REPL> struct SrcViewT {
   const KParams &P;
-  uint32_t lut_lane; // shared-window address of  LUT[0][lane]  (64 KB-aligned table | lane*4)
+  uint32_t lut_lane; // REPL: address of LUT[0][lane] (64 KB-aligned table | lane*4); plain: address of LUT[0]
+  static constexpr bool repl = REPL;
 };
+typedef SrcViewT<true> SrcView;
 
 // (i + w) % w with C remainder semantics (:43, 60-61, 114-117); a negative remainder (NaN
 // coordinate only, where the reference reads out of bounds) is defined as column 0.
@@ -189,8 +203,8 @@ template <int FMT, int C> struct Texel;
 // float32 interleaved — the reference's in-memory layout (src/reproject.cpp:49-51)
 template <int C> struct Texel<FMT_F32, C> {
   typedef const char *Row;
-  static LRP_DEV Row row(const SrcView &S, int y) { return byte_offset_rt(S.P.src, (unsigned)y * (unsigned)S.P.w, S.P.src_px_bytes); }
-  static LRP_DEV void load(const SrcView &S, Row r, int x, float (&v)[C]) {
+  template <class SV> static LRP_DEV Row row(const SV &S, int y) { return byte_offset_rt(S.P.src, (unsigned)y * (unsigned)S.P.w, S.P.src_px_bytes); }
+  template <class SV> static LRP_DEV void load(const SV &S, Row r, int x, float (&v)[C]) {
     const float *p = (const float *)byte_offset_rt(r, (unsigned)x, S.P.src_px_bytes);
     if (C == 4) {
       float4 t = __ldg((const float4 *)p);
@@ -208,26 +222,32 @@ template <int C> struct Texel<FMT_F32, C> {
 // so that ONE byte-permute forms the address and every lane hits its own bank (no conflicts).
 template <int C> struct Texel<FMT_U8, C> {
   typedef const char *Row;
-  static LRP_DEV Row row(const SrcView &S, int y) { return byte_offset_rt(S.P.src, (unsigned)y * (unsigned)S.P.w, S.P.src_px_bytes); }
+  template <class SV> static LRP_DEV Row row(const SV &S, int y) { return byte_offset_rt(S.P.src, (unsigned)y * (unsigned)S.P.w, S.P.src_px_bytes); }
   static LRP_DEV float lut(uint32_t addr) {
     float r;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
     return r;
   }
-  static LRP_DEV void load(const SrcView &S, Row r, int x, float (&v)[C]) {
+  template <class SV> static LRP_DEV void load(const SV &S, Row r, int x, float (&v)[C]) {
     static_assert(C == 3, "PNG sources decode to 3 channels");
     const uint32_t t = __ldg((const unsigned int *)byte_offset_rt(r, (unsigned)x, S.P.src_px_bytes));
-    v[0] = lut(__byte_perm(t, S.lut_lane, 0x7604));
-    v[1] = lut(__byte_perm(t, S.lut_lane, 0x7614));
-    v[2] = lut(__byte_perm(t, S.lut_lane, 0x7624));
+    if (SV::repl) {
+      v[0] = lut(__byte_perm(t, S.lut_lane, 0x7604));
+      v[1] = lut(__byte_perm(t, S.lut_lane, 0x7614));
+      v[2] = lut(__byte_perm(t, S.lut_lane, 0x7624));
+    } else { // plain 1 KB-aligned table: address = table | value << 2
+      v[0] = lut(S.lut_lane | ((t << 2) & 0x3FCu));
+      v[1] = lut(S.lut_lane | ((t >> 6) & 0x3FCu));
+      v[2] = lut(S.lut_lane | ((t >> 14) & 0x3FCu));
+    }
   }
 };
 
 // planar IEEE half (the HALF slices of read_exr); half -> float is exact
 template <int C> struct Texel<FMT_F16, C> {
   typedef const char *Row;
-  static LRP_DEV Row row(const SrcView &S, int y) { return byte_offset_rt(S.P.src, (unsigned)y * (unsigned)S.P.w, S.P.src_px_bytes); }
-  static LRP_DEV void load(const SrcView &S, Row r, int x, float (&v)[C]) {
+  template <class SV> static LRP_DEV Row row(const SV &S, int y) { return byte_offset_rt(S.P.src, (unsigned)y * (unsigned)S.P.w, S.P.src_px_bytes); }
+  template <class SV> static LRP_DEV void load(const SV &S, Row r, int x, float (&v)[C]) {
     const char *p = byte_offset_rt(r, (unsigned)x, S.P.src_px_bytes);
     const uint32_t plane_bytes = (uint32_t)S.P.src_plane * 2u; // w*h*2 < 2^32 (checked on the host)
 #pragma unroll
@@ -238,16 +258,16 @@ template <int C> struct Texel<FMT_F16, C> {
 
 // ---- samplers (reference :39-148) ----------------------------------------------------------
 
-template <bool WRAP, int FMT, int C>
-LRP_DEV void sample_nearest(const SrcView &S, float sx, float sy, float (&out)[C]) {
+template <bool WRAP, int FMT, int C, class SV>
+LRP_DEV void sample_nearest(const SV &S, float sx, float sy, float (&out)[C]) {
   const float off[1] = {0.5f};
   int xs[1], ys[1];
   tap_indices<WRAP, 1>(sx, sy, off, S.P.w, S.P.h, xs, ys); // :43-47
   Texel<FMT, C>::load(S, Texel<FMT, C>::row(S, ys[0]), xs[0], out);
 }
 
-template <bool WRAP, int FMT, int C>
-LRP_DEV void sample_bilinear(const SrcView &S, float sx, float sy, float (&out)[C]) {
+template <bool WRAP, int FMT, int C, class SV>
+LRP_DEV void sample_bilinear(const SV &S, float sx, float sy, float (&out)[C]) {
   const float off[2] = {0.0f, 1.0f};
   int xs[2], ys[2];
   tap_indices<WRAP, 2>(sx, sy, off, S.P.w, S.P.h, xs, ys); // :60-67  (s + 0.0f == s bit for bit, -0 -> index 0 either way)
@@ -290,8 +310,8 @@ LRP_DEV f2 cubic2(f2 p0, f2 p1, f2 p2, f2 p3, f2 t, f2 h, const Cubic2Consts &k)
   return add2(p1, mul2(h, mid, k.nz));
 }
 
-template <bool WRAP, int FMT, int C, bool PACKED>
-LRP_DEV void sample_bicubic(const SrcView &S, float sx, float sy, float (&out)[C]) {
+template <bool WRAP, int FMT, int C, bool PACKED, class SV>
+LRP_DEV void sample_bicubic(const SV &S, float sx, float sy, float (&out)[C]) {
   const float off[4] = {-1.0f, 0.0f, 1.0f, 2.0f}; // s + (-1.0f) == s - 1.0f bit for bit
   int xs[4], ys[4];
   tap_indices<WRAP, 4>(sx, sy, off, S.P.w, S.P.h, xs, ys);  // :114-127
@@ -357,17 +377,16 @@ LRP_DEV float post_process_value(float v, float exposure, float r2) {
 // evaluated exactly without a device powf: q(s) is monotone (proved over all floats in [0,1] by the
 // test-suite), so d = max{k : thr[k] <= s} with thr[1..255] built on the host from the host's own
 // powf, thr[0] = 0 and thr[256] = +inf.  Two MUFU approximations land within +-1 of d (proved
-// exhaustively on the device by tests/test_gpu_parity.py::test_png_encode_exhaustive); two table
-// probes correct it without a branch.
+// exhaustively on the device by tests/test_gpu_parity.py::test_png_encode_exhaustive); biased low,
+// the estimate is d or d - 1 and one table probe decides.
 LRP_DEV unsigned encode_u8(float s, const float *thr) {
   s = clamp01_std(s); // NaN -> 1.0 by operand order of std::min/max
   float lg, a;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(s)); // one MUFU each; a flushed denormal lands on k = 0, which is exact
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(fmul(lg, 0.45454545f)));
-  int k = min(255, __float2int_rz(fmul(255.9f, a)));
-  const float t0 = thr[k], t1 = thr[k + 1];
-  k += (s >= t1) ? 1 : 0;
-  k -= (s < t0) ? 1 : 0;
+  // biased low by 0.01 (the two approximations are good to ~3e-4 on this scale): k <= d <= k + 1, one probe decides
+  int k = __float2int_rz(__fmaf_rn(255.9f, a, -0.01f));
+  k += (s >= thr[k + 1]) ? 1 : 0;
   return (unsigned)k;
 }
 

@@ -1,0 +1,605 @@
+// lrp_staged.cuh — the footprint-staging variant of the fused reprojection kernel (sm_100a).
+//
+// Same arithmetic as lrp_kernel.cuh (reference src/reproject.cpp:273-346 + post_process :421-437 + the
+// codec edges of src/image_formats.cpp), different SOURCE ACCESS (north-star item 3):
+//
+//   A warp owns a 32 x 8 tile of output pixels.  It computes the source coordinates of a row (kept in
+//   shared memory), reduces the row's tap bounding box with redux.sync, and grows a GROUP of consecutive
+//   rows for as long as the union of their bounding boxes fits the warp's staging area.  A group is then
+//   processed in two steps:
+//     stage   every texel of the bounding box is fetched from global memory ONCE by the warp (coalesced
+//             along source rows), DECODED once (PNG gamma table / half -> float / channel gather) and
+//             stored as a float4 record — indexed in RAW tap-index space, i.e. border clamping and the
+//             horizontal wrap of a full panorama are applied while staging, so the records of the taps
+//             int(sx-1), int(sx), int(sx+1), int(sx+2) sit next to each other whatever the border does;
+//     sample  each pixel reads its taps with 16-byte shared-memory loads (immediate offsets when its raw
+//             indices are consecutive, which is every pixel away from the truncation-toward-zero kink at
+//             index 0) and runs the bicubic / bilinear arithmetic on packed f32x2 pairs straight out of
+//             the records.
+//   A row whose bounding box alone exceeds the staging area (strong minification, NaN rays, pole
+//   crossings) falls back to the per-tap global gather of lrp_kernel.cuh for that row — same results.
+//
+// Why staging pays even though the gather path already hits L1 93 % of the time: the kernel is bound by
+// instruction issue, not by bytes.  Per pixel the gather path spends 16 LDG + 32 address
+// instructions + 48 PRMT + 48 LDS (gamma table) + clamps; staging decodes each texel once per group
+// (0.3-1.5 texels per output pixel instead of 16) and a tap becomes one LDS.128.
+//
+// TMA / cp.async.bulk are deliberately not used for the stage step: the records are DECODED on the way
+// (table look-up, half->float, planar->interleaved), which needs the bytes in registers; a bulk copy would
+// add a shared->shared pass for 100-400 texels per group and save nothing the 16 resident warps do not
+// already hide.
+#pragma once
+#include "lrp_kernel.cuh"
+
+namespace lrp {
+
+#ifndef LRP_ST_WARPS
+#define LRP_ST_WARPS 16
+#endif
+constexpr int ST_WARPS = LRP_ST_WARPS;    // 16 warps = 512 threads: one persistent CTA per SM, up to 128 registers / thread
+constexpr int ST_THREADS = ST_WARPS * 32;
+constexpr int ST_ROWS = 8;                // tile = 32 x 8 output pixels per warp
+constexpr int ST_COORD_BYTES = ST_ROWS * 32 * 8;
+constexpr int ST_SMEM_BYTES = 232448;     // 227 KB: the opt-in maximum of dynamic shared memory per CTA
+constexpr int ST_FIXED_BYTES = 1088 + 1024 + 1024; // thresholds + 1 KB alignment slack + gamma table
+constexpr int ST_STAGE_BYTES = (((ST_SMEM_BYTES - ST_FIXED_BYTES) / ST_WARPS) - ST_COORD_BYTES) & ~15;
+
+// staging record: C <= 4 -> one float4 (c0, c1, c2, c3|next c2); C == 5 -> float4 + float2 (c4, next c4)
+template <int C> struct StageRec {
+  static constexpr int A_BYTES = 16;
+  static constexpr int B_BYTES = (C == 5) ? 8 : 0;
+  static constexpr int CAP = ST_STAGE_BYTES / (A_BYTES + B_BYTES); // texels per warp
+  static constexpr bool LONE = (C & 1) != 0; // odd channel count: the last channel travels as (value, value of the next column)
+};
+
+struct BBox {
+  int x0, x1, y0, y1;
+};
+
+// A group's records cover `eff`: the raw bounding box with the clamped axes (y always, x unless the source wraps)
+// cut to the image — taps outside resolve to the border texel anyway (reference :45-47, :62-67, :118-127).  When
+// the cut changed anything (`clamped`), the pixels of the group resolve their indices before addressing records.
+// A wrapping group must keep its raw x indices inside [-w, 2w) so that the branch-free wrap applies; every finite
+// coordinate of a full panorama does.
+// A row that holds a NaN / infinite / |s| >= 2^30 coordinate (x86 and CUDA float->int conversions differ there)
+// marks its box with this y range; such a row — and any group it would join — is gathered.
+LRP_DEV bool raw_poisoned(const BBox &b) { return b.y0 == (int)0x80000000 && b.y1 == 0x7fffffff; }
+
+struct GroupPlan {
+  BBox eff;
+  unsigned bw, bh;
+  bool clamped;
+};
+template <bool WRAP> LRP_DEV bool plan_group(const BBox &raw, int w, int h, unsigned cap, GroupPlan &g) {
+  // out-of-image tests on the RAW box (unsigned compare: negative indices are huge)
+  const bool cut_y = ((unsigned)raw.y0 >= (unsigned)h) || ((unsigned)raw.y1 >= (unsigned)h);
+  const bool cut_x = !WRAP && (((unsigned)raw.x0 >= (unsigned)w) || ((unsigned)raw.x1 >= (unsigned)w));
+  g.eff = raw;
+  g.eff.y0 = clampi(raw.y0, h);
+  g.eff.y1 = clampi(raw.y1, h);
+  bool ok = true;
+  if (WRAP) {
+    ok = (raw.x0 >= -w) && (raw.x1 < 2 * w);
+  } else {
+    g.eff.x0 = clampi(raw.x0, w);
+    g.eff.x1 = clampi(raw.x1, w);
+  }
+  g.clamped = cut_x || cut_y;
+  g.bw = (unsigned)g.eff.x1 - (unsigned)g.eff.x0 + 1u;
+  g.bh = (unsigned)g.eff.y1 - (unsigned)g.eff.y0 + 1u;
+  return ok && !raw_poisoned(raw) && g.bw <= 4096u && g.bh <= 4096u && g.bw * g.bh <= cap;
+}
+
+// (i + w) % w / clamp exactly as the gather path applies them to a raw tap index (reference :43-47, :60-67,
+// :114-127); staged groups only hold indices for which the branch-free wrap is exact
+template <bool WRAP> LRP_DEV int resolve_x(int i, int w) { return WRAP ? wrap_fast(i, w) : clampi(i, w); }
+
+// ---- stage: global -> decoded records -------------------------------------------------------
+
+template <int FMT, int C> struct StageLoad;
+
+template <int C> struct StageLoad<FMT_F32, C> {
+  static LRP_DEV void load(const KParams &P, uint32_t, unsigned pix, float (&v)[C]) {
+    const float *p = (const float *)byte_offset_rt(P.src, pix, P.src_px_bytes);
+    if (C == 4) {
+      const float4 t = __ldg((const float4 *)p);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[C - 1] = t.w;
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) v[c] = __ldg(p + c);
+    }
+  }
+};
+template <int C> struct StageLoad<FMT_U8, C> {
+  static LRP_DEV void load(const KParams &P, uint32_t lut, unsigned pix, float (&v)[C]) {
+    static_assert(C == 3, "PNG sources decode to 3 channels");
+    const uint32_t t = __ldg((const unsigned int *)byte_offset_rt(P.src, pix, 4u));
+    float r0, r1, r2; // powf(p / 255, 2.2) of src/image_formats.cpp:195-197 through the host-built table
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r0) : "r"(lut | ((t << 2) & 0x3FCu)));
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r1) : "r"(lut | ((t >> 6) & 0x3FCu)));
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r2) : "r"(lut | ((t >> 14) & 0x3FCu)));
+    v[0] = r0; v[1] = r1; v[2] = r2;
+  }
+};
+template <int C> struct StageLoad<FMT_F16, C> {
+  static LRP_DEV void load(const KParams &P, uint32_t, unsigned pix, float (&v)[C]) {
+    const __half *p = (const __half *)byte_offset_rt(P.src, pix, 2u);
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = __half2float(__ldg(p + (size_t)c * (size_t)P.src_plane));
+  }
+};
+
+// The warp stages the bw x bh records of `b` (the plan's `eff` box: inside the image in y, and in x unless the
+// source wraps).  Record ty * bw + tx holds source texel (resolve_x(b.x0 + tx), b.y0 + ty).  Lanes own columns
+// (their texel offset is computed once), the warp walks down the rows: one coalesced row segment per step.
+template <bool WRAP, int FMT, int C>
+LRP_DEV void stage_group(const KParams &P, uint32_t lut, unsigned char *stage, const BBox &b, unsigned bw, unsigned bh,
+                         int lane) {
+  typedef StageRec<C> Rec;
+  constexpr unsigned STEP = Rec::LONE ? 31u : 32u; // odd C: lane k needs lane k+1's texel, so column chunks overlap by one
+  float4 *recA = (float4 *)stage;
+  float2 *recB = (float2 *)(stage + Rec::CAP * Rec::A_BYTES);
+  for (unsigned c0 = 0; c0 < bw; c0 += STEP) {
+    const unsigned tx = c0 + (unsigned)lane;
+    const bool in = tx < bw;
+    const bool keep = in && (!Rec::LONE || lane < 31 || tx + 1u >= bw);
+    const int gx = in ? resolve_x<WRAP>((int)((unsigned)b.x0 + tx), P.w) : 0;
+    unsigned pix = (unsigned)b.y0 * (unsigned)P.w + (unsigned)gx;
+    unsigned t = tx;
+    for (unsigned ty = 0; ty < bh; ++ty, pix += (unsigned)P.w, t += bw) {
+      float v[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) v[c] = 0.0f;
+      if (in) StageLoad<FMT, C>::load(P, lut, pix, v);
+      float nxt = 0.0f;
+      if (Rec::LONE) nxt = __shfl_down_sync(0xffffffffu, v[C - 1], 1);
+      if (keep) {
+        if (C == 3) recA[t] = make_float4(v[0], v[1], v[2], nxt);
+        else recA[t] = make_float4(v[0], v[1], v[2], v[3 < C ? 3 : 0]);
+        if (C == 5) recB[t] = make_float2(v[C - 1], nxt);
+      }
+    }
+  }
+}
+
+// ---- sample: records -> one interpolated sample ------------------------------------------------
+
+struct StageView {
+  const unsigned char *stage; // this warp's records
+  int bx0, by0;               // tap index of record (0, 0)
+  unsigned bw;                // records per row
+  bool clamped;               // warp-uniform: resolve indices before addressing (border groups)
+  bool small;                 // warp-uniform: not clamped and every raw index of the group is below 32768
+};
+
+LRP_DEV f2 as_f2(unsigned long long v) {
+  f2 r;
+  r.v = v;
+  return r;
+}
+LRP_DEV float f2_lo(f2 a) { return __uint_as_float((unsigned)(a.v & 0xffffffffull)); }
+LRP_DEV float f2_hi(f2 a) { return __uint_as_float((unsigned)(a.v >> 32)); }
+LRP_DEV f2 fma2(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+
+// cubicInterpolate (:92-98) on two lanes.  X2: `2.0f*p0` and `4.0f*p2` are exact (power-of-two factors, and the
+// values of a PNG / half source cannot overflow), so  (2*p0 - 5*p1)  == fma(2, p0, -(5*p1))  and
+// (... + 4*p2) == fma(4, p2, ...)  bit for bit — two instructions fewer per cubic.  float32 sources may hold
+// values whose double overflows, so they keep the literal expression tree.
+struct CubicK {
+  f2 two, three, four, five, nfive;
+  unsigned long long nz;
+};
+template <bool X2> LRP_DEV f2 cubic2x(f2 p0, f2 p1, f2 p2, f2 p3, f2 t, f2 h, const CubicK &k) {
+  f2 a;
+  if (X2) {
+    const f2 m5n = mul2(k.nfive, p1, k.nz); // -(5*p1): rounding is sign-symmetric
+    a = sub2(fma2(k.four, p2, fma2(k.two, p0, m5n)), p3);
+  } else {
+    a = sub2(add2(sub2(mul2(k.two, p0, k.nz), mul2(k.five, p1, k.nz)), mul2(k.four, p2, k.nz)), p3);
+  }
+  const f2 b = sub2(add2(mul2(k.three, sub2(p1, p2), k.nz), p3), p0);
+  const f2 inner = add2(a, mul2(t, b, k.nz));
+  const f2 mid = add2(sub2(p2, p0), mul2(t, inner, k.nz));
+  return add2(p1, mul2(h, mid, k.nz));
+}
+template <bool X2> LRP_DEV float cubic1x(float p0, float p1, float p2, float p3, float t, float h) {
+  float a;
+  if (X2) {
+    const float m5n = fmul(-5.0f, p1);
+    a = fsub(__fmaf_rn(4.0f, p2, __fmaf_rn(2.0f, p0, m5n)), p3);
+  } else {
+    a = fsub(fadd(fsub(fmul(2.0f, p0), fmul(5.0f, p1)), fmul(4.0f, p2)), p3);
+  }
+  const float b = fsub(fadd(fmul(3.0f, fsub(p1, p2)), p3), p0);
+  const float inner = fadd(a, fmul(t, b));
+  const float mid = fadd(fsub(p2, p0), fmul(t, inner));
+  return fadd(p1, fmul(h, mid));
+}
+
+// Tap indices int(s + off[k]) of a staged pixel.  Staged groups only hold pixels with |s| < 2^30 (anything else
+// poisons the row's bounding box and is gathered), where cvt.rzi equals x86 cvttss2si.  Border groups resolve
+// the clamped axes here, as the records only cover the image.
+template <bool WRAP, int N>
+LRP_DEV void staged_indices(const KParams &P, const StageView &V, float sx, float sy, const float (&off)[N],
+                            int (&ix)[N], int (&iy)[N]) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    ix[k] = __float2int_rz(off[k] == 0.0f ? sx : fadd(sx, off[k]));
+    iy[k] = __float2int_rz(off[k] == 0.0f ? sy : fadd(sy, off[k]));
+  }
+  if (V.clamped) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      if (!WRAP) ix[k] = clampi(ix[k], P.w);
+      iy[k] = clampi(iy[k], P.h);
+    }
+  }
+}
+
+template <int C> LRP_DEV void unpack_rec(const float4 a, float (&out)[C]) {
+  out[0] = a.x;
+  if (C > 1) out[1 < C ? 1 : 0] = a.y;
+  if (C > 2) out[2 < C ? 2 : 0] = a.z;
+  if (C > 3) out[3 < C ? 3 : 0] = a.w;
+}
+
+template <bool WRAP, int C>
+LRP_DEV void staged_nearest(const KParams &P, const StageView &V, float sx, float sy, float (&out)[C]) {
+  typedef StageRec<C> Rec;
+  const float off[1] = {0.5f};
+  int ix[1], iy[1];
+  staged_indices<WRAP, 1>(P, V, sx, sy, off, ix, iy); // :43-47
+  const unsigned t = (unsigned)(iy[0] - V.by0) * V.bw + (unsigned)(ix[0] - V.bx0);
+  unpack_rec<C>(((const float4 *)V.stage)[t], out);
+  if (C == 5) out[C - 1] = ((const float2 *)(V.stage + Rec::CAP * Rec::A_BYTES))[t].x;
+}
+
+template <bool WRAP, int C>
+LRP_DEV void staged_bilinear(const KParams &P, const StageView &V, float sx, float sy, float (&out)[C]) {
+  typedef StageRec<C> Rec;
+  const float off[2] = {0.0f, 1.0f};
+  int ix[2], iy[2];
+  staged_indices<WRAP, 2>(P, V, sx, sy, off, ix, iy); // :60-67
+  const float fx = clamp01_std(fsub(sx, (float)resolve_x<WRAP>(ix[0], P.w))); // post-wrap/clamp lx, :70
+  const float fy = clamp01_std(fsub(sy, (float)clampi(iy[0], P.h)));
+  const float cfx = fsub(1.0f, fx), cfy = fsub(1.0f, fy);
+  const unsigned r0 = (unsigned)(iy[0] - V.by0) * V.bw, r1 = (unsigned)(iy[1] - V.by0) * V.bw;
+  const unsigned c0 = (unsigned)(ix[0] - V.bx0), c1 = (unsigned)(ix[1] - V.bx0);
+  const ulonglong2 *recA = (const ulonglong2 *)V.stage;
+  const ulonglong2 ll = recA[r0 + c0], lu = recA[r0 + c1], ul = recA[r1 + c0], uu = recA[r1 + c1];
+  const f2 fx2 = pack2(fx, fx), cfx2 = pack2(cfx, cfx), fy2 = pack2(fy, fy), cfy2 = pack2(cfy, cfy);
+  const unsigned long long nz = P.neg_zero2;
+  { // channels 0, 1
+    const f2 l = add2(mul2(fx2, as_f2(lu.x), nz), mul2(cfx2, as_f2(ll.x), nz)); // :83
+    const f2 u = add2(mul2(fx2, as_f2(uu.x), nz), mul2(cfx2, as_f2(ul.x), nz)); // :84
+    unpack2(add2(mul2(fy2, u, nz), mul2(cfy2, l, nz)), out[0], out[1]);         // :87
+  }
+  { // channels 2, 3 (the upper lane is a spare when C == 3)
+    const f2 l = add2(mul2(fx2, as_f2(lu.y), nz), mul2(cfx2, as_f2(ll.y), nz));
+    const f2 u = add2(mul2(fx2, as_f2(uu.y), nz), mul2(cfx2, as_f2(ul.y), nz));
+    float a, b;
+    unpack2(add2(mul2(fy2, u, nz), mul2(cfy2, l, nz)), a, b);
+    out[2] = a;
+    if (C >= 4) out[3 < C ? 3 : 0] = b;
+  }
+  if (C == 5) {
+    const float2 *recB = (const float2 *)(V.stage + Rec::CAP * Rec::A_BYTES);
+    const float vll = recB[r0 + c0].x, vlu = recB[r0 + c1].x, vul = recB[r1 + c0].x, vuu = recB[r1 + c1].x;
+    const float l = fadd(fmul(fx, vlu), fmul(cfx, vll));
+    const float u = fadd(fmul(fx, vuu), fmul(cfx, vul));
+    out[C - 1] = fadd(fmul(fy, u), fmul(cfy, l));
+  }
+}
+
+template <bool WRAP, int C, bool X2>
+LRP_DEV void staged_bicubic(const KParams &P, const StageView &V, float sx, float sy, float (&out)[C]) {
+  typedef StageRec<C> Rec;
+  const float off[4] = {-1.0f, 0.0f, 1.0f, 2.0f};
+  int ix[4], iy[4];
+  staged_indices<WRAP, 4>(P, V, sx, sy, off, ix, iy);                            // :114-127
+  const float fx = clamp01_std(fsub(sx, (float)resolve_x<WRAP>(ix[1], P.w)));   // :130 (post-wrap/clamp x1)
+  const float fy = clamp01_std(fsub(sy, (float)clampi(iy[1], P.h)));            // :131
+
+  // taps as packed pairs: P0[xi][yi] = (c0, c1), P1[xi][yi] = (c2, c3) for C >= 4,
+  // lone channel (odd C): L[h][yi] = (value at column 2h, value at column 2h + 1)
+  f2 P0[4][4], P1[4][4], L[2][4];
+  const unsigned rowrec = V.bw;
+  const unsigned t00 = (unsigned)(iy[0] - V.by0) * rowrec + (unsigned)(ix[0] - V.bx0);
+  // Consecutive indices i1-1, i1, i1+1, i1+2 on both axes?  Not implied by i3 - i0 == 3 (s + 1.0f may round up
+  // across an integer), so a SUFFICIENT condition is tested instead, on values already at hand: for
+  // 1 <= s < 32768, s - 1.0f is exact and the rounding error of s + 1.0f / s + 2.0f is below 2^-9, so with a
+  // fraction <= 0.99 no sum reaches the next integer.  (A fraction <= 0.99 also implies that the resolved
+  // index equals the raw one: a wrapped index gives sx - x1 >= w.)  Everything else takes the general path.
+  const bool regular = V.small && (sx >= 1.0f) && (sy >= 1.0f) && (fx <= 0.99f) && (fy <= 0.99f);
+  const ulonglong2 *recA = (const ulonglong2 *)V.stage;
+  const unsigned long long *recA64 = (const unsigned long long *)V.stage;
+  const unsigned long long *recB = (const unsigned long long *)(V.stage + Rec::CAP * Rec::A_BYTES);
+  if (regular) { // consecutive records: row base + immediate offsets
+#pragma unroll
+    for (int yi = 0; yi < 4; ++yi) {
+      const unsigned t = t00 + (unsigned)yi * rowrec;
+#pragma unroll
+      for (int xi = 0; xi < 4; ++xi) {
+        if (C == 3 && (xi & 1)) {
+          P0[xi][yi] = as_f2(recA64[2 * (t + xi)]); // (c0, c1) only: c2 came with the column to the left
+        } else {
+          const ulonglong2 q = recA[t + xi];
+          P0[xi][yi] = as_f2(q.x);
+          if (C == 3) L[xi >> 1][yi] = as_f2(q.y); // (c2 of this column, c2 of the next)
+          else P1[xi][yi] = as_f2(q.y);
+        }
+      }
+      if (C == 5) {
+        L[0][yi] = as_f2(recB[t]);
+        L[1][yi] = as_f2(recB[t + 2]);
+      }
+    }
+  } else { // truncation kink at index 0, x86 INT_MIN indices: address every tap on its own
+    unsigned cx[4], ry[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      cx[k] = (unsigned)(ix[k] - V.bx0);
+      ry[k] = (unsigned)(iy[k] - V.by0) * rowrec;
+    }
+#pragma unroll
+    for (int yi = 0; yi < 4; ++yi) {
+      float lone[4];
+#pragma unroll
+      for (int xi = 0; xi < 4; ++xi) {
+        const ulonglong2 q = recA[ry[yi] + cx[xi]];
+        P0[xi][yi] = as_f2(q.x);
+        if (C == 3) lone[xi] = f2_lo(as_f2(q.y));
+        else P1[xi][yi] = as_f2(q.y);
+        if (C == 5) lone[xi] = f2_lo(as_f2(recB[ry[yi] + cx[xi]]));
+      }
+      if (Rec::LONE) {
+        L[0][yi] = pack2(lone[0], lone[1]);
+        L[1][yi] = pack2(lone[2], lone[3]);
+      }
+    }
+  }
+
+  CubicK k;
+  k.two = pack2(2.0f, 2.0f);
+  k.three = pack2(3.0f, 3.0f);
+  k.four = pack2(4.0f, 4.0f);
+  k.five = pack2(5.0f, 5.0f);
+  k.nfive = pack2(-5.0f, -5.0f);
+  k.nz = P.neg_zero2;
+  const float hy = fmul(0.5f, fy), hx = fmul(0.5f, fx);
+  const f2 ty = pack2(fy, fy), hy2 = pack2(hy, hy), tx = pack2(fx, fx), hx2 = pack2(hx, hx);
+
+  // along y first (:102-105), then along x (:106)
+  f2 a0[4];
+#pragma unroll
+  for (int xi = 0; xi < 4; ++xi) a0[xi] = cubic2x<X2>(P0[xi][0], P0[xi][1], P0[xi][2], P0[xi][3], ty, hy2, k);
+  unpack2(cubic2x<X2>(a0[0], a0[1], a0[2], a0[3], tx, hx2, k), out[0], out[1 < C ? 1 : 0]);
+  if (C >= 4) {
+    f2 a1[4];
+#pragma unroll
+    for (int xi = 0; xi < 4; ++xi) a1[xi] = cubic2x<X2>(P1[xi][0], P1[xi][1], P1[xi][2], P1[xi][3], ty, hy2, k);
+    unpack2(cubic2x<X2>(a1[0], a1[1], a1[2], a1[3], tx, hx2, k), out[2 < C ? 2 : 0], out[3 < C ? 3 : 0]);
+  }
+  if (Rec::LONE) {
+    const f2 l01 = cubic2x<X2>(L[0][0], L[0][1], L[0][2], L[0][3], ty, hy2, k); // columns 0 and 1
+    const f2 l23 = cubic2x<X2>(L[1][0], L[1][1], L[1][2], L[1][3], ty, hy2, k); // columns 2 and 3
+    out[C - 1] = cubic1x<X2>(f2_lo(l01), f2_hi(l01), f2_lo(l23), f2_hi(l23), fx, hx);
+  }
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------
+//
+// Dynamic shared memory map (shared-window addresses):
+//   [0, 1088)                            thr[257] (+ padding)                       (8-bit sinks)
+//   next 1 KB boundary .. + 1 KB         gamma table, plain                         (FMT_U8)
+//   + ST_WARPS x 2 KB                    per-warp source coordinates of the tile    float2[8][32]
+//   + ST_WARPS x ST_STAGE_BYTES          per-warp staging records
+template <int COORD, int INTERP, int FMT, int C>
+__global__ void __launch_bounds__(ST_THREADS, 1) reproject_staged_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr bool WRAP = (COORD == COORD_ERECT_WRAP || COORD == COORD_TABLE_WRAP);
+  constexpr bool TABLE = (COORD == COORD_TABLE_CLAMP || COORD == COORD_TABLE_WRAP);
+  constexpr bool X2 = (FMT != FMT_F32);
+  constexpr int NT = (INTERP == INTERP_NN) ? 1 : (INTERP == INTERP_BL) ? 2 : 4;
+  typedef StageRec<C> Rec;
+
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  float *s_thr = (float *)smem_raw;
+  const uint32_t win0 = shared_addr(smem_raw);
+  const uint32_t lut_addr = (win0 + 1088u + 1023u) & ~1023u;
+  unsigned char *after_lut = smem_raw + (lut_addr - win0) + 1024u;
+  float2 *s_coord = (float2 *)(after_lut + wrp * ST_COORD_BYTES);
+  unsigned char *s_stage = after_lut + ST_WARPS * ST_COORD_BYTES + wrp * ST_STAGE_BYTES;
+
+  // ---- once per CTA: tables ----
+  if (P.dst_fmt == FMT_U8 && tid <= 256) s_thr[tid] = (tid < 256) ? P.thr[tid] : __int_as_float(0x7f800000);
+  if (FMT == FMT_U8 && tid < 256) ((float *)(smem_raw + (lut_addr - win0)))[tid] = __ldg(P.lut + tid);
+  __syncthreads(); // the only CTA-wide barrier
+
+  const SrcViewT<false> S{P, lut_addr};
+  const bool separable = !TABLE && (P.ol.type != LENS_EQUIDISTANT);
+  const bool out_rect = (P.ol.type == LENS_RECT);
+  const float Wf = (float)P.W, Hf = (float)P.H;
+  const float half_W = fmul(Wf, 0.5f), half_H = fmul(Hf, 0.5f);
+  // the first / last tap offsets of the sampler: the bounding box of a pixel's taps in raw index space
+  const float off_lo = (INTERP == INTERP_NN) ? 0.5f : (INTERP == INTERP_BL) ? 0.0f : -1.0f;
+  const float off_hi = (INTERP == INTERP_NN) ? 0.5f : (INTERP == INTERP_BL) ? 1.0f : 2.0f;
+  (void)NT;
+
+  const int tiles_x = (P.W + 31) / 32, tiles_y = (P.H + ST_ROWS - 1) / ST_ROWS;
+  const int n_tiles = tiles_x * tiles_y;
+  const int warps_total = gridDim.x * ST_WARPS;
+
+  for (int tile = blockIdx.x * ST_WARPS + wrp; tile < n_tiles; tile += warps_total) {
+    const int x0 = (tile % tiles_x) * 32, y0 = (tile / tiles_x) * ST_ROWS;
+    const int x = x0 + lane;
+    const bool xvalid = x < P.W;
+    const int R = min(ST_ROWS, P.H - y0);
+    const float cx = fsub(fadd((float)x, 0.5f), half_W); // :287; ns == 1: scx == cx exactly (:295)
+
+    // separable parts of the output rays (rect / equirect output lenses, reference :155-157, :249-256)
+    float col_vx = 0.0f, col_vz = -1.0f, row_vy = 0.0f;
+    if (separable) {
+      const float q = fdiv(fadd(0.0f, 1.0f), P.ss_den);
+      const float scx = fsub(fadd(cx, q), 0.5f);
+      const float cyl = fsub(fadd((float)(y0 + lane), 0.5f), half_H);
+      const float scyl = fsub(fadd(cyl, q), 0.5f);
+      if (out_rect) {
+        col_vx = fdiv(fmul(fdiv(scx, Wf), P.ol.sw), P.ol.p0);
+        row_vy = fdiv(fmul(fdiv(scyl, Hf), P.ol.sh), P.ol.p0);
+      } else {
+        const float lon = fadd(fmul(fadd(fdiv(scx, Wf), 0.5f), fsub(P.ol.p3, P.ol.p2)), P.ol.p2);
+        const float lat = fadd(fmul(fadd(fdiv(scyl, Hf), 0.5f), fsub(P.ol.p1, P.ol.p0)), P.ol.p0);
+        float sn, cs;
+        dev_sincosf(lon, P.use_fma != 0, &sn, &cs);
+        col_vx = sn;
+        col_vz = -cs;
+        dev_sincosf(lat, P.use_fma != 0, &row_vy, nullptr); // not scaled by cos(lat): reference quirk
+      }
+    }
+
+    // rotation :303-311 with the column-only products hoisted out of the row loop (same products, same sums):
+    //   n_i = (R[3i] * vx + R[3i+1] * vy) + R[3i+2] * vz,   vx and vz depend on the column only
+    float rvx[3] = {0.0f, 0.0f, 0.0f}, rvz[3] = {0.0f, 0.0f, 0.0f};
+    if (separable && P.has_rot) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        rvx[i] = fmul(P.R[3 * i], col_vx);
+        rvz[i] = fmul(P.R[3 * i + 2], col_vz);
+      }
+    }
+
+    int g0 = 0;
+    BBox gb = {0, 0, 0, 0}, rb = {0, 0, 0, 0};
+    for (int r = 0; r <= R; ++r) {
+      const bool have = r < R; // warp-uniform
+      if (have) {
+        // ---- coordinates of row r ----
+        const int y = y0 + r;
+        float sx = 0.0f, sy = 0.0f;
+        const float vy_row = __shfl_sync(0xffffffffu, row_vy, r);
+        if (TABLE) {
+          if (xvalid) {
+            const float2 s = __ldg(P.remap + (size_t)y * (size_t)P.W + (size_t)x);
+            sx = s.x;
+            sy = s.y;
+          }
+        } else if (xvalid) {
+          float vx, vy, vz;
+          if (separable) {
+            vx = col_vx;
+            vz = col_vz;
+            vy = vy_row;
+            if (P.has_rot) {
+              vx = fadd(fadd(rvx[0], fmul(P.R[1], vy_row)), rvz[0]);
+              vy = fadd(fadd(rvx[1], fmul(P.R[4], vy_row)), rvz[1]);
+              vz = fadd(fadd(rvx[2], fmul(P.R[7], vy_row)), rvz[2]);
+            }
+            rotated_to_source<COORD>(P, vx, vy, vz, sx, sy);
+          } else {
+            const float cy = fsub(fadd((float)y, 0.5f), half_H); // :288
+            const float q = fdiv(fadd(0.0f, 1.0f), P.ss_den);
+            target_to_vec(P, fsub(fadd(cx, q), 0.5f), fsub(fadd(cy, q), 0.5f), vx, vy, vz);
+            ray_to_source<COORD>(P, vx, vy, vz, sx, sy);
+          }
+        }
+        s_coord[r * 32 + lane] = make_float2(sx, sy);
+        // ---- the row's tap bounding box in raw index space ----
+        int xl = 0x7fffffff, xh = (int)0x80000000, yl = 0x7fffffff, yh = (int)0x80000000;
+        if (xvalid) {
+          if ((fabsf(sx) < 1073741824.0f) && (fabsf(sy) < 1073741824.0f)) {
+            xl = __float2int_rz(fadd(sx, off_lo));
+            xh = __float2int_rz(fadd(sx, off_hi));
+            yl = __float2int_rz(fadd(sy, off_lo));
+            yh = __float2int_rz(fadd(sy, off_hi));
+          } else { // NaN / inf / |s| >= 2^30 (x86 conversions differ from CUDA's): poison the box, the row is gathered
+            xl = yl = (int)0x80000000;
+            xh = yh = 0x7fffffff;
+          }
+        }
+        rb.x0 = __reduce_min_sync(0xffffffffu, xl);
+        rb.x1 = __reduce_max_sync(0xffffffffu, xh);
+        rb.y0 = __reduce_min_sync(0xffffffffu, yl);
+        rb.y1 = __reduce_max_sync(0xffffffffu, yh);
+        if (r == g0) { // first row of a group: it is the group, staged or (if it does not fit) gathered on its own
+          gb = rb;
+          continue;
+        }
+        BBox u;
+        u.x0 = min(gb.x0, rb.x0);
+        u.x1 = max(gb.x1, rb.x1);
+        u.y0 = min(gb.y0, rb.y0);
+        u.y1 = max(gb.y1, rb.y1);
+        GroupPlan pu;
+        if (plan_group<WRAP>(u, P.w, P.h, Rec::CAP, pu)) { // the group grows by this row
+          gb = u;
+          continue;
+        }
+      }
+      // ---- flush rows [g0, r) ----
+      GroupPlan plan;
+      const bool staged = plan_group<WRAP>(gb, P.w, P.h, Rec::CAP, plan);
+#ifdef LRP_DEBUG_STAGE
+      if (lane == 0 && x0 == 32 && y0 == 16)
+        printf("flush tile(%d,%d) rows[%d,%d) raw x[%d,%d] y[%d,%d] eff x[%d,%d] y[%d,%d] bw %u bh %u clamped %d staged %d\n", x0, y0,
+               g0, r, gb.x0, gb.x1, gb.y0, gb.y1, plan.eff.x0, plan.eff.x1, plan.eff.y0, plan.eff.y1, plan.bw, plan.bh,
+               (int)plan.clamped, (int)staged);
+#endif
+      if (staged) {
+        stage_group<WRAP, FMT, C>(P, lut_addr, s_stage, plan.eff, plan.bw, plan.bh, lane);
+        __syncwarp();
+      }
+      const StageView V{s_stage, plan.eff.x0, plan.eff.y0, plan.bw, plan.clamped,
+                        !plan.clamped && gb.x1 < 32768 && gb.y1 < 32768};
+      for (int rr = g0; rr < r; ++rr) {
+        if (!xvalid) continue;
+        const float2 s = s_coord[rr * 32 + lane];
+        float v[C];
+        if (staged) {
+          if (INTERP == INTERP_NN) staged_nearest<WRAP, C>(P, V, s.x, s.y, v);
+          else if (INTERP == INTERP_BL) staged_bilinear<WRAP, C>(P, V, s.x, s.y, v);
+          else staged_bicubic<WRAP, C, X2>(P, V, s.x, s.y, v);
+        } else {
+          if (INTERP == INTERP_NN) sample_nearest<WRAP, FMT, C>(S, s.x, s.y, v);
+          else if (INTERP == INTERP_BL) sample_bilinear<WRAP, FMT, C>(S, s.x, s.y, v);
+          else sample_bicubic<WRAP, FMT, C, true>(S, s.x, s.y, v);
+        }
+        // ns == 1: acc = 0.0f + sample (:334-336; turns -0 into +0), then * 1.0f (:338-341; exact)
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[c] = fadd(0.0f, v[c]);
+        if (P.post) { // fused post_process, :421-437
+#pragma unroll
+          for (int c = 0; c < (C < 3 ? C : 3); ++c) v[c] = post_process_value(v[c], P.exposure, P.r2);
+        }
+        store_pixel<C>(P, s_thr, x, y0 + rr, v);
+      }
+      __syncwarp(); // the records may be overwritten by the next group
+      g0 = r; // row r (which did not fit the flushed group) starts the next one
+      gb = rb;
+    }
+  }
+}
+
+template <int COORD, int INTERP, int FMT, int C>
+int launch_reproject_staged(const KParams &P, void *stream) {
+  auto kern = reproject_staged_kernel<COORD, INTERP, FMT, C>;
+  static thread_local int configured_device = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_device != dev) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    configured_device = dev;
+  }
+  const int tiles = ((P.W + 31) / 32) * ((P.H + ST_ROWS - 1) / ST_ROWS);
+  const int ctas_needed = (tiles + ST_WARPS - 1) / ST_WARPS;
+  const int grid = ctas_needed < P.num_sms ? ctas_needed : P.num_sms;
+  kern<<<grid, ST_THREADS, ST_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+  return (int)cudaGetLastError();
+}
+
+} // namespace lrp

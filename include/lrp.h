@@ -107,11 +107,14 @@ typedef struct lrp_params {
   int32_t variant;       /* lrp_variant: source-access strategy; 0 = library default        */
 } lrp_params;
 
-/* Source-access strategies (north-star item 3); results are bit-identical. */
+/* Source-access strategies (north-star item 3); results are bit-identical.  Orthogonal to
+ * where the coordinates come from (computed on the fly, or read from a remap table through
+ * lrp_reproject_device_remap). */
 typedef enum lrp_variant {
-  LRP_VARIANT_AUTO = 0,
-  LRP_VARIANT_GATHER = 1, /* on-the-fly coordinates, L1/L2 gather of the taps              */
-  LRP_VARIANT_REMAP = 2   /* coordinates read from a precomputed remap table (lrp_build_remap) */
+  LRP_VARIANT_AUTO = 0,   /* STAGED where it applies (num_samples == 1), else GATHER           */
+  LRP_VARIANT_GATHER = 1, /* every tap is a global load through L1/L2                            */
+  LRP_VARIANT_STAGED = 2  /* each warp stages + decodes the bounding box of its tile's taps in
+                             shared memory once; rows whose box does not fit are gathered      */
 } lrp_variant;
 
 typedef struct lrp_ctx lrp_ctx;     /* one per GPU; thread-safe                          */

@@ -135,17 +135,37 @@ def test_product_does_not_link_or_import_the_oracle(lrp):
 
 def test_packed_arithmetic_is_never_contracted(lrp):
     """ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false.  Every FFMA2
-    in the library must therefore have the opaque -0.0 pair as its addend (one and the same register
-    per kernel) — anything else is a contracted multiply-add that would break bit parity."""
+    in the library must therefore take the opaque -0.0 pair as its addend: a register whose latest
+    definition is the LDC.64 of that one kernel parameter — anything else is a contracted multiply-add
+    that would break bit parity.  The one deliberate exception: FFMA2 with the literal multiplier 2 or 4,
+    the exact power-of-two products of the staged kernel's cubic (2*p0 - 5*p1 == fma(2, p0, -(5*p1)) bit
+    for bit, lrp_staged.cuh)."""
     sass = subprocess.run(["cuobjdump", "-sass", os.path.join(PKG, "liblrp.so")], capture_output=True,
                           text=True).stdout
     kernels = sass.split("Function : ")[1:]
-    n_ffma2 = 0
+    n_ffma2 = n_exact = 0
+    ins = re.compile(r"^\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\w+\s+)?([A-Z0-9_.]+)\s+([^;]*);")
     for k in kernels:
         name = k.split("\n", 1)[0]
-        addends = set()
-        for m in re.finditer(r"FFMA2\s+[^;]*,\s*([^,;]+?)\s*;", k):
-            n_ffma2 += 1
-            addends.add(re.sub(r"\.reuse|\.F32x2\.\w+|\.F32", "", m.group(1)).strip())
-        assert len(addends) <= 1, (name, addends)
+        last_def, sources = {}, set()
+        for line in k.split("\n"):
+            m = ins.match(line)
+            if not m:
+                continue
+            op, args = m.group(1), [a.strip() for a in m.group(2).split(",")]
+            if op.startswith("FFMA2"):
+                ops = [re.sub(r"\.reuse|\.F32x2\.\w+|\.F32", "", o) for o in args]
+                assert len(ops) == 4, (name, line)
+                n_ffma2 += 1
+                if ops[2] in ("2", "4"):
+                    n_exact += 1
+                else:
+                    d = last_def.get(ops[3], "?")
+                    assert d.startswith(("LDC.64 c[0x0]", "LDCU.64 c[0x0]")), (name, line.strip(), d)
+                    sources.add(d.split(" ", 1)[1])
+            dst = re.sub(r"\.reuse", "", args[0]) if args else ""
+            if re.fullmatch(r"U?R\d+", dst):
+                last_def[dst] = op + " " + (args[1] if len(args) > 1 else "")
+        assert len(sources) <= 1, (name, sources)  # one parameter: neg_zero2
     assert n_ffma2 > 1000  # the packed bicubic kernels are really in there
+    assert n_exact > 100   # and so is the exact-product form

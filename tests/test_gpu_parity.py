@@ -36,6 +36,14 @@ def ctx(lrp):
     c.close()
 
 
+@pytest.fixture(params=["staged", "gather"])
+def variant(request, monkeypatch):
+    """Runs a pixel test once per source-access variant (liblrp reads LRP_FORCE_VARIANT at every launch when the
+    caller leaves lrp_params.variant at AUTO): the footprint-staging kernel and the per-tap gather kernel."""
+    monkeypatch.setenv("LRP_FORCE_VARIANT", request.param)
+    return request.param
+
+
 def L(lrp, lens):
     return lrp.lens_from(lens)
 
@@ -144,7 +152,7 @@ def test_coordinates_kats(lrp, ctx):
 # ---- Level 1: float32 pixels -------------------------------------------------------------------
 
 @pytest.mark.parametrize("o,i", list(itertools.product(LENS, LENS)))
-def test_pixels_lens_matrix(lrp, o, i):
+def test_pixels_lens_matrix(lrp, o, i, variant):
     W, H, w, h = 53, 38, 61, 47
     src = ol.noise(h, w, 3, seed=7)
     for interp in (ol.NEAREST, ol.BILINEAR, ol.BICUBIC):
@@ -156,7 +164,7 @@ def test_pixels_lens_matrix(lrp, o, i):
 
 @pytest.mark.parametrize("rn", sorted(ROTS))
 @pytest.mark.parametrize("c", [3, 4, 5])
-def test_pixels_channels_rotations(lrp, rn, c):
+def test_pixels_channels_rotations(lrp, rn, c, variant):
     W, H, w, h = 64, 33, 128, 64
     src = ol.noise(h, w, c, seed=11 + c)
     for o, i in (("rect", "erect"), ("erect", "equidistant"), ("equidistant", "rect")):
@@ -178,7 +186,7 @@ def test_pixels_supersampling(lrp, ns):
             assert_same(got, want, "%s<-%s interp %d ns %d" % (o, i, interp, ns))
 
 
-def test_pixels_special_values_and_nan_rays(lrp):
+def test_pixels_special_values_and_nan_rays(lrp, variant):
     # +inf / 1e10 depth, NaN texel; odd output size with identity rotation (on-axis NaN ray)
     w = h = 64
     src = ol.noise(h, w, 4, seed=2)
@@ -203,7 +211,7 @@ def test_pixels_special_values_and_nan_rays(lrp):
             assert_same(got, want, "nan-ray %s<-%s %d" % (o, i, interp))
 
 
-def test_pixels_ragged_and_tiny_sizes(lrp):
+def test_pixels_ragged_and_tiny_sizes(lrp, variant):
     for (W, H, w, h) in ((1, 1, 1, 1), (2, 3, 5, 1), (33, 9, 2, 2), (31, 7, 4, 300), (257, 5, 1024, 3)):
         src = ol.noise(h, w, 3, seed=W + H)
         for interp in (ol.NEAREST, ol.BILINEAR, ol.BICUBIC):
@@ -213,7 +221,7 @@ def test_pixels_ragged_and_tiny_sizes(lrp):
             assert_same(got, want, "ragged %r interp %d" % ((W, H, w, h), interp))
 
 
-def test_golden_fixtures_from_the_reference(lrp):
+def test_golden_fixtures_from_the_reference(lrp, variant):
     import golden.make_golden as mg
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.npz"))
     n = 0
@@ -226,7 +234,7 @@ def test_golden_fixtures_from_the_reference(lrp):
     assert n >= 20
 
 
-def test_against_compiled_reference_when_present(lrp):
+def test_against_compiled_reference_when_present(lrp, variant):
     ref = ol.reference()
     if ref is None:
         pytest.skip("oracle/_ref did not travel to this box")
@@ -243,7 +251,7 @@ def test_against_compiled_reference_when_present(lrp):
 # ---- post_process --------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("c", [3, 4, 5])
-def test_post_process_standalone_and_fused(lrp, c):
+def test_post_process_standalone_and_fused(lrp, c, variant):
     img = (ol.noise(37, 29, c, seed=4) * 3.0).astype(np.float32)
     for ex, rh in ((1.5, 4.0), (2.0 ** 0.5, 1.0), (1.0, 2.0), (0.25, 0.5)):
         assert_same(lrp.post_process_host(img, ex, rh), ORC.post_process(img, ex, rh), "post c%d" % c)
@@ -264,7 +272,7 @@ def _png_source(h, w, seed):
 
 
 @pytest.mark.parametrize("interp", [ol.NEAREST, ol.BILINEAR, ol.BICUBIC])
-def test_png_path_u8_to_u8(lrp, interp):
+def test_png_path_u8_to_u8(lrp, interp, variant):
     """read_png -> reproject -> post_process -> save_png, fused; tolerance <= 1 LSB, asserted 0 LSB."""
     W, H, w, h = 96, 54, 256, 128
     rgba = _png_source(h, w, 3)
@@ -317,7 +325,7 @@ def test_png_encode_every_threshold(lrp):
 
 
 @pytest.mark.parametrize("c", [3, 4, 5])
-def test_exr_path_f16_planar(lrp, c):
+def test_exr_path_f16_planar(lrp, c, variant):
     """read_exr (half planes) -> reproject -> post -> save_exr (half planes); bit-identical halves,
     including the inf depth samples that bicubic turns into NaN."""
     W, H, w, h = 80, 40, 96, 96
@@ -345,7 +353,7 @@ def test_exr_path_f16_planar(lrp, c):
             assert np.all(np.abs(g[fin] - wv[fin]) <= 1e-5 * np.abs(wv[fin]))
 
 
-def test_mixed_formats(lrp):
+def test_mixed_formats(lrp, variant):
     # EXR source -> PNG sink with 4 channels (4th channel gamma-encoded into alpha, as save_png does)
     W, H, w, h = 64, 48, 100, 50
     f = ol.noise(h, w, 4, seed=77)
@@ -365,7 +373,7 @@ def test_mixed_formats(lrp):
 
 # ---- source-access variants ---------------------------------------------------------------------------
 
-def test_remap_table_variant_is_bit_identical(lrp, ctx):
+def test_remap_table_variant_is_bit_identical(lrp, ctx, variant):
     import torch
     W, H, w, h = 120, 70, 256, 128
     src = ol.noise(h, w, 3, seed=13)
@@ -385,6 +393,78 @@ def test_remap_table_variant_is_bit_identical(lrp, ctx):
                 want = ORC.post_process(ORC.reproject(src, LENS[i](w, h), LENS[o](W, H), W, H, ns, interp,
                                                       rot("r30_20_10")), 1.5, 4.0)
                 assert_same(a.cpu().numpy(), want, "device path %s<-%s" % (o, i))
+
+
+def test_variants_are_selected_by_params_too(lrp, ctx):
+    """lrp_params.variant picks the kernel explicitly; both give the same bits as the oracle."""
+    import torch
+    W, H, w, h = 200, 120, 300, 150
+    src = ol.noise(h, w, 4, seed=3)
+    want = ORC.reproject(src, ol.erect(), ol.rect(18, 36, W, H), W, H, 1, ol.BICUBIC, rot("neg"))
+    src_t = torch.from_numpy(src).cuda()
+    for v in (lrp.VARIANT_AUTO, lrp.VARIANT_GATHER, lrp.VARIANT_STAGED):
+        out = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+        p = lrp.make_params(1, lrp.BICUBIC, rot("neg"), None, variant=v)
+        ctx.reproject(src_t, L(lrp, ol.erect()), lrp.FMT_F32, out, L(lrp, ol.rect(18, 36, W, H)), lrp.FMT_F32, p)
+        torch.cuda.synchronize()
+        assert_same(out.cpu().numpy(), want, "variant %d" % v)
+
+
+# ---- the staged kernel's own corner cases ---------------------------------------------------------------
+
+STAGED_CASES = [
+    # name, out lens, in lens, (W, H), (w, h), rotation        what it exercises
+    ("seam", "rect", "erect", (257, 131), (512, 256), "pan180"),           # groups straddling the wrap seam
+    ("pole", "rect", "erect", (200, 200), (512, 256), "pitch90"),          # pole: boxes as wide as the source -> gathered rows
+    ("border", "rect_tele", "rect", (230, 150), (200, 120), "r30_20_10"),  # most taps clamp outside the source
+    ("kink", "rect", "rect", (96, 64), (96, 64), "ident"),                 # 1:1, truncation kink at index 0
+    ("minify", "rect", "erect", (64, 40), (4096, 2048), "neg"),            # boxes that never fit -> all gathered
+    ("magnify", "rect_tele", "erect", (333, 77), (64, 32), "r30_20_10"),   # many pixels per texel
+    ("fisheye", "erect", "equidistant", (300, 150), (256, 256), "neg"),    # rotated footprints, back-hemisphere mirror
+    ("fish_out", "equidistant", "erect_part", (131, 131), (300, 200), "ident"),  # NaN ray on the axis, clamped partial pano
+]
+
+
+@pytest.mark.parametrize("case", STAGED_CASES, ids=[c[0] for c in STAGED_CASES])
+@pytest.mark.parametrize("c", [3, 4, 5])
+def test_staged_corner_cases_f32(lrp, ctx, case, c):
+    import torch
+    _, o, i, (W, H), (w, h), rn = case
+    src = ol.noise(h, w, c, seed=41 + c)
+    src[h // 3, w // 2, 0] = np.nan
+    src_t = torch.from_numpy(src).cuda()
+    for interp in (ol.NEAREST, ol.BILINEAR, ol.BICUBIC):
+        want = ORC.reproject(src, LENS[i](w, h), LENS[o](W, H), W, H, 1, interp, rot(rn))
+        outs = {}
+        for v in (lrp.VARIANT_STAGED, lrp.VARIANT_GATHER):
+            out = torch.empty((H, W, c), dtype=torch.float32, device="cuda")
+            p = lrp.make_params(1, interp, rot(rn), None, variant=v)
+            ctx.reproject(src_t, L(lrp, LENS[i](w, h)), lrp.FMT_F32, out, L(lrp, LENS[o](W, H)), lrp.FMT_F32, p)
+            torch.cuda.synchronize()
+            outs[v] = out.cpu().numpy()
+            assert_same(outs[v], want, "%s c%d interp %d variant %d" % (case[0], c, interp, v))
+
+
+@pytest.mark.parametrize("case", STAGED_CASES, ids=[c[0] for c in STAGED_CASES])
+def test_staged_corner_cases_codec_formats(lrp, case, variant):
+    _, o, i, (W, H), (w, h), rn = case
+    rgba = _png_source(h, w, 17)
+    src_f = ORC.png_decode(rgba)
+    f4 = ol.noise(h, w, 4, seed=19) * 2.0
+    f4[::13, ::11, 3] = 1e10
+    planes = ORC.f32_to_half_planar(f4)
+    src_h = ORC.half_planar_to_f32(planes)
+    for interp in (ol.BILINEAR, ol.BICUBIC):
+        want8 = ORC.png_encode(ORC.post_process(ORC.reproject(src_f, LENS[i](w, h), LENS[o](W, H), W, H, 1, interp,
+                                                              rot(rn)), 1.5, 4.0))
+        got8 = lrp.reproject_host(rgba, L(lrp, LENS[i](w, h)), L(lrp, LENS[o](W, H)), W, H, 1, interp, rot(rn),
+                                  post=(1.5, 4.0), in_fmt=lrp.FMT_U8_RGBA, out_fmt=lrp.FMT_U8_RGBA)
+        assert (got8 == want8).all(), "%s png interp %d: %d differ" % (case[0], interp, (got8 != want8).sum())
+        want16 = ORC.f32_to_half_planar(ORC.reproject(src_h, LENS[i](w, h), LENS[o](W, H), W, H, 1, interp, rot(rn)))
+        got16 = lrp.reproject_host(planes, L(lrp, LENS[i](w, h)), L(lrp, LENS[o](W, H)), W, H, 1, interp, rot(rn),
+                                   in_fmt=lrp.FMT_F16_PLANAR, out_fmt=lrp.FMT_F16_PLANAR)
+        same = (got16 == want16) | (((got16 & 0x7fff) > 0x7c00) & ((want16 & 0x7fff) > 0x7c00))
+        assert same.all(), "%s exr interp %d: %d differ" % (case[0], interp, (~same).sum())
 
 
 # ---- error behaviour (reference: message + exit(1)) ------------------------------------------------------
@@ -410,7 +490,7 @@ def test_unsupported_lenses_and_interp(lrp):
 
 # ---- headline configuration at full size ------------------------------------------------------------------
 
-def test_c2_full_size_png_path(lrp):
+def test_c2_full_size_png_path(lrp, variant):
     """BASELINE config #2 at full size: 8192x4096 equirectangular PNG -> rectilinear 3840x2160, rotation
     30,20,10, bicubic.  The oracle needs a few seconds for it; bit-identical RGBA8 is asserted."""
     w, h, W, H = 8192, 4096, 3840, 2160
