@@ -305,6 +305,24 @@ int prepare(const lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const
   K.neg_zero2 = 0x8000000080000000ull;
   K.num_sms = ctx->num_sms;
   K.src_px_bytes = in->format == LRP_FMT_F32 ? 4u * (unsigned)in->channels : in->format == LRP_FMT_U8_RGBA ? 4u : 2u;
+  { // lrp_fastlibm.cuh: the unguarded divisions need sane divisors (any real lens has them)
+    auto sane = [](float v) { return std::isfinite(v) && std::fabs(v) >= 0x1p-20f && std::fabs(v) <= 0x1p20f; };
+    const LensP &l = K.il;
+    bool ok = sane(l.sw);
+    if (l.type == LENS_RECT) ok = ok && sane(l.sh) && sane(l.p0);
+    else if (l.type == LENS_EQUIDISTANT) ok = ok && sane(l.p0) && sane(l.sw / l.p0);
+    else ok = sane(l.p3 - l.p2) && sane(l.p1 - l.p0) && std::fabs(l.p2) <= 0x1p20f && std::fabs(l.p0) <= 0x1p20f;
+    const char *nf = getenv("LRP_NO_FAST_LIBM"); // A/B switch: every ray through the fully guarded restatement
+    K.fast_lens = (ok && !(nf && nf[0] == '1')) ? 1 : 0;
+  }
+  { // what a gathered warp-step costs over a staged one (issue slots; measured per format):
+    // taps x (loads + address arithmetic + decode per tap).  A block is staged when its record count is below.
+    const int taps = p->interpolation == LRP_NEAREST ? 1 : p->interpolation == LRP_BILINEAR ? 4 : 16;
+    const int per_tap = in->format == LRP_FMT_U8_RGBA ? 6 : in->format == LRP_FMT_F16_PLANAR ? 3 * in->channels
+                        : (in->channels == 4 ? 2 : 2 * in->channels);
+    const char *sg = getenv("LRP_STAGE_GAIN");
+    K.stage_gain = sg ? atoi(sg) : taps * per_tap;
+  }
   switch (in->lens.type) {
   case LENS_RECT: coord = COORD_RECT; break;
   case LENS_EQUIDISTANT: coord = COORD_EQUIDISTANT; break;
@@ -705,7 +723,7 @@ int lrp_debug_coords(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, co
 }
 
 int lrp_debug_libm(lrp_ctx *ctx, int fn, const float *a, const float *b, float *out, size_t n, void *stream) {
-  if (!ctx || !a || !out || fn < 0 || fn > 4 || (fn == 4 && !b)) return LRP_E_BAD_ARG;
+  if (!ctx || !a || !out || fn < 0 || fn > 10 || ((fn == 4 || fn == 5 || fn == 7) && !b)) return LRP_E_BAD_ARG;
   DeviceGuard guard(ctx->phys_device);
   return map_cuda((cudaError_t)launch_libm(fn, a, b, out, n, host_tables().libm_fma != 0, stream));
 }

@@ -53,7 +53,8 @@ int launch_post_process(float *data, size_t n_pixels, int channels, float exposu
 }
 
 // test hook: the device libm restatement, element-wise
-__global__ void libm_kernel(int fn, const float *a, const float *b, float *out, size_t n, int use_fma) {
+__global__ void libm_kernel(int fn, const float *a, const float *b, float *out, size_t n, int use_fma,
+                            unsigned long long nz) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float x = a[i], r;
     switch (fn) {
@@ -61,14 +62,20 @@ __global__ void libm_kernel(int fn, const float *a, const float *b, float *out, 
     case 1: r = dev_asinf(x); break;
     case 2: dev_sincosf(x, use_fma != 0, &r, nullptr); break;
     case 3: dev_sincosf(x, use_fma != 0, nullptr, &r); break;
-    default: r = dev_atan2f(x, b[i]); break;
+    case 4: r = dev_atan2f(x, b[i]); break;
+    case 5: r = fdiv_fast(x, b[i]); break;
+    case 6: r = fsqrt_fast(x); break;
+    case 7: r = fdiv(x, b[i]); break;
+    case 8: r = fsqrt(x); break;
+    case 9: r = atan_core(x, nz); break;
+    default: r = asin_core(x); break;
     }
     out[i] = r;
   }
 }
 
 int launch_libm(int fn, const float *a, const float *b, float *out, size_t n, int use_fma, void *stream) {
-  libm_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(fn, a, b, out, n, use_fma);
+  libm_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(fn, a, b, out, n, use_fma, 0x8000000080000000ull);
   return (int)cudaGetLastError();
 }
 

@@ -14,7 +14,7 @@
 #pragma once
 #include <vector_types.h>
 
-#include "lrp_libm.cuh"
+#include "lrp_fastlibm.cuh"
 #include "lrp_params.h"
 
 namespace lrp {
@@ -58,10 +58,12 @@ LRP_DEV void target_to_vec(const KParams &P, float scx, float scy, float &x, flo
 }
 
 // reference vec_to_rectilinear :160-167, vec_to_equidistant :188-206,
-// vec_to_equirectangular :259-271.  Compile-time: it sits in the innermost loop.
+// vec_to_equirectangular :259-271 — every special case included.  Not inlined: it is the rare path
+// (rays with a component outside [2^-12, 2^12), degenerate lens parameters).
 template <int COORD>
-LRP_DEV void vec_to_source(const KParams &P, float x, float y, float z, float &cx, float &cy) {
+__device__ __noinline__ void vec_to_source_full(const KParams &P, float x, float y, float z, float *out) {
   const float w = (float)P.w, h = (float)P.h;
+  float cx, cy;
   if (COORD == COORD_RECT) {
     float nz = -z;
     x = fdiv(x, nz);
@@ -87,6 +89,48 @@ LRP_DEV void vec_to_source(const KParams &P, float x, float y, float z, float &c
     float lat_span = fsub(P.il.p1, P.il.p0);
     cx = fmul(fsub(fdiv(fsub(theta, P.il.p2), lon_span), 0.5f), w);
     cy = fmul(fsub(fdiv(fsub(phi, P.il.p0), lat_span), 0.5f), h);
+  }
+  out[0] = cx;
+  out[1] = cy;
+}
+
+// The same projections for the common case (lrp_fastlibm.cuh): all three ray components in
+// [2^-12, 2^12) and sane lens parameters (P.fast_lens, checked on the host) — same values, without
+// the per-operation guards.  Compile-time COORD: it sits in the innermost loop.
+template <int COORD>
+LRP_DEV void vec_to_source(const KParams &P, float x, float y, float z, float &cx, float &cy) {
+  if (!(P.fast_lens && mid_range(x) && mid_range(y) && mid_range(z))) {
+    float o[2];
+    vec_to_source_full<COORD>(P, x, y, z, o);
+    cx = o[0];
+    cy = o[1];
+    return;
+  }
+  const float w = (float)P.w, h = (float)P.h;
+  if (COORD == COORD_RECT) {
+    const float nz = -z;
+    x = fdiv_fast(x, nz);
+    y = fdiv_fast(y, nz);
+    cx = fmul(fdiv_fast(fmul(x, w), P.il.sw), P.il.p0);
+    cy = fmul(fdiv_fast(fmul(y, h), P.il.sh), P.il.p0);
+  } else if (COORD == COORD_EQUIDISTANT) {
+    const float nz = -z;
+    x = fdiv_fast(x, nz);
+    y = fdiv_fast(y, nz);
+    const float r = fsqrt_fast(fadd(fmul(x, x), fmul(y, y))); // 2^-24 < r < 2^25
+    const float theta = atan_core(r, P.neg_zero2);
+    const float focal = fdiv(P.il.sw, P.il.p0);
+    const float r_mm = fmul(focal, theta);
+    const float r_px = fmul(fdiv_fast(r_mm, P.il.sw), w); // width for both axes, as the reference
+    cx = fmul(fdiv_fast(x, r), r_px);
+    cy = fmul(fdiv_fast(y, r), r_px);
+  } else {
+    float theta, phi;
+    erect_angles_fast(x, y, z, P.neg_zero2, theta, phi);
+    const float lon_span = fsub(P.il.p3, P.il.p2);
+    const float lat_span = fsub(P.il.p1, P.il.p0);
+    cx = fmul(fsub(fdiv_fast(fsub(theta, P.il.p2), lon_span), 0.5f), w);
+    cy = fmul(fsub(fdiv_fast(fsub(phi, P.il.p0), lat_span), 0.5f), h);
   }
 }
 

@@ -55,6 +55,8 @@ struct KParams {
   unsigned long long neg_zero2; // packed (-0.0f, -0.0f); opaque to ptxas (see lrp_math.cuh)
   unsigned src_px_bytes;        // bytes between horizontally adjacent source texels (4*C, 4 or 2)
   int num_sms;                  // persistent grid size (SM count of the context's device)
+  int stage_gain;               // staged kernel: issue slots per step (2 x 16 pixels) that staged taps save over gathered ones
+  int fast_lens;                // input-lens divisors are normal numbers in [2^-20, 2^20]: unguarded divisions apply
 };
 
 typedef int (*LaunchFn)(const KParams &P, void *stream);

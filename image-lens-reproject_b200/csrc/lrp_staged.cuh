@@ -3,10 +3,10 @@
 // Same arithmetic as lrp_kernel.cuh (reference src/reproject.cpp:273-346 + post_process :421-437 + the
 // codec edges of src/image_formats.cpp), different SOURCE ACCESS (north-star item 3):
 //
-//   A warp owns a 32 x 8 tile of output pixels.  It computes the source coordinates of a row (kept in
-//   shared memory), reduces the row's tap bounding box with redux.sync, and grows a GROUP of consecutive
-//   rows for as long as the union of their bounding boxes fits the warp's staging area.  A group is then
-//   processed in two steps:
+//   A warp owns a 16 x 16 tile of output pixels.  It computes the source coordinates of the tile (kept in
+//   shared memory), reduces the tap bounding box with redux.sync and, if the box does not fit the warp's
+//   staging area (or costs more than it saves), halves the block of rows (16 -> 8 -> 4 -> 2) until it does.  A block is then processed in
+//   two steps:
 //     stage   every texel of the bounding box is fetched from global memory ONCE by the warp (coalesced
 //             along source rows), DECODED once (PNG gamma table / half -> float / channel gather) and
 //             stored as a float4 record — indexed in RAW tap-index space, i.e. border clamping and the
@@ -16,7 +16,7 @@
 //             indices are consecutive, which is every pixel away from the truncation-toward-zero kink at
 //             index 0) and runs the bicubic / bilinear arithmetic on packed f32x2 pairs straight out of
 //             the records.
-//   A row whose bounding box alone exceeds the staging area (strong minification, NaN rays, pole
+//   A pair of rows whose bounding box exceeds the staging area (strong minification, NaN rays, pole
 //   crossings) falls back to the per-tap global gather of lrp_kernel.cuh for that row — same results.
 //
 // Why staging pays even though the gather path already hits L1 93 % of the time: the kernel is bound by
@@ -38,8 +38,9 @@ namespace lrp {
 #endif
 constexpr int ST_WARPS = LRP_ST_WARPS;    // 16 warps = 512 threads: one persistent CTA per SM, up to 128 registers / thread
 constexpr int ST_THREADS = ST_WARPS * 32;
-constexpr int ST_ROWS = 8;                // tile = 32 x 8 output pixels per warp
-constexpr int ST_COORD_BYTES = ST_ROWS * 32 * 8;
+constexpr int ST_TILE_W = 16, ST_TILE_H = 16; // output tile per warp: square, so that rotated footprints stay compact
+constexpr int ST_STEPS = ST_TILE_H / 2;        // a warp covers two rows of 16 pixels per step (lane = 16 * row parity + column)
+constexpr int ST_COORD_BYTES = ST_STEPS * 32 * 8;
 constexpr int ST_SMEM_BYTES = 232448;     // 227 KB: the opt-in maximum of dynamic shared memory per CTA
 constexpr int ST_FIXED_BYTES = 1088 + 1024 + 1024; // thresholds + 1 KB alignment slack + gamma table
 constexpr int ST_STAGE_BYTES = (((ST_SMEM_BYTES - ST_FIXED_BYTES) / ST_WARPS) - ST_COORD_BYTES) & ~15;
@@ -61,10 +62,6 @@ struct BBox {
 // the cut changed anything (`clamped`), the pixels of the group resolve their indices before addressing records.
 // A wrapping group must keep its raw x indices inside [-w, 2w) so that the branch-free wrap applies; every finite
 // coordinate of a full panorama does.
-// A row that holds a NaN / infinite / |s| >= 2^30 coordinate (x86 and CUDA float->int conversions differ there)
-// marks its box with this y range; such a row — and any group it would join — is gathered.
-LRP_DEV bool raw_poisoned(const BBox &b) { return b.y0 == (int)0x80000000 && b.y1 == 0x7fffffff; }
-
 struct GroupPlan {
   BBox eff;
   unsigned bw, bh;
@@ -87,7 +84,7 @@ template <bool WRAP> LRP_DEV bool plan_group(const BBox &raw, int w, int h, unsi
   g.clamped = cut_x || cut_y;
   g.bw = (unsigned)g.eff.x1 - (unsigned)g.eff.x0 + 1u;
   g.bh = (unsigned)g.eff.y1 - (unsigned)g.eff.y0 + 1u;
-  return ok && !raw_poisoned(raw) && g.bw <= 4096u && g.bh <= 4096u && g.bw * g.bh <= cap;
+  return ok && g.bw <= 4096u && g.bh <= 4096u && g.bw * g.bh <= cap;
 }
 
 // (i + w) % w / clamp exactly as the gather path applies them to a raw tap index (reference :43-47, :60-67,
@@ -96,24 +93,35 @@ template <bool WRAP> LRP_DEV int resolve_x(int i, int w) { return WRAP ? wrap_fa
 
 // ---- stage: global -> decoded records -------------------------------------------------------
 
+// fetch = the global loads of one texel (raw bits, so that several texels can be in flight);
+// decode = its conversion to float channels
 template <int FMT, int C> struct StageLoad;
 
 template <int C> struct StageLoad<FMT_F32, C> {
-  static LRP_DEV void load(const KParams &P, uint32_t, unsigned pix, float (&v)[C]) {
+  struct Raw { float v[C]; };
+  static LRP_DEV void fetch(const KParams &P, unsigned pix, Raw &r) {
     const float *p = (const float *)byte_offset_rt(P.src, pix, P.src_px_bytes);
     if (C == 4) {
       const float4 t = __ldg((const float4 *)p);
-      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[C - 1] = t.w;
+      r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[C - 1] = t.w;
     } else {
 #pragma unroll
-      for (int c = 0; c < C; ++c) v[c] = __ldg(p + c);
+      for (int c = 0; c < C; ++c) r.v[c] = __ldg(p + c);
     }
+  }
+  static LRP_DEV void decode(uint32_t, const Raw &r, float (&v)[C]) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = r.v[c];
   }
 };
 template <int C> struct StageLoad<FMT_U8, C> {
-  static LRP_DEV void load(const KParams &P, uint32_t lut, unsigned pix, float (&v)[C]) {
+  struct Raw { uint32_t t; };
+  static LRP_DEV void fetch(const KParams &P, unsigned pix, Raw &r) {
     static_assert(C == 3, "PNG sources decode to 3 channels");
-    const uint32_t t = __ldg((const unsigned int *)byte_offset_rt(P.src, pix, 4u));
+    r.t = __ldg((const unsigned int *)byte_offset_rt(P.src, pix, 4u));
+  }
+  static LRP_DEV void decode(uint32_t lut, const Raw &r, float (&v)[C]) {
+    const uint32_t t = r.t;
     float r0, r1, r2; // powf(p / 255, 2.2) of src/image_formats.cpp:195-197 through the host-built table
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r0) : "r"(lut | ((t << 2) & 0x3FCu)));
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r1) : "r"(lut | ((t >> 6) & 0x3FCu)));
@@ -122,38 +130,56 @@ template <int C> struct StageLoad<FMT_U8, C> {
   }
 };
 template <int C> struct StageLoad<FMT_F16, C> {
-  static LRP_DEV void load(const KParams &P, uint32_t, unsigned pix, float (&v)[C]) {
+  struct Raw { __half v[C]; };
+  static LRP_DEV void fetch(const KParams &P, unsigned pix, Raw &r) {
     const __half *p = (const __half *)byte_offset_rt(P.src, pix, 2u);
 #pragma unroll
-    for (int c = 0; c < C; ++c) v[c] = __half2float(__ldg(p + (size_t)c * (size_t)P.src_plane));
+    for (int c = 0; c < C; ++c) r.v[c] = __ldg(p + (size_t)c * (size_t)P.src_plane);
+  }
+  static LRP_DEV void decode(uint32_t, const Raw &r, float (&v)[C]) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = __half2float(r.v[c]);
   }
 };
 
 // The warp stages the bw x bh records of `b` (the plan's `eff` box: inside the image in y, and in x unless the
-// source wraps).  Record ty * bw + tx holds source texel (resolve_x(b.x0 + tx), b.y0 + ty).  Lanes own columns
-// (their texel offset is computed once), the warp walks down the rows: one coalesced row segment per step.
+// source wraps).  Record t = ty * bw + tx holds source texel (resolve_x(b.x0 + tx), b.y0 + ty).  Records are
+// dealt to the lanes in flat order (consecutive lanes = consecutive texels of a source row, whatever the box
+// width), U x 32 at a time with all the global loads of a round issued before the first decode.
 template <bool WRAP, int FMT, int C>
 LRP_DEV void stage_group(const KParams &P, uint32_t lut, unsigned char *stage, const BBox &b, unsigned bw, unsigned bh,
                          int lane) {
   typedef StageRec<C> Rec;
-  constexpr unsigned STEP = Rec::LONE ? 31u : 32u; // odd C: lane k needs lane k+1's texel, so column chunks overlap by one
+  constexpr unsigned STEP = Rec::LONE ? 31u : 32u; // odd C: lane k needs lane k+1's texel, so rounds overlap by one record
+  constexpr int U = 4;
+  const unsigned n = bw * bh;
+  const unsigned magic = 0xFFFFFFFFu / bw + 1u; // ceil(2^32 / bw): exact quotients t / bw for t < 2^16, bw <= 4096 (bw == 1: below)
   float4 *recA = (float4 *)stage;
   float2 *recB = (float2 *)(stage + Rec::CAP * Rec::A_BYTES);
-  for (unsigned c0 = 0; c0 < bw; c0 += STEP) {
-    const unsigned tx = c0 + (unsigned)lane;
-    const bool in = tx < bw;
-    const bool keep = in && (!Rec::LONE || lane < 31 || tx + 1u >= bw);
-    const int gx = in ? resolve_x<WRAP>((int)((unsigned)b.x0 + tx), P.w) : 0;
-    unsigned pix = (unsigned)b.y0 * (unsigned)P.w + (unsigned)gx;
-    unsigned t = tx;
-    for (unsigned ty = 0; ty < bh; ++ty, pix += (unsigned)P.w, t += bw) {
+  for (unsigned t0 = 0; t0 < n; t0 += U * STEP) {
+    typename StageLoad<FMT, C>::Raw raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned t = t0 + (unsigned)u * STEP + (unsigned)lane;
+      if (t < n) {
+        const unsigned ty = (bw == 1u) ? t : __umulhi(t, magic);
+        const unsigned tx = t - ty * bw;
+        const int gx = resolve_x<WRAP>((int)((unsigned)b.x0 + tx), P.w);
+        StageLoad<FMT, C>::fetch(P, ((unsigned)b.y0 + ty) * (unsigned)P.w + (unsigned)gx, raw[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (t0 + (unsigned)u * STEP >= n) break; // warp-uniform
+      const unsigned t = t0 + (unsigned)u * STEP + (unsigned)lane;
+      const bool in = t < n;
       float v[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) v[c] = 0.0f;
-      if (in) StageLoad<FMT, C>::load(P, lut, pix, v);
+      if (in) StageLoad<FMT, C>::decode(lut, raw[u], v);
       float nxt = 0.0f;
       if (Rec::LONE) nxt = __shfl_down_sync(0xffffffffu, v[C - 1], 1);
-      if (keep) {
+      if (in && (!Rec::LONE || lane < 31 || t + 1u >= n)) {
         if (C == 3) recA[t] = make_float4(v[0], v[1], v[2], nxt);
         else recA[t] = make_float4(v[0], v[1], v[2], v[3 < C ? 3 : 0]);
         if (C == 5) recB[t] = make_float2(v[C - 1], nxt);
@@ -169,7 +195,7 @@ struct StageView {
   int bx0, by0;               // tap index of record (0, 0)
   unsigned bw;                // records per row
   bool clamped;               // warp-uniform: resolve indices before addressing (border groups)
-  bool small;                 // warp-uniform: not clamped and every raw index of the group is below 32768
+  float frac_max;             // warp-uniform: largest fraction for which indices are provably consecutive
 };
 
 LRP_DEV f2 as_f2(unsigned long long v) {
@@ -310,11 +336,12 @@ LRP_DEV void staged_bicubic(const KParams &P, const StageView &V, float sx, floa
   const unsigned rowrec = V.bw;
   const unsigned t00 = (unsigned)(iy[0] - V.by0) * rowrec + (unsigned)(ix[0] - V.bx0);
   // Consecutive indices i1-1, i1, i1+1, i1+2 on both axes?  Not implied by i3 - i0 == 3 (s + 1.0f may round up
-  // across an integer), so a SUFFICIENT condition is tested instead, on values already at hand: for
-  // 1 <= s < 32768, s - 1.0f is exact and the rounding error of s + 1.0f / s + 2.0f is below 2^-9, so with a
-  // fraction <= 0.99 no sum reaches the next integer.  (A fraction <= 0.99 also implies that the resolved
-  // index equals the raw one: a wrapped index gives sx - x1 >= w.)  Everything else takes the general path.
-  const bool regular = V.small && (sx >= 1.0f) && (sy >= 1.0f) && (fx <= 0.99f) && (fy <= 0.99f);
+  // across an integer), so a SUFFICIENT condition is tested instead, on values already at hand: for s >= 1,
+  // s - 1.0f is exact, and s + 1.0f / s + 2.0f cannot reach the next integer when the fraction of s is at most
+  // V.frac_max = 1 - 2^-23 * (largest index of the block + 4), twice their rounding error below 1.  (Such a
+  // fraction also implies that the resolved index equals the raw one: a wrapped index gives sx - x1 >= w.)
+  // Everything else takes the general path.
+  const bool regular = !V.clamped && (sx >= 1.0f) && (sy >= 1.0f) && (fx <= V.frac_max) && (fy <= V.frac_max);
   const ulonglong2 *recA = (const ulonglong2 *)V.stage;
   const unsigned long long *recA64 = (const unsigned long long *)V.stage;
   const unsigned long long *recB = (const unsigned long long *)(V.stage + Rec::CAP * Rec::A_BYTES);
@@ -430,23 +457,25 @@ __global__ void __launch_bounds__(ST_THREADS, 1) reproject_staged_kernel(const _
   const float off_hi = (INTERP == INTERP_NN) ? 0.5f : (INTERP == INTERP_BL) ? 1.0f : 2.0f;
   (void)NT;
 
-  const int tiles_x = (P.W + 31) / 32, tiles_y = (P.H + ST_ROWS - 1) / ST_ROWS;
+  const int tiles_x = (P.W + ST_TILE_W - 1) / ST_TILE_W, tiles_y = (P.H + ST_TILE_H - 1) / ST_TILE_H;
   const int n_tiles = tiles_x * tiles_y;
   const int warps_total = gridDim.x * ST_WARPS;
+  const int lx = lane & (ST_TILE_W - 1), ly = lane >> 4; // lane -> (column, row parity) of the 16 x 16 tile
 
   for (int tile = blockIdx.x * ST_WARPS + wrp; tile < n_tiles; tile += warps_total) {
-    const int x0 = (tile % tiles_x) * 32, y0 = (tile / tiles_x) * ST_ROWS;
-    const int x = x0 + lane;
+    const int x0 = (tile % tiles_x) * ST_TILE_W, y0 = (tile / tiles_x) * ST_TILE_H;
+    const int x = x0 + lx;
     const bool xvalid = x < P.W;
-    const int R = min(ST_ROWS, P.H - y0);
+    const int R = (min(ST_TILE_H, P.H - y0) + 1) >> 1; // steps: a step is two rows of 16 pixels
     const float cx = fsub(fadd((float)x, 0.5f), half_W); // :287; ns == 1: scx == cx exactly (:295)
 
-    // separable parts of the output rays (rect / equirect output lenses, reference :155-157, :249-256)
+    // separable parts of the output rays (rect / equirect output lenses, reference :155-157, :249-256):
+    // every lane holds its column's part; lane k (k < 16) computes the row part of row y0 + k
     float col_vx = 0.0f, col_vz = -1.0f, row_vy = 0.0f;
     if (separable) {
       const float q = fdiv(fadd(0.0f, 1.0f), P.ss_den);
       const float scx = fsub(fadd(cx, q), 0.5f);
-      const float cyl = fsub(fadd((float)(y0 + lane), 0.5f), half_H);
+      const float cyl = fsub(fadd((float)(y0 + lx), 0.5f), half_H);
       const float scyl = fsub(fadd(cyl, q), 0.5f);
       if (out_rect) {
         col_vx = fdiv(fmul(fdiv(scx, Wf), P.ol.sw), P.ol.p0);
@@ -473,90 +502,93 @@ __global__ void __launch_bounds__(ST_THREADS, 1) reproject_staged_kernel(const _
       }
     }
 
-    int g0 = 0;
-    BBox gb = {0, 0, 0, 0}, rb = {0, 0, 0, 0};
-    for (int r = 0; r <= R; ++r) {
-      const bool have = r < R; // warp-uniform
-      if (have) {
-        // ---- coordinates of row r ----
-        const int y = y0 + r;
-        float sx = 0.0f, sy = 0.0f;
-        const float vy_row = __shfl_sync(0xffffffffu, row_vy, r);
-        if (TABLE) {
-          if (xvalid) {
-            const float2 s = __ldg(P.remap + (size_t)y * (size_t)P.W + (size_t)x);
-            sx = s.x;
-            sy = s.y;
+    // ---- phase A: source coordinates of the tile -> shared memory (lane-private slots) ----
+    if (TABLE) { // all steps' table reads in flight at once
+      float2 s[ST_STEPS];
+#pragma unroll
+      for (int r = 0; r < ST_STEPS; ++r) {
+        const int y = y0 + 2 * r + ly;
+        s[r] = make_float2(0.0f, 0.0f);
+        if (xvalid && y < P.H) s[r] = __ldg(P.remap + (size_t)y * (size_t)P.W + (size_t)x);
+      }
+#pragma unroll
+      for (int r = 0; r < ST_STEPS; ++r) s_coord[r * 32 + lane] = s[r];
+    }
+    for (int r = 0; r < (TABLE ? 0 : R); ++r) {
+      const int y = y0 + 2 * r + ly;
+      float sx = 0.0f, sy = 0.0f;
+      const float vy_row = __shfl_sync(0xffffffffu, row_vy, 2 * r + ly);
+      if (xvalid && y < P.H) {
+        float vx, vy, vz;
+        if (separable) {
+          vx = col_vx;
+          vz = col_vz;
+          vy = vy_row;
+          if (P.has_rot) {
+            vx = fadd(fadd(rvx[0], fmul(P.R[1], vy_row)), rvz[0]);
+            vy = fadd(fadd(rvx[1], fmul(P.R[4], vy_row)), rvz[1]);
+            vz = fadd(fadd(rvx[2], fmul(P.R[7], vy_row)), rvz[2]);
           }
-        } else if (xvalid) {
-          float vx, vy, vz;
-          if (separable) {
-            vx = col_vx;
-            vz = col_vz;
-            vy = vy_row;
-            if (P.has_rot) {
-              vx = fadd(fadd(rvx[0], fmul(P.R[1], vy_row)), rvz[0]);
-              vy = fadd(fadd(rvx[1], fmul(P.R[4], vy_row)), rvz[1]);
-              vz = fadd(fadd(rvx[2], fmul(P.R[7], vy_row)), rvz[2]);
-            }
-            rotated_to_source<COORD>(P, vx, vy, vz, sx, sy);
-          } else {
-            const float cy = fsub(fadd((float)y, 0.5f), half_H); // :288
-            const float q = fdiv(fadd(0.0f, 1.0f), P.ss_den);
-            target_to_vec(P, fsub(fadd(cx, q), 0.5f), fsub(fadd(cy, q), 0.5f), vx, vy, vz);
-            ray_to_source<COORD>(P, vx, vy, vz, sx, sy);
-          }
-        }
-        s_coord[r * 32 + lane] = make_float2(sx, sy);
-        // ---- the row's tap bounding box in raw index space ----
-        int xl = 0x7fffffff, xh = (int)0x80000000, yl = 0x7fffffff, yh = (int)0x80000000;
-        if (xvalid) {
-          if ((fabsf(sx) < 1073741824.0f) && (fabsf(sy) < 1073741824.0f)) {
-            xl = __float2int_rz(fadd(sx, off_lo));
-            xh = __float2int_rz(fadd(sx, off_hi));
-            yl = __float2int_rz(fadd(sy, off_lo));
-            yh = __float2int_rz(fadd(sy, off_hi));
-          } else { // NaN / inf / |s| >= 2^30 (x86 conversions differ from CUDA's): poison the box, the row is gathered
-            xl = yl = (int)0x80000000;
-            xh = yh = 0x7fffffff;
-          }
-        }
-        rb.x0 = __reduce_min_sync(0xffffffffu, xl);
-        rb.x1 = __reduce_max_sync(0xffffffffu, xh);
-        rb.y0 = __reduce_min_sync(0xffffffffu, yl);
-        rb.y1 = __reduce_max_sync(0xffffffffu, yh);
-        if (r == g0) { // first row of a group: it is the group, staged or (if it does not fit) gathered on its own
-          gb = rb;
-          continue;
-        }
-        BBox u;
-        u.x0 = min(gb.x0, rb.x0);
-        u.x1 = max(gb.x1, rb.x1);
-        u.y0 = min(gb.y0, rb.y0);
-        u.y1 = max(gb.y1, rb.y1);
-        GroupPlan pu;
-        if (plan_group<WRAP>(u, P.w, P.h, Rec::CAP, pu)) { // the group grows by this row
-          gb = u;
-          continue;
+          rotated_to_source<COORD>(P, vx, vy, vz, sx, sy);
+        } else {
+          const float cy = fsub(fadd((float)y, 0.5f), half_H); // :288
+          const float q = fdiv(fadd(0.0f, 1.0f), P.ss_den);
+          target_to_vec(P, fsub(fadd(cx, q), 0.5f), fsub(fadd(cy, q), 0.5f), vx, vy, vz);
+          ray_to_source<COORD>(P, vx, vy, vz, sx, sy);
         }
       }
-      // ---- flush rows [g0, r) ----
+      s_coord[r * 32 + lane] = make_float2(sx, sy);
+    }
+
+    // ---- phase B: aligned power-of-two blocks of steps, the largest whose tap bounding box is worth staging ----
+    int start = 0;
+    while (start < R) {
+      int len = (start | ST_STEPS) & -(start | ST_STEPS); // alignment of `start` within the tile
       GroupPlan plan;
-      const bool staged = plan_group<WRAP>(gb, P.w, P.h, Rec::CAP, plan);
-#ifdef LRP_DEBUG_STAGE
-      if (lane == 0 && x0 == 32 && y0 == 16)
-        printf("flush tile(%d,%d) rows[%d,%d) raw x[%d,%d] y[%d,%d] eff x[%d,%d] y[%d,%d] bw %u bh %u clamped %d staged %d\n", x0, y0,
-               g0, r, gb.x0, gb.x1, gb.y0, gb.y1, plan.eff.x0, plan.eff.x1, plan.eff.y0, plan.eff.y1, plan.bw, plan.bh,
-               (int)plan.clamped, (int)staged);
-#endif
+      bool staged;
+      for (;;) {
+        const int end = min(start + len, R);
+        // the block's bounding box: float min / max per lane, one conversion, four warp reductions
+        float mnx = __int_as_float(0x7f800000), mxx = __int_as_float(0xff800000), mny = mnx, mxy = mxx;
+        bool bad = false;
+        if (xvalid) {
+          for (int rr = start; rr < end; ++rr) {
+            if (y0 + 2 * rr + ly >= P.H) break;
+            const float2 s = s_coord[rr * 32 + lane];
+            // NaN / inf / |s| >= 2^30: x86 and CUDA float->int conversions differ there -> the block is gathered
+            bad = bad || !((fabsf(s.x) < 1073741824.0f) && (fabsf(s.y) < 1073741824.0f));
+            mnx = fminf(mnx, s.x);
+            mxx = fmaxf(mxx, s.x);
+            mny = fminf(mny, s.y);
+            mxy = fmaxf(mxy, s.y);
+          }
+        }
+        BBox raw; // int(s + off) is monotone in s; idle lanes hold +-inf, which convert to INT_MAX / INT_MIN
+        raw.x0 = __reduce_min_sync(0xffffffffu, __float2int_rz(fadd(mnx, off_lo)));
+        raw.x1 = __reduce_max_sync(0xffffffffu, __float2int_rz(fadd(mxx, off_hi)));
+        raw.y0 = __reduce_min_sync(0xffffffffu, __float2int_rz(fadd(mny, off_lo)));
+        raw.y1 = __reduce_max_sync(0xffffffffu, __float2int_rz(fadd(mxy, off_hi)));
+        const bool any_bad = __any_sync(0xffffffffu, bad);
+        // worth it: the records fit, and staging them (about one issue slot per record) costs less than the
+        // per-tap global loads + decodes it replaces (P.stage_gain issue slots per step, set by the host per format)
+        staged = plan_group<WRAP>(raw, P.w, P.h, Rec::CAP, plan) && !any_bad &&
+                 plan.bw * plan.bh <= (unsigned)(P.stage_gain * (end - start));
+        if (staged || len == 1) break;
+        len >>= 1;
+      }
+      const int end = min(start + len, R);
       if (staged) {
         stage_group<WRAP, FMT, C>(P, lut_addr, s_stage, plan.eff, plan.bw, plan.bh, lane);
         __syncwarp();
       }
+      // fraction bound of the sampler's consecutive-index shortcut: rounding error of s + 2.0f <= ulp / 2,
+      // ulp(M) <= M * 2^-23; the bound leaves twice that
+      const float big = (float)(max(plan.eff.x1, plan.eff.y1) + 4);
       const StageView V{s_stage, plan.eff.x0, plan.eff.y0, plan.bw, plan.clamped,
-                        !plan.clamped && gb.x1 < 32768 && gb.y1 < 32768};
-      for (int rr = g0; rr < r; ++rr) {
-        if (!xvalid) continue;
+                        fsub(1.0f, fmul(big, 1.1920929e-7f))};
+      for (int rr = start; rr < end; ++rr) {
+        const int y = y0 + 2 * rr + ly;
+        if (!xvalid || y >= P.H) continue;
         const float2 s = s_coord[rr * 32 + lane];
         float v[C];
         if (staged) {
@@ -575,11 +607,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) reproject_staged_kernel(const _
 #pragma unroll
           for (int c = 0; c < (C < 3 ? C : 3); ++c) v[c] = post_process_value(v[c], P.exposure, P.r2);
         }
-        store_pixel<C>(P, s_thr, x, y0 + rr, v);
+        store_pixel<C>(P, s_thr, x, y, v);
       }
-      __syncwarp(); // the records may be overwritten by the next group
-      g0 = r; // row r (which did not fit the flushed group) starts the next one
-      gb = rb;
+      __syncwarp(); // the records may be overwritten by the next block
+      start = end;
     }
   }
 }
@@ -595,7 +626,7 @@ int launch_reproject_staged(const KParams &P, void *stream) {
     if (e != cudaSuccess) return (int)e;
     configured_device = dev;
   }
-  const int tiles = ((P.W + 31) / 32) * ((P.H + ST_ROWS - 1) / ST_ROWS);
+  const int tiles = ((P.W + ST_TILE_W - 1) / ST_TILE_W) * ((P.H + ST_TILE_H - 1) / ST_TILE_H);
   const int ctas_needed = (tiles + ST_WARPS - 1) / ST_WARPS;
   const int grid = ctas_needed < P.num_sms ? ctas_needed : P.num_sms;
   kern<<<grid, ST_THREADS, ST_SMEM_BYTES, (cudaStream_t)stream>>>(P);

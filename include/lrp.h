@@ -219,7 +219,9 @@ int lrp_sched_stats(const lrp_sched *s, int64_t *jobs_per_device);
 /* per-pixel (sx, sy) of sub-sample (0,0): out_sxy_dev = float[H*W*2] on device */
 int lrp_debug_coords(lrp_ctx *ctx, const lrp_image *in_geom, const lrp_image *out_geom,
                      const lrp_params *p, float *out_sxy_dev, void *cuda_stream);
-/* device libm restatement: fn 0 atanf, 1 asinf, 2 sinf, 3 cosf, 4 atan2f(a,b) */
+/* device libm restatement: fn 0 atanf, 1 asinf, 2 sinf, 3 cosf, 4 atan2f(a,b); the unguarded
+ * common-case sequences and what they must equal: 5 fdiv_fast(a,b), 6 fsqrt_fast, 7 div.rn(a,b),
+ * 8 sqrt.rn, 9 atan_core (== atanf on [2^-29, 2^25)), 10 asin_core (== asinf on 2^-27 <= |a| < 1) */
 int lrp_debug_libm(lrp_ctx *ctx, int fn, const float *a_dev, const float *b_dev, float *out_dev,
                    size_t n, void *cuda_stream);
 

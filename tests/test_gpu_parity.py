@@ -109,6 +109,78 @@ def test_device_libm_matches_host_libm(lrp, ctx):
     assert_same(got, ORC.host_libm(4, y, x), "atan2f")
 
 
+def _bits_range(lo, hi, chunk=1 << 26):
+    import torch
+    for start in range(lo, hi, chunk):
+        stop = min(hi, start + chunk)
+        yield torch.arange(start, stop, dtype=torch.int64, device="cuda").to(torch.int32).view(torch.float32)
+
+
+def _same_bits_t(a, b):
+    import torch
+    return bool(torch.equal(a.view(torch.int32), b.view(torch.int32)))
+
+
+def test_unguarded_sqrt_and_libm_cores_exhaustive(lrp, ctx):
+    """lrp_fastlibm.cuh: the bare Newton square root equals sqrt.rn on EVERY float of its range
+    [2^-100, 2^126); atan_core equals the full atanf restatement on every float of [2^-29, 2^25) and
+    asin_core equals the full asinf restatement on every float with 2^-27 <= |x| < 1."""
+    import torch
+    for x in _bits_range(0x0d800000, 0x7e800000):
+        assert _same_bits_t(ctx.debug_libm(6, x), ctx.debug_libm(8, x)), "fsqrt_fast"
+    for x in _bits_range(0x31000000, 0x4c000000):
+        assert _same_bits_t(ctx.debug_libm(9, x), ctx.debug_libm(0, x)), "atan_core"
+    for x in _bits_range(0x32000000, 0x3f800000):
+        assert _same_bits_t(ctx.debug_libm(10, x), ctx.debug_libm(1, x)), "asin_core +"
+        assert _same_bits_t(ctx.debug_libm(10, -x), ctx.debug_libm(1, -x)), "asin_core -"
+
+
+def test_unguarded_division(lrp, ctx):
+    """fdiv_fast == div.rn for normal operands with a normal quotient: 2^31 random pairs with exponents in
+    [-40, 40], operands that differ in the last bits (quotients next to 1), exact quotients, powers of two."""
+    import torch
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    n = 1 << 26
+
+    def rnd(emin, emax):
+        mant = torch.randint(0, 1 << 23, (n,), device="cuda", generator=g, dtype=torch.int32)
+        exp = torch.randint(127 + emin, 127 + emax + 1, (n,), device="cuda", generator=g, dtype=torch.int32)
+        sign = torch.randint(0, 2, (n,), device="cuda", generator=g, dtype=torch.int32) << 31
+        return (sign | (exp << 23) | mant).view(torch.float32)
+
+    for rnd_i in range(32):
+        a, b = rnd(-40, 40), rnd(-40, 40)
+        if rnd_i % 4 == 1:  # nearly equal operands
+            b = (a.view(torch.int32) + torch.randint(-8, 9, (n,), device="cuda", generator=g, dtype=torch.int32)).view(torch.float32)
+        if rnd_i % 4 == 2:  # exact quotients: a = b * small integer
+            a = b * torch.randint(1, 4096, (n,), device="cuda", generator=g, dtype=torch.int32).to(torch.float32)
+        if rnd_i % 4 == 3:  # the ranges the kernels use: numerators / denominators of the lens projections
+            a, b = rnd(-26, 26), rnd(-13, 13)
+        assert _same_bits_t(ctx.debug_libm(5, a, b), ctx.debug_libm(7, a, b)), "fdiv_fast round %d" % rnd_i
+    z = torch.zeros(1024, device="cuda")
+    b = rnd(-20, 20)[:1024].abs()
+    assert _same_bits_t(ctx.debug_libm(5, z, b), ctx.debug_libm(7, z, b)), "+0 / positive"
+
+
+def test_fast_and_full_projections_agree(lrp, ctx, monkeypatch):
+    """the guarded common-case projections (P.fast_lens) against the fully guarded restatement on whole
+    coordinate images, every input lens, rotations that put rays on and off the axes."""
+    W, H, w, h = 1024, 768, 2000, 1000
+    for i in ("rect", "equidistant", "erect", "erect_part"):
+        for o in ("rect", "equidistant", "erect"):
+            for rn in ("r30_20_10", "ident", "pitch90", "neg"):
+                p = lrp.make_params(1, lrp.BICUBIC, rot(rn))
+                monkeypatch.setenv("LRP_NO_FAST_LIBM", "0")
+                a = ctx.debug_coords(L(lrp, LENS[i](w, h)), w, h, L(lrp, LENS[o](W, H)), W, H, p)
+                monkeypatch.setenv("LRP_NO_FAST_LIBM", "1")
+                b = ctx.debug_coords(L(lrp, LENS[i](w, h)), w, h, L(lrp, LENS[o](W, H)), W, H, p)
+                import torch
+                same = (a.view(torch.int32) == b.view(torch.int32)) | (a.isnan() & b.isnan())
+                assert bool(same.all()), "%s<-%s %s: %d coordinates differ" % (o, i, rn, int((~same).sum()))
+    monkeypatch.delenv("LRP_NO_FAST_LIBM")
+
+
 def test_png_encode_exhaustive(lrp, ctx):
     """the fused 8-bit quantiser over EVERY float in [0, 1] (1,065,353,217 values) plus out-of-range / special
     values, against uint8(255.9f * powf(clamp(s), 1/2.2f)) evaluated by the host's own powf."""

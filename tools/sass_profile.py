@@ -113,7 +113,7 @@ def main():
         if n / total >= 0.002:
             print("%-18s %4d %8.1f %5.1f%% smp %5d | %s" % (f, l, n / units, 100.0 * n / total, outer_smp[(f, l)], text(f, l)))
     print("\n== by innermost own-source line (top 60) ==")
-    for (f, l), n in inner.most_common(60):
+    for (f, l), n in inner.most_common(int(os.environ.get("TOPN", "60"))):
         print("%-18s %4d %8.1f %5.1f%% | %s" % (f, l, n / units, 100.0 * n / total, text(f, l)))
 
 
