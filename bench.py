@@ -180,6 +180,7 @@ def run_reference_arm(args, rank, world):
 def run_gpu_arm(args, rank, world, local_rank):
     import torch
     import lrp
+    from lrp import sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this framework has no CPU fallback")
@@ -203,12 +204,15 @@ def run_gpu_arm(args, rank, world, local_rank):
     out_lens = lrp.lens_rectilinear(18.0, 36.0, OUT_W, OUT_H)
     rot = lrp.rotation_from_degrees(*ROTATION_DEG)
     variant = {"auto": lrp.VARIANT_AUTO, "gather": lrp.VARIANT_GATHER, "staged": lrp.VARIANT_STAGED}[args.variant]
-    params = lrp.make_params(1, interp, rot, None, variant=variant)
+    upload = {"auto": lrp.UPLOAD_AUTO, "full": lrp.UPLOAD_FULL}[args.upload]
+    params = lrp.make_params(1, interp, rot, None, variant=variant, upload=upload)
 
     B = FRAMES_PER_STEP
     g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    srcs = [torch.randint(0, 256, (SRC_H, SRC_W, 4), dtype=torch.uint8, device=dev, generator=g) for _ in range(B)]
+    srcs = []
+    for frame in sharding.weak_batch(B, rank, world):  # global frame index: the same frames whatever the world size
+        g.manual_seed(1234 + frame)
+        srcs.append(torch.randint(0, 256, (SRC_H, SRC_W, 4), dtype=torch.uint8, device=dev, generator=g))
     dsts = [torch.empty((OUT_H, OUT_W, 4), dtype=torch.uint8, device=dev) for _ in range(B)]
     remap = ctx.build_remap(in_lens, SRC_W, SRC_H, out_lens, OUT_W, OUT_H, params) if args.coords == "table" else None
 
@@ -252,23 +256,27 @@ def run_gpu_arm(args, rank, world, local_rank):
             ctx.submit(j)
         ctx.wait_all()
 
-    e2e_step()  # warm-up: allocates the per-stream staging buffers
+    e2e_step()  # warm-up: allocates the per-stream staging buffers, computes the geometry's source footprint
     barrier()
+    moved0 = ctx.transfer_stats()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    moved1 = ctx.transfer_stats()
+    h2d_per_step = (moved1[0] - moved0[0]) // e2e_steps  # counted by the library from the copies it enqueued
+    d2h_per_step = (moved1[1] - moved0[1]) // e2e_steps
+    roi = ctx.source_footprint(in_lens, SRC_W, SRC_H, out_lens, OUT_W, OUT_H, params)
     e2e_ok = bool((torch.from_numpy(hdst[0]).to(dev) == dsts[0]).all().item())
 
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+    ms, e2e_ms = sharding.max_over_ranks([ms, e2e_s * 1e3], dist, dev)  # the slowest rank defines the job's time
+    launches_all, e2e_frames_all, h2d_all, d2h_all = sharding.sum_over_ranks(
+        [launches, e2e_steps * B, h2d_per_step, d2h_per_step], dist, dev)
 
     if rank == 0:
-        value = world * launches * N_OUT / (ms * 1e-3) / 1e9
-        e2e_value = world * e2e_steps * B * N_OUT / (e2e_ms * 1e-3) / 1e9
+        value = sharding.whole_job_rate(launches_all * N_OUT, ms * 1e-3) / 1e9
+        e2e_value = sharding.whole_job_rate(e2e_frames_all * N_OUT, e2e_ms * 1e-3) / 1e9
         balg = algorithmic_bytes(args.interp)
         per_launch_s = ms * 1e-3 / launches
         achieved = balg / per_launch_s / 1e9
@@ -278,7 +286,7 @@ def run_gpu_arm(args, rank, world, local_rank):
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "interp": args.interp, "variant": args.variant, "coords": args.coords,
-                       "frames_per_step": B, "frames_per_gpu": B,
+                       "frames_per_step": world * B, "frames_per_gpu": B,
                        "l2": "inputs larger than L2: each step walks %d distinct 134 MB sources (%.2f GB) and "
                              "%d distinct 33 MB sinks per GPU" % (B, B * in_bytes / 1e9, B),
                        "parallelism": "images sharded over %d GPU(s), no collective" % world},
@@ -289,10 +297,14 @@ def run_gpu_arm(args, rank, world, local_rank):
                              "reproject_kernel" if args.variant == "gather" else "reproject_staged_kernel",
                              "COORD_TABLE_WRAP" if args.coords == "table" else "COORD_ERECT_WRAP",
                              {"nn": "NEAREST", "bl": "BILINEAR", "bc": "BICUBIC"}[args.interp])},
-            "e2e": {"value": e2e_value, "unit": "Gpix/s", "h2d_bytes_per_step": B * in_bytes,
-                    "d2h_bytes_per_step": B * out_bytes, "steps": e2e_steps, "matches_device_path": e2e_ok,
-                    "api": "lrp_submit/lrp_wait_all (C ABI, pinned host buffers, 4 streams)"},
-            "gpu_launches": launches, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Gpix/s", "h2d_bytes_per_step": int(h2d_all),
+                    "d2h_bytes_per_step": int(d2h_all), "steps": e2e_steps, "matches_device_path": e2e_ok,
+                    "api": "lrp_submit/lrp_wait_all (C ABI, pinned host buffers, 4 streams)",
+                    "upload": args.upload, "source_bytes_per_step": world * B * in_bytes,
+                    "source_footprint_xxyy": list(roi),
+                    "note": "upload=auto copies only the bounding box of the source texels the geometry can touch "
+                            "(lrp_source_footprint, cached per geometry); results are bit-identical to a full upload"},
+            "gpu_launches": int(launches_all), "clocks": clocks,
             "host_libm_fma": lrp.host_libm_uses_fma(),
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -323,6 +335,8 @@ def main():
                     help="source access: footprint staging in shared memory (auto = the library default) or per-tap gather")
     ap.add_argument("--coords", default="fly", choices=["fly", "table"],
                     help="source coordinates computed on the fly, or read from a per-batch remap table")
+    ap.add_argument("--upload", default="auto", choices=["auto", "full"],
+                    help="e2e leg: upload the source footprint's bounding box (library default) or the whole source")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

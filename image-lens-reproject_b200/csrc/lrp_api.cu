@@ -17,6 +17,7 @@
 #include <deque>
 #include <map>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -36,6 +37,7 @@ LRP_DECL(2, 0) LRP_DECL(2, 1) LRP_DECL(2, 2) LRP_DECL(3, 0) LRP_DECL(3, 1) LRP_D
 LRP_DECL(4, 0) LRP_DECL(4, 1) LRP_DECL(4, 2) LRP_DECL(5, 0) LRP_DECL(5, 1) LRP_DECL(5, 2)
 #undef LRP_DECL
 int launch_coords(const KParams &P, int coord, void *stream);
+int launch_footprint(const KParams &P, int coord, int interp, int wrap, void *stream);
 int launch_post_process(float *data, size_t n_pixels, int channels, float exposure, float reinhard, void *stream);
 int launch_libm(int fn, const float *a, const float *b, float *out, size_t n, int use_fma, void *stream);
 int launch_encode_u8(const float *in, unsigned char *out, size_t n, const float *thr, void *stream);
@@ -188,6 +190,12 @@ size_t format_bytes(int fmt, int w, int h, int c) {
 
 // ---- context ---------------------------------------------------------------------------------
 
+struct Roi { // inclusive bounding box of the source texels a geometry can touch
+  int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
+  int width() const { return x1 - x0 + 1; }
+  int height() const { return y1 - y0 + 1; }
+};
+
 struct Slot { // one stream with grow-only device staging buffers
   cudaStream_t stream = nullptr;
   void *d_in = nullptr, *d_out = nullptr;
@@ -205,6 +213,12 @@ struct lrp_ctx {
   std::mutex mu;
   std::condition_variable cv;
   struct Pool *pool = nullptr; // lazily created by lrp_submit
+  // source footprints per geometry (lrp_source_footprint): computed once on fp_stream, then served from the map
+  std::mutex fp_mu;
+  std::map<std::string, Roi> fp_cache;
+  cudaStream_t fp_stream = nullptr;
+  int *d_bbox = nullptr, *h_bbox = nullptr;
+  std::atomic<uint64_t> h2d_bytes{0}, d2h_bytes{0}; // moved by the host-buffer paths (lrp_ctx_transfer_stats)
 };
 
 namespace {
@@ -263,6 +277,7 @@ int prepare(const lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const
   if (!lens_supported(in->lens.type)) return LRP_E_UNSUPPORTED_INPUT_LENS;   // reference :395-397
   if (p->interpolation < 0 || p->interpolation > 2) return LRP_E_UNSUPPORTED_INTERP; // :364-366
   if (p->variant < LRP_VARIANT_AUTO || p->variant > LRP_VARIANT_STAGED) return LRP_E_BAD_ARG;
+  if (p->upload < LRP_UPLOAD_AUTO || p->upload > LRP_UPLOAD_FULL) return LRP_E_BAD_ARG;
   if (need_data) {
     if (!in->data || !out->data) return LRP_E_BAD_ARG;
     if (in->channels != out->channels) return LRP_E_BAD_ARG; // reference: output.channels = input.channels
@@ -304,6 +319,7 @@ int prepare(const lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const
   K.thr = ctx->d_thr;
   K.neg_zero2 = 0x8000000080000000ull;
   K.num_sms = ctx->num_sms;
+  K.src_pitch = (unsigned)in->width;
   K.src_px_bytes = in->format == LRP_FMT_F32 ? 4u * (unsigned)in->channels : in->format == LRP_FMT_U8_RGBA ? 4u : 2u;
   { // lrp_fastlibm.cuh: the unguarded divisions need sane divisors (any real lens has them)
     auto sane = [](float v) { return std::isfinite(v) && std::fabs(v) >= 0x1p-20f && std::fabs(v) <= 0x1p20f; };
@@ -345,14 +361,22 @@ struct DeviceGuard {
   }
 };
 
+// `win` (host-buffer paths): in->data holds only the texels of that region of the source, rows of win->width()
+// texels (planes of width x height for planar formats).  The kernels keep addressing texel (x, y) of the whole
+// image: the source pointer is moved to where texel (0, 0) would be and the row pitch becomes the region's width.
 int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const lrp_params *p,
-                 const void *remap, cudaStream_t stream) {
+                 const void *remap, cudaStream_t stream, const Roi *win = nullptr) {
   if (!ctx) return LRP_E_BAD_ARG;
   DeviceGuard guard(ctx->phys_device);
   KParams K;
   int coord = 0, fc = 0;
   int rc = prepare(ctx, in, out, p, true, K, coord, fc);
   if (rc != LRP_OK) return rc;
+  if (win) {
+    K.src_pitch = (unsigned)win->width();
+    K.src_plane = (long long)win->width() * win->height();
+    K.src = (const char *)in->data - ((size_t)win->y0 * K.src_pitch + (size_t)win->x0) * K.src_px_bytes;
+  }
   if (remap) {
     K.remap = (const float2 *)remap;
     coord = (coord == COORD_ERECT_WRAP) ? COORD_TABLE_WRAP : COORD_TABLE_CLAMP;
@@ -365,6 +389,101 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
   LaunchFn fn = get_launcher(coord, p->interpolation, fc, staged);
   if (!fn) return LRP_E_UNSUPPORTED_FORMAT;
   return map_cuda((cudaError_t)fn(K, stream));
+}
+
+std::string geometry_key(const lrp_image *in, const lrp_image *out, const lrp_params *p) {
+  std::string k;
+  auto put = [&k](const void *d, size_t n) { k.append((const char *)d, n); };
+  put(&in->lens, sizeof(in->lens));
+  put(&in->width, 4);
+  put(&in->height, 4);
+  put(&out->lens, sizeof(out->lens));
+  put(&out->width, 4);
+  put(&out->height, 4);
+  put(&p->num_samples, 4);
+  put(&p->interpolation, 4);
+  const int32_t hr = p->has_rotation ? 1 : 0;
+  put(&hr, 4);
+  if (hr) put(p->rotation, sizeof(p->rotation));
+  return k;
+}
+
+// lrp_source_footprint: cached per geometry; the first request of a geometry runs the footprint kernel
+int source_footprint(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const lrp_params *p, Roi &roi) {
+  KParams K;
+  int coord = 0, fc = 0;
+  int rc = prepare(ctx, in, out, p, false, K, coord, fc);
+  if (rc != LRP_OK) return rc;
+  const std::string key = geometry_key(in, out, p);
+  std::lock_guard<std::mutex> lk(ctx->fp_mu);
+  auto it = ctx->fp_cache.find(key);
+  if (it != ctx->fp_cache.end()) {
+    roi = it->second;
+    return LRP_OK;
+  }
+  DeviceGuard guard(ctx->phys_device);
+  if (!ctx->fp_stream) {
+    LRP_CUDA(cudaStreamCreateWithFlags(&ctx->fp_stream, cudaStreamNonBlocking));
+    LRP_CUDA(cudaMalloc(&ctx->d_bbox, 4 * sizeof(int)));
+    LRP_CUDA(cudaHostAlloc(&ctx->h_bbox, 4 * sizeof(int), cudaHostAllocPortable));
+  }
+  const int wrap = coord == COORD_ERECT_WRAP;
+  if (wrap) coord = COORD_ERECT_CLAMP; // the wrap only affects the sampler's index resolution
+  ctx->h_bbox[0] = ctx->h_bbox[2] = 0x7fffffff;
+  ctx->h_bbox[1] = ctx->h_bbox[3] = (int)0x80000000;
+  LRP_CUDA(cudaMemcpyAsync(ctx->d_bbox, ctx->h_bbox, 4 * sizeof(int), cudaMemcpyHostToDevice, ctx->fp_stream));
+  K.footprint_out = ctx->d_bbox;
+  LRP_CUDA((cudaError_t)launch_footprint(K, coord, p->interpolation, wrap, ctx->fp_stream));
+  LRP_CUDA(cudaMemcpyAsync(ctx->h_bbox, ctx->d_bbox, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->fp_stream));
+  LRP_CUDA(cudaStreamSynchronize(ctx->fp_stream));
+  Roi r;
+  r.x0 = ctx->h_bbox[0];
+  r.x1 = ctx->h_bbox[1];
+  r.y0 = ctx->h_bbox[2];
+  r.y1 = ctx->h_bbox[3];
+  // resolved indices are inside the image by construction; anything else is a bug, not a region
+  if (r.x0 < 0 || r.y0 < 0 || r.x1 >= in->width || r.y1 >= in->height || r.x0 > r.x1 || r.y0 > r.y1) return LRP_E_CUDA;
+  if (ctx->fp_cache.size() > 4096) ctx->fp_cache.clear();
+  ctx->fp_cache[key] = r;
+  roi = r;
+  return LRP_OK;
+}
+
+// The host->device leg of the host-buffer paths: reserves the slot's buffers, enqueues the copy of the source
+// (its footprint region when that is clearly smaller than the image, see lrp_upload) and describes what now
+// sits in slot.d_in.  `use_win` tells launch_fused whether `win` applies.
+int upload_source(lrp_ctx *ctx, Slot &slot, const lrp_image *in, const lrp_image *out, const lrp_params *p,
+                  size_t out_bytes, Roi &win, bool &use_win, size_t *h2d_bytes) {
+  const size_t in_bytes = lrp_image_bytes(in);
+  use_win = false;
+  const char *no = getenv("LRP_NO_ROI"); // A/B switch for unmodified callers
+  if (p->upload == LRP_UPLOAD_AUTO && !(no && no[0] == '1')) {
+    int rc = source_footprint(ctx, in, out, p, win);
+    if (rc != LRP_OK) return rc;
+    // 16-byte aligned rows in the device buffer whatever the format: columns in multiples of 8 texels
+    win.x0 &= ~7;
+    win.x1 = std::min(in->width - 1, win.x1 | 7);
+    use_win = (double)win.width() * win.height() <= 0.85 * (double)in->width * in->height;
+  }
+  if (!use_win) {
+    int rc = slot_reserve(slot, in_bytes, out_bytes);
+    if (rc != LRP_OK) return rc;
+    LRP_CUDA(cudaMemcpyAsync(slot.d_in, in->data, in_bytes, cudaMemcpyHostToDevice, slot.stream));
+    if (h2d_bytes) *h2d_bytes = in_bytes;
+    return LRP_OK;
+  }
+  const size_t px = in->format == LRP_FMT_F32 ? 4u * (size_t)in->channels : in->format == LRP_FMT_U8_RGBA ? 4u : 2u;
+  const int planes = in->format == LRP_FMT_F16_PLANAR ? in->channels : 1;
+  const size_t row = (size_t)win.width() * px, plane = row * (size_t)win.height();
+  int rc = slot_reserve(slot, plane * planes, out_bytes);
+  if (rc != LRP_OK) return rc;
+  for (int c = 0; c < planes; ++c) {
+    const char *src = (const char *)in->data + ((size_t)c * in->width * in->height + (size_t)win.y0 * in->width + win.x0) * px;
+    LRP_CUDA(cudaMemcpy2DAsync((char *)slot.d_in + (size_t)c * plane, row, src, (size_t)in->width * px, row,
+                               (size_t)win.height(), cudaMemcpyHostToDevice, slot.stream));
+  }
+  if (h2d_bytes) *h2d_bytes = plane * planes;
+  return LRP_OK;
 }
 
 } // namespace
@@ -399,16 +518,20 @@ struct Pool {
     LRP_CUDA(cudaSetDevice(ctx->phys_device));
     const size_t in_bytes = lrp_image_bytes(&job.in), out_bytes = lrp_image_bytes(&job.out);
     if (!in_bytes || !out_bytes || !job.in.data || !job.out.data) return LRP_E_BAD_ARG;
-    int rc = slot_reserve(w->slot, in_bytes, out_bytes);
+    Roi win;
+    bool use_win = false;
+    size_t h2d = 0;
+    int rc = upload_source(ctx, w->slot, &job.in, &job.out, &job.params, out_bytes, win, use_win, &h2d);
     if (rc != LRP_OK) return rc;
+    ctx->h2d_bytes += h2d;
     lrp_image din = job.in, dout = job.out;
     din.data = w->slot.d_in;
     dout.data = w->slot.d_out;
-    LRP_CUDA(cudaMemcpyAsync(w->slot.d_in, job.in.data, in_bytes, cudaMemcpyHostToDevice, w->slot.stream));
-    rc = launch_fused(ctx, &din, &dout, &job.params, nullptr, w->slot.stream);
+    rc = launch_fused(ctx, &din, &dout, &job.params, nullptr, w->slot.stream, use_win ? &win : nullptr);
     if (rc != LRP_OK) return rc;
     LRP_CUDA(cudaMemcpyAsync(job.out.data, w->slot.d_out, out_bytes, cudaMemcpyDeviceToHost, w->slot.stream));
     LRP_CUDA(cudaStreamSynchronize(w->slot.stream));
+    ctx->d2h_bytes += out_bytes;
     return LRP_OK;
   }
 
@@ -658,6 +781,9 @@ int lrp_ctx_destroy(lrp_ctx *c) {
   for (auto &s : c->slots) slot_destroy(s);
   if (c->d_lut) cudaFree(c->d_lut);
   if (c->d_thr) cudaFree(c->d_thr);
+  if (c->fp_stream) cudaStreamDestroy(c->fp_stream);
+  if (c->d_bbox) cudaFree(c->d_bbox);
+  if (c->h_bbox) cudaFreeHost(c->h_bbox);
   delete c;
   return LRP_OK;
 }
@@ -706,6 +832,26 @@ int lrp_reproject_device_remap(lrp_ctx *ctx, const lrp_image *in, const lrp_imag
                                const void *remap_dev, void *stream) {
   if (!ctx || !remap_dev) return LRP_E_BAD_ARG;
   return launch_fused(ctx, in, out, p, remap_dev, (cudaStream_t)stream);
+}
+
+int lrp_source_footprint(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const lrp_params *p,
+                         int32_t roi[4]) {
+  if (!ctx || !in || !out || !p || !roi) return LRP_E_BAD_ARG;
+  Roi r;
+  int rc = source_footprint(ctx, in, out, p, r);
+  if (rc != LRP_OK) return rc;
+  roi[0] = r.x0;
+  roi[1] = r.x1;
+  roi[2] = r.y0;
+  roi[3] = r.y1;
+  return LRP_OK;
+}
+
+int lrp_ctx_transfer_stats(const lrp_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
+  if (!ctx) return LRP_E_BAD_ARG;
+  if (h2d_bytes) *h2d_bytes = ctx->h2d_bytes.load();
+  if (d2h_bytes) *d2h_bytes = ctx->d2h_bytes.load();
+  return LRP_OK;
 }
 
 int lrp_debug_coords(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const lrp_params *p,
@@ -834,18 +980,22 @@ int lrp_reproject_host(const lrp_image *in, lrp_image *out, const lrp_params *p,
   }
   LRP_CUDA(cudaSetDevice(ctx->phys_device));
   SlotLease lease(ctx);
-  const size_t in_bytes = lrp_image_bytes(in), out_bytes = lrp_image_bytes(out);
-  rc = slot_reserve(*lease.s, in_bytes, out_bytes);
+  const size_t out_bytes = lrp_image_bytes(out);
+  Roi win;
+  bool use_win = false;
+  size_t h2d = 0;
+  rc = upload_source(ctx, *lease.s, in, out, p, out_bytes, win, use_win, &h2d);
   if (rc != LRP_OK) return rc;
   cudaStream_t st = lease.s->stream;
   lrp_image din = *in, dout = *out;
   din.data = lease.s->d_in;
   dout.data = lease.s->d_out;
-  LRP_CUDA(cudaMemcpyAsync(lease.s->d_in, in->data, in_bytes, cudaMemcpyHostToDevice, st));
-  rc = launch_fused(ctx, &din, &dout, p, nullptr, st);
+  rc = launch_fused(ctx, &din, &dout, p, nullptr, st, use_win ? &win : nullptr);
   if (rc != LRP_OK) return rc;
   LRP_CUDA(cudaMemcpyAsync(out->data, lease.s->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
   LRP_CUDA(cudaStreamSynchronize(st));
+  ctx->h2d_bytes += h2d;
+  ctx->d2h_bytes += out_bytes;
   return LRP_OK;
 }
 

@@ -33,6 +33,73 @@ int launch_coords(const KParams &P, int coord, void *stream) {
   return (int)cudaGetLastError();
 }
 
+// Source footprint of a reprojection: the bounding box {min x, max x, min y, max y} of every RESOLVED tap
+// index (after the reference's wrap / clamp, :43-47, :60-67, :114-127) over all output pixels and sub-samples,
+// from the same device functions the fused kernels use — so a region of interest uploaded from it holds every
+// texel a launch can touch, by construction.  It depends on the geometry only (lenses, sizes, rotation,
+// sampler), not on pixel data: the host caches it per geometry and uploads just that region of each source.
+template <bool WRAP, int N>
+__device__ void footprint_pixel(const KParams &P, int coord, int x, int y, const float (&off)[N], int (&bb)[4]) {
+  const float cx = fsub(fadd((float)x, 0.5f), fmul((float)P.W, 0.5f));
+  const float cy = fsub(fadd((float)y, 0.5f), fmul((float)P.H, 0.5f));
+  for (int ssx = 0; ssx < P.ns; ++ssx)
+    for (int ssy = 0; ssy < P.ns; ++ssy) {
+      const float scx = fsub(fadd(cx, fdiv(fadd((float)ssx, 1.0f), P.ss_den)), 0.5f);
+      const float scy = fsub(fadd(cy, fdiv(fadd((float)ssy, 1.0f), P.ss_den)), 0.5f);
+      float sx, sy;
+      if (coord == COORD_RECT) source_coord<COORD_RECT>(P, scx, scy, sx, sy);
+      else if (coord == COORD_EQUIDISTANT) source_coord<COORD_EQUIDISTANT>(P, scx, scy, sx, sy);
+      else source_coord<COORD_ERECT_CLAMP>(P, scx, scy, sx, sy);
+      int xs[N], ys[N];
+      tap_indices<WRAP, N>(sx, sy, off, P.w, P.h, xs, ys);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        bb[0] = min(bb[0], xs[k]);
+        bb[1] = max(bb[1], xs[k]);
+        bb[2] = min(bb[2], ys[k]);
+        bb[3] = max(bb[3], ys[k]);
+      }
+    }
+}
+
+__global__ void __launch_bounds__(256) footprint_kernel(const __grid_constant__ KParams P, int coord, int interp,
+                                                        int wrap) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  int bb[4] = {0x7fffffff, (int)0x80000000, 0x7fffffff, (int)0x80000000};
+  if (x < P.W && y < P.H) {
+    const float o1[1] = {0.5f}, o2[2] = {0.0f, 1.0f}, o4[4] = {-1.0f, 0.0f, 1.0f, 2.0f};
+    if (interp == INTERP_NN) {
+      if (wrap) footprint_pixel<true, 1>(P, coord, x, y, o1, bb);
+      else footprint_pixel<false, 1>(P, coord, x, y, o1, bb);
+    } else if (interp == INTERP_BL) {
+      if (wrap) footprint_pixel<true, 2>(P, coord, x, y, o2, bb);
+      else footprint_pixel<false, 2>(P, coord, x, y, o2, bb);
+    } else {
+      if (wrap) footprint_pixel<true, 4>(P, coord, x, y, o4, bb);
+      else footprint_pixel<false, 4>(P, coord, x, y, o4, bb);
+    }
+  }
+  bb[0] = __reduce_min_sync(0xffffffffu, bb[0]);
+  bb[1] = __reduce_max_sync(0xffffffffu, bb[1]);
+  bb[2] = __reduce_min_sync(0xffffffffu, bb[2]);
+  bb[3] = __reduce_max_sync(0xffffffffu, bb[3]);
+  if (threadIdx.x == 0 && bb[0] <= bb[1]) {
+    atomicMin(P.footprint_out + 0, bb[0]);
+    atomicMax(P.footprint_out + 1, bb[1]);
+    atomicMin(P.footprint_out + 2, bb[2]);
+    atomicMax(P.footprint_out + 3, bb[3]);
+  }
+}
+
+// `P.footprint_out` must hold {INT_MAX, INT_MIN, INT_MAX, INT_MIN} before the launch
+int launch_footprint(const KParams &P, int coord, int interp, int wrap, void *stream) {
+  dim3 block(32, 8);
+  dim3 grid((P.W + 31) / 32, (P.H + 7) / 8);
+  footprint_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(P, coord, interp, wrap);
+  return (int)cudaGetLastError();
+}
+
 // reproject::post_process (reference src/reproject.cpp:421-437) on an interleaved float32
 // image, in place: first min(C,3) channels of every pixel.
 __global__ void post_process_kernel(float *data, size_t n_pixels, int channels, float exposure, float r2) {

@@ -247,7 +247,7 @@ template <int FMT, int C> struct Texel;
 // float32 interleaved — the reference's in-memory layout (src/reproject.cpp:49-51)
 template <int C> struct Texel<FMT_F32, C> {
   typedef const char *Row;
-  template <class SV> static LRP_DEV Row row(const SV &S, int y) { return byte_offset_rt(S.P.src, (unsigned)y * (unsigned)S.P.w, S.P.src_px_bytes); }
+  template <class SV> static LRP_DEV Row row(const SV &S, int y) { return byte_offset_rt(S.P.src, (unsigned)y * S.P.src_pitch, S.P.src_px_bytes); }
   template <class SV> static LRP_DEV void load(const SV &S, Row r, int x, float (&v)[C]) {
     const float *p = (const float *)byte_offset_rt(r, (unsigned)x, S.P.src_px_bytes);
     if (C == 4) {
@@ -266,7 +266,7 @@ template <int C> struct Texel<FMT_F32, C> {
 // so that ONE byte-permute forms the address and every lane hits its own bank (no conflicts).
 template <int C> struct Texel<FMT_U8, C> {
   typedef const char *Row;
-  template <class SV> static LRP_DEV Row row(const SV &S, int y) { return byte_offset_rt(S.P.src, (unsigned)y * (unsigned)S.P.w, S.P.src_px_bytes); }
+  template <class SV> static LRP_DEV Row row(const SV &S, int y) { return byte_offset_rt(S.P.src, (unsigned)y * S.P.src_pitch, S.P.src_px_bytes); }
   static LRP_DEV float lut(uint32_t addr) {
     float r;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
@@ -290,7 +290,7 @@ template <int C> struct Texel<FMT_U8, C> {
 // planar IEEE half (the HALF slices of read_exr); half -> float is exact
 template <int C> struct Texel<FMT_F16, C> {
   typedef const char *Row;
-  template <class SV> static LRP_DEV Row row(const SV &S, int y) { return byte_offset_rt(S.P.src, (unsigned)y * (unsigned)S.P.w, S.P.src_px_bytes); }
+  template <class SV> static LRP_DEV Row row(const SV &S, int y) { return byte_offset_rt(S.P.src, (unsigned)y * S.P.src_pitch, S.P.src_px_bytes); }
   template <class SV> static LRP_DEV void load(const SV &S, Row r, int x, float (&v)[C]) {
     const char *p = byte_offset_rt(r, (unsigned)x, S.P.src_px_bytes);
     const uint32_t plane_bytes = (uint32_t)S.P.src_plane * 2u; // w*h*2 < 2^32 (checked on the host)

@@ -54,6 +54,9 @@ struct KParams {
   int coords_planes;     // how many sub-sample planes the coords kernel writes
   unsigned long long neg_zero2; // packed (-0.0f, -0.0f); opaque to ptxas (see lrp_math.cuh)
   unsigned src_px_bytes;        // bytes between horizontally adjacent source texels (4*C, 4 or 2)
+  unsigned src_pitch;           // texels between vertically adjacent source texels IN THE DEVICE BUFFER: w, or the
+                                // width of the uploaded region of interest (src then points at the virtual texel (0, 0))
+  int *footprint_out;           // footprint kernel: {min x, max x, min y, max y} of every resolved tap index
   int num_sms;                  // persistent grid size (SM count of the context's device)
   int stage_gain;               // staged kernel: issue slots per step (2 x 16 pixels) that staged taps save over gathered ones
   int fast_lens;                // input-lens divisors are normal numbers in [2^-20, 2^20]: unguarded divisions apply

@@ -165,7 +165,7 @@ LRP_DEV void stage_group(const KParams &P, uint32_t lut, unsigned char *stage, c
         const unsigned ty = (bw == 1u) ? t : __umulhi(t, magic);
         const unsigned tx = t - ty * bw;
         const int gx = resolve_x<WRAP>((int)((unsigned)b.x0 + tx), P.w);
-        StageLoad<FMT, C>::fetch(P, ((unsigned)b.y0 + ty) * (unsigned)P.w + (unsigned)gx, raw[u]);
+        StageLoad<FMT, C>::fetch(P, ((unsigned)b.y0 + ty) * P.src_pitch + (unsigned)gx, raw[u]);
       }
     }
 #pragma unroll

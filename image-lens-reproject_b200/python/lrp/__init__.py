@@ -23,6 +23,7 @@ RGB, RGBA, RGBZ, RGBAZ = range(4)
 NEAREST, BILINEAR, BICUBIC = range(3)
 FMT_F32, FMT_U8_RGBA, FMT_F16_PLANAR = range(3)
 VARIANT_AUTO, VARIANT_GATHER, VARIANT_STAGED = range(3)
+UPLOAD_AUTO, UPLOAD_FULL = range(2)
 
 
 class LrpError(RuntimeError):
@@ -44,7 +45,7 @@ class Image(C.Structure):
 class Params(C.Structure):
     _fields_ = [("num_samples", C.c_int32), ("interpolation", C.c_int32), ("has_rotation", C.c_int32),
                 ("rotation", C.c_float * 9), ("apply_post", C.c_int32), ("exposure", C.c_float),
-                ("reinhard", C.c_float), ("variant", C.c_int32)]
+                ("reinhard", C.c_float), ("variant", C.c_int32), ("upload", C.c_int32)]
 
 
 DONE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int)
@@ -113,6 +114,8 @@ def lib():
         L.lrp_sched_num_devices.argtypes = [vp]
         L.lrp_sched_stats.argtypes = [vp, C.POINTER(C.c_int64)]
         L.lrp_debug_coords.argtypes = [vp, ip, ip, pp, vp, vp]
+        L.lrp_source_footprint.argtypes = [vp, ip, ip, pp, C.POINTER(C.c_int32)]
+        L.lrp_ctx_transfer_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.lrp_debug_libm.argtypes = [vp, C.c_int, vp, vp, vp, C.c_size_t, vp]
         L.lrp_debug_encode_u8.argtypes = [vp, vp, vp, C.c_size_t, vp]
         _lib = L
@@ -191,7 +194,7 @@ def rotation_matrix(pan, pitch, roll):
     return np.array(m, dtype=np.float32)
 
 
-def make_params(ns=1, interp=BICUBIC, rot=None, post=None, variant=VARIANT_AUTO):
+def make_params(ns=1, interp=BICUBIC, rot=None, post=None, variant=VARIANT_AUTO, upload=UPLOAD_AUTO):
     """post = (exposure, reinhard) or None — main() calls post_process only when either differs
     from 1.0 (reference src/main.cpp:601)."""
     p = Params()
@@ -206,6 +209,7 @@ def make_params(ns=1, interp=BICUBIC, rot=None, post=None, variant=VARIANT_AUTO)
     p.exposure = 1.0 if post is None else post[0]
     p.reinhard = 1.0 if post is None else post[1]
     p.variant = variant
+    p.upload = upload
     return p
 
 
@@ -241,7 +245,7 @@ def _describe(arr, fmt):
 # ---- synchronous host drop-in --------------------------------------------------------------------
 
 def reproject_host(src, in_lens, out_lens, W, H, ns=1, interp=BICUBIC, rot=None, post=None,
-                   in_fmt=FMT_F32, out_fmt=None, device=0, channels=None):
+                   in_fmt=FMT_F32, out_fmt=None, device=0, channels=None, upload=UPLOAD_AUTO):
     """reproject::reproject() (+ post_process) on HOST numpy buffers through lrp_reproject_host."""
     out_fmt = in_fmt if out_fmt is None else out_fmt
     _, dt = _shape_of(in_fmt, 1, 1, 1)
@@ -253,7 +257,7 @@ def reproject_host(src, in_lens, out_lens, W, H, ns=1, interp=BICUBIC, rot=None,
     out = np.empty(oshape, dtype=odt)
     iim = make_image(in_lens, w, h, c, in_fmt, src.ctypes.data)
     oim = make_image(out_lens, W, H, c, out_fmt, out.ctypes.data)
-    p = make_params(ns, interp, rot, post)
+    p = make_params(ns, interp, rot, post, upload=upload)
     check(lib().lrp_reproject_host(C.byref(iim), C.byref(oim), C.byref(p), device), "lrp_reproject_host")
     return out
 
@@ -333,6 +337,20 @@ class Context:
         check(lib().lrp_debug_coords(self.h, C.byref(iim), C.byref(oim), C.byref(params),
                                      C.c_void_p(t.data_ptr()), self._stream(stream)), "lrp_debug_coords")
         return t
+
+    def source_footprint(self, in_lens, w, h, out_lens, W, H, params):
+        """(x_min, x_max, y_min, y_max) of the source texels the geometry can touch (lrp_source_footprint)."""
+        roi = (C.c_int32 * 4)()
+        iim = make_image(in_lens, w, h, 3, FMT_F32, None)
+        oim = make_image(out_lens, W, H, 3, FMT_F32, None)
+        check(lib().lrp_source_footprint(self.h, C.byref(iim), C.byref(oim), C.byref(params), roi),
+              "lrp_source_footprint")
+        return tuple(roi)
+
+    def transfer_stats(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        check(lib().lrp_ctx_transfer_stats(self.h, C.byref(a), C.byref(b)), "lrp_ctx_transfer_stats")
+        return a.value, b.value
 
     def debug_libm(self, fn, a_t, b_t=None, stream=None):
         import torch

@@ -105,7 +105,18 @@ typedef struct lrp_params {
   float exposure;        /* linear multiplier (2^EV)                                        */
   float reinhard;        /* extended-Reinhard white point                                   */
   int32_t variant;       /* lrp_variant: source-access strategy; 0 = library default        */
+  int32_t upload;        /* lrp_upload: what the HOST-buffer entry points copy to the GPU   */
 } lrp_params;
+
+/* What lrp_reproject_host / lrp_submit / lrp_sched_submit upload of a host source.  The texels a
+ * launch can touch depend on the geometry only (lenses, sizes, rotation, sampler) — for the 8K
+ * panorama -> 4K view of the headline config that is a quarter of the source — so by default only
+ * the bounding box of that footprint (lrp_source_footprint, cached per geometry) crosses PCIe.
+ * Results are bit-identical either way. */
+typedef enum lrp_upload {
+  LRP_UPLOAD_AUTO = 0, /* the footprint's bounding box when it is clearly smaller than the image */
+  LRP_UPLOAD_FULL = 1  /* the whole source, as the reference's worker holds it                   */
+} lrp_upload;
 
 /* Source-access strategies (north-star item 3); results are bit-identical.  Orthogonal to
  * where the coordinates come from (computed on the fly, or read from a remap table through
@@ -178,6 +189,18 @@ int lrp_build_remap(lrp_ctx *ctx, const lrp_image *in_geom, const lrp_image *out
                     const lrp_params *p, void *remap_dev, void *cuda_stream);
 int lrp_reproject_device_remap(lrp_ctx *ctx, const lrp_image *in_dev, const lrp_image *out_dev,
                                const lrp_params *p, const void *remap_dev, void *cuda_stream);
+
+/* Source footprint of a geometry: roi = {x_min, x_max, y_min, y_max} (inclusive) of every source
+ * texel index any tap of any output pixel / sub-sample resolves to (after the reference's wrap /
+ * clamp, src/reproject.cpp:43-47, 60-67, 114-127), computed on the GPU by the same device functions
+ * as the fused kernels and cached in the context per geometry.  Only `lens`, `width`, `height` of
+ * the images and `num_samples`, `interpolation`, rotation of the params are read. */
+int lrp_source_footprint(lrp_ctx *ctx, const lrp_image *in_geom, const lrp_image *out_geom,
+                         const lrp_params *p, int32_t roi[4]);
+
+/* Bytes the host-buffer entry points have moved over PCIe through this context so far
+ * (lrp_reproject_host on its default context is not visible here; lrp_submit / lrp_sched_* are). */
+int lrp_ctx_transfer_stats(const lrp_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 
 /* memory helpers (pinned host buffers for the pipeline; device buffers) */
 int lrp_alloc_pinned(size_t bytes, void **out);

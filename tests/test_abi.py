@@ -57,7 +57,24 @@ def test_struct_layouts_match_header(lrp):
     assert C.sizeof(lrp.Lens) == 28  # == sizeof(reproject::LensInfo), reference src/config.hpp:15-37
     assert C.sizeof(ol.Lens) == 28
     assert lrp.Image.data.offset == 48 and C.sizeof(lrp.Image) == 56
-    assert C.sizeof(lrp.Params) == 12 + 36 + 16
+    assert C.sizeof(lrp.Params) == 12 + 36 + 20
+    assert lrp.Params.variant.offset == 60 and lrp.Params.upload.offset == 64
+
+
+def test_ctypes_mirrors_match_the_compiled_header(lrp, tmp_path):
+    """sizeof / offsetof as gcc sees include/lrp.h against the ctypes structures the tests marshal through"""
+    c = tmp_path / "layout.c"
+    c.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "lrp.h"\nint main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", '
+                 'sizeof(lrp_lens), sizeof(lrp_image), offsetof(lrp_image, data), sizeof(lrp_params), '
+                 'offsetof(lrp_params, rotation), offsetof(lrp_params, upload), sizeof(lrp_job), offsetof(lrp_job, params), '
+                 'offsetof(lrp_job, on_done)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.dirname(HDR), str(c), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(lrp.Lens), C.sizeof(lrp.Image), lrp.Image.data.offset, C.sizeof(lrp.Params),
+            lrp.Params.rotation.offset, lrp.Params.upload.offset, C.sizeof(lrp.Job), lrp.Job.params.offset,
+            lrp.Job.on_done.offset]
+    assert got == want
 
 
 def test_rotation_matrix_matches_reference_kat(lrp):
