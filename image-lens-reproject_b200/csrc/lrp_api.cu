@@ -30,11 +30,13 @@ namespace lrp {
 LRP_DECL(0, 0) LRP_DECL(0, 1) LRP_DECL(0, 2) LRP_DECL(1, 0) LRP_DECL(1, 1) LRP_DECL(1, 2)
 LRP_DECL(2, 0) LRP_DECL(2, 1) LRP_DECL(2, 2) LRP_DECL(3, 0) LRP_DECL(3, 1) LRP_DECL(3, 2)
 LRP_DECL(4, 0) LRP_DECL(4, 1) LRP_DECL(4, 2) LRP_DECL(5, 0) LRP_DECL(5, 1) LRP_DECL(5, 2)
+LRP_DECL(6, 0) LRP_DECL(6, 1) LRP_DECL(6, 2) LRP_DECL(7, 0) LRP_DECL(7, 1) LRP_DECL(7, 2)
 #undef LRP_DECL
 #define LRP_DECL(c, i) LaunchFn get_staged_launcher_c##c##_i##i(int fc);
 LRP_DECL(0, 0) LRP_DECL(0, 1) LRP_DECL(0, 2) LRP_DECL(1, 0) LRP_DECL(1, 1) LRP_DECL(1, 2)
 LRP_DECL(2, 0) LRP_DECL(2, 1) LRP_DECL(2, 2) LRP_DECL(3, 0) LRP_DECL(3, 1) LRP_DECL(3, 2)
 LRP_DECL(4, 0) LRP_DECL(4, 1) LRP_DECL(4, 2) LRP_DECL(5, 0) LRP_DECL(5, 1) LRP_DECL(5, 2)
+LRP_DECL(6, 0) LRP_DECL(6, 1) LRP_DECL(6, 2) LRP_DECL(7, 0) LRP_DECL(7, 1) LRP_DECL(7, 2)
 #undef LRP_DECL
 int launch_coords(const KParams &P, int coord, void *stream);
 int launch_footprint(const KParams &P, int coord, int interp, int wrap, void *stream);
@@ -51,6 +53,8 @@ static LaunchFn get_launcher(int coord, int interp, int fc, bool staged) {
       {get_staged_launcher_c3_i0, get_staged_launcher_c3_i1, get_staged_launcher_c3_i2},
       {get_staged_launcher_c4_i0, get_staged_launcher_c4_i1, get_staged_launcher_c4_i2},
       {get_staged_launcher_c5_i0, get_staged_launcher_c5_i1, get_staged_launcher_c5_i2},
+      {get_staged_launcher_c6_i0, get_staged_launcher_c6_i1, get_staged_launcher_c6_i2},
+      {get_staged_launcher_c7_i0, get_staged_launcher_c7_i1, get_staged_launcher_c7_i2},
   };
   if (staged) return staged_table[coord][interp](fc);
   static const Getter table[COORD_COUNT][3] = {
@@ -60,6 +64,8 @@ static LaunchFn get_launcher(int coord, int interp, int fc, bool staged) {
       {get_launcher_c3_i0, get_launcher_c3_i1, get_launcher_c3_i2},
       {get_launcher_c4_i0, get_launcher_c4_i1, get_launcher_c4_i2},
       {get_launcher_c5_i0, get_launcher_c5_i1, get_launcher_c5_i2},
+      {get_launcher_c6_i0, get_launcher_c6_i1, get_launcher_c6_i2},
+      {get_launcher_c7_i0, get_launcher_c7_i1, get_launcher_c7_i2},
   };
   return table[coord][interp](fc);
 }
@@ -155,7 +161,12 @@ int map_cuda(cudaError_t e) {
     }                                           \
   } while (0)
 
-bool lens_supported(int t) { return t == LENS_RECT || t == LENS_EQUIDISTANT || t == LENS_ERECT; }
+// the reference's kernel implements three lens types (src/reproject.cpp:378-397, 407-417); the equisolid /
+// stereographic models are an opt-in extension (lrp_params.extensions & LRP_EXT_FISHEYE_MODELS)
+bool lens_supported(int t, int extensions) {
+  if (t == LENS_RECT || t == LENS_EQUIDISTANT || t == LENS_ERECT) return true;
+  return (extensions & LRP_EXT_FISHEYE_MODELS) && (t == LENS_EQUISOLID || t == LENS_STEREO);
+}
 
 LensP to_lensp(const lrp_lens &l) {
   LensP r;
@@ -273,8 +284,9 @@ int prepare(const lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const
   // pixel indices are 32-bit on the device (the reference's own index arithmetic is `int`)
   if ((uint64_t)in->width * (uint64_t)in->height >= (1ull << 31)) return LRP_E_BAD_ARG;
   if ((uint64_t)out->width * (uint64_t)out->height >= (1ull << 31)) return LRP_E_BAD_ARG;
-  if (!lens_supported(out->lens.type)) return LRP_E_UNSUPPORTED_OUTPUT_LENS; // reference :415-417
-  if (!lens_supported(in->lens.type)) return LRP_E_UNSUPPORTED_INPUT_LENS;   // reference :395-397
+  if (p->extensions & ~LRP_EXT_FISHEYE_MODELS) return LRP_E_BAD_ARG;
+  if (!lens_supported(out->lens.type, p->extensions)) return LRP_E_UNSUPPORTED_OUTPUT_LENS; // reference :415-417
+  if (!lens_supported(in->lens.type, p->extensions)) return LRP_E_UNSUPPORTED_INPUT_LENS;   // reference :395-397
   if (p->interpolation < 0 || p->interpolation > 2) return LRP_E_UNSUPPORTED_INTERP; // :364-366
   if (p->variant < LRP_VARIANT_AUTO || p->variant > LRP_VARIANT_STAGED) return LRP_E_BAD_ARG;
   if (p->upload < LRP_UPLOAD_AUTO || p->upload > LRP_UPLOAD_FULL) return LRP_E_BAD_ARG;
@@ -327,6 +339,7 @@ int prepare(const lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const
     bool ok = sane(l.sw);
     if (l.type == LENS_RECT) ok = ok && sane(l.sh) && sane(l.p0);
     else if (l.type == LENS_EQUIDISTANT) ok = ok && sane(l.p0) && sane(l.sw / l.p0);
+    else if (l.type == LENS_EQUISOLID || l.type == LENS_STEREO) ok = false; // always the guarded restatement
     else ok = sane(l.p3 - l.p2) && sane(l.p1 - l.p0) && std::fabs(l.p2) <= 0x1p20f && std::fabs(l.p0) <= 0x1p20f;
     const char *nf = getenv("LRP_NO_FAST_LIBM"); // A/B switch: every ray through the fully guarded restatement
     K.fast_lens = (ok && !(nf && nf[0] == '1')) ? 1 : 0;
@@ -342,6 +355,8 @@ int prepare(const lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const
   switch (in->lens.type) {
   case LENS_RECT: coord = COORD_RECT; break;
   case LENS_EQUIDISTANT: coord = COORD_EQUIDISTANT; break;
+  case LENS_EQUISOLID: coord = COORD_EQUISOLID; break;
+  case LENS_STEREO: coord = COORD_STEREO; break;
   default: coord = loops_horizontally(in->lens) ? COORD_ERECT_WRAP : COORD_ERECT_CLAMP; break;
   }
   return LRP_OK;
@@ -713,6 +728,11 @@ void lrp_lens_equisolid(float focal_length, float sensor_width, float fov, int r
   o->u.fisheye_equisolid.fov = fov;
   o->sensor_width = sensor_width;
   o->sensor_height = (float)res_y / (float)res_x * o->sensor_width;
+}
+// extension: same tuple as --equisolid (the reference's LensType has the enumerator, its CLI no parser)
+void lrp_lens_stereographic(float focal_length, float sensor_width, float fov, int res_x, int res_y, lrp_lens *o) {
+  lrp_lens_equisolid(focal_length, sensor_width, fov, res_x, res_y, o);
+  o->type = LRP_FISHEYE_STEREOGRAPHIC;
 }
 // reference src/main.cpp:62-66
 void lrp_lens_equirectangular_full(lrp_lens *o) {

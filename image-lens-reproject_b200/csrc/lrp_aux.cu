@@ -4,6 +4,15 @@
 
 namespace lrp {
 
+// runtime dispatch over the input-lens projection (the wrap variants only differ in the sampler)
+LRP_DEV void source_coord_rt(const KParams &P, int coord, float scx, float scy, float &sx, float &sy) {
+  if (coord == COORD_RECT) source_coord<COORD_RECT>(P, scx, scy, sx, sy);
+  else if (coord == COORD_EQUIDISTANT) source_coord<COORD_EQUIDISTANT>(P, scx, scy, sx, sy);
+  else if (coord == COORD_EQUISOLID) source_coord<COORD_EQUISOLID>(P, scx, scy, sx, sy);
+  else if (coord == COORD_STEREO) source_coord<COORD_STEREO>(P, scx, scy, sx, sy);
+  else source_coord<COORD_ERECT_CLAMP>(P, scx, scy, sx, sy);
+}
+
 // Writes (sx, sy) of every output pixel for the first `coords_planes` sub-samples
 // ([ssx*ns + ssy][H][W] float2).  Serves lrp_build_remap (all ns*ns planes) and
 // lrp_debug_coords (plane 0).  Same device functions as the fused kernel, so a remap
@@ -19,9 +28,7 @@ __global__ void __launch_bounds__(256) coords_kernel(const __grid_constant__ KPa
     const float scx = fsub(fadd(cx, fdiv(fadd((float)ssx, 1.0f), P.ss_den)), 0.5f);
     const float scy = fsub(fadd(cy, fdiv(fadd((float)ssy, 1.0f), P.ss_den)), 0.5f);
     float sx, sy;
-    if (coord == COORD_RECT) source_coord<COORD_RECT>(P, scx, scy, sx, sy);
-    else if (coord == COORD_EQUIDISTANT) source_coord<COORD_EQUIDISTANT>(P, scx, scy, sx, sy);
-    else source_coord<COORD_ERECT_CLAMP>(P, scx, scy, sx, sy);
+    source_coord_rt(P, coord, scx, scy, sx, sy);
     P.coords_out[((size_t)plane * (size_t)P.H + (size_t)y) * (size_t)P.W + (size_t)x] = make_float2(sx, sy);
   }
 }
@@ -47,9 +54,7 @@ __device__ void footprint_pixel(const KParams &P, int coord, int x, int y, const
       const float scx = fsub(fadd(cx, fdiv(fadd((float)ssx, 1.0f), P.ss_den)), 0.5f);
       const float scy = fsub(fadd(cy, fdiv(fadd((float)ssy, 1.0f), P.ss_den)), 0.5f);
       float sx, sy;
-      if (coord == COORD_RECT) source_coord<COORD_RECT>(P, scx, scy, sx, sy);
-      else if (coord == COORD_EQUIDISTANT) source_coord<COORD_EQUIDISTANT>(P, scx, scy, sx, sy);
-      else source_coord<COORD_ERECT_CLAMP>(P, scx, scy, sx, sy);
+      source_coord_rt(P, coord, scx, scy, sx, sy);
       int xs[N], ys[N];
       tap_indices<WRAP, N>(sx, sy, off, P.w, P.h, xs, ys);
 #pragma unroll

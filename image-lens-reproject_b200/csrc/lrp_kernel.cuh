@@ -43,6 +43,19 @@ LRP_DEV void target_to_vec(const KParams &P, float scx, float scy, float &x, flo
     x = fmul(s, scx);
     y = fmul(s, scy);
     z = cs; // +cos: the reference's equidistant OUTPUT is point-mirrored
+  } else if (P.ol.type == LENS_EQUISOLID || P.ol.type == LENS_STEREO) {
+    // extension lens models, specified by oracle/lrp_oracle.c (the reference refuses them, :415-417):
+    // r_mm = 2 f sin(theta / 2)  /  2 f tan(theta / 2), radius through sensor_width / image width, -z forward
+    float r_px = fsqrt(fadd(fmul(scx, scx), fmul(scy, scy)));
+    float r_mm = fmul(fdiv(r_px, W), P.ol.sw);
+    float half = fdiv(r_mm, fmul(2.0f, P.ol.p0));
+    float theta = fmul(2.0f, (P.ol.type == LENS_EQUISOLID) ? dev_asinf(half) : dev_atanf(half));
+    float sn, cs;
+    dev_sincosf(theta, P.use_fma != 0, &sn, &cs);
+    float s = fdiv(sn, r_px);
+    x = fmul(s, scx);
+    y = fmul(s, scy);
+    z = -cs;
   } else {
     float lon_span = fsub(P.ol.p3, P.ol.p2);
     float lat_span = fsub(P.ol.p1, P.ol.p0);
@@ -81,6 +94,18 @@ __device__ __noinline__ void vec_to_source_full(const KParams &P, float x, float
     float r_px = fmul(fdiv(r_mm, P.il.sw), w); // width for both axes, as the reference
     cx = fmul(fdiv(x, r), r_px);
     cy = fmul(fdiv(y, r), r_px);
+  } else if (COORD == COORD_EQUISOLID || COORD == COORD_STEREO) {
+    // extension lens models (specified by oracle/lrp_oracle.c): theta from atan2f, so the whole sphere projects
+    float rho = fsqrt(fadd(fmul(x, x), fmul(y, y)));
+    float theta = dev_atan2f(rho, -z);
+    float half = fmul(theta, 0.5f);
+    float sn, cs;
+    dev_sincosf(half, P.use_fma != 0, &sn, &cs);
+    float t = (COORD == COORD_EQUISOLID) ? sn : fdiv(sn, cs);
+    float r_mm = fmul(fmul(2.0f, P.il.p0), t);
+    float r_px = fmul(fdiv(r_mm, P.il.sw), w);
+    cx = fmul(fdiv(x, rho), r_px);
+    cy = fmul(fdiv(y, rho), r_px);
   } else {
     float theta = -dev_atan2f(-x, -z);
     float len = fsqrt(fadd(fadd(fmul(x, x), fmul(y, y)), fmul(z, z)));
@@ -99,7 +124,7 @@ __device__ __noinline__ void vec_to_source_full(const KParams &P, float x, float
 // the per-operation guards.  Compile-time COORD: it sits in the innermost loop.
 template <int COORD>
 LRP_DEV void vec_to_source(const KParams &P, float x, float y, float z, float &cx, float &cy) {
-  if (!(P.fast_lens && mid_range(x) && mid_range(y) && mid_range(z))) {
+  if (COORD == COORD_EQUISOLID || COORD == COORD_STEREO || !(P.fast_lens && mid_range(x) && mid_range(y) && mid_range(z))) {
     float o[2];
     vec_to_source_full<COORD>(P, x, y, z, o);
     cx = o[0];
@@ -511,7 +536,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) reproject_kernel(const __grid_con
   const SrcView S{P, lut_lane};
   // separable output rays from registers need one value per sub-sample column: ns == 1 only;
   // supersampled launches recompute the ray per sub-sample (its cost is amortised over ns^2 taps sets)
-  const bool separable = !TABLE && (P.ol.type != LENS_EQUIDISTANT) && (P.ns == 1);
+  const bool separable = !TABLE && (P.ol.type == LENS_RECT || P.ol.type == LENS_ERECT) && (P.ns == 1);
   const bool out_rect = (P.ol.type == LENS_RECT);
   const float Wf = (float)P.W, Hf = (float)P.H;
   const float half_W = fmul(Wf, 0.5f), half_H = fmul(Hf, 0.5f);

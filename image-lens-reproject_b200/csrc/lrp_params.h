@@ -19,7 +19,9 @@ enum : int {
   COORD_ERECT_WRAP = 3,
   COORD_TABLE_CLAMP = 4,
   COORD_TABLE_WRAP = 5,
-  COORD_COUNT = 6
+  COORD_EQUISOLID = 6, // extension lens models (no reference arithmetic; see lrp.h LRP_EXT_FISHEYE_MODELS)
+  COORD_STEREO = 7,
+  COORD_COUNT = 8
 };
 
 // (source format, channels) combinations that are instantiated

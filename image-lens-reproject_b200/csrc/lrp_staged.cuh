@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) reproject_staged_kernel(const _
   __syncthreads(); // the only CTA-wide barrier
 
   const SrcViewT<false> S{P, lut_addr};
-  const bool separable = !TABLE && (P.ol.type != LENS_EQUIDISTANT);
+  const bool separable = !TABLE && (P.ol.type == LENS_RECT || P.ol.type == LENS_ERECT);
   const bool out_rect = (P.ol.type == LENS_RECT);
   const float Wf = (float)P.W, Hf = (float)P.H;
   const float half_W = fmul(Wf, 0.5f), half_H = fmul(Hf, 0.5f);

@@ -59,7 +59,8 @@ inline lrp_image to_abi(const Image *im) {
   a.data = im->data;
   return a;
 }
-inline lrp_params to_params(int num_samples, Interpolation interpolation, const float *rotation_matrix) {
+inline lrp_params to_params(int num_samples, Interpolation interpolation, const float *rotation_matrix,
+                            int extensions = 0) {
   lrp_params p;
   std::memset(&p, 0, sizeof(p));
   p.num_samples = num_samples;
@@ -68,15 +69,16 @@ inline lrp_params to_params(int num_samples, Interpolation interpolation, const 
   if (rotation_matrix) std::memcpy(p.rotation, rotation_matrix, sizeof(p.rotation));
   p.exposure = 1.0f;
   p.reinhard = 1.0f;
+  p.extensions = extensions; // LRP_EXT_*: 0 = the reference's behaviour (equisolid / stereographic refused)
   return p;
 }
 } // namespace detail
 
 // reproject::reproject — reference src/reproject.cpp:405
 inline void reproject(const Image *in, Image *out, int num_samples, Interpolation interpolation,
-                      const float *rotation_matrix, int device = 0) {
+                      const float *rotation_matrix, int device = 0, int extensions = 0) {
   lrp_image a = detail::to_abi(in), b = detail::to_abi(out);
-  lrp_params p = detail::to_params(num_samples, interpolation, rotation_matrix);
+  lrp_params p = detail::to_params(num_samples, interpolation, rotation_matrix, extensions);
   int rc = lrp_reproject_host(&a, &b, &p, device);
   if (rc != LRP_OK) throw error(rc);
 }
@@ -91,9 +93,9 @@ inline void post_process(const Image *img, float exposure, float reinhard, int d
 // the worker's reproject() + conditional post_process() (reference src/main.cpp:597-603), one launch
 inline void reproject_and_post_process(const Image *in, Image *out, int num_samples, Interpolation interpolation,
                                        const float *rotation_matrix, double exposure, double reinhard,
-                                       int device = 0) {
+                                       int device = 0, int extensions = 0) {
   lrp_image a = detail::to_abi(in), b = detail::to_abi(out);
-  lrp_params p = detail::to_params(num_samples, interpolation, rotation_matrix);
+  lrp_params p = detail::to_params(num_samples, interpolation, rotation_matrix, extensions);
   if (exposure != 1.0 || reinhard != 1.0) { // the reference compares the doubles, src/main.cpp:601
     p.apply_post = 1;
     p.exposure = (float)exposure;

@@ -24,6 +24,7 @@ NEAREST, BILINEAR, BICUBIC = range(3)
 FMT_F32, FMT_U8_RGBA, FMT_F16_PLANAR = range(3)
 VARIANT_AUTO, VARIANT_GATHER, VARIANT_STAGED = range(3)
 UPLOAD_AUTO, UPLOAD_FULL = range(2)
+EXT_FISHEYE_MODELS = 1
 
 
 class LrpError(RuntimeError):
@@ -45,7 +46,8 @@ class Image(C.Structure):
 class Params(C.Structure):
     _fields_ = [("num_samples", C.c_int32), ("interpolation", C.c_int32), ("has_rotation", C.c_int32),
                 ("rotation", C.c_float * 9), ("apply_post", C.c_int32), ("exposure", C.c_float),
-                ("reinhard", C.c_float), ("variant", C.c_int32), ("upload", C.c_int32)]
+                ("reinhard", C.c_float), ("variant", C.c_int32), ("upload", C.c_int32),
+                ("extensions", C.c_int32)]
 
 
 DONE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int)
@@ -81,6 +83,7 @@ def lib():
         L.lrp_lens_rectilinear.argtypes = [C.c_float, C.c_float, C.c_int, C.c_int, lp]
         L.lrp_lens_equidistant.argtypes = [C.c_float, lp]
         L.lrp_lens_equisolid.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, lp]
+        L.lrp_lens_stereographic.argtypes = [C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, lp]
         L.lrp_lens_equirectangular_full.argtypes = [lp]
         L.lrp_lens_equirectangular.argtypes = [C.c_float] * 4 + [lp]
         L.lrp_reproject_host.argtypes = [ip, ip, pp, C.c_int]
@@ -166,6 +169,12 @@ def lens_equisolid(focal, sensor_width, fov, res_x, res_y):
     return l
 
 
+def lens_stereographic(focal, sensor_width, fov, res_x, res_y):
+    l = Lens()
+    lib().lrp_lens_stereographic(focal, sensor_width, fov, res_x, res_y, C.byref(l))
+    return l
+
+
 def lens_equirectangular(lon_min=None, lon_max=None, lat_min=None, lat_max=None):
     l = Lens()
     if lon_min is None:
@@ -194,7 +203,7 @@ def rotation_matrix(pan, pitch, roll):
     return np.array(m, dtype=np.float32)
 
 
-def make_params(ns=1, interp=BICUBIC, rot=None, post=None, variant=VARIANT_AUTO, upload=UPLOAD_AUTO):
+def make_params(ns=1, interp=BICUBIC, rot=None, post=None, variant=VARIANT_AUTO, upload=UPLOAD_AUTO, ext=0):
     """post = (exposure, reinhard) or None — main() calls post_process only when either differs
     from 1.0 (reference src/main.cpp:601)."""
     p = Params()
@@ -210,6 +219,7 @@ def make_params(ns=1, interp=BICUBIC, rot=None, post=None, variant=VARIANT_AUTO,
     p.reinhard = 1.0 if post is None else post[1]
     p.variant = variant
     p.upload = upload
+    p.extensions = ext
     return p
 
 
@@ -245,7 +255,7 @@ def _describe(arr, fmt):
 # ---- synchronous host drop-in --------------------------------------------------------------------
 
 def reproject_host(src, in_lens, out_lens, W, H, ns=1, interp=BICUBIC, rot=None, post=None,
-                   in_fmt=FMT_F32, out_fmt=None, device=0, channels=None, upload=UPLOAD_AUTO):
+                   in_fmt=FMT_F32, out_fmt=None, device=0, channels=None, upload=UPLOAD_AUTO, ext=0):
     """reproject::reproject() (+ post_process) on HOST numpy buffers through lrp_reproject_host."""
     out_fmt = in_fmt if out_fmt is None else out_fmt
     _, dt = _shape_of(in_fmt, 1, 1, 1)
@@ -257,7 +267,7 @@ def reproject_host(src, in_lens, out_lens, W, H, ns=1, interp=BICUBIC, rot=None,
     out = np.empty(oshape, dtype=odt)
     iim = make_image(in_lens, w, h, c, in_fmt, src.ctypes.data)
     oim = make_image(out_lens, W, H, c, out_fmt, out.ctypes.data)
-    p = make_params(ns, interp, rot, post, upload=upload)
+    p = make_params(ns, interp, rot, post, upload=upload, ext=ext)
     check(lib().lrp_reproject_host(C.byref(iim), C.byref(oim), C.byref(p), device), "lrp_reproject_host")
     return out
 

@@ -106,7 +106,26 @@ typedef struct lrp_params {
   float reinhard;        /* extended-Reinhard white point                                   */
   int32_t variant;       /* lrp_variant: source-access strategy; 0 = library default        */
   int32_t upload;        /* lrp_upload: what the HOST-buffer entry points copy to the GPU   */
+  int32_t extensions;    /* LRP_EXT_* bits; 0 = exactly the reference's behaviour           */
 } lrp_params;
+
+/* Opt-in behaviour beyond the reference.
+ *
+ * LRP_EXT_FISHEYE_MODELS  FISHEYE_EQUISOLID and FISHEYE_STEREOGRAPHIC as input and output lenses.  The
+ *   reference parses --equisolid / --i-equisolid (src/main.cpp:31-47, 402-404, 460-462) and carries the
+ *   lens through its configs (src/config.cpp:23-27, 84-87), but its kernel refuses both types
+ *   (src/reproject.cpp:395-397, 415-417), so there is no reference arithmetic to match: the models are
+ *   DEFINED by oracle/lrp_oracle.c in the reference's conventions (pixel-centre coordinates, radius in
+ *   mm through sensor_width / image WIDTH, -z forward):
+ *     output  r_px = sqrt(cx^2+cy^2); r_mm = r_px/W*sw; h = r_mm/(2f);
+ *             theta = 2*asinf(h) [equisolid] | 2*atanf(h) [stereographic];
+ *             s = sinf(theta)/r_px; ray = (s*cx, s*cy, -cosf(theta))
+ *     input   rho = sqrt(x^2+y^2); theta = atan2f(rho, -z); t = sinf(theta/2) | sinf(theta/2)/cosf(theta/2);
+ *             r_px = (2f*t)/sw*w; (cx, cy) = (x/rho*r_px, y/rho*r_px)
+ *   Both lens types use the fisheye_equisolid payload (focal_length, fov); fov is carried, not applied (the
+ *   reference never masks by field of view).  Without the bit both types return LRP_E_UNSUPPORTED_*_LENS
+ *   exactly as the reference exit(1)s. */
+#define LRP_EXT_FISHEYE_MODELS 1
 
 /* What lrp_reproject_host / lrp_submit / lrp_sched_submit upload of a host source.  The texels a
  * launch can touch depend on the geometry only (lenses, sizes, rotation, sampler) — for the 8K
@@ -153,6 +172,9 @@ void lrp_lens_rectilinear(float focal_length, float sensor_width, int res_x, int
 void lrp_lens_equidistant(float fov, lrp_lens *out);
 void lrp_lens_equisolid(float focal_length, float sensor_width, float fov, int res_x, int res_y,
                         lrp_lens *out);
+/* extension (LRP_EXT_FISHEYE_MODELS): same tuple as --equisolid */
+void lrp_lens_stereographic(float focal_length, float sensor_width, float fov, int res_x, int res_y,
+                            lrp_lens *out);
 void lrp_lens_equirectangular_full(lrp_lens *out);
 void lrp_lens_equirectangular(float lon_min, float lon_max, float lat_min, float lat_max, lrp_lens *out);
 

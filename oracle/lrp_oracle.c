@@ -159,6 +159,34 @@ static int target_to_vec(const orc_lens *li, float W, float H, float cx, float c
     *y = sinf(lat);
     return 0;
   }
+  /* ---- extension (no reference arithmetic exists: the reference's kernel refuses these lens types,
+   * src/reproject.cpp:395-397, 415-417).  Defined here in the reference's own conventions — pixel-centre
+   * coordinates, radius in mm through sensor_width / image WIDTH as equidistant_to_vec (:175-177), -z
+   * forward as rectilinear_to_vec (:157) — with the textbook projections
+   *   equisolid      r = 2 f sin(theta / 2)        stereographic  r = 2 f tan(theta / 2).
+   * PARITY UNPINNED for these two lens types: this file IS their specification. ---- */
+  case L_EQUISOLID: {
+    float r_px = sqrtf(cx * cx + cy * cy);
+    float r_mm = r_px / W * li->sensor_width;
+    float half = r_mm / (2.0f * li->p[0]); /* sin(theta / 2); > 1 outside the image circle -> NaN ray */
+    float theta = 2.0f * asinf(half);
+    float s = sinf(theta) / r_px;
+    *x = s * cx;
+    *y = s * cy;
+    *z = -cosf(theta);
+    return 0;
+  }
+  case L_STEREO: {
+    float r_px = sqrtf(cx * cx + cy * cy);
+    float r_mm = r_px / W * li->sensor_width;
+    float half = r_mm / (2.0f * li->p[0]); /* tan(theta / 2) */
+    float theta = 2.0f * atanf(half);
+    float s = sinf(theta) / r_px;
+    *x = s * cx;
+    *y = s * cy;
+    *z = -cosf(theta);
+    return 0;
+  }
   default: return 1;
   }
 }
@@ -194,6 +222,26 @@ static int vec_to_source(const orc_lens *li, float w, float h, float x, float y,
     *cy = ((phi - li->p[0]) / lat_span - 0.5f) * h;
     return 0;
   }
+  /* ---- extension, see target_to_vec: the whole sphere is covered (theta from atan2f, not from x / -z) */
+  case L_EQUISOLID: {
+    float rho = sqrtf(x * x + y * y);
+    float theta = atan2f(rho, -z);
+    float r_mm = 2.0f * li->p[0] * sinf(theta * 0.5f);
+    float r_px = r_mm / li->sensor_width * w;
+    *cx = x / rho * r_px;
+    *cy = y / rho * r_px;
+    return 0;
+  }
+  case L_STEREO: {
+    float rho = sqrtf(x * x + y * y);
+    float theta = atan2f(rho, -z);
+    float half = theta * 0.5f;
+    float r_mm = 2.0f * li->p[0] * (sinf(half) / cosf(half));
+    float r_px = r_mm / li->sensor_width * w;
+    *cx = x / rho * r_px;
+    *cy = y / rho * r_px;
+    return 0;
+  }
   default: return 1;
   }
 }
@@ -205,7 +253,13 @@ static int loops_horizontally(const orc_lens *in_lens) {
   return fabs((double)long_range - (2 * M_PI)) < (double)1e-5f;
 }
 
-static int lens_supported(int t) { return t == L_RECT || t == L_EQUIDISTANT || t == L_ERECT; }
+/* 0 (default): exactly the reference's lens support; 1: the equisolid / stereographic extension too */
+static int g_extensions = 0;
+void orc_set_extensions(int on) { g_extensions = on; }
+static int lens_supported(int t) {
+  if (t == L_RECT || t == L_EQUIDISTANT || t == L_ERECT) return 1;
+  return g_extensions && (t == L_EQUISOLID || t == L_STEREO);
+}
 
 /* one sub-sample's coordinate chain, reference :301-324 */
 static void chain(const orc_lens *ol, int W, int H, const orc_lens *il, int w, int h,

@@ -33,6 +33,11 @@ int orc_reproject(const orc_lens *in_lens, int w, int h, int c, const float *in_
                   const orc_lens *out_lens, int W, int H, float *out_data, int num_samples,
                   int interpolation, const float *rotation);
 
+/* Extension switch (default 0 = the reference's lens support).  With 1, FISHEYE_EQUISOLID (p[0] = focal
+ * length, p[1] = fov) and FISHEYE_STEREOGRAPHIC (same payload) are accepted as input and output lenses;
+ * the reference has no arithmetic for them, so lrp_oracle.c defines it (PARITY UNPINNED for those two). */
+void orc_set_extensions(int on);
+
 /* reference src/reproject.cpp:421-437 */
 void orc_post_process(int W, int H, int c, float *data, float exposure, float reinhard);
 

@@ -64,6 +64,13 @@ def equisolid(focal, sensor_w, fov, res_x, res_y):
     return l
 
 
+def stereographic(focal, sensor_w, fov, res_x, res_y):
+    """extension lens (no reference parser): the --equisolid tuple with type FISHEYE_STEREOGRAPHIC"""
+    l = equisolid(focal, sensor_w, fov, res_x, res_y)
+    l.type = STEREOGRAPHIC
+    return l
+
+
 def erect(lon_min=None, lon_max=None, lat_min=None, lat_max=None):
     """reference src/main.cpp:58-95 parse_equirectangular; no args = 'full'"""
     l = Lens()
@@ -217,6 +224,10 @@ class _Oracle(_Checker):
         L.orc_gamma_encode_eval.restype = None
         L.orc_gamma_monotone_violations.argtypes = [C.c_uint32, C.c_uint32]
         L.orc_gamma_monotone_violations.restype = C.c_int64
+
+    def set_extensions(self, on):
+        """1: accept the equisolid / stereographic extension lenses (specified by the oracle itself)"""
+        self.lib.orc_set_extensions(int(on))
 
     def host_libm(self, fn, a, b=None):
         """host glibc atanf/asinf/sinf/cosf/atan2f (fn 0..4) over arrays"""

@@ -2,7 +2,9 @@
 """Kernel-level timing of the BASELINE configurations other than the headline (bench.py measures c2):
 device-resident synthetic frames, CUDA events, B distinct frames per pass (working set >> L2).
 
-  c1t  1920x1080 RGBA8 rect(36,36) -> equidistant(pi) 1920x1080        (twin of c1; equisolid has no reference)
+  c1   1920x1080 RGBA8 rect(36,36) -> equisolid(12.5,36,pi) 1920x1080    (extension lens: LRP_EXT_FISHEYE_MODELS)
+  c4   3840x2160 half RGBZ rect(36,36) -> equisolid(12.5,36,pi) 3840x2160 (per frame; extension lens)
+  c1t  1920x1080 RGBA8 rect(36,36) -> equidistant(pi) 1920x1080        (reference-runnable twin of c1)
   c2   8192x4096 RGBA8 equirect full -> rect(18,36) 3840x2160, rot 30,20,10
   c3   4096x4096 half RGBZ equidistant(pi) -> equirect full 4096x2048, exposure 1.5, reinhard 4
   c4t  3840x2160 half RGBZ rect(36,36) -> equidistant(pi) 3840x2160     (twin of c4, per frame)
@@ -23,6 +25,8 @@ sys.path.insert(0, os.path.join(ROOT, "image-lens-reproject_b200", "python"))
 
 CONFIGS = {
     # name: (in lens ctor, (w, h), out lens ctor, (W, H), fmt, channels, rotation deg, post, N_touched bc, frames)
+    "c1": ("rect36", (1920, 1080), "equisolid", (1920, 1080), "u8", 3, None, None, 2073600, 16),
+    "c4": ("rect36", (3840, 2160), "equisolid", (3840, 2160), "f16", 4, None, None, 8294400, 8),
     "c1t": ("rect36", (1920, 1080), "equidistant", (1920, 1080), "u8", 3, None, None, 2073600, 16),
     "c2": ("erect", (8192, 4096), "rect18", (3840, 2160), "u8", 3, (30, 20, 10), None, 2673058, 8),
     "c3": ("equidistant", (4096, 4096), "erect", (4096, 2048), "f16", 4, None, (1.5, 4.0), 9023406, 8),
@@ -34,7 +38,7 @@ CONFIGS = {
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="c1t,c3,c4t,c5e,c5p")
+    ap.add_argument("--configs", default="c1,c1t,c3,c4,c4t,c5e,c5p")
     ap.add_argument("--variants", default="staged,gather")
     ap.add_argument("--coords", default="fly")
     ap.add_argument("--interp", default="bc")
@@ -54,6 +58,8 @@ def main():
             return lrp.lens_rectilinear(18.0, 36.0, w, h)
         if kind == "equidistant":
             return lrp.lens_equidistant(3.14159)
+        if kind == "equisolid":
+            return lrp.lens_equisolid(12.5, 36.0, 3.14159, w, h)
         return lrp.lens_equirectangular()
 
     for name in args.configs.split(","):
@@ -74,7 +80,7 @@ def main():
         for variant in args.variants.split(","):
             for coords in args.coords.split(","):
                 v = {"staged": lrp.VARIANT_STAGED, "gather": lrp.VARIANT_GATHER}[variant]
-                p = lrp.make_params(1, interp, rot, post, variant=v)
+                p = lrp.make_params(1, interp, rot, post, variant=v, ext=lrp.EXT_FISHEYE_MODELS)
                 remap = ctx.build_remap(il, w, h, ol, W, H, p) if coords == "table" else None
 
                 def step():
