@@ -230,6 +230,22 @@ struct lrp_ctx {
   cudaStream_t fp_stream = nullptr;
   int *d_bbox = nullptr, *h_bbox = nullptr;
   std::atomic<uint64_t> h2d_bytes{0}, d2h_bytes{0}; // moved by the host-buffer paths (lrp_ctx_transfer_stats)
+  // tile scheduler counters (lrp_kernel.cuh): one self-resetting {tickets, retired} pair per stream ever launched on —
+  // launches of one stream run in order, so they can share a pair; launches of different streams may overlap
+  static constexpr int SCHED_PAIRS = 1024;
+  int *d_sched = nullptr;
+  std::mutex sched_mu;
+  std::map<cudaStream_t, int> sched_of_stream;
+  int *sched_for(cudaStream_t st) {
+    if (!d_sched || st == cudaStreamPerThread) return nullptr; // one handle, a different stream per host thread
+    std::lock_guard<std::mutex> lk(sched_mu);
+    auto it = sched_of_stream.find(st);
+    if (it == sched_of_stream.end()) {
+      if ((int)sched_of_stream.size() >= SCHED_PAIRS) return nullptr; // static tile stride for the streams beyond
+      it = sched_of_stream.emplace(st, (int)sched_of_stream.size()).first;
+    }
+    return d_sched + 2 * it->second;
+  }
 };
 
 namespace {
@@ -395,6 +411,10 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
   if (remap) {
     K.remap = (const float2 *)remap;
     coord = (coord == COORD_ERECT_WRAP) ? COORD_TABLE_WRAP : COORD_TABLE_CLAMP;
+  }
+  {
+    const char *ss = getenv("LRP_STATIC_TILES"); // A/B switch: static tile stride instead of the ticket counter
+    K.sched = (ss && ss[0] == '1') ? nullptr : ctx->sched_for(stream);
   }
   // source access: the staged kernel handles one sample per pixel; supersampled launches gather
   const char *force = getenv("LRP_FORCE_VARIANT"); // A/B runs of unmodified callers: "gather" | "staged"
@@ -770,6 +790,8 @@ int lrp_ctx_create(int device, int n_streams, lrp_ctx **out) {
   if (c->num_sms <= 0) c->num_sms = 148;
   cudaError_t e = cudaMalloc(&c->d_lut, sizeof(T.lut));
   if (e == cudaSuccess) e = cudaMalloc(&c->d_thr, sizeof(T.thr));
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_sched, 2 * lrp_ctx::SCHED_PAIRS * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(c->d_sched, 0, 2 * lrp_ctx::SCHED_PAIRS * sizeof(int));
   if (e == cudaSuccess) e = cudaMemcpy(c->d_lut, T.lut, sizeof(T.lut), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(c->d_thr, T.thr, sizeof(T.thr), cudaMemcpyHostToDevice);
   for (int i = 0; i < n_streams && e == cudaSuccess; ++i) {
@@ -801,6 +823,7 @@ int lrp_ctx_destroy(lrp_ctx *c) {
   for (auto &s : c->slots) slot_destroy(s);
   if (c->d_lut) cudaFree(c->d_lut);
   if (c->d_thr) cudaFree(c->d_thr);
+  if (c->d_sched) cudaFree(c->d_sched);
   if (c->fp_stream) cudaStreamDestroy(c->fp_stream);
   if (c->d_bbox) cudaFree(c->d_bbox);
   if (c->h_bbox) cudaFreeHost(c->h_bbox);

@@ -510,6 +510,29 @@ constexpr int TILE_ROWS = 8;
 
 LRP_DEV uint32_t shared_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// ---- tile scheduler ------------------------------------------------------------------------------
+// Persistent warps take their first tile statically (global warp index) and every further one from a
+// global counter: sched[0] = tickets handed out, sched[1] = warps retired.  Both are zero when a launch
+// starts; the last warp to retire zeroes them again, so a counter pair serves every launch of one stream
+// (the host hands out one pair per stream, lrp_api.cu).  sched == nullptr: static stride.
+LRP_DEV int take_ticket(int *sched, int lane) {
+  int t = 0;
+  if (sched != nullptr && lane == 0) t = atomicAdd(sched, 1);
+  return t;
+}
+LRP_DEV int next_tile(int *sched, int ticket, int tile, int warps_total) {
+  if (sched == nullptr) return tile + warps_total;
+  return warps_total + __shfl_sync(0xffffffffu, ticket, 0);
+}
+LRP_DEV void retire_warp(int *sched, int lane, int warps_total) {
+  if (sched == nullptr || lane != 0) return;
+  __threadfence();
+  if (atomicAdd(sched + 1, 1) == warps_total - 1) { // every other warp has taken its last ticket
+    sched[0] = 0;
+    sched[1] = 0;
+  }
+}
+
 template <int COORD, int INTERP, int FMT, int C, bool PACKED>
 __global__ void __launch_bounds__(NTHREADS, 1) reproject_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -545,7 +568,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) reproject_kernel(const __grid_con
   const int n_tiles = tiles_x * tiles_y;
   const int warps_total = gridDim.x * (NTHREADS / 32);
 
-  for (int tile = blockIdx.x * (NTHREADS / 32) + wrp; tile < n_tiles; tile += warps_total) {
+  int tile = blockIdx.x * (NTHREADS / 32) + wrp;
+  while (tile < n_tiles) {
+    const int ticket = take_ticket(P.sched, lane);
     const int x0 = (tile % tiles_x) * TILE, y0 = (tile / tiles_x) * TILE_ROWS;
     const int x = x0 + lane;
     const float cx = fsub(fadd((float)x, 0.5f), half_W); // pixel centre, image centred on (0,0): :287
@@ -620,7 +645,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) reproject_kernel(const __grid_con
       }
       store_pixel<C>(P, s_thr, x, y, v);
     }
+    tile = next_tile(P.sched, ticket, tile, warps_total);
   }
+  retire_warp(P.sched, lane, warps_total);
 }
 
 // dynamic shared memory a launch needs (see the map above)

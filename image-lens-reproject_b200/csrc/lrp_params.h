@@ -61,6 +61,7 @@ struct KParams {
   int *footprint_out;           // footprint kernel: {min x, max x, min y, max y} of every resolved tap index
   int num_sms;                  // persistent grid size (SM count of the context's device)
   int stage_gain;               // staged kernel: issue slots per step (2 x 16 pixels) that staged taps save over gathered ones
+  int *sched;                   // tile scheduler counters {tickets, retired warps} of this launch's stream, or nullptr
   int fast_lens;                // input-lens divisors are normal numbers in [2^-20, 2^20]: unguarded divisions apply
 };
 

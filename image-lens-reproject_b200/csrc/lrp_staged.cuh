@@ -33,23 +33,33 @@
 
 namespace lrp {
 
-#ifndef LRP_ST_WARPS
-#define LRP_ST_WARPS 16
+// Warps per persistent CTA (one CTA per SM; the register file allows 65536 / (32 x warps) registers per thread and
+// every warp gets an equal share of the 227 KB of shared memory as staging space).  Measured on B200
+// (profiles/r1_bench_warps.jsonl, r1_bench_configs_warps.jsonl):
+//   bicubic, 3 channels        20 warps (96 registers, no spills): c2 201 -> 184 us, c5e 433 -> 404 us
+//   bicubic, 4-5 channels      16 warps: the 32 packed tap pairs need the 128 registers (20 warps spill; c3 307 -> 368 us)
+//   bilinear / nearest, 3 ch   24 warps (80 registers): c2 bl 148 -> 140 us, nn 189 -> 180 us
+// -DLRP_ST_WARPS=<n> forces one value for A/B builds.
+__host__ __device__ constexpr int st_warps(int interp, int channels) {
+#ifdef LRP_ST_WARPS
+  return LRP_ST_WARPS;
+#else
+  return (channels != 3) ? 16 : (interp == INTERP_BC) ? 20 : 24;
 #endif
-constexpr int ST_WARPS = LRP_ST_WARPS;    // 16 warps = 512 threads: one persistent CTA per SM, up to 128 registers / thread
-constexpr int ST_THREADS = ST_WARPS * 32;
+}
 constexpr int ST_TILE_W = 16, ST_TILE_H = 16; // output tile per warp: square, so that rotated footprints stay compact
 constexpr int ST_STEPS = ST_TILE_H / 2;        // a warp covers two rows of 16 pixels per step (lane = 16 * row parity + column)
 constexpr int ST_COORD_BYTES = ST_STEPS * 32 * 8;
 constexpr int ST_SMEM_BYTES = 232448;     // 227 KB: the opt-in maximum of dynamic shared memory per CTA
 constexpr int ST_FIXED_BYTES = 1088 + 1024 + 1024; // thresholds + 1 KB alignment slack + gamma table
-constexpr int ST_STAGE_BYTES = (((ST_SMEM_BYTES - ST_FIXED_BYTES) / ST_WARPS) - ST_COORD_BYTES) & ~15;
 
 // staging record: C <= 4 -> one float4 (c0, c1, c2, c3|next c2); C == 5 -> float4 + float2 (c4, next c4)
-template <int C> struct StageRec {
+// NW = warps per CTA: a warp's staging area is its share of the dynamic shared memory
+template <int C, int NW> struct StageRec {
+  static constexpr int STAGE_BYTES = (((ST_SMEM_BYTES - ST_FIXED_BYTES) / NW) - ST_COORD_BYTES) & ~15;
   static constexpr int A_BYTES = 16;
   static constexpr int B_BYTES = (C == 5) ? 8 : 0;
-  static constexpr int CAP = ST_STAGE_BYTES / (A_BYTES + B_BYTES); // texels per warp
+  static constexpr int CAP = STAGE_BYTES / (A_BYTES + B_BYTES); // texels per warp
   static constexpr bool LONE = (C & 1) != 0; // odd channel count: the last channel travels as (value, value of the next column)
 };
 
@@ -146,10 +156,10 @@ template <int C> struct StageLoad<FMT_F16, C> {
 // source wraps).  Record t = ty * bw + tx holds source texel (resolve_x(b.x0 + tx), b.y0 + ty).  Records are
 // dealt to the lanes in flat order (consecutive lanes = consecutive texels of a source row, whatever the box
 // width), U x 32 at a time with all the global loads of a round issued before the first decode.
-template <bool WRAP, int FMT, int C>
+template <bool WRAP, int FMT, int C, int NW>
 LRP_DEV void stage_group(const KParams &P, uint32_t lut, unsigned char *stage, const BBox &b, unsigned bw, unsigned bh,
                          int lane) {
-  typedef StageRec<C> Rec;
+  typedef StageRec<C, NW> Rec;
   constexpr unsigned STEP = Rec::LONE ? 31u : 32u; // odd C: lane k needs lane k+1's texel, so rounds overlap by one record
   constexpr int U = 4;
   const unsigned n = bw * bh;
@@ -273,9 +283,9 @@ template <int C> LRP_DEV void unpack_rec(const float4 a, float (&out)[C]) {
   if (C > 3) out[3 < C ? 3 : 0] = a.w;
 }
 
-template <bool WRAP, int C>
+template <bool WRAP, int C, int NW>
 LRP_DEV void staged_nearest(const KParams &P, const StageView &V, float sx, float sy, float (&out)[C]) {
-  typedef StageRec<C> Rec;
+  typedef StageRec<C, NW> Rec;
   const float off[1] = {0.5f};
   int ix[1], iy[1];
   staged_indices<WRAP, 1>(P, V, sx, sy, off, ix, iy); // :43-47
@@ -284,9 +294,9 @@ LRP_DEV void staged_nearest(const KParams &P, const StageView &V, float sx, floa
   if (C == 5) out[C - 1] = ((const float2 *)(V.stage + Rec::CAP * Rec::A_BYTES))[t].x;
 }
 
-template <bool WRAP, int C>
+template <bool WRAP, int C, int NW>
 LRP_DEV void staged_bilinear(const KParams &P, const StageView &V, float sx, float sy, float (&out)[C]) {
-  typedef StageRec<C> Rec;
+  typedef StageRec<C, NW> Rec;
   const float off[2] = {0.0f, 1.0f};
   int ix[2], iy[2];
   staged_indices<WRAP, 2>(P, V, sx, sy, off, ix, iy); // :60-67
@@ -321,31 +331,30 @@ LRP_DEV void staged_bilinear(const KParams &P, const StageView &V, float sx, flo
   }
 }
 
-template <bool WRAP, int C, bool X2>
+template <bool WRAP, int C, bool X2, int NW>
 LRP_DEV void staged_bicubic(const KParams &P, const StageView &V, float sx, float sy, float (&out)[C]) {
-  typedef StageRec<C> Rec;
-  const float off[4] = {-1.0f, 0.0f, 1.0f, 2.0f};
-  int ix[4], iy[4];
-  staged_indices<WRAP, 4>(P, V, sx, sy, off, ix, iy);                            // :114-127
-  const float fx = clamp01_std(fsub(sx, (float)resolve_x<WRAP>(ix[1], P.w)));   // :130 (post-wrap/clamp x1)
-  const float fy = clamp01_std(fsub(sy, (float)clampi(iy[1], P.h)));            // :131
+  typedef StageRec<C, NW> Rec;
+  // Consecutive tap indices i1-1, i1, i1+1, i1+2 on both axes?  Not implied by i3 - i0 == 3 (s + 1.0f may round up
+  // across an integer), so a SUFFICIENT condition is tested instead, on the middle index alone: for s >= 1,
+  // s - 1.0f is exact (so int(s - 1.0f) == int(s) - 1), and s + 1.0f / s + 2.0f cannot reach the next integer when
+  // the fraction of s is at most V.frac_max = 1 - 2^-23 * (largest index of the block + 4), twice their rounding
+  // error below 1.  (Such a fraction also implies that the resolved index equals the raw one: a wrapped index
+  // gives sx - x1 >= w.)  Only the pixels that fail the test — the truncation kink at index 0, border groups —
+  // evaluate the four truncations per axis of the reference (:114-127).
+  const int x1 = __float2int_rz(sx), y1 = __float2int_rz(sy); // staged pixels have |s| < 2^30: cvt.rzi == cvttss2si
+  const float fx = clamp01_std(fsub(sx, (float)resolve_x<WRAP>(x1, P.w))); // :130 (post-wrap/clamp x1)
+  const float fy = clamp01_std(fsub(sy, (float)clampi(y1, P.h)));     // :131
 
   // taps as packed pairs: P0[xi][yi] = (c0, c1), P1[xi][yi] = (c2, c3) for C >= 4,
   // lone channel (odd C): L[h][yi] = (value at column 2h, value at column 2h + 1)
   f2 P0[4][4], P1[4][4], L[2][4];
   const unsigned rowrec = V.bw;
-  const unsigned t00 = (unsigned)(iy[0] - V.by0) * rowrec + (unsigned)(ix[0] - V.bx0);
-  // Consecutive indices i1-1, i1, i1+1, i1+2 on both axes?  Not implied by i3 - i0 == 3 (s + 1.0f may round up
-  // across an integer), so a SUFFICIENT condition is tested instead, on values already at hand: for s >= 1,
-  // s - 1.0f is exact, and s + 1.0f / s + 2.0f cannot reach the next integer when the fraction of s is at most
-  // V.frac_max = 1 - 2^-23 * (largest index of the block + 4), twice their rounding error below 1.  (Such a
-  // fraction also implies that the resolved index equals the raw one: a wrapped index gives sx - x1 >= w.)
-  // Everything else takes the general path.
   const bool regular = !V.clamped && (sx >= 1.0f) && (sy >= 1.0f) && (fx <= V.frac_max) && (fy <= V.frac_max);
   const ulonglong2 *recA = (const ulonglong2 *)V.stage;
   const unsigned long long *recA64 = (const unsigned long long *)V.stage;
   const unsigned long long *recB = (const unsigned long long *)(V.stage + Rec::CAP * Rec::A_BYTES);
   if (regular) { // consecutive records: row base + immediate offsets
+    const unsigned t00 = (unsigned)(y1 - 1 - V.by0) * rowrec + (unsigned)(x1 - 1 - V.bx0);
 #pragma unroll
     for (int yi = 0; yi < 4; ++yi) {
       const unsigned t = t00 + (unsigned)yi * rowrec;
@@ -366,6 +375,9 @@ LRP_DEV void staged_bicubic(const KParams &P, const StageView &V, float sx, floa
       }
     }
   } else { // truncation kink at index 0, x86 INT_MIN indices: address every tap on its own
+    const float off[4] = {-1.0f, 0.0f, 1.0f, 2.0f};
+    int ix[4], iy[4];
+    staged_indices<WRAP, 4>(P, V, sx, sy, off, ix, iy); // :114-127
     unsigned cx[4], ry[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -423,16 +435,17 @@ LRP_DEV void staged_bicubic(const KParams &P, const StageView &V, float sx, floa
 // Dynamic shared memory map (shared-window addresses):
 //   [0, 1088)                            thr[257] (+ padding)                       (8-bit sinks)
 //   next 1 KB boundary .. + 1 KB         gamma table, plain                         (FMT_U8)
-//   + ST_WARPS x 2 KB                    per-warp source coordinates of the tile    float2[8][32]
-//   + ST_WARPS x ST_STAGE_BYTES          per-warp staging records
+//   + NW x 2 KB                          per-warp source coordinates of the tile    float2[8][32]
+//   + NW x Rec::STAGE_BYTES              per-warp staging records
 template <int COORD, int INTERP, int FMT, int C>
-__global__ void __launch_bounds__(ST_THREADS, 1) reproject_staged_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool WRAP = (COORD == COORD_ERECT_WRAP || COORD == COORD_TABLE_WRAP);
   constexpr bool TABLE = (COORD == COORD_TABLE_CLAMP || COORD == COORD_TABLE_WRAP);
   constexpr bool X2 = (FMT != FMT_F32);
   constexpr int NT = (INTERP == INTERP_NN) ? 1 : (INTERP == INTERP_BL) ? 2 : 4;
-  typedef StageRec<C> Rec;
+  constexpr int NW = st_warps(INTERP, C);
+  typedef StageRec<C, NW> Rec;
 
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   float *s_thr = (float *)smem_raw;
@@ -440,7 +453,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) reproject_staged_kernel(const _
   const uint32_t lut_addr = (win0 + 1088u + 1023u) & ~1023u;
   unsigned char *after_lut = smem_raw + (lut_addr - win0) + 1024u;
   float2 *s_coord = (float2 *)(after_lut + wrp * ST_COORD_BYTES);
-  unsigned char *s_stage = after_lut + ST_WARPS * ST_COORD_BYTES + wrp * ST_STAGE_BYTES;
+  unsigned char *s_stage = after_lut + NW * ST_COORD_BYTES + wrp * Rec::STAGE_BYTES;
 
   // ---- once per CTA: tables ----
   if (P.dst_fmt == FMT_U8 && tid <= 256) s_thr[tid] = (tid < 256) ? P.thr[tid] : __int_as_float(0x7f800000);
@@ -459,10 +472,15 @@ __global__ void __launch_bounds__(ST_THREADS, 1) reproject_staged_kernel(const _
 
   const int tiles_x = (P.W + ST_TILE_W - 1) / ST_TILE_W, tiles_y = (P.H + ST_TILE_H - 1) / ST_TILE_H;
   const int n_tiles = tiles_x * tiles_y;
-  const int warps_total = gridDim.x * ST_WARPS;
+  const int warps_total = gridDim.x * NW;
   const int lx = lane & (ST_TILE_W - 1), ly = lane >> 4; // lane -> (column, row parity) of the 16 x 16 tile
 
-  for (int tile = blockIdx.x * ST_WARPS + wrp; tile < n_tiles; tile += warps_total) {
+  // Tiles are handed out dynamically (lrp_kernel.cuh, "tile scheduler"): the first round is static, every
+  // further tile comes from the launch's global counter, so that no warp idles through a tail round
+  // (tiles differ in cost — border clamps, pole crossings, gathered blocks; measured c3 393 -> 307 us, c5p 783 -> 612 us).
+  int tile = blockIdx.x * NW + wrp;
+  while (tile < n_tiles) {
+    const int ticket = take_ticket(P.sched, lane); // issued now, consumed after the tile: the atomic's latency is hidden
     const int x0 = (tile % tiles_x) * ST_TILE_W, y0 = (tile / tiles_x) * ST_TILE_H;
     const int x = x0 + lx;
     const bool xvalid = x < P.W;
@@ -578,7 +596,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) reproject_staged_kernel(const _
       }
       const int end = min(start + len, R);
       if (staged) {
-        stage_group<WRAP, FMT, C>(P, lut_addr, s_stage, plan.eff, plan.bw, plan.bh, lane);
+        stage_group<WRAP, FMT, C, NW>(P, lut_addr, s_stage, plan.eff, plan.bw, plan.bh, lane);
         __syncwarp();
       }
       // fraction bound of the sampler's consecutive-index shortcut: rounding error of s + 2.0f <= ulp / 2,
@@ -592,9 +610,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) reproject_staged_kernel(const _
         const float2 s = s_coord[rr * 32 + lane];
         float v[C];
         if (staged) {
-          if (INTERP == INTERP_NN) staged_nearest<WRAP, C>(P, V, s.x, s.y, v);
-          else if (INTERP == INTERP_BL) staged_bilinear<WRAP, C>(P, V, s.x, s.y, v);
-          else staged_bicubic<WRAP, C, X2>(P, V, s.x, s.y, v);
+          if (INTERP == INTERP_NN) staged_nearest<WRAP, C, NW>(P, V, s.x, s.y, v);
+          else if (INTERP == INTERP_BL) staged_bilinear<WRAP, C, NW>(P, V, s.x, s.y, v);
+          else staged_bicubic<WRAP, C, X2, NW>(P, V, s.x, s.y, v);
         } else {
           if (INTERP == INTERP_NN) sample_nearest<WRAP, FMT, C>(S, s.x, s.y, v);
           else if (INTERP == INTERP_BL) sample_bilinear<WRAP, FMT, C>(S, s.x, s.y, v);
@@ -612,7 +630,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) reproject_staged_kernel(const _
       __syncwarp(); // the records may be overwritten by the next block
       start = end;
     }
+    tile = next_tile(P.sched, ticket, tile, warps_total);
   }
+  retire_warp(P.sched, lane, warps_total);
 }
 
 template <int COORD, int INTERP, int FMT, int C>
@@ -627,9 +647,10 @@ int launch_reproject_staged(const KParams &P, void *stream) {
     configured_device = dev;
   }
   const int tiles = ((P.W + ST_TILE_W - 1) / ST_TILE_W) * ((P.H + ST_TILE_H - 1) / ST_TILE_H);
-  const int ctas_needed = (tiles + ST_WARPS - 1) / ST_WARPS;
+  constexpr int NW = st_warps(INTERP, C);
+  const int ctas_needed = (tiles + NW - 1) / NW;
   const int grid = ctas_needed < P.num_sms ? ctas_needed : P.num_sms;
-  kern<<<grid, ST_THREADS, ST_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+  kern<<<grid, NW * 32, ST_SMEM_BYTES, (cudaStream_t)stream>>>(P);
   return (int)cudaGetLastError();
 }
 
