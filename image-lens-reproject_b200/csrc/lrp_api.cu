@@ -420,7 +420,12 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
   const char *force = getenv("LRP_FORCE_VARIANT"); // A/B runs of unmodified callers: "gather" | "staged"
   int variant = p->variant;
   if (force && variant == LRP_VARIANT_AUTO) variant = force[0] == 'g' ? LRP_VARIANT_GATHER : LRP_VARIANT_STAGED;
-  const bool staged = (variant != LRP_VARIANT_GATHER) && p->num_samples == 1;
+  // AUTO follows the measurements (profiles/r1_bench_configs_s6*.jsonl): footprint staging pays for the 16 taps of
+  // bicubic on every config (c2 185 vs 209 us, c4t 249 vs 340 us); the 1 / 4 taps of nearest / bilinear are cheaper
+  // gathered through L1 (c2 nn 107 vs 179 us, bl 124 vs 139 us; c3 bl 137 vs 235 us)
+  const bool want_staged = (variant == LRP_VARIANT_STAGED) ||
+                           (variant == LRP_VARIANT_AUTO && p->interpolation == LRP_BICUBIC);
+  const bool staged = want_staged && p->num_samples == 1;
   LaunchFn fn = get_launcher(coord, p->interpolation, fc, staged);
   if (!fn) return LRP_E_UNSUPPORTED_FORMAT;
   return map_cuda((cudaError_t)fn(K, stream));
@@ -832,6 +837,7 @@ int lrp_ctx_destroy(lrp_ctx *c) {
 }
 
 int lrp_ctx_device(const lrp_ctx *c) { return c ? c->device : -1; }
+int lrp_ctx_phys_device_(const lrp_ctx *c) { return c ? c->phys_device : 0; } // for the library's other translation units
 int lrp_ctx_num_streams(const lrp_ctx *c) { return c ? (int)c->streams.size() : 0; }
 void *lrp_ctx_stream(lrp_ctx *c, int idx) {
   if (!c || idx < 0 || idx >= (int)c->streams.size()) return nullptr;

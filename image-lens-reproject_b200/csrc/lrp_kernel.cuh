@@ -124,7 +124,7 @@ __device__ __noinline__ void vec_to_source_full(const KParams &P, float x, float
 // the per-operation guards.  Compile-time COORD: it sits in the innermost loop.
 template <int COORD>
 LRP_DEV void vec_to_source(const KParams &P, float x, float y, float z, float &cx, float &cy) {
-  if (COORD == COORD_EQUISOLID || COORD == COORD_STEREO || !(P.fast_lens && mid_range(x) && mid_range(y) && mid_range(z))) {
+  if (COORD == COORD_EQUISOLID || COORD == COORD_STEREO || !(P.fast_lens && mid_range3(x, y, z))) {
     float o[2];
     vec_to_source_full<COORD>(P, x, y, z, o);
     cx = o[0];

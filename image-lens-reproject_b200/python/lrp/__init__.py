@@ -121,6 +121,16 @@ def lib():
         L.lrp_ctx_transfer_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.lrp_debug_libm.argtypes = [vp, C.c_int, vp, vp, vp, C.c_size_t, vp]
         L.lrp_debug_encode_u8.argtypes = [vp, vp, vp, C.c_size_t, vp]
+        i32 = C.c_int32
+        for f in (L.lrp_png_packed_bytes, L.lrp_exr_packed_bytes):
+            f.argtypes, f.restype = [i32, i32, i32], C.c_size_t
+        for f in (L.lrp_png_pack_device, L.lrp_exr_pack_device):
+            f.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+        for f in (L.lrp_png_assemble, L.lrp_exr_assemble):
+            f.argtypes = [vp, i32, i32, i32, i32, i32, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        for f in (L.lrp_save_png_device, L.lrp_save_exr_device):
+            f.argtypes = [vp, vp, i32, i32, i32, i32, i32, C.c_char_p, vp]
+        L.lrp_free_bytes.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -378,6 +388,35 @@ class Context:
                                         self._stream(stream)), "lrp_debug_encode_u8")
         return out
 
+    # -- encode side: device pack kernels (the host halves are module-level functions) --
+    def png_pack(self, rgba_t, png_channels=3, stream=None):
+        """RGBA8 sink [H, W, 4] on the device -> PNG scan-line stream (filter byte + filtered bytes) on the device."""
+        import torch
+        h, w = int(rgba_t.shape[0]), int(rgba_t.shape[1])
+        out = torch.empty(lib().lrp_png_packed_bytes(w, h, png_channels), dtype=torch.uint8, device=rgba_t.device)
+        check(lib().lrp_png_pack_device(self.h, C.c_void_p(rgba_t.data_ptr()), w, h, png_channels,
+                                        C.c_void_p(out.data_ptr()), self._stream(stream)), "lrp_png_pack_device")
+        return out
+
+    def exr_pack(self, planar_t, stream=None):
+        """planar half sink [C, H, W] on the device -> OpenEXR ZIP blocks, byte planes + predictor applied."""
+        import torch
+        c, h, w = (int(v) for v in planar_t.shape)
+        out = torch.empty(lib().lrp_exr_packed_bytes(w, h, c), dtype=torch.uint8, device=planar_t.device)
+        check(lib().lrp_exr_pack_device(self.h, C.c_void_p(planar_t.data_ptr()), w, h, c,
+                                        C.c_void_p(out.data_ptr()), self._stream(stream)), "lrp_exr_pack_device")
+        return out
+
+    def save_png(self, rgba_t, path, png_channels=3, level=6, threads=8, stream=None):
+        h, w = int(rgba_t.shape[0]), int(rgba_t.shape[1])
+        check(lib().lrp_save_png_device(self.h, C.c_void_p(rgba_t.data_ptr()), w, h, png_channels, level, threads,
+                                        os.fsencode(path), self._stream(stream)), "lrp_save_png_device")
+
+    def save_exr(self, planar_t, path, level=9, threads=8, stream=None):
+        c, h, w = (int(v) for v in planar_t.shape)
+        check(lib().lrp_save_exr_device(self.h, C.c_void_p(planar_t.data_ptr()), w, h, c, level, threads,
+                                        os.fsencode(path), self._stream(stream)), "lrp_save_exr_device")
+
     # -- asynchronous host-buffer jobs on this context's worker streams --
     def submit(self, job):
         t = C.c_uint64(0)
@@ -389,6 +428,27 @@ class Context:
 
     def wait_all(self):
         check(lib().lrp_wait_all(self.h), "lrp_wait_all")
+
+
+def _assemble(fn, packed, w, h, c, level, threads):
+    import numpy as np
+    packed = np.ascontiguousarray(packed, dtype=np.uint8)
+    out, n = C.c_void_p(None), C.c_size_t(0)
+    check(fn(C.c_void_p(packed.ctypes.data), w, h, c, level, threads, C.byref(out), C.byref(n)), fn.__name__)
+    try:
+        return C.string_at(out.value, n.value)
+    finally:
+        lib().lrp_free_bytes(out)
+
+
+def png_assemble(packed, w, h, png_channels=3, level=6, threads=8):
+    """host half of the PNG writer: packed scan-line stream -> the bytes of a .png file"""
+    return _assemble(lib().lrp_png_assemble, packed, w, h, png_channels, level, threads)
+
+
+def exr_assemble(packed, w, h, channels, level=9, threads=8):
+    """host half of the EXR writer: packed ZIP blocks -> the bytes of a .exr file"""
+    return _assemble(lib().lrp_exr_assemble, packed, w, h, channels, level, threads)
 
 
 def make_job(src_ptr, in_lens, w, h, c, in_fmt, dst_ptr, out_lens, W, H, out_fmt, params):

@@ -141,7 +141,7 @@ typedef enum lrp_upload {
  * where the coordinates come from (computed on the fly, or read from a remap table through
  * lrp_reproject_device_remap). */
 typedef enum lrp_variant {
-  LRP_VARIANT_AUTO = 0,   /* STAGED where it applies (num_samples == 1), else GATHER           */
+  LRP_VARIANT_AUTO = 0,   /* by measurement: STAGED for bicubic with num_samples == 1, else GATHER */
   LRP_VARIANT_GATHER = 1, /* every tap is a global load through L1/L2                            */
   LRP_VARIANT_STAGED = 2  /* each warp stages + decodes the bounding box of its tile's taps in
                              shared memory once; rows whose box does not fit are gathered      */
@@ -259,6 +259,45 @@ int lrp_sched_destroy(lrp_sched *s);
 int lrp_sched_num_devices(const lrp_sched *s);
 /* jobs completed per device so far (array of n_devices) — for tests / stats */
 int lrp_sched_stats(const lrp_sched *s, int64_t *jobs_per_device);
+
+/* ---- encode side --------------------------------------------------------
+ * Replaces what follows the kernel in the reference's writers: reproject::save_png
+ * (src/image_formats.cpp:144-172 -> lodepng::encode: drop constant alpha, minimum-sum scan-line filtering,
+ * one deflated IDAT) and reproject::save_exr (:305-345 -> OpenEXR scan-line ZIP: 16-line blocks, byte planes,
+ * delta predictor, one deflate stream per block).  The data-parallel half runs on the device directly on the
+ * fused kernel's sinks (LRP_FMT_U8_RGBA / LRP_FMT_F16_PLANAR); the packed stream is what crosses PCIe; the
+ * host half deflates it on `threads` cores and adds the container bytes.  The files decode with the
+ * reference's readers (lodepng::decode, Imf::InputFile) to exactly the samples the reference's writers store. */
+
+/* PNG.  png_channels: 3 = colour type 2 (the alpha byte of the sink is dropped, what lodepng's auto_convert does
+ * for save_png's constant alpha), 4 = colour type 6.  Packed stream = per scan line 1 filter-type byte +
+ * png_channels * width filtered bytes. */
+size_t lrp_png_packed_bytes(int32_t width, int32_t height, int32_t png_channels);
+int lrp_png_pack_device(lrp_ctx *ctx, const void *rgba_dev, int32_t width, int32_t height, int32_t png_channels,
+                        void *packed_dev, void *cuda_stream);
+/* host: packed stream -> complete PNG file image (malloc'ed; release with lrp_free_bytes).  level = zlib 0..9 */
+int lrp_png_assemble(const void *packed_host, int32_t width, int32_t height, int32_t png_channels, int32_t level,
+                     int32_t threads, void **out_bytes, size_t *out_size);
+
+/* EXR.  Source = `channels` (1..5) planes of IEEE half, plane stride width * height; plane i is written as channel
+ * "RGBAZ"[i] exactly as save_exr names them.  Packed stream = the blocks of 16 scan lines back to back, each
+ * already split into byte planes and delta-predicted (what OpenEXR hands to deflate). */
+size_t lrp_exr_packed_bytes(int32_t width, int32_t height, int32_t channels);
+int lrp_exr_pack_device(lrp_ctx *ctx, const void *half_planar_dev, int32_t width, int32_t height, int32_t channels,
+                        void *packed_dev, void *cuda_stream);
+/* host: packed stream -> complete single-part scan-line EXR file image (ZIP_COMPRESSION; the reference uses
+ * level 9).  malloc'ed; release with lrp_free_bytes. */
+int lrp_exr_assemble(const void *packed_host, int32_t width, int32_t height, int32_t channels, int32_t level,
+                     int32_t threads, void **out_bytes, size_t *out_size);
+int lrp_free_bytes(void *p);
+
+/* save_png / save_exr for a sink that is resident on the device: pack on `cuda_stream`, copy the packed stream to
+ * the host, assemble on `threads` cores, write `path`.  Synchronous.  (Pipelines that keep their own pinned buffers
+ * call the three steps themselves.) */
+int lrp_save_png_device(lrp_ctx *ctx, const void *rgba_dev, int32_t width, int32_t height, int32_t png_channels,
+                        int32_t level, int32_t threads, const char *path, void *cuda_stream);
+int lrp_save_exr_device(lrp_ctx *ctx, const void *half_planar_dev, int32_t width, int32_t height, int32_t channels,
+                        int32_t level, int32_t threads, const char *path, void *cuda_stream);
 
 /* ---- test hooks (Level-0 parity) -------------------------- */
 /* per-pixel (sx, sy) of sub-sample (0,0): out_sxy_dev = float[H*W*2] on device */

@@ -9,6 +9,7 @@ import ctypes as C
 import math
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -361,3 +362,60 @@ def same_bits(a, b):
     b = np.ascontiguousarray(b, np.float32)
     eq = (bits(a) == bits(b)) | (np.isnan(a) & np.isnan(b))
     return bool(eq.all())
+
+
+# ---- encode side ---------------------------------------------------
+
+def codec_oracle():
+    """numpy restatement of the PNG filter / EXR block packing + independent decoders (oracle/lrp_codec_oracle.py)"""
+    if ORACLE_DIR not in sys.path:
+        sys.path.insert(0, ORACLE_DIR)
+    import lrp_codec_oracle
+    return lrp_codec_oracle
+
+
+class _RefLodepng:
+    """The reference's vendored lodepng (reader + writer), compiled by oracle/Makefile into oracle/_ref."""
+
+    def __init__(self, lib):
+        self.lib = lib
+        lib.ref_png_decode_rgba.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+        lib.ref_png_decode_rgba.restype = C.c_uint
+        lib.ref_png_encode_rgba.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_size_t]
+        lib.ref_png_encode_rgba.restype = C.c_size_t
+
+    def decode(self, png):
+        """lodepng::decode as read_png calls it -> uint8 [H, W, 4]"""
+        w, h = C.c_uint(0), C.c_uint(0)
+        err = self.lib.ref_png_decode_rgba(png, len(png), None, C.byref(w), C.byref(h))
+        assert err == 0, "lodepng error %d" % err
+        out = np.empty((h.value, w.value, 4), dtype=np.uint8)
+        err = self.lib.ref_png_decode_rgba(png, len(png), out.ctypes.data, C.byref(w), C.byref(h))
+        assert err == 0, "lodepng error %d" % err
+        return out
+
+    def encode(self, rgba):
+        """lodepng::encode as save_png calls it -> bytes of the .png"""
+        rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+        h, w = rgba.shape[:2]
+        cap = rgba.size + rgba.size // 8 + (1 << 16)
+        buf = np.empty(cap, dtype=np.uint8)
+        n = self.lib.ref_png_encode_rgba(rgba.ctypes.data, w, h, buf.ctypes.data, cap)
+        assert 0 < n <= cap
+        return buf[:n].tobytes()
+
+
+_ref_png = None
+
+
+def reference_lodepng():
+    """The compiled reference lodepng, or None when oracle/_ref was never built."""
+    global _ref_png
+    if _ref_png is None:
+        path = os.path.join(ORACLE_DIR, "_ref", "libref_lodepng.so")
+        if not os.path.exists(path) and os.path.exists("/root/reference/lib/lodepng/lodepng.cpp"):
+            _build()
+        lib = _load(path)
+        if lib is not None:
+            _ref_png = _RefLodepng(lib)
+    return _ref_png

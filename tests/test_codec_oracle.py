@@ -1,0 +1,149 @@
+"""Encode side, CPU part (`-m "not gpu"`): the numpy restatement of the PNG filter stage and of OpenEXR's ZIP block
+packing is pinned against the reference's own codecs, and the HOST half of liblrp's writers (parallel deflate +
+containers: lrp_png_assemble / lrp_exr_assemble, no GPU involved) is checked through independent readers:
+the reference's lodepng (oracle/_ref), Pillow, the OpenEXR library inside cv2, and the oracle's own parsers."""
+import io
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+co = ol.codec_oracle()
+REF_PNG = ol.reference_lodepng()
+
+
+@pytest.fixture(scope="module")
+def lrp():
+    import lrp as m
+    m.lib()
+    return m
+
+
+def images():
+    rng = np.random.default_rng(7)
+    y, x = np.mgrid[0:45, 0:67]
+    smooth = np.stack([(x * 3 + y) & 255, (x + y * 2) & 255, (x * y) & 255], axis=-1).astype(np.uint8)
+    return {"noise": rng.integers(0, 256, (33, 50, 3), dtype=np.uint8), "smooth": smooth,
+            "mixed": np.concatenate([smooth[:20, :50], rng.integers(0, 256, (13, 50, 3), dtype=np.uint8)]),
+            "row": rng.integers(0, 256, (1, 300, 3), dtype=np.uint8),
+            "col": rng.integers(0, 256, (40, 1, 3), dtype=np.uint8)}
+
+
+# ---- pinning the restatement ----
+
+@pytest.mark.skipif(REF_PNG is None, reason="oracle/_ref/libref_lodepng.so not built")
+@pytest.mark.parametrize("name", ["noise", "smooth", "mixed", "row"])
+def test_filter_restatement_matches_the_reference_lodepng(name):
+    """lodepng::encode as save_png calls it: its IDAT, inflated, IS the filtered scan-line stream — byte for byte
+    what the restatement (and therefore the device kernel) produces."""
+    img = images()[name]
+    rgba = np.concatenate([img, np.full(img.shape[:2] + (1,), 255, np.uint8)], axis=-1)
+    w, h, depth, ctype, idat = co.png_parse(REF_PNG.encode(rgba))
+    assert (w, h, depth, ctype) == (img.shape[1], img.shape[0], 8, 2), "auto_convert drops the constant alpha"
+    want = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(h, 1 + 3 * w)
+    got = co.png_filter_minsum(img)
+    assert (got[:, 0] == want[:, 0]).all(), "filter types differ"
+    assert (got == want).all()
+
+
+@pytest.mark.parametrize("name", ["noise", "smooth", "mixed", "row", "col"])
+def test_filter_roundtrip(name):
+    img = images()[name]
+    h, w, pc = img.shape
+    assert (co.png_unfilter(co.png_filter_minsum(img).tobytes(), w, h, pc) == img).all()
+
+
+# ---- host half of the PNG writer ----
+
+@pytest.mark.parametrize("name,threads,level", [("noise", 1, 6), ("smooth", 4, 9), ("mixed", 3, 1), ("row", 8, 6),
+                                                ("col", 2, 0)])
+def test_png_assemble_decodes_everywhere(lrp, name, threads, level):
+    from PIL import Image
+    img = images()[name]
+    h, w, _ = img.shape
+    png = lrp.png_assemble(co.png_filter_minsum(img), w, h, 3, level, threads)
+    assert (co.png_decode(png) == img).all()
+    assert (np.asarray(Image.open(io.BytesIO(png)).convert("RGB")) == img).all()
+    if REF_PNG is not None:  # read_png's decoder (src/image_formats.cpp:174-183)
+        out = REF_PNG.decode(png)
+        assert (out[..., :3] == img).all() and (out[..., 3] == 255).all()
+
+
+def test_png_assemble_many_bands_and_rgba(lrp):
+    """enough rows for several deflate bands per thread: the stitched stream must be ONE valid zlib stream"""
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    y, x = np.mgrid[0:1500, 0:400]
+    img = np.stack([(x + y) & 255, (x * 2) & 255, (y * 3) & 255, 255 - ((x + y) & 255)], axis=-1).astype(np.uint8)
+    img[::7] = rng.integers(0, 256, img[::7].shape, dtype=np.uint8)
+    a = lrp.png_assemble(co.png_filter_minsum(img), 400, 1500, 4, 6, 8)
+    b = lrp.png_assemble(co.png_filter_minsum(img), 400, 1500, 4, 6, 1)
+    for png in (a, b):
+        assert (np.asarray(Image.open(io.BytesIO(png))) == img).all()
+        _, _, _, ctype, idat = co.png_parse(png)
+        assert ctype == 6 and len(zlib.decompress(idat)) == 1500 * 1601
+    assert len(a) < 1.02 * len(b), "band seams cost more than 2 % of the file"
+    if REF_PNG is not None:
+        assert (REF_PNG.decode(a) == img).all()
+
+
+def test_png_assemble_rejects_bad_arguments(lrp):
+    with pytest.raises(lrp.LrpError):
+        lrp.png_assemble(np.zeros(10, np.uint8), 0, 1, 3)
+    with pytest.raises(lrp.LrpError):
+        lrp.png_assemble(np.zeros(10, np.uint8), 3, 1, 2)
+    with pytest.raises(lrp.LrpError):
+        lrp.png_assemble(np.zeros(10, np.uint8), 3, 1, 3, level=11)
+
+
+# ---- EXR ----
+
+def half_planes(c, h, w, seed=5, finite=True):
+    rng = np.random.default_rng(seed)
+    if finite:
+        v = (rng.random((c, h, w), dtype=np.float32) * 4 - 1).astype(np.float16)
+        v[:, ::5, ::3] = np.float16(0.5)  # flat runs, so that blocks compress
+        return v.view(np.uint16)
+    return rng.integers(0, 65536, (c, h, w), dtype=np.uint16)  # every bit pattern, incompressible
+
+
+@pytest.mark.parametrize("c,h,w", [(3, 40, 33), (4, 16, 64), (5, 17, 7), (1, 1, 1), (3, 48, 1)])
+def test_exr_restatement_roundtrip_and_file_order(c, h, w):
+    planes = half_planes(c, h, w)
+    idx, names = co.exr_file_order(c)
+    assert names == sorted(names) and [co.EXR_NAMES[i] for i in idx] == names
+    packed = co.exr_pack(planes)
+    assert packed.size == c * h * w * 2
+
+
+@pytest.mark.parametrize("c,h,w,threads,level,finite", [(3, 40, 33, 1, 9, True), (4, 100, 64, 4, 6, True),
+                                                        (5, 17, 7, 2, 1, True), (1, 1, 1, 1, 9, True),
+                                                        (4, 33, 50, 3, 9, False)])
+def test_exr_assemble_decodes(lrp, tmp_path, c, h, w, threads, level, finite):
+    planes = half_planes(c, h, w, finite=finite)
+    exr = lrp.exr_assemble(co.exr_pack(planes), w, h, c, level, threads)
+    names, data = co.exr_decode(exr)
+    assert names == co.exr_file_order(c)[1]
+    assert (co.exr_to_planes(names, data, c) == planes).all()
+    if finite and c in (3, 4):  # the OpenEXR library itself (inside cv2): B,G,R(,A) as float32
+        os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+        import cv2
+        p = tmp_path / "t.exr"
+        p.write_bytes(exr)
+        img = cv2.imread(str(p), cv2.IMREAD_UNCHANGED)
+        assert img is not None and img.shape == (h, w, c)
+        want = planes.view(np.float16).astype(np.float32)
+        order = [2, 1, 0] + ([3] if c == 4 else [])  # cv2 channel k <- plane order[k]
+        for k, pl in enumerate(order):
+            assert (img[..., k] == want[pl]).all()
+
+
+def test_exr_incompressible_blocks_are_stored_raw(lrp):
+    planes = half_planes(3, 32, 40, finite=False)
+    exr = lrp.exr_assemble(co.exr_pack(planes), 40, 32, 3, 9, 2)
+    assert len(exr) < planes.nbytes + 1024  # raw blocks: never larger than the pixels + header
+    names, data = co.exr_decode(exr)
+    assert (co.exr_to_planes(names, data, 3) == planes).all()

@@ -1,0 +1,131 @@
+"""Encode side, GPU part (`-m gpu`): the device pack kernels of csrc/lrp_codec.cu against the numpy restatement
+(oracle/lrp_codec_oracle.py, itself pinned to the reference's lodepng / to OpenEXR) — bit-exact — and whole files
+written from the fused kernel's sinks, read back through the reference's reader."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+co = ol.codec_oracle()
+
+
+@pytest.fixture(scope="module")
+def lrp():
+    import lrp as m
+    m.lib()
+    return m
+
+
+@pytest.fixture(scope="module")
+def ctx(lrp):
+    c = lrp.Context(0, 2)
+    yield c
+    c.close()
+
+
+def rgba_image(h, w, seed, kind):
+    rng = np.random.default_rng(seed)
+    if kind == "noise":
+        img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    else:
+        y, x = np.mgrid[0:h, 0:w]
+        img = np.stack([(x * 3 + y) & 255, (x + 2 * y) & 255, (x * y) & 255, (x ^ y) & 255], axis=-1).astype(np.uint8)
+        img[h // 2:] = rng.integers(0, 256, img[h // 2:].shape, dtype=np.uint8)
+    return img
+
+
+@pytest.mark.parametrize("h,w", [(1, 1), (3, 5), (17, 255), (16, 256), (33, 257), (64, 1000), (5, 5000), (270, 480)])
+@pytest.mark.parametrize("pc", [3, 4])
+@pytest.mark.parametrize("kind", ["noise", "mixed"])
+def test_png_pack_is_bit_exact(lrp, ctx, h, w, pc, kind):
+    import torch
+    img = rgba_image(h, w, h * 1000 + w, kind)
+    got = ctx.png_pack(torch.from_numpy(img).cuda(), pc)
+    torch.cuda.synchronize()
+    want = co.png_filter_minsum(img[..., :pc])
+    got = got.cpu().numpy().reshape(h, 1 + pc * w)
+    assert (got[:, 0] == want[:, 0]).all(), "filter types differ in rows %s" % np.nonzero(got[:, 0] != want[:, 0])[0][:8]
+    assert (got == want).all()
+
+
+@pytest.mark.parametrize("c,h,w", [(1, 1, 1), (3, 16, 8), (3, 40, 33), (4, 17, 64), (5, 50, 7), (4, 31, 1001),
+                                   (3, 135, 240), (5, 16, 16)])
+def test_exr_pack_is_bit_exact(lrp, ctx, c, h, w):
+    import torch
+    planes = np.random.default_rng(c * h + w).integers(0, 65536, (c, h, w), dtype=np.uint16)
+    got = ctx.exr_pack(torch.from_numpy(planes.view(np.int16)).cuda())
+    torch.cuda.synchronize()
+    assert (got.cpu().numpy() == co.exr_pack(planes)).all()
+
+
+def test_full_size_pack_properties(lrp, ctx):
+    """c2 / c4 output sizes: size-independent checks — every row unfilters to the sink (type 0/2 rows are checked in
+    numpy, all rows through zlib + the reference reader), the EXR stream inverts to the planes."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(11)
+    rgba = torch.randint(0, 256, (2160, 3840, 4), dtype=torch.uint8, device="cuda", generator=g)
+    rgba[:1080] = (rgba[:1080] // 64) * 64  # compressible half
+    rgba[..., 3] = 255
+    packed = ctx.png_pack(rgba, 3).cpu().numpy()
+    png = lrp.png_assemble(packed, 3840, 2160, 3, 1, 16)
+    ref = ol.reference_lodepng()
+    img = rgba.cpu().numpy()
+    if ref is not None:
+        assert (ref.decode(png) == img).all()
+    else:
+        from PIL import Image
+        import io
+        assert (np.asarray(Image.open(io.BytesIO(png)).convert("RGB")) == img[..., :3]).all()
+    planes = torch.randint(0, 65536, (4, 2160, 3840), dtype=torch.int32, device="cuda", generator=g).to(torch.int16)
+    planes[:, ::2] = 15360  # 1.0h rows: compressible
+    exr = lrp.exr_assemble(ctx.exr_pack(planes).cpu().numpy(), 3840, 2160, 4, 1, 16)
+    names, data = co.exr_decode(exr)
+    assert (co.exr_to_planes(names, data, 4) == planes.cpu().numpy().view(np.uint16)).all()
+
+
+def test_reproject_then_save_png_and_exr(lrp, ctx, tmp_path):
+    """the reference's tail: reproject -> save_png / save_exr, here kernel sink -> file; the files are read back with the
+    reference's PNG reader and with the OpenEXR library and must hold the sink's samples."""
+    import torch
+    orc = ol.oracle()
+    w, h, W, H = 256, 128, 160, 90
+    rng = np.random.default_rng(2)
+    rot = orc.rotation_from_degrees(30, 20, 10)
+    il, olens = ol.erect(), ol.rect(18.0, 36.0, W, H)
+    p = lrp.make_params(1, lrp.BICUBIC, rot, None)
+    # PNG path
+    src = torch.from_numpy(rng.integers(0, 256, (h, w, 4), dtype=np.uint8)).cuda()
+    dst = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
+    ctx.reproject(src, lrp.lens_from(il), lrp.FMT_U8_RGBA, dst, lrp.lens_from(olens), lrp.FMT_U8_RGBA, p)
+    path = str(tmp_path / "out.png")
+    ctx.save_png(dst, path, 3, 6, 4)
+    sink = dst.cpu().numpy()
+    want = orc.png_encode(orc.reproject(orc.png_decode(src.cpu().numpy()), il, olens, W, H, 1, ol.BICUBIC, rot))
+    assert (sink == want).all()
+    ref = ol.reference_lodepng()
+    data = open(path, "rb").read()
+    got = ref.decode(data) if ref is not None else np.dstack([co.png_decode(data), np.full((H, W), 255, np.uint8)])
+    assert (got == sink).all()
+    # EXR path (RGBZ: the fourth plane is written as "A", as save_exr does)
+    srcf = torch.from_numpy(rng.random((4, h, w), dtype=np.float32)).cuda().to(torch.float16)
+    dstf = torch.empty((4, H, W), dtype=torch.float16, device="cuda")
+    ctx.reproject(srcf, lrp.lens_from(il), lrp.FMT_F16_PLANAR, dstf, lrp.lens_from(olens), lrp.FMT_F16_PLANAR, p)
+    path = str(tmp_path / "out.exr")
+    ctx.save_exr(dstf, path, 9, 4)
+    sinkf = dstf.cpu().numpy()
+    names, filedata = co.exr_decode(open(path, "rb").read())
+    assert names == ["A", "B", "G", "R"]
+    assert (co.exr_to_planes(names, filedata, 4) == sinkf.view(np.uint16)).all()
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    try:
+        import cv2
+    except ImportError:
+        return
+    img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    assert img is not None and img.shape == (H, W, 4)
+    for k, pl in enumerate([2, 1, 0, 3]):
+        a, b = img[..., k], sinkf[pl].astype(np.float32)
+        assert ((a == b) | (np.isnan(a) & np.isnan(b))).all()
