@@ -1,0 +1,613 @@
+// lrp_deflate.cu — the entropy coder of the encode side ON THE DEVICE.
+//
+// The reference's writers end in a CPU deflate: lodepng's own (save_png, src/image_formats.cpp:166-167) and zlib at
+// level 9 inside OpenEXR (save_exr, :332).  That deflate is 66 % / 82 % of the reference's wall time per frame and,
+// once the reprojection itself takes 0.2 ms, all of it.  Here the packed streams of lrp_codec.cu (filtered PNG scan
+// lines / predicted EXR byte planes) are deflated by the GPU into streams every inflate implementation accepts
+// (RFC 1950 / 1951), so that what crosses PCIe is the COMPRESSED file body:
+//
+//   * the stream is cut into bands of 32 KB; one CTA per band builds the band's own canonical Huffman code
+//     (histogram in shared memory -> bitonic sort -> two-queue Huffman merge -> code lengths) and emits ONE dynamic
+//     block of literals (no LZ77 matches: on filtered photographic scan lines a Huffman-only block is as small as
+//     zlib's level 6 output or smaller — tools/bench_encode.py prints both sizes);
+//   * the code is length-limited by construction: symbol weights are floored at total / 1024, which bounds the depth
+//     of a Huffman tree at log_phi(1280) < 15 (Katona–Nemetz), the limit of deflate;
+//   * every band ends with an empty stored block (the zlib "sync flush" marker), i.e. on a byte boundary, so bands
+//     are concatenated with byte copies; a band that would not shrink is emitted as a stored block;
+//   * Adler-32 is computed per band and combined per stream on the device.
+//   * a second, small kernel lays the bands of every stream out back to back behind the 2-byte zlib header and
+//     appends the final empty block + the stream's Adler-32: PNG = one stream (the IDAT payload), EXR = one stream per
+//     block of 16 scan lines.
+// The host adds the container bytes only (PNG chunk framing + CRC-32, EXR header + offset table).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h> // crc32 for the PNG chunk framing (host)
+
+#include <algorithm>
+#include <chrono>
+#include <vector>
+
+#include "../../include/lrp.h"
+
+extern "C" int lrp_ctx_phys_device_(const lrp_ctx *ctx); // lrp_api.cu
+
+namespace lrp {
+
+constexpr int DF_BAND = 32768;                  // input bytes per band (<= 65535: a stored block must hold one)
+constexpr int DF_THREADS = 256;
+constexpr int DF_CHUNK = DF_BAND / DF_THREADS;  // bytes per thread
+constexpr int DF_SLOT = DF_BAND + 64;           // output bytes reserved per band
+constexpr int DF_SYMS = 257;                    // literals + end-of-block
+constexpr int DF_HDR_BITS = 3 + 5 + 5 + 4 + 19 * 3 + DF_SYMS * 4 + 4;
+constexpr unsigned ADLER_MOD = 65521u;
+
+struct DeflateParams {
+  const unsigned char *in; // n bytes, streams of stream_bytes (the last one may be shorter)
+  size_t n, stream_bytes;
+  unsigned bands_per_stream, n_streams;
+  unsigned char *slots;    // n_bands x DF_SLOT
+  unsigned *band_len;      // bytes emitted per band
+  unsigned *band_adler;    // Adler-32 of the band's input, started from 1
+  unsigned *band_in;       // input bytes of the band
+};
+
+struct BitWriter { // LSB-first bit packing into zero-initialised shared words; neighbours share words -> atomicOr
+  unsigned *words;
+  unsigned w;
+  unsigned long long acc;
+  unsigned fill;
+  __device__ BitWriter(unsigned *base, unsigned bit_offset) : words(base), w(bit_offset >> 5), acc(0), fill(bit_offset & 31) {}
+  __device__ void put(unsigned bits, unsigned n) {
+    acc |= (unsigned long long)bits << fill;
+    fill += n;
+    if (fill >= 32) {
+      atomicOr(words + w, (unsigned)acc);
+      ++w;
+      acc >>= 32;
+      fill -= 32;
+    }
+  }
+  __device__ void flush() {
+    if (fill > 0) atomicOr(words + w, (unsigned)acc);
+  }
+};
+
+__device__ __forceinline__ unsigned reverse_bits(unsigned code, unsigned len) { return __brev(code) >> (32 - len); }
+
+__global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateParams P) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned char *band = smem;                               // DF_BAND
+  unsigned *outw = (unsigned *)(smem + DF_BAND);            // DF_SLOT bytes
+  __shared__ unsigned hist[512];                            // counts, then sort keys (weight << 9 | symbol)
+  __shared__ unsigned short parent[2 * DF_SYMS];
+  __shared__ unsigned nodew[2 * DF_SYMS];
+  __shared__ unsigned char depth[2 * DF_SYMS];
+  __shared__ unsigned codelen[DF_SYMS];                     // reversed code << 4 | length
+  __shared__ unsigned warp_tot[DF_THREADS / 32];
+  __shared__ unsigned long long red[2][DF_THREADS / 32];
+
+  const unsigned b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const unsigned s = b / P.bands_per_stream, k = b % P.bands_per_stream;
+  const size_t s_begin = (size_t)s * P.stream_bytes;
+  const size_t s_end = s_begin + P.stream_bytes < P.n ? s_begin + P.stream_bytes : P.n;
+  const size_t start = s_begin + (size_t)k * DF_BAND;
+  const unsigned len = start >= s_end ? 0u : (unsigned)(s_end - start < (size_t)DF_BAND ? s_end - start : (size_t)DF_BAND);
+  unsigned char *slot = P.slots + (size_t)b * DF_SLOT;
+  if (len == 0) { // a short last stream has fewer bands
+    if (tid == 0) {
+      P.band_len[b] = 0;
+      P.band_adler[b] = 1;
+      P.band_in[b] = 0;
+    }
+    return;
+  }
+
+  // ---- load the band, clear the output words and the histogram ----
+  const unsigned char *src = P.in + start;
+  if ((((size_t)src) & 15) == 0) {
+    for (unsigned i = tid; i < (len + 15) / 16; i += DF_THREADS) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (16 * i + 16 <= len) v = __ldg((const uint4 *)src + i);
+      else
+        for (unsigned j = 0; 16 * i + j < len; ++j) ((unsigned char *)&v)[j] = src[16 * i + j];
+      ((uint4 *)band)[i] = v;
+    }
+  } else {
+    for (unsigned i = tid; i < len; i += DF_THREADS) band[i] = src[i];
+  }
+  for (unsigned i = tid; i < DF_SLOT / 4; i += DF_THREADS) outw[i] = 0;
+  for (unsigned i = tid; i < 512; i += DF_THREADS) hist[i] = 0;
+  __syncthreads();
+
+  // ---- histogram + Adler-32 partial sums over this thread's chunk ----
+  const unsigned base = tid * DF_CHUNK;
+  const unsigned cnt = base >= len ? 0u : (len - base < (unsigned)DF_CHUNK ? len - base : (unsigned)DF_CHUNK);
+  unsigned long long s1 = 0, s2 = 0;
+  const unsigned rot = cnt ? (lane * 4u) % cnt : 0u; // rotated start: the lanes of a warp hit different banks
+  for (unsigned j = 0; j < cnt; ++j) {
+    unsigned jj = j + rot;
+    if (jj >= cnt) jj -= cnt;
+    const unsigned d = band[base + jj];
+    atomicAdd(&hist[d], 1u);
+    s1 += d;
+    s2 += (unsigned long long)(cnt - jj) * d;
+  }
+  // b = len + sum_i (len - i) d_i  with  (len - base - j) = (len - base - cnt) + (cnt - j)
+  unsigned long long pa = s1, pb = cnt ? ((unsigned long long)(len - base - cnt) * s1 + s2) % ADLER_MOD : 0ull;
+  for (int o = 16; o > 0; o >>= 1) {
+    pa += __shfl_down_sync(0xffffffffu, pa, o);
+    pb += __shfl_down_sync(0xffffffffu, pb, o);
+  }
+  if (lane == 0) {
+    red[0][wrp] = pa;
+    red[1][wrp] = pb;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long a = 1, bb = len;
+    for (int w = 0; w < DF_THREADS / 32; ++w) {
+      a += red[0][w];
+      bb += red[1][w];
+    }
+    P.band_adler[b] = (unsigned)((bb % ADLER_MOD) << 16) | (unsigned)(a % ADLER_MOD);
+    P.band_in[b] = len;
+    hist[256] = 1; // end-of-block
+  }
+  __syncthreads();
+
+  // ---- sort keys: weight floored at total / 1024 (depth bound), absent symbols last ----
+  {
+    const unsigned floor_w = (len + 1 + 1023) / 1024;
+    for (unsigned i = tid; i < 512; i += DF_THREADS) {
+      const unsigned c = hist[i];
+      hist[i] = (i < DF_SYMS && c > 0) ? ((c > floor_w ? c : floor_w) << 9) | i : 0xFFFFFFFFu;
+    }
+  }
+  __syncthreads();
+  for (unsigned size = 2; size <= 512; size <<= 1) {
+    for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+      const unsigned i = 2 * tid - (tid & (stride - 1)); // the lower index of this thread's pair
+      const unsigned j = i + stride;
+      const bool up = (i & size) == 0;
+      const unsigned a = hist[i], c = hist[j];
+      if ((a > c) == up) {
+        hist[i] = c;
+        hist[j] = a;
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- Huffman merge (two queues), depths, canonical codes: one thread, ~10 us ----
+  if (tid == 0) {
+    unsigned m = 0;
+    while (m < DF_SYMS && hist[m] != 0xFFFFFFFFu) ++m; // present symbols (>= 2: a literal and end-of-block)
+    unsigned li = 0, ii = m, nn = m;
+    for (unsigned k2 = 0; k2 + 1 < m; ++k2) {
+      unsigned pick[2];
+      for (int t = 0; t < 2; ++t) {
+        const bool leaf = li < m && (ii >= nn || (hist[li] >> 9) <= nodew[ii]);
+        pick[t] = leaf ? li++ : ii++;
+      }
+      const unsigned wa = pick[0] < m ? hist[pick[0]] >> 9 : nodew[pick[0]];
+      const unsigned wb = pick[1] < m ? hist[pick[1]] >> 9 : nodew[pick[1]];
+      nodew[nn] = wa + wb;
+      parent[pick[0]] = (unsigned short)nn;
+      parent[pick[1]] = (unsigned short)nn;
+      ++nn;
+    }
+    depth[2 * m - 2] = 0;
+    for (int node = (int)(2 * m - 3); node >= 0; --node) depth[node] = depth[parent[node]] + 1;
+    unsigned bl_count[16], next_code[16];
+    for (int i = 0; i < 16; ++i) bl_count[i] = 0;
+    for (unsigned i = 0; i < DF_SYMS; ++i) codelen[i] = 0;
+    for (unsigned i = 0; i < m; ++i) {
+      unsigned d = depth[i];
+      if (d > 15) d = 15; // unreachable by the depth bound; keeps the stream well-formed rather than undefined
+      codelen[hist[i] & 511u] = d;
+      ++bl_count[d];
+    }
+    unsigned code = 0;
+    bl_count[0] = 0;
+    for (int bits = 1; bits <= 15; ++bits) {
+      code = (code + bl_count[bits - 1]) << 1;
+      next_code[bits] = code;
+    }
+    for (unsigned i = 0; i < DF_SYMS; ++i) {
+      const unsigned l = codelen[i];
+      if (l) codelen[i] = (reverse_bits(next_code[l]++, l) << 4) | l;
+    }
+  }
+  __syncthreads();
+
+  // ---- payload size: per-thread bit counts, exclusive scan ----
+  unsigned bits = 0;
+  for (unsigned j = 0; j < cnt; ++j) {
+    unsigned jj = j + rot;
+    if (jj >= cnt) jj -= cnt;
+    bits += codelen[band[base + jj]] & 15u;
+  }
+  unsigned incl = bits;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (unsigned)o) incl += v;
+  }
+  if (lane == 31) warp_tot[wrp] = incl;
+  __syncthreads();
+  unsigned warp_base = 0, all = 0;
+  for (int w = 0; w < DF_THREADS / 32; ++w) {
+    if (w < (int)wrp) warp_base += warp_tot[w];
+    all += warp_tot[w];
+  }
+  const unsigned eob = codelen[256];
+  const unsigned total_bits = DF_HDR_BITS + all + (eob & 15u);
+  const unsigned dyn_bytes = (total_bits + 3 + 7) / 8 + 4; // + empty stored block: 3 header bits, pad, 00 00 FF FF
+  const bool stored = dyn_bytes >= len + 5;
+  unsigned out_bytes;
+
+  if (!stored) {
+    if (tid == 0) { // block header: BFINAL=0, BTYPE=dynamic, HLIT=0 (257 codes), HDIST=0 (1 code), HCLEN=15 (19 lengths)
+      BitWriter bw(outw, 0);
+      bw.put(0u | (2u << 1), 3);
+      bw.put(0, 5);
+      bw.put(0, 5);
+      bw.put(15, 4);
+      // code-length code: symbols 0..15 get 4 bits each (a complete code), the run-length symbols 16, 17, 18 none;
+      // transmitted in the order 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15
+      for (int i = 0; i < 19; ++i) bw.put(i < 3 ? 0u : 4u, 3);
+      for (unsigned i = 0; i < DF_SYMS; ++i) bw.put(reverse_bits(codelen[i] & 15u, 4), 4); // canonical: code == symbol
+      bw.put(reverse_bits(1u, 4), 4); // one distance code of one bit (never used: the block has no matches)
+      bw.flush();
+    }
+    BitWriter bw(outw, DF_HDR_BITS + warp_base + incl - bits);
+    for (unsigned j = 0; j < cnt; ++j) {
+      const unsigned c = codelen[band[base + j]];
+      bw.put(c >> 4, c & 15u);
+    }
+    if (cnt > 0 && base + cnt == len) bw.put(eob >> 4, eob & 15u); // the thread holding the last byte closes the block
+    bw.flush();
+    __syncthreads();
+    const unsigned pos = (total_bits + 3 + 7) / 8; // stored-block header bits are zeros already
+    if (tid == 0) {
+      unsigned char *ob = (unsigned char *)outw;
+      ob[pos] = 0, ob[pos + 1] = 0, ob[pos + 2] = 0xFF, ob[pos + 3] = 0xFF;
+    }
+    out_bytes = pos + 4;
+  } else { // BFINAL=0, BTYPE=stored (byte 0), LEN, ~LEN, the bytes
+    unsigned char *ob = (unsigned char *)outw;
+    if (tid == 0) {
+      ob[0] = 0;
+      ob[1] = (unsigned char)(len & 255u), ob[2] = (unsigned char)(len >> 8);
+      ob[3] = (unsigned char)(~len & 255u), ob[4] = (unsigned char)((~len >> 8) & 255u);
+    }
+    for (unsigned i = tid; i < len; i += DF_THREADS) ob[5 + i] = band[i];
+    out_bytes = len + 5;
+  }
+  __syncthreads();
+  for (unsigned i = tid; i < (out_bytes + 15) / 16; i += DF_THREADS) ((uint4 *)slot)[i] = ((const uint4 *)outw)[i];
+  if (tid == 0) P.band_len[b] = out_bytes;
+}
+
+// Per stream: offsets of its bands in the compact output, the combined Adler-32, the stream's total size.
+// Compact layout of stream s, starting at stream_off[s]:  78 01 | bands ... | 03 00 | adler32 (big endian)
+struct LayoutParams {
+  const unsigned *band_len, *band_adler, *band_in;
+  unsigned bands_per_stream, n_streams;
+  unsigned long long *band_off;   // n_bands: absolute byte offset of each band in the compact buffer
+  unsigned long long *stream_off; // n_streams + 1
+  unsigned *stream_adler;
+};
+
+__global__ void deflate_layout_kernel(const LayoutParams P) {
+  // one thread per stream computes its size and checksum; thread 0 then prefix-sums the streams (<= a few thousand)
+  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_streams; s += gridDim.x * blockDim.x) {
+    unsigned long long bytes = 2;
+    unsigned a = 1, b = 0;
+    for (unsigned k = 0; k < P.bands_per_stream; ++k) {
+      const unsigned i = s * P.bands_per_stream + k;
+      P.band_off[i] = bytes; // relative for now
+      bytes += P.band_len[i];
+      const unsigned ad = P.band_adler[i], n2 = P.band_in[i] % ADLER_MOD;
+      // adler32_combine: a' = a + a2 - 1,  b' = b + b2 + len2 * (a - 1)   (mod 65521)
+      const unsigned a2 = ad & 0xffffu, b2 = ad >> 16;
+      b = (unsigned)(((unsigned long long)b + b2 + (unsigned long long)n2 * ((a + ADLER_MOD - 1) % ADLER_MOD)) % ADLER_MOD);
+      a = (a + a2 + ADLER_MOD - 1) % ADLER_MOD;
+    }
+    P.stream_adler[s] = (b << 16) | a;
+    P.stream_off[s + 1] = bytes + 2 + 4; // size for now
+  }
+}
+__global__ void deflate_offsets_kernel(const LayoutParams P) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long off = 0;
+    P.stream_off[0] = 0;
+    for (unsigned s = 0; s < P.n_streams; ++s) {
+      const unsigned long long size = P.stream_off[s + 1];
+      P.stream_off[s + 1] = off + size;
+      off += size;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) deflate_gather_kernel(const LayoutParams P, const unsigned char *slots,
+                                                             unsigned char *out) {
+  const unsigned b = blockIdx.x, s = b / P.bands_per_stream, k = b % P.bands_per_stream;
+  const unsigned long long sbase = P.stream_off[s];
+  unsigned char *dst = out + sbase + P.band_off[b];
+  const unsigned char *src = slots + (size_t)b * DF_SLOT;
+  const unsigned n = P.band_len[b];
+  // bytes up to the first 16-byte boundary of dst, then aligned 16-byte stores fed by unaligned 4-byte loads
+  unsigned head = (unsigned)((16 - ((size_t)dst & 15)) & 15);
+  if (head > n) head = n;
+  for (unsigned i = threadIdx.x; i < head; i += blockDim.x) dst[i] = src[i];
+  const unsigned body = (n - head) / 16;
+  for (unsigned i = threadIdx.x; i < body; i += blockDim.x) {
+    const unsigned char *p = src + head + 16 * i;
+    uint4 v;
+    unsigned char *vb = (unsigned char *)&v;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) vb[j] = p[j];
+    *(uint4 *)(dst + head + 16 * i) = v;
+  }
+  for (unsigned i = head + 16 * body + threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+  if (k == 0 && threadIdx.x == 0) { // stream framing
+    unsigned char *st = out + sbase;
+    st[0] = 0x78, st[1] = 0x01; // deflate / 32 KB window, check bits, "fastest" hint
+    unsigned char *tail = out + P.stream_off[s + 1] - 6;
+    const unsigned ad = P.stream_adler[s];
+    tail[0] = 0x03, tail[1] = 0x00; // final block: fixed Huffman, end-of-block only
+    tail[2] = (unsigned char)(ad >> 24), tail[3] = (unsigned char)(ad >> 16), tail[4] = (unsigned char)(ad >> 8), tail[5] = (unsigned char)ad;
+  }
+}
+
+} // namespace lrp
+
+using namespace lrp;
+
+// ---- the encoder object: device + pinned workspaces for frames up to a maximum size ----
+struct lrp_encoder {
+  lrp_ctx *ctx = nullptr;
+  int device = 0;
+  size_t cap_packed = 0, cap_bands = 0, cap_streams = 0;
+  unsigned char *d_packed = nullptr, *d_slots = nullptr, *d_compact = nullptr, *h_compact = nullptr;
+  unsigned *d_band_len = nullptr, *d_band_adler = nullptr, *d_band_in = nullptr, *d_stream_adler = nullptr;
+  unsigned long long *d_band_off = nullptr, *d_stream_off = nullptr, *h_stream_off = nullptr;
+  std::vector<unsigned char> file;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  double last_ms[3] = {0, 0, 0}; // device (pack + deflate + layout), copy of the compressed body, container on the host
+};
+
+static size_t compact_bound(size_t n, size_t bands, size_t streams) { return n + 5 * bands + 16 * bands + 8 * streams + 64; }
+
+static void encoder_free(lrp_encoder *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaFree(e->d_packed), cudaFree(e->d_slots), cudaFree(e->d_compact);
+  cudaFree(e->d_band_len), cudaFree(e->d_band_adler), cudaFree(e->d_band_in), cudaFree(e->d_stream_adler);
+  cudaFree(e->d_band_off), cudaFree(e->d_stream_off);
+  if (e->h_compact) cudaFreeHost(e->h_compact);
+  if (e->h_stream_off) cudaFreeHost(e->h_stream_off);
+  for (auto ev : e->ev)
+    if (ev) cudaEventDestroy(ev);
+  delete e;
+}
+
+// Runs pack output `d_packed` (n bytes, streams of stream_bytes) through the deflate kernels and brings the compact
+// result to the encoder's pinned buffer.  On return h_stream_off[0..n_streams] delimit the zlib streams in h_compact.
+static int deflate_to_host(lrp_encoder *e, size_t n, size_t stream_bytes, cudaStream_t st) {
+  const unsigned bps = (unsigned)((stream_bytes + DF_BAND - 1) / DF_BAND);
+  const unsigned n_streams = (unsigned)((n + stream_bytes - 1) / stream_bytes);
+  const unsigned n_bands = bps * n_streams;
+  if (n > e->cap_packed || n_bands > e->cap_bands || n_streams > e->cap_streams) return LRP_E_BAD_ARG;
+  DeflateParams D;
+  D.in = e->d_packed, D.n = n, D.stream_bytes = stream_bytes, D.bands_per_stream = bps, D.n_streams = n_streams;
+  D.slots = e->d_slots, D.band_len = e->d_band_len, D.band_adler = e->d_band_adler, D.band_in = e->d_band_in;
+  const size_t smem = DF_BAND + DF_SLOT;
+  static thread_local int configured = -1;
+  if (configured != e->device) {
+    if (cudaFuncSetAttribute(deflate_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return LRP_E_CUDA;
+    configured = e->device;
+  }
+  deflate_band_kernel<<<n_bands, DF_THREADS, smem, st>>>(D);
+  LayoutParams L;
+  L.band_len = e->d_band_len, L.band_adler = e->d_band_adler, L.band_in = e->d_band_in;
+  L.bands_per_stream = bps, L.n_streams = n_streams;
+  L.band_off = e->d_band_off, L.stream_off = e->d_stream_off, L.stream_adler = e->d_stream_adler;
+  deflate_layout_kernel<<<(n_streams + 127) / 128, 128, 0, st>>>(L);
+  deflate_offsets_kernel<<<1, 32, 0, st>>>(L);
+  deflate_gather_kernel<<<n_bands, 256, 0, st>>>(L, e->d_slots, e->d_compact);
+  cudaEventRecord(e->ev[1], st);
+  if (cudaMemcpyAsync(e->h_stream_off, e->d_stream_off, (n_streams + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess)
+    return LRP_E_CUDA;
+  const size_t total = (size_t)e->h_stream_off[n_streams];
+  if (cudaMemcpyAsync(e->h_compact, e->d_compact, total, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaEventRecord(e->ev[2], st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+    return LRP_E_CUDA;
+  float a = 0, b = 0;
+  cudaEventElapsedTime(&a, e->ev[0], e->ev[1]);
+  cudaEventElapsedTime(&b, e->ev[1], e->ev[2]);
+  e->last_ms[0] = a, e->last_ms[1] = b;
+  return LRP_OK;
+}
+
+static void put32be(std::vector<unsigned char> &v, uint32_t x) {
+  v.push_back(x >> 24), v.push_back(x >> 16), v.push_back(x >> 8), v.push_back(x);
+}
+
+extern "C" {
+
+int lrp_encoder_create(lrp_ctx *ctx, int32_t max_width, int32_t max_height, int32_t max_channels, lrp_encoder **out) {
+  if (!ctx || !out || max_width <= 0 || max_height <= 0 || max_channels < 1 || max_channels > 5) return LRP_E_BAD_ARG;
+  *out = nullptr;
+  const int dev = lrp_ctx_phys_device_(ctx);
+  if (cudaSetDevice(dev) != cudaSuccess) return LRP_E_CUDA;
+  lrp_encoder *e = new lrp_encoder();
+  e->ctx = ctx, e->device = dev;
+  const size_t png_n = lrp_png_packed_bytes(max_width, max_height, 4);
+  const size_t exr_n = (size_t)max_width * max_height * max_channels * 2;
+  const size_t exr_stream = (size_t)16 * max_channels * max_width * 2;
+  e->cap_packed = std::max(png_n, exr_n);
+  e->cap_streams = std::max<size_t>(1, ((size_t)max_height + 15) / 16);
+  e->cap_bands = std::max((png_n + DF_BAND - 1) / DF_BAND, e->cap_streams * ((exr_stream + DF_BAND - 1) / DF_BAND)) + 1;
+  const size_t cb = compact_bound(e->cap_packed, e->cap_bands, e->cap_streams);
+  bool ok = cudaMalloc(&e->d_packed, e->cap_packed) == cudaSuccess &&
+            cudaMalloc(&e->d_slots, e->cap_bands * DF_SLOT) == cudaSuccess && cudaMalloc(&e->d_compact, cb) == cudaSuccess &&
+            cudaMalloc(&e->d_band_len, e->cap_bands * 4) == cudaSuccess && cudaMalloc(&e->d_band_adler, e->cap_bands * 4) == cudaSuccess &&
+            cudaMalloc(&e->d_band_in, e->cap_bands * 4) == cudaSuccess && cudaMalloc(&e->d_stream_adler, e->cap_streams * 4) == cudaSuccess &&
+            cudaMalloc(&e->d_band_off, e->cap_bands * 8) == cudaSuccess && cudaMalloc(&e->d_stream_off, (e->cap_streams + 1) * 8) == cudaSuccess &&
+            cudaMallocHost(&e->h_compact, cb) == cudaSuccess && cudaMallocHost(&e->h_stream_off, (e->cap_streams + 1) * 8) == cudaSuccess &&
+            cudaEventCreate(&e->ev[0]) == cudaSuccess && cudaEventCreate(&e->ev[1]) == cudaSuccess && cudaEventCreate(&e->ev[2]) == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    encoder_free(e);
+    return LRP_E_OOM;
+  }
+  *out = e;
+  return LRP_OK;
+}
+
+int lrp_encoder_destroy(lrp_encoder *e) {
+  if (!e) return LRP_E_BAD_ARG;
+  encoder_free(e);
+  return LRP_OK;
+}
+
+int lrp_encoder_png(lrp_encoder *e, const void *rgba_dev, int32_t width, int32_t height, int32_t png_channels,
+                    void *cuda_stream, const void **file_bytes, size_t *file_size) {
+  if (!e || !rgba_dev || !file_bytes || !file_size) return LRP_E_BAD_ARG;
+  const size_t n = lrp_png_packed_bytes(width, height, png_channels);
+  if (n == 0 || n > e->cap_packed) return LRP_E_BAD_ARG;
+  if (cudaSetDevice(e->device) != cudaSuccess) return LRP_E_CUDA;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  cudaEventRecord(e->ev[0], st);
+  int rc = lrp_png_pack_device(e->ctx, rgba_dev, width, height, png_channels, e->d_packed, cuda_stream);
+  if (rc != LRP_OK) return rc;
+  rc = deflate_to_host(e, n, n, st);
+  if (rc != LRP_OK) return rc;
+  const auto t_host = std::chrono::steady_clock::now();
+  const size_t zn = (size_t)e->h_stream_off[1];
+  std::vector<unsigned char> &f = e->file;
+  f.clear();
+  f.reserve(zn + 128 + 12 * (zn / 0x7fffffffu + 1));
+  static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+  f.insert(f.end(), sig, sig + 8);
+  auto chunk = [&f](const char *type, const unsigned char *data, size_t len) {
+    put32be(f, (uint32_t)len);
+    uLong c = crc32(0L, (const Bytef *)type, 4);
+    f.insert(f.end(), type, type + 4);
+    for (size_t p = 0; p < len; p += 1u << 30) c = crc32(c, data + p, (uInt)std::min<size_t>(len - p, 1u << 30));
+    if (len) f.insert(f.end(), data, data + len);
+    put32be(f, (uint32_t)c);
+  };
+  unsigned char ihdr[13];
+  const uint32_t wh[2] = {(uint32_t)width, (uint32_t)height};
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 4; ++j) ihdr[4 * i + j] = (unsigned char)(wh[i] >> (24 - 8 * j));
+  ihdr[8] = 8, ihdr[9] = png_channels == 3 ? 2 : 6, ihdr[10] = 0, ihdr[11] = 0, ihdr[12] = 0;
+  chunk("IHDR", ihdr, 13);
+  for (size_t p = 0; p < zn; p += 0x7fffffffu) chunk("IDAT", e->h_compact + p, std::min<size_t>(zn - p, 0x7fffffffu));
+  chunk("IEND", nullptr, 0);
+  *file_bytes = f.data();
+  *file_size = f.size();
+  e->last_ms[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host).count();
+  return LRP_OK;
+}
+
+int lrp_encoder_exr(lrp_encoder *e, const void *half_planar_dev, int32_t width, int32_t height, int32_t channels,
+                    void *cuda_stream, const void **file_bytes, size_t *file_size) {
+  if (!e || !half_planar_dev || !file_bytes || !file_size) return LRP_E_BAD_ARG;
+  const size_t n = lrp_exr_packed_bytes(width, height, channels);
+  if (n == 0 || n > e->cap_packed) return LRP_E_BAD_ARG;
+  if (cudaSetDevice(e->device) != cudaSuccess) return LRP_E_CUDA;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  cudaEventRecord(e->ev[0], st);
+  int rc = lrp_exr_pack_device(e->ctx, half_planar_dev, width, height, channels, e->d_packed, cuda_stream);
+  if (rc != LRP_OK) return rc;
+  const size_t line_bytes = (size_t)channels * width * 2, stream_bytes = 16 * line_bytes;
+  rc = deflate_to_host(e, n, stream_bytes, st);
+  if (rc != LRP_OK) return rc;
+  const auto t_host = std::chrono::steady_clock::now();
+  const size_t blocks = ((size_t)height + 15) / 16;
+  // blocks that did not shrink must be stored RAW (un-predicted, interleaved): fetch their packed bytes and invert
+  std::vector<std::vector<unsigned char>> raw(blocks);
+  for (size_t b = 0; b < blocks; ++b) {
+    const size_t lines = std::min<size_t>(16, (size_t)height - 16 * b), raw_n = lines * line_bytes;
+    const size_t zn = (size_t)(e->h_stream_off[b + 1] - e->h_stream_off[b]);
+    if (zn < raw_n) continue;
+    std::vector<unsigned char> t(raw_n);
+    if (cudaMemcpyAsync(t.data(), e->d_packed + b * stream_bytes, raw_n, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess)
+      return LRP_E_CUDA;
+    for (size_t i = 1; i < raw_n; ++i) t[i] = (unsigned char)(t[i - 1] + t[i] - 128);
+    raw[b].resize(raw_n);
+    const size_t h = (raw_n + 1) / 2;
+    for (size_t i = 0; i < raw_n; ++i) raw[b][i] = (i & 1) ? t[h + i / 2] : t[i / 2];
+  }
+  { // container: Imf::Header(width, height) defaults + channel list + ZIP_COMPRESSION, offset table, blocks
+    std::vector<unsigned char> &f = e->file;
+    f.clear();
+    f.reserve((size_t)e->h_stream_off[blocks] + 16 * blocks + 1024);
+    const unsigned char magic[8] = {0x76, 0x2f, 0x31, 0x01, 2, 0, 0, 0};
+    f.insert(f.end(), magic, magic + 8);
+    auto attr = [&f](const char *name, const char *type, const void *data, uint32_t len) {
+      f.insert(f.end(), name, name + strlen(name) + 1);
+      f.insert(f.end(), type, type + strlen(type) + 1);
+      f.insert(f.end(), (const unsigned char *)&len, (const unsigned char *)&len + 4);
+      f.insert(f.end(), (const unsigned char *)data, (const unsigned char *)data + len);
+    };
+    static const char all[5] = {'R', 'G', 'B', 'A', 'Z'}; // save_exr names plane i "RGBAZ"[i]; the file lists them sorted
+    int idx[5] = {0, 1, 2, 3, 4};
+    std::sort(idx, idx + channels, [](int a, int b) { return all[a] < all[b]; });
+    std::vector<unsigned char> ch;
+    for (int k = 0; k < channels; ++k) {
+      ch.push_back((unsigned char)all[idx[k]]), ch.push_back(0);
+      const int32_t rec[4] = {1, 0, 1, 1};
+      ch.insert(ch.end(), (const unsigned char *)rec, (const unsigned char *)rec + 16);
+    }
+    ch.push_back(0);
+    attr("channels", "chlist", ch.data(), (uint32_t)ch.size());
+    const unsigned char zip = 3, inc_y = 0;
+    attr("compression", "compression", &zip, 1);
+    const int32_t box[4] = {0, 0, width - 1, height - 1};
+    attr("dataWindow", "box2i", box, 16);
+    attr("displayWindow", "box2i", box, 16);
+    attr("lineOrder", "lineOrder", &inc_y, 1);
+    const float one = 1.0f, v2[2] = {0.0f, 0.0f};
+    attr("pixelAspectRatio", "float", &one, 4);
+    attr("screenWindowCenter", "v2f", v2, 8);
+    attr("screenWindowWidth", "float", &one, 4);
+    f.push_back(0);
+    uint64_t off = f.size() + 8 * blocks;
+    for (size_t b = 0; b < blocks; ++b) {
+      f.insert(f.end(), (const unsigned char *)&off, (const unsigned char *)&off + 8);
+      const size_t zn = raw[b].empty() ? (size_t)(e->h_stream_off[b + 1] - e->h_stream_off[b]) : raw[b].size();
+      off += 8 + zn;
+    }
+    f.reserve((size_t)off);
+    for (size_t b = 0; b < blocks; ++b) {
+      const unsigned char *data = raw[b].empty() ? e->h_compact + e->h_stream_off[b] : raw[b].data();
+      const size_t zn = raw[b].empty() ? (size_t)(e->h_stream_off[b + 1] - e->h_stream_off[b]) : raw[b].size();
+      const int32_t hdr[2] = {(int32_t)(16 * b), (int32_t)zn};
+      f.insert(f.end(), (const unsigned char *)hdr, (const unsigned char *)hdr + 8);
+      f.insert(f.end(), data, data + zn);
+    }
+    *file_bytes = f.data();
+    *file_size = f.size();
+  }
+  e->last_ms[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host).count();
+  return LRP_OK;
+}
+
+/* milliseconds of the encoder's last call: [0] device (pack + deflate + layout), [1] device->host copy of the
+ * compressed body, [2] container bytes on the host */
+int lrp_encoder_last_timing(const lrp_encoder *e, double *ms3) {
+  if (!e || !ms3) return LRP_E_BAD_ARG;
+  for (int i = 0; i < 3; ++i) ms3[i] = e->last_ms[i];
+  return LRP_OK;
+}
+
+} // extern "C"

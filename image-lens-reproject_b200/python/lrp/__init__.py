@@ -131,6 +131,11 @@ def lib():
         for f in (L.lrp_save_png_device, L.lrp_save_exr_device):
             f.argtypes = [vp, vp, i32, i32, i32, i32, i32, C.c_char_p, vp]
         L.lrp_free_bytes.argtypes = [vp]
+        L.lrp_encoder_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
+        L.lrp_encoder_destroy.argtypes = [vp]
+        L.lrp_encoder_last_timing.argtypes = [vp, C.POINTER(C.c_double)]
+        for f in (L.lrp_encoder_png, L.lrp_encoder_exr):
+            f.argtypes = [vp, vp, i32, i32, i32, vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
         _lib = L
     return _lib
 
@@ -428,6 +433,38 @@ class Context:
 
     def wait_all(self):
         check(lib().lrp_wait_all(self.h), "lrp_wait_all")
+
+
+class Encoder:
+    """lrp_encoder: the whole PNG / EXR writer on the device (pack + GPU deflate); bytes of the file come back."""
+
+    def __init__(self, ctx, max_w, max_h, max_c=4):
+        self.h, self.ctx = C.c_void_p(None), ctx
+        check(lib().lrp_encoder_create(ctx.h, max_w, max_h, max_c, C.byref(self.h)), "lrp_encoder_create")
+
+    def close(self):
+        if self.h:
+            lib().lrp_encoder_destroy(self.h)
+            self.h = C.c_void_p(None)
+
+    def _run(self, fn, t, w, h, c, stream):
+        out, n = C.c_void_p(None), C.c_size_t(0)
+        check(fn(self.h, C.c_void_p(t.data_ptr()), w, h, c, self.ctx._stream(stream), C.byref(out), C.byref(n)),
+              fn.__name__)
+        return C.string_at(out.value, n.value)
+
+    def last_timing(self):
+        """ms of the last call: (device kernels, D2H of the compressed body, host container)"""
+        ms = (C.c_double * 3)()
+        check(lib().lrp_encoder_last_timing(self.h, ms), "lrp_encoder_last_timing")
+        return tuple(ms)
+
+    def png(self, rgba_t, png_channels=3, stream=None):
+        return self._run(lib().lrp_encoder_png, rgba_t, int(rgba_t.shape[1]), int(rgba_t.shape[0]), png_channels, stream)
+
+    def exr(self, planar_t, stream=None):
+        c, h, w = (int(v) for v in planar_t.shape)
+        return self._run(lib().lrp_encoder_exr, planar_t, w, h, c, stream)
 
 
 def _assemble(fn, packed, w, h, c, level, threads):

@@ -299,6 +299,23 @@ int lrp_save_png_device(lrp_ctx *ctx, const void *rgba_dev, int32_t width, int32
 int lrp_save_exr_device(lrp_ctx *ctx, const void *half_planar_dev, int32_t width, int32_t height, int32_t channels,
                         int32_t level, int32_t threads, const char *path, void *cuda_stream);
 
+/* The whole writer on the device: pack + DEFLATE on the GPU (one dynamic-Huffman block of literals per 32 KB band,
+ * bands joined on byte boundaries with empty stored blocks, Adler-32 on the device: csrc/lrp_deflate.cu), so that
+ * only the compressed file body crosses PCIe and the host adds the container bytes.  An encoder owns device and
+ * pinned workspaces for frames up to the given size; use one per host thread.  *file_bytes points into the
+ * encoder and stays valid until its next call.  The files are plain PNG / OpenEXR-ZIP files: any reader inflates
+ * them (the reference's lodepng::decode and Imf::InputFile included) to the sink's samples. */
+typedef struct lrp_encoder lrp_encoder;
+int lrp_encoder_create(lrp_ctx *ctx, int32_t max_width, int32_t max_height, int32_t max_channels, lrp_encoder **out);
+int lrp_encoder_destroy(lrp_encoder *enc);
+int lrp_encoder_png(lrp_encoder *enc, const void *rgba_dev, int32_t width, int32_t height, int32_t png_channels,
+                    void *cuda_stream, const void **file_bytes, size_t *file_size);
+int lrp_encoder_exr(lrp_encoder *enc, const void *half_planar_dev, int32_t width, int32_t height, int32_t channels,
+                    void *cuda_stream, const void **file_bytes, size_t *file_size);
+/* milliseconds of the encoder's last call: [0] device (pack + deflate + layout kernels), [1] device->host copy of the
+ * compressed body, [2] container bytes on the host */
+int lrp_encoder_last_timing(const lrp_encoder *enc, double *ms3);
+
 /* ---- test hooks (Level-0 parity) -------------------------- */
 /* per-pixel (sx, sy) of sub-sample (0,0): out_sxy_dev = float[H*W*2] on device */
 int lrp_debug_coords(lrp_ctx *ctx, const lrp_image *in_geom, const lrp_image *out_geom,

@@ -129,3 +129,110 @@ def test_reproject_then_save_png_and_exr(lrp, ctx, tmp_path):
     for k, pl in enumerate([2, 1, 0, 3]):
         a, b = img[..., k], sinkf[pl].astype(np.float32)
         assert ((a == b) | (np.isnan(a) & np.isnan(b))).all()
+
+
+# ---- the whole writer on the device: pack + GPU deflate (csrc/lrp_deflate.cu) ----
+
+def _decode_png(data):
+    ref = ol.reference_lodepng()
+    if ref is not None:
+        return ref.decode(data)  # the reference's reader (read_png, src/image_formats.cpp:174-183)
+    img = co.png_decode(data)
+    return img if img.shape[2] == 4 else np.dstack([img, np.full(img.shape[:2], 255, np.uint8)])
+
+
+@pytest.mark.parametrize("h,w,kind", [(1, 1, "noise"), (7, 33, "mixed"), (100, 109, "noise"), (128, 256, "flat"),
+                                      (300, 500, "mixed"), (270, 480, "smooth"), (1080, 1920, "mixed")])
+@pytest.mark.parametrize("pc", [3, 4])
+def test_device_deflate_png_decodes_to_the_sink(lrp, ctx, h, w, kind, pc):
+    """bands of every kind: shorter than 32 KB, many bands, incompressible (stored blocks), two-symbol alphabets"""
+    import io
+    import torch
+    import zlib
+    from PIL import Image
+    if kind == "flat":
+        img = np.full((h, w, 4), 77, np.uint8)
+    elif kind == "smooth":
+        y, x = np.mgrid[0:h, 0:w]
+        img = np.stack([(x // 3 + y // 5) & 255, (x // 2) & 255, (y // 2) & 255, (x // 7) & 255], axis=-1).astype(np.uint8)
+    else:
+        img = rgba_image(h, w, h + w, kind)
+    if pc == 3:
+        img[..., 3] = 255
+    enc = lrp.Encoder(ctx, 1920, 1080, 4)
+    try:
+        png = enc.png(torch.from_numpy(img).cuda(), pc)
+        png2 = enc.png(torch.from_numpy(img).cuda(), pc)  # the workspaces are reused
+    finally:
+        enc.close()
+    assert png == png2
+    assert (_decode_png(png) == img).all()
+    pil = np.asarray(Image.open(io.BytesIO(png)).convert("RGBA"))  # zlib's inflate
+    assert (pil == img).all()
+    _, _, _, ctype, idat = co.png_parse(png)
+    assert ctype == (2 if pc == 3 else 6)
+    stream = zlib.decompress(idat)  # checks the Adler-32 computed on the device
+    assert stream == co.png_filter_minsum(img[..., :pc]).tobytes()
+    assert len(idat) <= len(stream) + 5 * (len(stream) // 32768 + 1) + 8, "a band never grows by more than a stored header"
+
+
+@pytest.mark.parametrize("c,h,w,finite", [(3, 16, 8, True), (4, 40, 333, True), (5, 17, 7, True), (4, 135, 240, True),
+                                          (3, 50, 1000, False), (4, 270, 480, True)])
+def test_device_deflate_exr_decodes_to_the_sink(lrp, ctx, tmp_path, c, h, w, finite):
+    import torch
+    rng = np.random.default_rng(c + h + w)
+    if finite:
+        v = (rng.random((c, h, w), dtype=np.float32) * 2).astype(np.float16)
+        v[:, ::3] = np.float16(0.25)
+        planes = v.view(np.uint16)
+    else:
+        planes = rng.integers(0, 65536, (c, h, w), dtype=np.uint16)  # incompressible: blocks are stored raw
+    enc = lrp.Encoder(ctx, 1000, 300, 5)
+    try:
+        exr = enc.exr(torch.from_numpy(planes.view(np.int16)).cuda())
+    finally:
+        enc.close()
+    names, data = co.exr_decode(exr)
+    assert names == co.exr_file_order(c)[1]
+    assert (co.exr_to_planes(names, data, c) == planes).all()
+    if not finite:
+        assert len(exr) < planes.nbytes + 4096
+    if finite and c in (3, 4):  # the OpenEXR library (inside cv2)
+        os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+        try:
+            import cv2
+        except ImportError:
+            return
+        p = tmp_path / "t.exr"
+        p.write_bytes(exr)
+        img = cv2.imread(str(p), cv2.IMREAD_UNCHANGED)
+        assert img is not None and img.shape == (h, w, c)
+        want = planes.view(np.float16).astype(np.float32)
+        for k, pl in enumerate([2, 1, 0] + ([3] if c == 4 else [])):
+            assert (img[..., k] == want[pl]).all()
+
+
+def test_device_deflate_ratio_on_a_reprojected_frame(lrp, ctx):
+    """size sanity on the kernel's own output of a smooth + noisy panorama: the Huffman-only stream must be within
+    15 % of zlib level 6 on the same filtered scan lines (measured: it is smaller)"""
+    import torch
+    import zlib
+    W, H = 960, 540
+    y, x = torch.meshgrid(torch.arange(1024, device="cuda"), torch.arange(2048, device="cuda"), indexing="ij")
+    pano = torch.stack([128 + 100 * torch.sin(x * 0.008) * torch.cos(y * 0.012), 128 + 90 * torch.cos(x * 0.005 + y * 0.008),
+                        128 + 80 * torch.sin((x + y) * 0.003), torch.full_like(x, 255.0)], dim=-1)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    pano[..., :3] += torch.randn((1024, 2048, 3), device="cuda", generator=g) * 2.0
+    pano = pano.clamp(0, 255).to(torch.uint8).contiguous()
+    dst = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
+    p = lrp.make_params(1, lrp.BICUBIC, lrp.rotation_from_degrees(30, 20, 10), None)
+    ctx.reproject(pano, lrp.lens_equirectangular(), lrp.FMT_U8_RGBA, dst, lrp.lens_rectilinear(18.0, 36.0, W, H),
+                  lrp.FMT_U8_RGBA, p)
+    enc = lrp.Encoder(ctx, W, H, 4)
+    try:
+        png = enc.png(dst, 3)
+    finally:
+        enc.close()
+    assert (_decode_png(png) == dst.cpu().numpy()).all()
+    stream = ctx.png_pack(dst, 3).cpu().numpy().tobytes()
+    assert len(png) < 1.15 * len(zlib.compress(stream, 6))

@@ -101,6 +101,21 @@ def main():
         exr = lrp.exr_assemble(epacked, W, H, 4, 9, T)
         dt = time.perf_counter() - t0
         out["exr_assemble_level9_T%d" % T] = {"s": dt, "mpix_per_s": W * H / dt / 1e6, "file_bytes": len(exr)}
+    # the whole writer on the device (pack + GPU deflate + D2H of the compressed body + container/CRC on the host)
+    enc = lrp.Encoder(ctx, W, H, 4)
+    for name, fn, frames in (("png_encoder_device", lambda t: enc.png(t, 3), sinks), ("exr_encoder_device", enc.exr, planes)):
+        data = fn(frames[0])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(8):
+            data = fn(frames[i % 8])
+        dt = (time.perf_counter() - t0) / 8
+        ms = enc.last_timing()
+        out[name] = {"s": dt, "mpix_per_s": W * H / dt / 1e6, "file_bytes": len(data), "device_ms": ms[0], "d2h_ms": ms[1],
+                     "host_container_ms": ms[2]}
+    if ref is not None:
+        assert (ref.decode(enc.png(dst, 3)) == dst.cpu().numpy()).all(), "device-deflated file does not decode to the sink"
+    enc.close()
     out["host_threads"] = args.threads
     print(json.dumps(out))
     ctx.close()
