@@ -300,23 +300,51 @@ struct LayoutParams {
   unsigned *stream_adler;
 };
 
-__global__ void deflate_layout_kernel(const LayoutParams P) {
-  // one thread per stream computes its size and checksum; thread 0 then prefix-sums the streams (<= a few thousand)
-  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n_streams; s += gridDim.x * blockDim.x) {
-    unsigned long long bytes = 2;
-    unsigned a = 1, b = 0;
-    for (unsigned k = 0; k < P.bands_per_stream; ++k) {
-      const unsigned i = s * P.bands_per_stream + k;
-      P.band_off[i] = bytes; // relative for now
-      bytes += P.band_len[i];
-      const unsigned ad = P.band_adler[i], n2 = P.band_in[i] % ADLER_MOD;
-      // adler32_combine: a' = a + a2 - 1,  b' = b + b2 + len2 * (a - 1)   (mod 65521)
-      const unsigned a2 = ad & 0xffffu, b2 = ad >> 16;
-      b = (unsigned)(((unsigned long long)b + b2 + (unsigned long long)n2 * ((a + ADLER_MOD - 1) % ADLER_MOD)) % ADLER_MOD);
-      a = (a + a2 + ADLER_MOD - 1) % ADLER_MOD;
-    }
-    P.stream_adler[s] = (b << 16) | a;
-    P.stream_off[s + 1] = bytes + 2 + 4; // size for now
+// One CTA per stream.  adler32_combine over the bands, in closed form so that it scans:
+//   a = 1 + sum_j (a_j - 1),   b = sum_i [ b_i + len_i * sum_{j<i} (a_j - 1) ]      (mod 65521)
+constexpr int LAYOUT_THREADS = 256;
+__device__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long *warp_sums, unsigned long long &total) {
+  const unsigned lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  unsigned long long incl = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (unsigned)o) incl += t;
+  }
+  __syncthreads(); // warp_sums may still be read from the previous call
+  if (lane == 31) warp_sums[wrp] = incl;
+  __syncthreads();
+  unsigned long long base = 0;
+  total = 0;
+  for (int w = 0; w < LAYOUT_THREADS / 32; ++w) {
+    if (w < (int)wrp) base += warp_sums[w];
+    total += warp_sums[w];
+  }
+  return base + incl - v;
+}
+
+__global__ void __launch_bounds__(LAYOUT_THREADS) deflate_layout_kernel(const LayoutParams P) {
+  __shared__ unsigned long long ws[LAYOUT_THREADS / 32];
+  const unsigned s = blockIdx.x, tid = threadIdx.x;
+  unsigned long long bytes = 2, asum = 0, bsum = 0; // running: offset in the stream, sum (a_j - 1), sum of b terms
+  for (unsigned k0 = 0; k0 < P.bands_per_stream; k0 += LAYOUT_THREADS) {
+    const unsigned k = k0 + tid;
+    const bool in = k < P.bands_per_stream;
+    const unsigned i = s * P.bands_per_stream + (in ? k : 0);
+    const unsigned len = in ? P.band_len[i] : 0u, ad = in ? P.band_adler[i] : 1u, n2 = in ? P.band_in[i] % ADLER_MOD : 0u;
+    const unsigned am1 = ((ad & 0xffffu) + ADLER_MOD - 1) % ADLER_MOD;
+    unsigned long long tot_len, tot_a, tot_b;
+    const unsigned long long off = block_exclusive_scan(len, ws, tot_len);
+    const unsigned long long abefore = block_exclusive_scan(am1, ws, tot_a);
+    if (in) P.band_off[i] = bytes + off; // relative to the stream's start
+    const unsigned long long term = in ? ((ad >> 16) + (unsigned long long)n2 * ((asum + abefore) % ADLER_MOD)) % ADLER_MOD : 0ull;
+    block_exclusive_scan(term, ws, tot_b);
+    bytes += tot_len;
+    asum = (asum + tot_a) % ADLER_MOD;
+    bsum = (bsum + tot_b) % ADLER_MOD;
+  }
+  if (tid == 0) {
+    P.stream_adler[s] = (unsigned)(bsum << 16) | (unsigned)((1 + asum) % ADLER_MOD);
+    P.stream_off[s + 1] = bytes + 2 + 4; // the stream's size for now; deflate_offsets_kernel turns sizes into offsets
   }
 }
 __global__ void deflate_offsets_kernel(const LayoutParams P) {
@@ -416,7 +444,7 @@ static int deflate_to_host(lrp_encoder *e, size_t n, size_t stream_bytes, cudaSt
   L.band_len = e->d_band_len, L.band_adler = e->d_band_adler, L.band_in = e->d_band_in;
   L.bands_per_stream = bps, L.n_streams = n_streams;
   L.band_off = e->d_band_off, L.stream_off = e->d_stream_off, L.stream_adler = e->d_stream_adler;
-  deflate_layout_kernel<<<(n_streams + 127) / 128, 128, 0, st>>>(L);
+  deflate_layout_kernel<<<n_streams, LAYOUT_THREADS, 0, st>>>(L);
   deflate_offsets_kernel<<<1, 32, 0, st>>>(L);
   deflate_gather_kernel<<<n_bands, 256, 0, st>>>(L, e->d_slots, e->d_compact);
   cudaEventRecord(e->ev[1], st);
