@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateP
   __shared__ unsigned hist[512];                            // counts, then sort keys (weight << 9 | symbol)
   __shared__ unsigned short parent[2 * DF_SYMS];
   __shared__ unsigned nodew[2 * DF_SYMS];
-  __shared__ unsigned char depth[2 * DF_SYMS];
+  __shared__ unsigned char lens[DF_SYMS + 3];
+  __shared__ unsigned bl_count[16], next_code[16];
   __shared__ unsigned codelen[DF_SYMS];                     // reversed code << 4 | length
   __shared__ unsigned warp_tot[DF_THREADS / 32];
   __shared__ unsigned long long red[2][DF_THREADS / 32];
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateP
     unsigned jj = j + rot;
     if (jj >= cnt) jj -= cnt;
     const unsigned d = band[base + jj];
-    atomicAdd(&hist[d], 1u);
+    atomicAdd(&outw[d * 32u + lane], 1u); // lane-replicated bins: every lane of a warp owns a bank, no conflicts
     s1 += d;
     s2 += (unsigned long long)(cnt - jj) * d;
   }
@@ -155,6 +156,13 @@ __global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateP
     P.band_in[b] = len;
     hist[256] = 1; // end-of-block
   }
+  { // fold the 32 replicas (rotated start: the threads of a warp read different banks), then clear the words again
+    unsigned c = 0;
+    for (unsigned j = 0; j < 32; ++j) c += outw[tid * 32u + ((j + tid) & 31u)];
+    hist[tid] = c;
+  }
+  __syncthreads();
+  for (unsigned i = tid; i < 256 * 32; i += DF_THREADS) outw[i] = 0;
   __syncthreads();
 
   // ---- sort keys: weight floored at total / 1024 (depth bound), absent symbols last ----
@@ -180,45 +188,66 @@ __global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateP
     }
   }
 
-  // ---- Huffman merge (two queues), depths, canonical codes: one thread, ~10 us ----
+  // ---- Huffman merge (two queues): the one serial step, queue heads kept in registers ----
+  const unsigned m = (unsigned)__syncthreads_count(hist[tid] != 0xFFFFFFFFu) +
+                     (unsigned)__syncthreads_count(hist[tid + 256] != 0xFFFFFFFFu); // present symbols (>= 2)
   if (tid == 0) {
-    unsigned m = 0;
-    while (m < DF_SYMS && hist[m] != 0xFFFFFFFFu) ++m; // present symbols (>= 2: a literal and end-of-block)
+    const unsigned INF = 0xFFFFFFFFu;
     unsigned li = 0, ii = m, nn = m;
+    unsigned lw = hist[0] >> 9, iw = INF; // weights at the heads of the leaf / internal-node queues
     for (unsigned k2 = 0; k2 + 1 < m; ++k2) {
-      unsigned pick[2];
+      unsigned pick[2], w[2];
+#pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const bool leaf = li < m && (ii >= nn || (hist[li] >> 9) <= nodew[ii]);
-        pick[t] = leaf ? li++ : ii++;
+        if (lw <= iw) { // (an exhausted queue holds INF; both cannot be exhausted here)
+          pick[t] = li, w[t] = lw;
+          ++li;
+          lw = li < m ? hist[li] >> 9 : INF;
+        } else {
+          pick[t] = ii, w[t] = iw;
+          ++ii;
+          iw = ii < nn ? nodew[ii] : INF;
+        }
       }
-      const unsigned wa = pick[0] < m ? hist[pick[0]] >> 9 : nodew[pick[0]];
-      const unsigned wb = pick[1] < m ? hist[pick[1]] >> 9 : nodew[pick[1]];
-      nodew[nn] = wa + wb;
+      const unsigned sum = w[0] + w[1];
+      nodew[nn] = sum;
       parent[pick[0]] = (unsigned short)nn;
       parent[pick[1]] = (unsigned short)nn;
+      if (ii == nn) iw = sum; // the internal queue was empty: the new node is its head
       ++nn;
     }
-    depth[2 * m - 2] = 0;
-    for (int node = (int)(2 * m - 3); node >= 0; --node) depth[node] = depth[parent[node]] + 1;
-    unsigned bl_count[16], next_code[16];
-    for (int i = 0; i < 16; ++i) bl_count[i] = 0;
-    for (unsigned i = 0; i < DF_SYMS; ++i) codelen[i] = 0;
-    for (unsigned i = 0; i < m; ++i) {
-      unsigned d = depth[i];
-      if (d > 15) d = 15; // unreachable by the depth bound; keeps the stream well-formed rather than undefined
-      codelen[hist[i] & 511u] = d;
-      ++bl_count[d];
+  }
+  for (unsigned i = tid; i < 16; i += DF_THREADS) bl_count[i] = 0;
+  for (unsigned i = tid; i < DF_SYMS; i += DF_THREADS) lens[i] = 0;
+  __syncthreads();
+
+  // ---- depths of the leaves (pointer chasing, <= 15 steps), length histogram ----
+  for (unsigned i = tid; i < m; i += DF_THREADS) {
+    unsigned d = 0, node = i;
+    const unsigned root = 2 * m - 2;
+    while (node != root && d < 15) { // d < 15 always holds by the depth bound; the test keeps a broken tree finite
+      node = parent[node];
+      ++d;
     }
-    unsigned code = 0;
-    bl_count[0] = 0;
+    lens[hist[i] & 511u] = (unsigned char)d;
+    atomicAdd(&bl_count[d], 1u);
+  }
+  __syncthreads();
+  // ---- canonical codes: first code of every length, then rank among the symbols of the same length ----
+  if (tid == 0) {
+    unsigned code = 0, prev = 0;
     for (int bits = 1; bits <= 15; ++bits) {
-      code = (code + bl_count[bits - 1]) << 1;
+      code = (code + prev) << 1;
+      prev = bl_count[bits];
       next_code[bits] = code;
     }
-    for (unsigned i = 0; i < DF_SYMS; ++i) {
-      const unsigned l = codelen[i];
-      if (l) codelen[i] = (reverse_bits(next_code[l]++, l) << 4) | l;
-    }
+  }
+  __syncthreads();
+  for (unsigned sym = tid; sym < DF_SYMS; sym += DF_THREADS) {
+    const unsigned l = lens[sym];
+    unsigned rank = 0;
+    for (unsigned j = 0; j < sym; ++j) rank += (lens[j] == l) ? 1u : 0u;
+    codelen[sym] = l ? (reverse_bits(next_code[l] + rank, l) << 4) | l : 0u;
   }
   __syncthreads();
 
@@ -227,7 +256,7 @@ __global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateP
   for (unsigned j = 0; j < cnt; ++j) {
     unsigned jj = j + rot;
     if (jj >= cnt) jj -= cnt;
-    bits += codelen[band[base + jj]] & 15u;
+    bits += lens[band[base + jj]];
   }
   unsigned incl = bits;
   for (int o = 1; o < 32; o <<= 1) {
@@ -257,14 +286,34 @@ __global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateP
       // code-length code: symbols 0..15 get 4 bits each (a complete code), the run-length symbols 16, 17, 18 none;
       // transmitted in the order 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15
       for (int i = 0; i < 19; ++i) bw.put(i < 3 ? 0u : 4u, 3);
-      for (unsigned i = 0; i < DF_SYMS; ++i) bw.put(reverse_bits(codelen[i] & 15u, 4), 4); // canonical: code == symbol
-      bw.put(reverse_bits(1u, 4), 4); // one distance code of one bit (never used: the block has no matches)
       bw.flush();
+      // one distance code of one bit (never used: the block has no matches), behind the 257 literal/length lengths
+      BitWriter bd(outw, DF_HDR_BITS - 4);
+      bd.put(reverse_bits(1u, 4), 4);
+      bd.flush();
+    }
+    for (unsigned sym = tid; sym < DF_SYMS; sym += DF_THREADS) { // canonical 4-bit code of a length == the length itself
+      BitWriter bl(outw, DF_HDR_BITS - 4 - 4 * DF_SYMS + 4 * sym);
+      bl.put(reverse_bits(codelen[sym] & 15u, 4), 4);
+      bl.flush();
     }
     BitWriter bw(outw, DF_HDR_BITS + warp_base + incl - bits);
-    for (unsigned j = 0; j < cnt; ++j) {
-      const unsigned c = codelen[band[base + j]];
-      bw.put(c >> 4, c & 15u);
+    if (cnt == (unsigned)DF_CHUNK) { // 16 bytes per shared-memory load (a thread's bytes must go out in order)
+#pragma unroll 2
+      for (unsigned q = 0; q < DF_CHUNK / 16; ++q) {
+        const uint4 v = ((const uint4 *)(band + base))[q];
+        const unsigned wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const unsigned c = codelen[(wds[t >> 2] >> (8 * (t & 3))) & 255u];
+          bw.put(c >> 4, c & 15u);
+        }
+      }
+    } else {
+      for (unsigned j = 0; j < cnt; ++j) {
+        const unsigned c = codelen[band[base + j]];
+        bw.put(c >> 4, c & 15u);
+      }
     }
     if (cnt > 0 && base + cnt == len) bw.put(eob >> 4, eob & 15u); // the thread holding the last byte closes the block
     bw.flush();

@@ -92,3 +92,55 @@ def test_sync_dropin_is_reentrant(lrp):
     [t.join() for t in th]
     for g, wv in zip(got, want):
         assert ol.same_bits(g, wv)
+
+
+# ---- the in-kernel tile scheduler (lrp_kernel.cuh "tile scheduler") ----
+
+@pytest.mark.parametrize("variant", ["staged", "gather"])
+def test_tile_tickets_many_launches_on_concurrent_streams(lrp, monkeypatch, variant):
+    """Tiles are handed out from a self-resetting counter pair per stream: launches queued back to back on one stream
+    reuse the pair, launches on different streams run concurrently on their own pairs.  Every output must still be the
+    oracle's, bit for bit (a lost or doubled ticket would leave a tile unwritten / written from a stale ticket)."""
+    import torch
+    monkeypatch.setenv("LRP_FORCE_VARIANT", variant)
+    ctx = lrp.Context(0, 2)
+    W, H, w, h = 400, 300, 512, 256  # 475 staged tiles / 494 gather tiles: several rounds of tickets per launch
+    il, olens = ol.erect(), ol.rect(18.0, 36.0, W, H)
+    rot = ORC.rotation_from_degrees(30, 20, 10)
+    p = lrp.make_params(1, lrp.BICUBIC, rot, None)
+    rng = np.random.default_rng(5)
+    srcs = [rng.integers(0, 256, (h, w, 4), dtype=np.uint8) for _ in range(3)]
+    want = [ORC.png_encode(ORC.reproject(ORC.png_decode(s), il, olens, W, H, 1, ol.BICUBIC, rot)) for s in srcs]
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    src_t = [torch.from_numpy(s).cuda() for s in srcs]
+    outs = []
+    torch.cuda.synchronize()
+    for rep in range(6):
+        for si, st in enumerate(streams):
+            k = (rep + si) % 3
+            d = torch.full((H, W, 4), 7, dtype=torch.uint8, device="cuda")
+            torch.cuda.current_stream().synchronize()
+            ctx.reproject(src_t[k], lrp.lens_from(il), lrp.FMT_U8_RGBA, d, lrp.lens_from(olens), lrp.FMT_U8_RGBA, p,
+                          stream=st.cuda_stream)
+            outs.append((k, d))
+    torch.cuda.synchronize()
+    for k, d in outs:
+        assert (d.cpu().numpy() == want[k]).all()
+    ctx.close()
+
+
+def test_static_tile_stride_switch_gives_the_same_bits(lrp, monkeypatch):
+    import torch
+    ctx = lrp.Context(0, 1)
+    W, H, w, h = 333, 222, 300, 150
+    il, olens = ol.equidistant(3.14159), ol.erect()
+    src = ol.noise(h, w, 4, seed=9)
+    want = ORC.reproject(src, il, olens, W, H, 1, ol.BICUBIC, None)
+    for static in ("0", "1"):
+        monkeypatch.setenv("LRP_STATIC_TILES", static)
+        d = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+        ctx.reproject(torch.from_numpy(src).cuda(), lrp.lens_from(il), lrp.FMT_F32, d, lrp.lens_from(olens), lrp.FMT_F32,
+                      lrp.make_params(1, lrp.BICUBIC, None, None))
+        torch.cuda.synchronize()
+        assert ol.same_bits(d.cpu().numpy(), want)
+    ctx.close()
