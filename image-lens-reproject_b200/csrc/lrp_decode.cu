@@ -1,0 +1,499 @@
+// lrp_decode.cu — the DECODE side of the hot path: from the bytes of a .png / .exr file to
+// the codec-native source the fused kernel reads (LRP_FMT_U8_RGBA / LRP_FMT_F16_PLANAR), without the reference's
+// float32 expansion passes.
+//
+// Reference: reproject::read_png (src/image_formats.cpp:174-204) = lodepng::decode to RGBA8 + a pow() loop to float;
+// reproject::read_exr (:208-303) = Imf::InputFile::readPixels into HALF planes + a half->float interleaving loop that maps
+// channel names to indices (R, G, B -> 0, 1, 2; A / Z -> 3 or 4 by data layout, :266-285).  The pow() / half->float
+// arithmetic already lives in the kernel's texel load; what remains is the container + entropy decoding:
+//   EXR  host: header + offset table, one zlib inflate per block of scan lines on `threads` cores (blocks are
+//        independent).  device: exr_unpack_kernel undoes OpenEXR's predictor (a byte-wise prefix sum, scanned per
+//        warp) and byte-plane split (lib/openexr/src/lib/OpenEXRCore/internal_zip.c:47-160 "reconstruct" +
+//        "interleave") and scatters the channel-interleaved scan lines into the reference's plane order.
+//   PNG  host: chunks, one zlib inflate of the IDAT stream, scan-line un-filtering (inherently sequential along a
+//        line), expansion to RGBA8 as lodepng::decode delivers it; the pixels land in pinned memory and are uploaded.
+// Scope: what the reference's pipeline reads — single-part scan-line EXR with HALF channels named from {R,G,B,A,Z},
+// NONE / ZIPS / ZIP compression; non-interlaced 8-bit PNG of colour type 0, 2, 3, 4 or 6.  Anything else returns
+// LRP_E_UNSUPPORTED_FORMAT (the reference would go through lodepng / OpenEXR's other code paths).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/lrp.h"
+
+extern "C" int lrp_ctx_phys_device_(const lrp_ctx *ctx); // lrp_api.cu
+
+namespace lrp {
+
+// ---- EXR: predictor + byte planes + channel scatter on the device ---------------------------------------
+struct ExrUnpackParams {
+  const unsigned char *src;      // blocks back to back, each either predicted byte planes (inflate output) or raw
+  const unsigned char *is_raw;   // per block
+  unsigned short *dst;           // planar half, plane stride W * H
+  int W, H, C, lines_per_block;
+  int plane_of[5];               // destination plane of the k-th channel in file order
+};
+
+constexpr int UNPACK_WARPS = 32;
+
+__device__ __forceinline__ unsigned bytesum(unsigned long long v) { // sum of the 8 bytes, mod 256 is taken by the caller
+  return __vsadu4((unsigned)v, 0u) + __vsadu4((unsigned)(v >> 32), 0u);
+}
+
+__global__ void __launch_bounds__(UNPACK_WARPS * 32) exr_unpack_kernel(const ExrUnpackParams P) {
+  __shared__ unsigned seg_lo[UNPACK_WARPS], seg_hi[UNPACK_WARPS];
+  const int block = blockIdx.x, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int y0 = block * P.lines_per_block, lines = min(P.lines_per_block, P.H - y0);
+  const unsigned W = (unsigned)P.W, C = (unsigned)P.C;
+  const unsigned halfs = (unsigned)lines * C * W;
+  const unsigned char *src = P.src + (size_t)y0 * C * W * 2;
+  const size_t plane = (size_t)W * P.H;
+  const bool raw = P.is_raw[block] != 0;
+
+  auto store8 = [&](unsigned i0, const unsigned short (&v)[8], unsigned m) { // halfs [i0, i0 + m) of the block's raw order
+    const unsigned rowc = i0 / W, x = i0 - rowc * W;
+    if (m == 8 && x + 8 <= W) {
+      const unsigned ly = rowc / C, k = rowc - ly * C;
+      unsigned short *d = P.dst + (size_t)P.plane_of[k] * plane + (size_t)(y0 + ly) * W + x;
+      if ((((size_t)d) & 15) == 0) {
+        uint4 q;
+        q.x = v[0] | ((unsigned)v[1] << 16), q.y = v[2] | ((unsigned)v[3] << 16);
+        q.z = v[4] | ((unsigned)v[5] << 16), q.w = v[6] | ((unsigned)v[7] << 16);
+        *(uint4 *)d = q;
+        return;
+      }
+    }
+    for (unsigned j = 0; j < m; ++j) {
+      const unsigned i = i0 + j, rc = i / W, xx = i - rc * W, ly = rc / C, k = rc - ly * C;
+      P.dst[(size_t)P.plane_of[k] * plane + (size_t)(y0 + ly) * W + xx] = v[j];
+    }
+  };
+
+  // a warp owns a contiguous run of 8-half chunks; lanes take consecutive chunks, so loads and stores coalesce
+  const unsigned chunks = (halfs + 7) / 8, per_warp = (chunks + UNPACK_WARPS - 1) / UNPACK_WARPS;
+  const unsigned c_begin = min(chunks, wrp * per_warp), c_end = min(chunks, c_begin + per_warp);
+  const unsigned char *lo = src, *hi = src + halfs; // byte planes (n = 2 * halfs is even: h = halfs)
+  const bool aligned = (((size_t)lo | (size_t)hi) & 7) == 0;
+  auto load8 = [&](const unsigned char *p, unsigned i0, unsigned m) -> unsigned long long {
+    if (m == 8 && aligned) return *(const unsigned long long *)(p + i0);
+    unsigned long long v = 0;
+    for (unsigned j = 0; j < m; ++j) v |= (unsigned long long)p[i0 + j] << (8 * j);
+    return v;
+  };
+
+  if (raw) { // stored block: little-endian halfs in raw order
+    for (unsigned c = c_begin + lane; c < c_end; c += 32) {
+      const unsigned i0 = 8 * c, m = min(8u, halfs - i0);
+      unsigned short v[8];
+      for (unsigned j = 0; j < 8; ++j) v[j] = j < m ? (unsigned short)(src[2 * (i0 + j)] | (src[2 * (i0 + j) + 1] << 8)) : 0;
+      store8(i0, v, m);
+    }
+    return;
+  }
+
+  // pass 1: byte sums of this warp's run in both planes.  t[i] = t[i-1] + t'[i] - 128 = sum_j (t'[j] + 128) - 128 (mod 256)
+  unsigned s_lo = 0, s_hi = 0;
+  for (unsigned c = c_begin + lane; c < c_end; c += 32) {
+    const unsigned i0 = 8 * c, m = min(8u, halfs - i0);
+    s_lo += bytesum(load8(lo, i0, m)) + 128u * m;
+    s_hi += bytesum(load8(hi, i0, m)) + 128u * m;
+  }
+  s_lo = __reduce_add_sync(0xffffffffu, s_lo);
+  s_hi = __reduce_add_sync(0xffffffffu, s_hi);
+  if (lane == 0) {
+    seg_lo[wrp] = s_lo;
+    seg_hi[wrp] = s_hi;
+  }
+  __syncthreads();
+  unsigned base_lo = 128u, base_hi = 128u; // the stream's first byte carries no +128: start 128 short (mod 256)
+  for (int w = 0; w < UNPACK_WARPS; ++w) {
+    base_hi += seg_lo[w]; // the high plane continues the running sum of the whole low plane
+    if (w < wrp) {
+      base_lo += seg_lo[w];
+      base_hi += seg_hi[w];
+    }
+  }
+  // pass 2: 32 chunks per step, a warp scan of the chunk sums carries the running bytes
+  for (unsigned c0 = c_begin; c0 < c_end; c0 += 32) {
+    const unsigned c = c0 + lane;
+    const bool in = c < c_end;
+    const unsigned i0 = 8 * c, m = in ? min(8u, halfs - i0) : 0u;
+    const unsigned long long vl = in ? load8(lo, i0, m) : 0ull, vh = in ? load8(hi, i0, m) : 0ull;
+    unsigned cl = bytesum(vl) + 128u * m, ch = bytesum(vh) + 128u * m; // this chunk's contribution
+    unsigned il = cl, ih = ch;                                          // inclusive scans over the lanes
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned tl = __shfl_up_sync(0xffffffffu, il, o), th = __shfl_up_sync(0xffffffffu, ih, o);
+      if (lane >= o) il += tl, ih += th;
+    }
+    unsigned run_l = base_lo + il - cl, run_h = base_hi + ih - ch; // running byte before this chunk
+    if (in) {
+      unsigned short v[8];
+#pragma unroll
+      for (unsigned j = 0; j < 8; ++j) {
+        run_l += (unsigned)((vl >> (8 * j)) & 255u) + 128u;
+        run_h += (unsigned)((vh >> (8 * j)) & 255u) + 128u;
+        v[j] = (unsigned short)((run_l & 255u) | ((run_h & 255u) << 8));
+      }
+      store8(i0, v, m);
+    }
+    base_lo += __shfl_sync(0xffffffffu, il, 31);
+    base_hi += __shfl_sync(0xffffffffu, ih, 31);
+  }
+}
+
+// ---- host: EXR container ---------------------------------------------------------------------------------
+struct ExrInfo {
+  int w = 0, h = 0, c = 0, compression = 0, lines_per_block = 1;
+  int plane_of[5] = {0, 0, 0, 0, 0}; // destination plane of the k-th channel in file order (read_exr's dstC)
+  size_t table = 0;                  // offset of the line offset table
+};
+
+static int exr_parse(const unsigned char *f, size_t n, ExrInfo &I) {
+  if (!f || n < 16 || memcmp(f, "\x76\x2f\x31\x01", 4) != 0) return LRP_E_BAD_ARG;
+  uint32_t version;
+  memcpy(&version, f + 4, 4);
+  if ((version & 0xff) != 2 || (version & ~0x4ffu) != 0) return LRP_E_UNSUPPORTED_FORMAT; // tiles / deep / multi-part
+  size_t pos = 8;
+  bool have_ch = false, have_dw = false;
+  std::vector<std::string> names;
+  while (pos < n && f[pos] != 0) {
+    const void *e = memchr(f + pos, 0, n - pos);
+    if (!e) return LRP_E_BAD_ARG;
+    std::string name((const char *)f + pos);
+    pos = (const unsigned char *)e - f + 1;
+    e = memchr(f + pos, 0, n - pos);
+    if (!e) return LRP_E_BAD_ARG;
+    std::string type((const char *)f + pos);
+    pos = (const unsigned char *)e - f + 1;
+    if (pos + 4 > n) return LRP_E_BAD_ARG;
+    int32_t len;
+    memcpy(&len, f + pos, 4);
+    pos += 4;
+    if (len < 0 || pos + (size_t)len > n) return LRP_E_BAD_ARG;
+    const unsigned char *d = f + pos;
+    if (name == "channels") {
+      size_t p = 0;
+      while (p < (size_t)len && d[p] != 0) {
+        const void *z = memchr(d + p, 0, len - p);
+        if (!z) return LRP_E_BAD_ARG;
+        names.emplace_back((const char *)d + p);
+        p = (const unsigned char *)z - d + 1;
+        if (p + 16 > (size_t)len) return LRP_E_BAD_ARG;
+        int32_t rec[4];
+        memcpy(rec, d + p, 16);
+        if (rec[0] != 1 || rec[2] != 1 || rec[3] != 1) return LRP_E_UNSUPPORTED_FORMAT; // HALF, no sub-sampling
+        p += 16;
+      }
+      have_ch = true;
+    } else if (name == "compression") {
+      I.compression = d[0];
+    } else if (name == "dataWindow") {
+      int32_t b[4];
+      memcpy(b, d, 16);
+      I.w = b[2] - b[0] + 1, I.h = b[3] - b[1] + 1;
+      have_dw = true;
+    } else if (name == "lineOrder") {
+      if (d[0] > 1) return LRP_E_UNSUPPORTED_FORMAT; // the offset table is in increasing y for both 0 and 1
+    }
+    pos += len;
+  }
+  if (!have_ch || !have_dw || I.w <= 0 || I.h <= 0) return LRP_E_BAD_ARG;
+  if (I.compression == 0 || I.compression == 2) I.lines_per_block = 1;
+  else if (I.compression == 3) I.lines_per_block = 16;
+  else return LRP_E_UNSUPPORTED_FORMAT; // RLE / PIZ / PXR24 / B44 / DWA
+  I.table = pos + 1;
+  I.c = (int)names.size();
+  if (I.c < 3 || I.c > 5) return LRP_E_UNSUPPORTED_FORMAT;
+  // read_exr's name -> index mapping (:266-285): layout by the presence of A and Z
+  bool hasA = false, hasZ = false, rgb[3] = {false, false, false};
+  for (auto &s : names) {
+    hasA |= s == "A", hasZ |= s == "Z";
+    if (s == "R") rgb[0] = true;
+    if (s == "G") rgb[1] = true;
+    if (s == "B") rgb[2] = true;
+  }
+  if (!(rgb[0] && rgb[1] && rgb[2]) || I.c != 3 + (hasA ? 1 : 0) + (hasZ ? 1 : 0)) return LRP_E_UNSUPPORTED_FORMAT;
+  for (int k = 0; k < I.c; ++k) {
+    const std::string &s = names[k];
+    I.plane_of[k] = s == "R" ? 0 : s == "G" ? 1 : s == "B" ? 2 : s == "A" ? 3 : (hasA ? 4 : 3);
+  }
+  return LRP_OK;
+}
+
+template <class F> static void parallel_for(size_t n, int threads, F fn) {
+  threads = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, threads), n));
+  if (threads == 1) {
+    for (size_t i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([&] {
+      for (size_t i = next++; i < n; i = next++) fn(i);
+    });
+  for (auto &t : pool) t.join();
+}
+
+// ---- host: PNG ---------------------------------------------------------------------------------------------
+struct PngInfo {
+  uint32_t w = 0, h = 0;
+  int depth = 0, ctype = 0, channels = 0;
+};
+
+static uint32_t be32(const unsigned char *p) { return ((uint32_t)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3]; }
+
+static int png_parse(const unsigned char *f, size_t n, PngInfo &I, std::vector<unsigned char> &idat,
+                     std::vector<unsigned char> &plte, std::vector<unsigned char> &trns) {
+  static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+  if (!f || n < 8 + 25 || memcmp(f, sig, 8) != 0) return LRP_E_BAD_ARG;
+  size_t pos = 8;
+  bool have_ihdr = false;
+  while (pos + 12 <= n) {
+    const uint32_t len = be32(f + pos);
+    if (pos + 12 + (size_t)len > n) return LRP_E_BAD_ARG;
+    const unsigned char *type = f + pos + 4, *data = f + pos + 8;
+    if (!memcmp(type, "IHDR", 4)) {
+      if (len != 13) return LRP_E_BAD_ARG;
+      I.w = be32(data), I.h = be32(data + 4), I.depth = data[8], I.ctype = data[9];
+      if (data[10] != 0 || data[11] != 0) return LRP_E_BAD_ARG;
+      if (data[12] != 0 || I.depth != 8) return LRP_E_UNSUPPORTED_FORMAT; // interlaced / other bit depths
+      I.channels = I.ctype == 0 ? 1 : I.ctype == 2 ? 3 : I.ctype == 3 ? 1 : I.ctype == 4 ? 2 : I.ctype == 6 ? 4 : 0;
+      if (!I.channels || I.w == 0 || I.h == 0) return LRP_E_UNSUPPORTED_FORMAT;
+      have_ihdr = true;
+    } else if (!memcmp(type, "IDAT", 4)) {
+      idat.insert(idat.end(), data, data + len);
+    } else if (!memcmp(type, "PLTE", 4)) {
+      plte.assign(data, data + len);
+    } else if (!memcmp(type, "tRNS", 4)) {
+      trns.assign(data, data + len);
+    } else if (!memcmp(type, "IEND", 4)) {
+      break;
+    }
+    pos += 12 + len;
+  }
+  return have_ihdr && !idat.empty() ? LRP_OK : LRP_E_BAD_ARG;
+}
+
+// PNG specification section 9: reconstruction of one scan line in place (bpp = bytes per complete pixel)
+static int png_unfilter_line(unsigned char *cur, const unsigned char *prev, size_t n, int bpp, int type) {
+  switch (type) {
+  case 0: break;
+  case 1:
+    for (size_t i = bpp; i < n; ++i) cur[i] = (unsigned char)(cur[i] + cur[i - bpp]);
+    break;
+  case 2:
+    if (prev)
+      for (size_t i = 0; i < n; ++i) cur[i] = (unsigned char)(cur[i] + prev[i]);
+    break;
+  case 3:
+    for (size_t i = 0; i < n; ++i) {
+      const int a = i >= (size_t)bpp ? cur[i - bpp] : 0, b = prev ? prev[i] : 0;
+      cur[i] = (unsigned char)(cur[i] + ((a + b) >> 1));
+    }
+    break;
+  case 4:
+    for (size_t i = 0; i < n; ++i) {
+      const int a = i >= (size_t)bpp ? cur[i - bpp] : 0, b = prev ? prev[i] : 0, c = (prev && i >= (size_t)bpp) ? prev[i - bpp] : 0;
+      const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
+      cur[i] = (unsigned char)(cur[i] + ((pa <= pb && pa <= pc) ? a : (pb <= pc) ? b : c));
+    }
+    break;
+  default: return LRP_E_BAD_ARG;
+  }
+  return LRP_OK;
+}
+
+} // namespace lrp
+
+using namespace lrp;
+
+struct lrp_decoder {
+  lrp_ctx *ctx = nullptr;
+  int device = 0;
+  size_t cap = 0, cap_blocks = 0;
+  unsigned char *h_buf = nullptr, *d_buf = nullptr, *h_raw = nullptr, *d_raw = nullptr;
+  std::vector<unsigned char> scratch;
+};
+
+extern "C" {
+
+int lrp_exr_info(const void *file, size_t n, int32_t *width, int32_t *height, int32_t *channels) {
+  ExrInfo I;
+  const int rc = exr_parse((const unsigned char *)file, n, I);
+  if (rc != LRP_OK) return rc;
+  if (width) *width = I.w;
+  if (height) *height = I.h;
+  if (channels) *channels = I.c;
+  return LRP_OK;
+}
+
+int lrp_png_info(const void *file, size_t n, int32_t *width, int32_t *height) {
+  PngInfo I;
+  std::vector<unsigned char> idat, plte, trns;
+  const int rc = png_parse((const unsigned char *)file, n, I, idat, plte, trns);
+  if (rc != LRP_OK) return rc;
+  if (width) *width = (int32_t)I.w;
+  if (height) *height = (int32_t)I.h;
+  return LRP_OK;
+}
+
+int lrp_decoder_create(lrp_ctx *ctx, int32_t max_width, int32_t max_height, int32_t max_channels, lrp_decoder **out) {
+  if (!ctx || !out || max_width <= 0 || max_height <= 0 || max_channels < 1 || max_channels > 5) return LRP_E_BAD_ARG;
+  *out = nullptr;
+  const int dev = lrp_ctx_phys_device_(ctx);
+  if (cudaSetDevice(dev) != cudaSuccess) return LRP_E_CUDA;
+  lrp_decoder *d = new lrp_decoder();
+  d->ctx = ctx, d->device = dev;
+  d->cap = std::max((size_t)max_width * max_height * 4, (size_t)max_width * max_height * max_channels * 2);
+  d->cap_blocks = (size_t)max_height;
+  const bool ok = cudaMallocHost(&d->h_buf, d->cap) == cudaSuccess && cudaMalloc(&d->d_buf, d->cap) == cudaSuccess &&
+                  cudaMallocHost(&d->h_raw, d->cap_blocks) == cudaSuccess && cudaMalloc(&d->d_raw, d->cap_blocks) == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    if (d->h_buf) cudaFreeHost(d->h_buf);
+    if (d->h_raw) cudaFreeHost(d->h_raw);
+    cudaFree(d->d_buf), cudaFree(d->d_raw);
+    delete d;
+    return LRP_E_OOM;
+  }
+  *out = d;
+  return LRP_OK;
+}
+
+int lrp_decoder_destroy(lrp_decoder *d) {
+  if (!d) return LRP_E_BAD_ARG;
+  cudaSetDevice(d->device);
+  cudaFreeHost(d->h_buf), cudaFreeHost(d->h_raw);
+  cudaFree(d->d_buf), cudaFree(d->d_raw);
+  delete d;
+  return LRP_OK;
+}
+
+// read_exr for a device-resident source: planes R, G, B, [A], [Z] of IEEE half at out_half_planar_dev
+int lrp_decoder_exr(lrp_decoder *d, const void *file, size_t n, int32_t threads, void *out_half_planar_dev,
+                    void *cuda_stream) {
+  if (!d || !file || !out_half_planar_dev) return LRP_E_BAD_ARG;
+  const unsigned char *f = (const unsigned char *)file;
+  ExrInfo I;
+  int rc = exr_parse(f, n, I);
+  if (rc != LRP_OK) return rc;
+  const size_t line_bytes = (size_t)I.c * I.w * 2, total = line_bytes * I.h;
+  const size_t blocks = ((size_t)I.h + I.lines_per_block - 1) / I.lines_per_block;
+  if (total > d->cap || blocks > d->cap_blocks) return LRP_E_BAD_ARG;
+  if (I.table + 8 * blocks > n) return LRP_E_BAD_ARG;
+  std::atomic<int> status{LRP_OK};
+  parallel_for(blocks, threads, [&](size_t b) {
+    uint64_t off;
+    memcpy(&off, f + I.table + 8 * b, 8);
+    if (off + 8 > n) {
+      status = LRP_E_BAD_ARG;
+      return;
+    }
+    int32_t hdr[2];
+    memcpy(hdr, f + off, 8);
+    // blocks are addressed by their first scan line (any line order); data window origin y is 0 for what save_exr writes,
+    // other origins shift by the same amount for every block
+    const size_t lines = std::min<size_t>(I.lines_per_block, (size_t)I.h - b * I.lines_per_block), raw_n = lines * line_bytes;
+    if (hdr[1] < 0 || off + 8 + (size_t)hdr[1] > n) {
+      status = LRP_E_BAD_ARG;
+      return;
+    }
+    unsigned char *dst = d->h_buf + b * I.lines_per_block * line_bytes;
+    if ((size_t)hdr[1] == raw_n || I.compression == 0) { // stored (NO_COMPRESSION, or a block that did not shrink)
+      if ((size_t)hdr[1] != raw_n) {
+        status = LRP_E_BAD_ARG;
+        return;
+      }
+      memcpy(dst, f + off + 8, raw_n);
+      d->h_raw[b] = 1;
+    } else {
+      uLongf got = (uLongf)raw_n;
+      if (uncompress(dst, &got, f + off + 8, (uLong)hdr[1]) != Z_OK || got != raw_n) {
+        status = LRP_E_BAD_ARG;
+        return;
+      }
+      d->h_raw[b] = 0;
+    }
+  });
+  if (status != LRP_OK) return status;
+  if (cudaSetDevice(d->device) != cudaSuccess) return LRP_E_CUDA;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (cudaMemcpyAsync(d->d_buf, d->h_buf, total, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(d->d_raw, d->h_raw, blocks, cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return LRP_E_CUDA;
+  ExrUnpackParams P;
+  P.src = d->d_buf, P.is_raw = d->d_raw, P.dst = (unsigned short *)out_half_planar_dev;
+  P.W = I.w, P.H = I.h, P.C = I.c, P.lines_per_block = I.lines_per_block;
+  for (int k = 0; k < 5; ++k) P.plane_of[k] = I.plane_of[k];
+  exr_unpack_kernel<<<(unsigned)blocks, UNPACK_WARPS * 32, 0, st>>>(P);
+  if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return LRP_E_CUDA; // h_buf is reused
+  return LRP_OK;
+}
+
+// read_png for a device-resident source: RGBA8 exactly as lodepng::decode delivers it
+int lrp_decoder_png(lrp_decoder *d, const void *file, size_t n, void *out_rgba_dev, void *cuda_stream) {
+  if (!d || !file || !out_rgba_dev) return LRP_E_BAD_ARG;
+  PngInfo I;
+  std::vector<unsigned char> idat, plte, trns;
+  int rc = png_parse((const unsigned char *)file, n, I, idat, plte, trns);
+  if (rc != LRP_OK) return rc;
+  const size_t row = (size_t)I.w * I.channels, px = (size_t)I.w * I.h;
+  if (px * 4 > d->cap) return LRP_E_BAD_ARG;
+  if (I.ctype == 3 && plte.size() < 3) return LRP_E_BAD_ARG;
+  d->scratch.resize((row + 1) * I.h);
+  uLongf got = (uLongf)d->scratch.size();
+  if (uncompress(d->scratch.data(), &got, idat.data(), (uLong)idat.size()) != Z_OK || got != d->scratch.size())
+    return LRP_E_BAD_ARG;
+  unsigned char *out = d->h_buf;
+  const unsigned char *prev = nullptr;
+  for (uint32_t y = 0; y < I.h; ++y) {
+    unsigned char *line = d->scratch.data() + (size_t)y * (row + 1);
+    rc = png_unfilter_line(line + 1, prev, row, I.channels, line[0]);
+    if (rc != LRP_OK) return rc;
+    prev = line + 1;
+    unsigned char *o = out + (size_t)y * I.w * 4;
+    const unsigned char *s = line + 1;
+    switch (I.ctype) { // to RGBA8, as lodepng::decode's default conversion
+    case 6: memcpy(o, s, (size_t)I.w * 4); break;
+    case 2:
+      for (uint32_t x = 0; x < I.w; ++x) {
+        o[4 * x] = s[3 * x], o[4 * x + 1] = s[3 * x + 1], o[4 * x + 2] = s[3 * x + 2];
+        o[4 * x + 3] = (trns.size() >= 6 && s[3 * x] == trns[1] && s[3 * x + 1] == trns[3] && s[3 * x + 2] == trns[5]) ? 0 : 255;
+      }
+      break;
+    case 0:
+      for (uint32_t x = 0; x < I.w; ++x) {
+        o[4 * x] = o[4 * x + 1] = o[4 * x + 2] = s[x];
+        o[4 * x + 3] = (trns.size() >= 2 && s[x] == trns[1]) ? 0 : 255;
+      }
+      break;
+    case 4:
+      for (uint32_t x = 0; x < I.w; ++x) o[4 * x] = o[4 * x + 1] = o[4 * x + 2] = s[2 * x], o[4 * x + 3] = s[2 * x + 1];
+      break;
+    default: // 3: palette
+      for (uint32_t x = 0; x < I.w; ++x) {
+        const size_t i = s[x];
+        if (3 * i + 2 >= plte.size()) return LRP_E_BAD_ARG;
+        o[4 * x] = plte[3 * i], o[4 * x + 1] = plte[3 * i + 1], o[4 * x + 2] = plte[3 * i + 2];
+        o[4 * x + 3] = i < trns.size() ? trns[i] : 255;
+      }
+    }
+  }
+  if (cudaSetDevice(d->device) != cudaSuccess) return LRP_E_CUDA;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (cudaMemcpyAsync(out_rgba_dev, d->h_buf, px * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess)
+    return LRP_E_CUDA;
+  return LRP_OK;
+}
+
+} // extern "C"

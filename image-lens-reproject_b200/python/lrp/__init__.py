@@ -131,6 +131,12 @@ def lib():
         for f in (L.lrp_save_png_device, L.lrp_save_exr_device):
             f.argtypes = [vp, vp, i32, i32, i32, i32, i32, C.c_char_p, vp]
         L.lrp_free_bytes.argtypes = [vp]
+        L.lrp_exr_info.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+        L.lrp_png_info.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(i32), C.POINTER(i32)]
+        L.lrp_decoder_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
+        L.lrp_decoder_destroy.argtypes = [vp]
+        L.lrp_decoder_exr.argtypes = [vp, C.c_char_p, C.c_size_t, i32, vp, vp]
+        L.lrp_decoder_png.argtypes = [vp, C.c_char_p, C.c_size_t, vp, vp]
         L.lrp_encoder_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
         L.lrp_encoder_destroy.argtypes = [vp]
         L.lrp_encoder_last_timing.argtypes = [vp, C.POINTER(C.c_double)]
@@ -465,6 +471,49 @@ class Encoder:
     def exr(self, planar_t, stream=None):
         c, h, w = (int(v) for v in planar_t.shape)
         return self._run(lib().lrp_encoder_exr, planar_t, w, h, c, stream)
+
+
+def exr_info(data):
+    w, h, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    check(lib().lrp_exr_info(data, len(data), C.byref(w), C.byref(h), C.byref(c)), "lrp_exr_info")
+    return w.value, h.value, c.value
+
+
+def png_info(data):
+    w, h = C.c_int32(0), C.c_int32(0)
+    check(lib().lrp_png_info(data, len(data), C.byref(w), C.byref(h)), "lrp_png_info")
+    return w.value, h.value
+
+
+class Decoder:
+    """lrp_decoder: file bytes -> the kernel's codec-native source on the device (read_png / read_exr)."""
+
+    def __init__(self, ctx, max_w, max_h, max_c=4):
+        self.h, self.ctx = C.c_void_p(None), ctx
+        check(lib().lrp_decoder_create(ctx.h, max_w, max_h, max_c, C.byref(self.h)), "lrp_decoder_create")
+
+    def close(self):
+        if self.h:
+            lib().lrp_decoder_destroy(self.h)
+            self.h = C.c_void_p(None)
+
+    def exr(self, data, threads=8, stream=None):
+        """-> torch.float16 [C, H, W] on the device, planes R, G, B, [A], [Z]"""
+        import torch
+        w, h, c = exr_info(data)
+        out = torch.empty((c, h, w), dtype=torch.float16, device="cuda:%d" % self.ctx.device)
+        check(lib().lrp_decoder_exr(self.h, data, len(data), threads, C.c_void_p(out.data_ptr()), self.ctx._stream(stream)),
+              "lrp_decoder_exr")
+        return out
+
+    def png(self, data, stream=None):
+        """-> torch.uint8 [H, W, 4] on the device"""
+        import torch
+        w, h = png_info(data)
+        out = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda:%d" % self.ctx.device)
+        check(lib().lrp_decoder_png(self.h, data, len(data), C.c_void_p(out.data_ptr()), self.ctx._stream(stream)),
+              "lrp_decoder_png")
+        return out
 
 
 def _assemble(fn, packed, w, h, c, level, threads):

@@ -316,6 +316,25 @@ int lrp_encoder_exr(lrp_encoder *enc, const void *half_planar_dev, int32_t width
  * compressed body, [2] container bytes on the host */
 int lrp_encoder_last_timing(const lrp_encoder *enc, double *ms3);
 
+/* ---- decode side --------------------------------------------------------
+ * From the bytes of a file to the codec-native source of the kernel, replacing reproject::read_png
+ * (src/image_formats.cpp:174-204: lodepng::decode + pow loop) and reproject::read_exr (:208-303: readPixels + half->float
+ * loop with the name -> index mapping of :266-285); the pow / half->float arithmetic itself is fused into the kernel's
+ * texel load.  EXR: blocks are inflated on `threads` host cores, the predictor / byte-plane / channel scatter runs on the
+ * device.  PNG: inflate + un-filtering are sequential and stay on the host; the RGBA8 pixels go up from pinned memory.
+ * Supported: single-part scan-line EXR, HALF channels R,G,B[,A][,Z], NONE / ZIPS / ZIP; non-interlaced 8-bit PNG of any
+ * colour type.  Everything else: LRP_E_UNSUPPORTED_FORMAT.  A decoder owns pinned + device workspaces; one per thread. */
+typedef struct lrp_decoder lrp_decoder;
+int lrp_exr_info(const void *file, size_t n, int32_t *width, int32_t *height, int32_t *channels);
+int lrp_png_info(const void *file, size_t n, int32_t *width, int32_t *height);
+int lrp_decoder_create(lrp_ctx *ctx, int32_t max_width, int32_t max_height, int32_t max_channels, lrp_decoder **out);
+int lrp_decoder_destroy(lrp_decoder *dec);
+/* planes R, G, B, [A], [Z] (the reference's channel order) of IEEE half, plane stride width * height */
+int lrp_decoder_exr(lrp_decoder *dec, const void *file, size_t n, int32_t threads, void *out_half_planar_dev,
+                    void *cuda_stream);
+/* RGBA8 as lodepng::decode delivers it (the kernel reads it as LRP_FMT_U8_RGBA with channels = 3) */
+int lrp_decoder_png(lrp_decoder *dec, const void *file, size_t n, void *out_rgba_dev, void *cuda_stream);
+
 /* ---- test hooks (Level-0 parity) -------------------------- */
 /* per-pixel (sx, sy) of sub-sample (0,0): out_sxy_dev = float[H*W*2] on device */
 int lrp_debug_coords(lrp_ctx *ctx, const lrp_image *in_geom, const lrp_image *out_geom,

@@ -147,3 +147,19 @@ def test_exr_incompressible_blocks_are_stored_raw(lrp):
     assert len(exr) < planes.nbytes + 1024  # raw blocks: never larger than the pixels + header
     names, data = co.exr_decode(exr)
     assert (co.exr_to_planes(names, data, 3) == planes).all()
+
+
+# ---- decode side: container parsing on the host (no GPU involved) ----
+
+def test_exr_and_png_info(lrp):
+    planes = half_planes(4, 33, 50)
+    exr = lrp.exr_assemble(co.exr_pack(planes), 50, 33, 4, 6, 1)
+    assert lrp.exr_info(exr) == (50, 33, 4)
+    img = images()["noise"]
+    png = lrp.png_assemble(co.png_filter_minsum(img), img.shape[1], img.shape[0], 3, 6, 1)
+    assert lrp.png_info(png) == (img.shape[1], img.shape[0])
+    for bad in (b"", b"\x89PNG\r\n\x1a\n", exr[:20], png[:30]):
+        with pytest.raises(lrp.LrpError):
+            lrp.exr_info(bad)
+        with pytest.raises(lrp.LrpError):
+            lrp.png_info(bad)

@@ -1,0 +1,174 @@
+"""Decode side (`-m gpu`): lrp_decoder_exr / lrp_decoder_png against the reference's own readers on files written by
+independent writers — OpenEXR itself (inside cv2: ZIP, ZIPS, uncompressed), the reference's lodepng, Pillow (every
+filter type, palette / grey / alpha images) and liblrp's own encoders (device deflate)."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+co = ol.codec_oracle()
+os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+
+
+@pytest.fixture(scope="module")
+def lrp():
+    import lrp as m
+    m.lib()
+    return m
+
+
+@pytest.fixture(scope="module")
+def ctx(lrp):
+    c = lrp.Context(0, 2)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def dec(lrp, ctx):
+    d = lrp.Decoder(ctx, 2048, 1100, 5)
+    yield d
+    d.close()
+
+
+def _half_image(h, w, c, seed):
+    rng = np.random.default_rng(seed)
+    v = (rng.random((h, w, c), dtype=np.float32) * 3 - 1).astype(np.float16)
+    v[::4, ::3] = np.float16(0.5)
+    return v
+
+
+@pytest.mark.parametrize("h,w,c", [(1, 1, 3), (16, 8, 3), (17, 33, 4), (40, 1001, 3), (135, 240, 4), (1080, 1920, 4)])
+@pytest.mark.parametrize("comp", ["zip", "zips", "none"])
+def test_exr_written_by_openexr_decodes_like_openexr(lrp, dec, tmp_path, h, w, c, comp):
+    """cv2 writes with the OpenEXR library (B,G,R[,A] order, HALF); our planes must hold the same bit patterns in the
+    reference's R,G,B[,A] order — and equal what OpenEXR's own reader returns."""
+    import cv2
+    img = _half_image(h, w, c, h * w + c)
+    p = str(tmp_path / "t.exr")
+    flag = {"zip": cv2.IMWRITE_EXR_COMPRESSION_ZIP, "zips": cv2.IMWRITE_EXR_COMPRESSION_ZIPS,
+            "none": cv2.IMWRITE_EXR_COMPRESSION_NO}[comp]
+    assert cv2.imwrite(p, img.astype(np.float32), [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF,
+                                                   cv2.IMWRITE_EXR_COMPRESSION, flag])
+    data = open(p, "rb").read()
+    assert lrp.exr_info(data) == (w, h, c)
+    got = dec.exr(data, 4).cpu().numpy().view(np.uint16)
+    back = cv2.imread(p, cv2.IMREAD_UNCHANGED).astype(np.float16).reshape(h, w, c)  # OpenEXR's reader
+    order = [2, 1, 0] + ([3] if c == 4 else [])  # cv2 channel of plane R, G, B, A
+    for plane, k in enumerate(order):
+        assert (got[plane] == img[..., k].view(np.uint16)).all()
+        assert (got[plane] == back[..., k].view(np.uint16)).all()
+
+
+@pytest.mark.parametrize("c,h,w,finite", [(3, 40, 33, True), (4, 100, 64, True), (5, 17, 7, True), (4, 33, 50, False)])
+def test_exr_roundtrip_through_our_writers(lrp, ctx, dec, c, h, w, finite):
+    """host-deflated and device-deflated files (raw blocks included), 5-channel RGBAZ included: planes come back in
+    save_exr's order, which is read_exr's order"""
+    import torch
+    rng = np.random.default_rng(c * h)
+    planes = _half_image(h, w, c, 3).transpose(2, 0, 1).copy().view(np.uint16) if finite else \
+        rng.integers(0, 65536, (c, h, w), dtype=np.uint16)
+    t = torch.from_numpy(planes.view(np.int16)).cuda()
+    enc = lrp.Encoder(ctx, 2048, 1100, 5)
+    try:
+        files = [enc.exr(t), lrp.exr_assemble(co.exr_pack(planes), w, h, c, 6, 2)]
+    finally:
+        enc.close()
+    for data in files:
+        got = dec.exr(data, 3).cpu().numpy().view(np.uint16)
+        assert (got == planes).all()
+
+
+def test_exr_unsupported_and_malformed(lrp, dec, tmp_path):
+    import cv2
+    p = str(tmp_path / "f.exr")
+    cv2.imwrite(p, np.zeros((8, 8, 3), np.float32), [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_FLOAT])
+    with pytest.raises(lrp.LrpError):  # FLOAT channels: read_exr asks OpenEXR to convert; not supported here
+        dec.exr(open(p, "rb").read())
+    cv2.imwrite(p, np.zeros((8, 8, 3), np.float32), [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF,
+                                                     cv2.IMWRITE_EXR_COMPRESSION, cv2.IMWRITE_EXR_COMPRESSION_PIZ])
+    with pytest.raises(lrp.LrpError):
+        dec.exr(open(p, "rb").read())
+    good = lrp.exr_assemble(co.exr_pack(np.zeros((3, 20, 10), np.uint16)), 10, 20, 3, 6, 1)
+    for bad in (good[:50], good[:-7], b"nope" + good[4:]):
+        with pytest.raises(lrp.LrpError):
+            dec.exr(bad)
+
+
+def _png_cases():
+    from PIL import Image
+    rng = np.random.default_rng(4)
+    y, x = np.mgrid[0:61, 0:83]
+    rgb = np.stack([(x * 3 + y) & 255, (x + y * 2) & 255, (x * y) & 255], axis=-1).astype(np.uint8)
+    rgb[30:] = rng.integers(0, 256, rgb[30:].shape, dtype=np.uint8)
+    rgba = np.dstack([rgb, ((x * 5) & 255).astype(np.uint8)])
+    cases = {}
+    for name, im in (("rgb", Image.fromarray(rgb)), ("rgba", Image.fromarray(rgba)),
+                     ("grey", Image.fromarray(rgb[..., 0])), ("la", Image.fromarray(rgba).convert("LA")),
+                     ("palette", Image.fromarray(rgb).quantize(64))):
+        for opt in (False, True):
+            b = io.BytesIO()
+            im.save(b, "PNG", optimize=opt, compress_level=9 if opt else 1)
+            cases["%s_%d" % (name, opt)] = b.getvalue()
+    return cases
+
+
+@pytest.mark.parametrize("name", sorted(_png_cases()))
+def test_png_written_by_pillow_decodes_like_lodepng(lrp, dec, name):
+    from PIL import Image
+    data = _png_cases()[name]
+    got = dec.png(data).cpu().numpy()
+    ref = ol.reference_lodepng()
+    want = ref.decode(data) if ref is not None else np.asarray(Image.open(io.BytesIO(data)).convert("RGBA"))
+    assert got.shape == want.shape and (got == want).all()
+
+
+def test_png_written_by_the_reference_and_by_us(lrp, ctx, dec):
+    import torch
+    rng = np.random.default_rng(8)
+    img = rng.integers(0, 256, (200, 333, 4), dtype=np.uint8)
+    img[:100] = (img[:100] // 32) * 32
+    img[..., 3] = 255
+    files = []
+    ref = ol.reference_lodepng()
+    if ref is not None:
+        files.append(ref.encode(img))  # save_png's writer: every filter type occurs
+    enc = lrp.Encoder(ctx, 2048, 1100, 4)
+    try:
+        files.append(enc.png(torch.from_numpy(img).cuda(), 3))
+    finally:
+        enc.close()
+    files.append(lrp.png_assemble(co.png_filter_minsum(img[..., :3]), 333, 200, 3, 6, 4))
+    for data in files:
+        assert lrp.png_info(data) == (333, 200)
+        assert (dec.png(data).cpu().numpy() == img).all()
+
+
+def test_file_to_file_png_pipeline_matches_the_reference_chain(lrp, ctx, dec):
+    """read_png -> reproject -> save_png, here: decoder -> fused kernel -> device encoder; the written file, read by the
+    reference's lodepng, holds what the oracle's chain (png_decode -> reproject -> png_encode) computes."""
+    import torch
+    orc = ol.oracle()
+    w, h, W, H = 256, 128, 160, 90
+    src = np.random.default_rng(6).integers(0, 256, (h, w, 4), dtype=np.uint8)
+    src[..., 3] = 255
+    file_in = lrp.png_assemble(co.png_filter_minsum(src[..., :3]), w, h, 3, 6, 2)
+    rot = orc.rotation_from_degrees(30, 20, 10)
+    il, olens = ol.erect(), ol.rect(18.0, 36.0, W, H)
+    src_t = dec.png(file_in)
+    dst_t = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
+    ctx.reproject(src_t, lrp.lens_from(il), lrp.FMT_U8_RGBA, dst_t, lrp.lens_from(olens), lrp.FMT_U8_RGBA,
+                  lrp.make_params(1, lrp.BICUBIC, rot, None))
+    enc = lrp.Encoder(ctx, W, H, 4)
+    try:
+        file_out = enc.png(dst_t, 3)
+    finally:
+        enc.close()
+    want = orc.png_encode(orc.reproject(orc.png_decode(src), il, olens, W, H, 1, ol.BICUBIC, rot))
+    ref = ol.reference_lodepng()
+    got = ref.decode(file_out) if ref is not None else np.dstack([co.png_decode(file_out), np.full((H, W), 255, np.uint8)])
+    assert (got == want).all()
