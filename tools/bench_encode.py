@@ -116,6 +116,35 @@ def main():
     if ref is not None:
         assert (ref.decode(enc.png(dst, 3)) == dst.cpu().numpy()).all(), "device-deflated file does not decode to the sink"
     enc.close()
+    # ---- decode side: file bytes -> device-resident codec-native source ----
+    dec = lrp.Decoder(ctx, 8192, 4096, 4)
+    enc = lrp.Encoder(ctx, W, H, 4)
+    smooth = (torch.rand((4, H, W), device=dev) * 0.01 + torch.linspace(0, 2, W, device=dev)).to(torch.float16)
+    exr_file = enc.exr(smooth)  # a compressible RGBA half frame, device-deflated
+    enc.close()
+    for T in sorted({1, args.threads}):
+        dec.exr(exr_file, T)
+        t0 = time.perf_counter()
+        for _ in range(4):
+            dec.exr(exr_file, T)
+        dt = (time.perf_counter() - t0) / 4
+        out["exr_decoder_T%d" % T] = {"s": dt, "mpix_per_s": W * H / dt / 1e6, "file_bytes": len(exr_file)}
+    if ref is not None:  # the c2 source size: 8192 x 4096, written by the reference's own writer
+        big = torch.cat([dst, dst], dim=1)[:, :7680]
+        big = torch.cat([big, big], dim=0)[:4096].contiguous()
+        png_file = ref.encode(big.cpu().numpy())
+        dec.png(png_file)
+        t0 = time.perf_counter()
+        got = dec.png(png_file)
+        dt = time.perf_counter() - t0
+        px = big.shape[0] * big.shape[1]
+        out["png_decoder"] = {"s": dt, "mpix_per_s": px / dt / 1e6, "file_bytes": len(png_file), "size": list(big.shape[:2])}
+        t0 = time.perf_counter()
+        want = ref.decode(png_file)
+        dt = time.perf_counter() - t0
+        out["reference_lodepng_decode"] = {"s": dt, "mpix_per_s": px / dt / 1e6}
+        assert (got.cpu().numpy() == want).all()
+    dec.close()
     out["host_threads"] = args.threads
     print(json.dumps(out))
     ctx.close()
