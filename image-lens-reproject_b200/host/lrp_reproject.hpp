@@ -8,6 +8,7 @@
 //   * reproject_and_post_process() fuses the two calls the worker makes back to back
 //     (reference src/main.cpp:597-603) into one kernel launch.
 #pragma once
+#include <cstdio>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -111,5 +112,70 @@ inline void computeRotationMatrix(float pan, float pitch, float roll, float matr
 }
 
 inline void test_conversion_math() {} // reference src/reproject.cpp:467 is an empty stub
+
+// ---- codec edges for device-resident images (reference src/image_formats.cpp) ----
+// The reference's readers / writers work on float32 `Image`s in host memory; their B200 counterparts keep the image in
+// its codec-native form on the device (RGBA8 / planar half), so these mirrors take a device pointer instead of an Image.
+
+// save_png (:144-172) / save_exr (:305-345) for a sink the fused kernel wrote: encodes on the device, writes `path`
+class Encoder {
+public:
+  Encoder(lrp_ctx *ctx, int max_width, int max_height, int max_channels = 5) {
+    int rc = lrp_encoder_create(ctx, max_width, max_height, max_channels, &e_);
+    if (rc != LRP_OK) throw error(rc);
+  }
+  ~Encoder() { lrp_encoder_destroy(e_); }
+  Encoder(const Encoder &) = delete;
+  Encoder &operator=(const Encoder &) = delete;
+  void save_png(const void *rgba_dev, int width, int height, const std::string &path, void *stream = nullptr) {
+    const void *bytes = nullptr;
+    size_t n = 0;
+    int rc = lrp_encoder_png(e_, rgba_dev, width, height, 3, stream, &bytes, &n);
+    if (rc != LRP_OK) throw error(rc);
+    write(path, bytes, n);
+  }
+  void save_exr(const void *half_planar_dev, int width, int height, int channels, const std::string &path,
+                void *stream = nullptr) {
+    const void *bytes = nullptr;
+    size_t n = 0;
+    int rc = lrp_encoder_exr(e_, half_planar_dev, width, height, channels, stream, &bytes, &n);
+    if (rc != LRP_OK) throw error(rc);
+    write(path, bytes, n);
+  }
+
+private:
+  static void write(const std::string &path, const void *bytes, size_t n) {
+    std::FILE *f = std::fopen(path.c_str(), "wb");
+    if (!f || std::fwrite(bytes, 1, n, f) != n) {
+      if (f) std::fclose(f);
+      throw std::runtime_error("cannot write " + path); // the reference's writers throw / abort on I/O errors too
+    }
+    std::fclose(f);
+  }
+  lrp_encoder *e_ = nullptr;
+};
+
+// read_png (:174-204) / read_exr (:208-303) into a device buffer the fused kernel reads
+class Decoder {
+public:
+  Decoder(lrp_ctx *ctx, int max_width, int max_height, int max_channels = 5) {
+    int rc = lrp_decoder_create(ctx, max_width, max_height, max_channels, &d_);
+    if (rc != LRP_OK) throw error(rc);
+  }
+  ~Decoder() { lrp_decoder_destroy(d_); }
+  Decoder(const Decoder &) = delete;
+  Decoder &operator=(const Decoder &) = delete;
+  void read_png(const void *file, size_t n, void *rgba_dev, void *stream = nullptr) {
+    int rc = lrp_decoder_png(d_, file, n, rgba_dev, stream);
+    if (rc != LRP_OK) throw error(rc);
+  }
+  void read_exr(const void *file, size_t n, int threads, void *half_planar_dev, void *stream = nullptr) {
+    int rc = lrp_decoder_exr(d_, file, n, threads, half_planar_dev, stream);
+    if (rc != LRP_OK) throw error(rc);
+  }
+
+private:
+  lrp_decoder *d_ = nullptr;
+};
 
 } // namespace lrp_b200

@@ -186,3 +186,16 @@ def test_packed_arithmetic_is_never_contracted(lrp):
         assert len(sources) <= 1, (name, sources)  # one parameter: neg_zero2
     assert n_ffma2 > 1000  # the packed bicubic kernels are really in there
     assert n_exact > 100   # and so is the exact-product form
+
+
+def test_cpp_host_mirror_compiles_and_links(lrp, tmp_path):
+    """host/lrp_reproject.hpp (namespace lrp_b200: the reference's `namespace reproject` signatures + the codec-edge
+    wrappers) is valid C++17 against include/lrp.h and links against liblrp.so"""
+    c = tmp_path / "m.cpp"
+    c.write_text('#include "lrp_reproject.hpp"\n'
+                 'int main() { lrp_b200::Image im; (void)im; float m[9]; lrp_b200::computeRotationMatrix(0.1f, 0.2f, 0.3f, m);\n'
+                 '  return (sizeof(lrp_b200::Encoder) && sizeof(lrp_b200::Decoder) && m[0] == m[0]) ? 0 : 1; }\n')
+    exe = tmp_path / "m"
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(PKG, "host"), str(c), "-o", str(exe),
+                    "-L", PKG, "-llrp", "-Wl,-rpath," + PKG], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
