@@ -20,7 +20,10 @@
 namespace lrp {
 
 constexpr int TILE = 32;        // 32x32 output pixels per tile; one warp = 32 consecutive pixels of a row
-constexpr int NTHREADS = 1024;  // one persistent CTA per SM
+#ifndef LRP_GATHER_THREADS
+#define LRP_GATHER_THREADS 1024
+#endif
+constexpr int NTHREADS = LRP_GATHER_THREADS;  // one persistent CTA per SM
 
 // ---- lens functions -----------------------------------------------------------------------
 

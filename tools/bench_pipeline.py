@@ -1,0 +1,127 @@
+#!/usr/bin/env python
+"""File -> file pipeline on one B200 (north-star: "decode/encode pipelined against the GPU with pinned buffers and per-GPU
+CUDA streams"): T host threads, each with its own stream, lrp_decoder and lrp_encoder, pull PNG files (c2: 8192x4096
+equirect) from a queue: decode (host inflate + unfilter) -> upload -> fused reproject kernel -> PNG filter + deflate on the
+GPU -> file bytes.  Beside it, the reference's chain for ONE frame on ONE core, step by step, with the reference's own
+code where it compiled here (lodepng decode / encode, reproject()); the float conversions are numpy restatements of
+read_png's / save_png's loops (src/image_formats.cpp:189-199, 150-165).
+
+usage: python tools/bench_pipeline.py [--threads T] [--frames N]
+"""
+import argparse
+import json
+import os
+import queue
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "image-lens-reproject_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--threads", type=int, default=len(os.sched_getaffinity(0)))
+    ap.add_argument("--frames", type=int, default=64)
+    args = ap.parse_args()
+    import numpy as np
+    import torch
+    import lrp
+    import oracle_lib as ol
+    lrp.lib()
+    dev = torch.device("cuda", 0)
+    ctx = lrp.Context(0, 2)
+    w, h, W, H = 8192, 4096, 3840, 2160
+    il, olens = lrp.lens_equirectangular(), lrp.lens_rectilinear(18.0, 36.0, W, H)
+    rot = lrp.rotation_from_degrees(30, 20, 10)
+    p = lrp.make_params(1, lrp.BICUBIC, rot, None)
+
+    # two distinct synthetic panoramas (smooth + sensor-like noise), written as PNG by the device encoder
+    enc0 = lrp.Encoder(ctx, w, h, 4)
+    files = []
+    for k in range(2):
+        y, x = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")
+        pano = torch.stack([128 + 100 * torch.sin(x * 0.002 + k) * torch.cos(y * 0.003), 128 + 90 * torch.cos(x * 0.0013 + y * 0.0021),
+                            128 + 80 * torch.sin((x + y) * 0.0008 + k), torch.full_like(x, 255.0)], dim=-1)
+        pano[..., :3] += torch.randn((h, w, 3), device=dev) * 2.0
+        files.append(enc0.png(pano.clamp(0, 255).to(torch.uint8).contiguous(), 3))
+        del pano
+    enc0.close()
+
+    q = queue.Queue()
+    for i in range(args.frames):
+        q.put(files[i % 2])
+    out_bytes, lock = [0], threading.Lock()
+    stage_s = {"decode": 0.0, "gpu+encode": 0.0}
+
+    ready = threading.Barrier(args.threads + 1)
+
+    def worker():
+        torch.cuda.set_device(0)
+        st = torch.cuda.Stream()
+        dec, enc = lrp.Decoder(ctx, w, h, 4), lrp.Encoder(ctx, W, H, 4)  # pinned + device workspaces: set-up, not timed
+        dst = torch.empty((H, W, 4), dtype=torch.uint8, device=dev)
+        ready.wait()
+        while True:
+            try:
+                data = q.get_nowait()
+            except queue.Empty:
+                break
+            t0 = time.perf_counter()
+            src = dec.png(data, stream=st.cuda_stream)
+            t1 = time.perf_counter()
+            ctx.reproject(src, il, lrp.FMT_U8_RGBA, dst, olens, lrp.FMT_U8_RGBA, p, stream=st.cuda_stream)
+            png = enc.png(dst, 3, stream=st.cuda_stream)
+            t2 = time.perf_counter()
+            with lock:
+                out_bytes[0] += len(png)
+                stage_s["decode"] += t1 - t0
+                stage_s["gpu+encode"] += t2 - t1
+        dec.close()
+        enc.close()
+
+    ths = [threading.Thread(target=worker) for _ in range(args.threads)]
+    for t in ths:
+        t.start()
+    ready.wait()
+    t0 = time.perf_counter()
+    for t in ths:
+        t.join()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    res = {"frames": args.frames, "threads": args.threads, "seconds": dt, "frames_per_s": args.frames / dt,
+           "output_gpix_per_s": args.frames * W * H / dt / 1e9, "in_file_bytes": len(files[0]),
+           "out_file_bytes_avg": out_bytes[0] / args.frames,
+           "per_frame_thread_s": {k: v / args.frames for k, v in stage_s.items()}}
+
+    # the reference's chain, one frame, one core
+    ref_png, ref = ol.reference_lodepng(), ol.reference()
+    if ref_png is not None and ref is not None:
+        orc = ol.oracle()
+        steps = {}
+        t = time.perf_counter()
+        rgba = ref_png.decode(files[0])
+        steps["lodepng::decode"] = time.perf_counter() - t
+        t = time.perf_counter()
+        f32 = np.power(rgba[..., :3].astype(np.float32) / np.float32(255.0), np.float32(2.2))
+        steps["read_png pow loop (numpy)"] = time.perf_counter() - t
+        t = time.perf_counter()
+        out = ref.reproject(f32, ol.erect(), ol.rect(18.0, 36.0, W, H), W, H, 1, ol.BICUBIC, orc.rotation_from_degrees(30, 20, 10))
+        steps["reproject()"] = time.perf_counter() - t
+        t = time.perf_counter()
+        u8 = orc.png_encode(out)
+        steps["save_png quantise loop (oracle C)"] = time.perf_counter() - t
+        t = time.perf_counter()
+        ref_png.encode(u8)
+        steps["lodepng::encode"] = time.perf_counter() - t
+        res["reference_one_frame_one_core_s"] = steps
+        tot = sum(steps.values())
+        res["reference_frames_per_s_if_all_%d_cores_scale" % args.threads] = args.threads / tot
+    print(json.dumps(res))
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
