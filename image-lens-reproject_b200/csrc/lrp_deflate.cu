@@ -517,19 +517,13 @@ static void put32be(std::vector<unsigned char> &v, uint32_t x) {
 
 extern "C" {
 
-int lrp_encoder_create(lrp_ctx *ctx, int32_t max_width, int32_t max_height, int32_t max_channels, lrp_encoder **out) {
-  if (!ctx || !out || max_width <= 0 || max_height <= 0 || max_channels < 1 || max_channels > 5) return LRP_E_BAD_ARG;
+static int encoder_alloc(lrp_ctx *ctx, size_t cap_packed, size_t cap_bands, size_t cap_streams, lrp_encoder **out) {
   *out = nullptr;
   const int dev = lrp_ctx_phys_device_(ctx);
   if (cudaSetDevice(dev) != cudaSuccess) return LRP_E_CUDA;
   lrp_encoder *e = new lrp_encoder();
   e->ctx = ctx, e->device = dev;
-  const size_t png_n = lrp_png_packed_bytes(max_width, max_height, 4);
-  const size_t exr_n = (size_t)max_width * max_height * max_channels * 2;
-  const size_t exr_stream = (size_t)16 * max_channels * max_width * 2;
-  e->cap_packed = std::max(png_n, exr_n);
-  e->cap_streams = std::max<size_t>(1, ((size_t)max_height + 15) / 16);
-  e->cap_bands = std::max((png_n + DF_BAND - 1) / DF_BAND, e->cap_streams * ((exr_stream + DF_BAND - 1) / DF_BAND)) + 1;
+  e->cap_packed = cap_packed, e->cap_bands = cap_bands, e->cap_streams = cap_streams;
   const size_t cb = compact_bound(e->cap_packed, e->cap_bands, e->cap_streams);
   bool ok = cudaMalloc(&e->d_packed, e->cap_packed) == cudaSuccess &&
             cudaMalloc(&e->d_slots, e->cap_bands * DF_SLOT) == cudaSuccess && cudaMalloc(&e->d_compact, cb) == cudaSuccess &&
@@ -545,6 +539,43 @@ int lrp_encoder_create(lrp_ctx *ctx, int32_t max_width, int32_t max_height, int3
   }
   *out = e;
   return LRP_OK;
+}
+
+int lrp_encoder_create(lrp_ctx *ctx, int32_t max_width, int32_t max_height, int32_t max_channels, lrp_encoder **out) {
+  if (!ctx || !out || max_width <= 0 || max_height <= 0 || max_channels < 1 || max_channels > 5) return LRP_E_BAD_ARG;
+  const size_t png_n = lrp_png_packed_bytes(max_width, max_height, 4);
+  const size_t exr_n = (size_t)max_width * max_height * max_channels * 2;
+  const size_t exr_stream = (size_t)16 * max_channels * max_width * 2;
+  const size_t streams = std::max<size_t>(1, ((size_t)max_height + 15) / 16);
+  const size_t bands = std::max((png_n + DF_BAND - 1) / DF_BAND, streams * ((exr_stream + DF_BAND - 1) / DF_BAND)) + 1;
+  return encoder_alloc(ctx, std::max(png_n, exr_n), bands, streams, out);
+}
+
+/* test hook: the device deflate alone.  `in_dev` (n bytes) is cut into zlib streams of stream_bytes; the streams come
+ * back concatenated (malloc'ed, release with lrp_free_bytes), stream i at [offsets[i], offsets[i + 1]). */
+int lrp_debug_deflate(lrp_ctx *ctx, const void *in_dev, size_t n, size_t stream_bytes, void *cuda_stream, void **out_bytes,
+                      uint64_t *offsets /* n_streams + 1 */) {
+  if (!ctx || !in_dev || !out_bytes || !offsets || n == 0 || stream_bytes == 0) return LRP_E_BAD_ARG;
+  const size_t streams = (n + stream_bytes - 1) / stream_bytes, bps = (stream_bytes + DF_BAND - 1) / DF_BAND;
+  lrp_encoder *e = nullptr;
+  int rc = encoder_alloc(ctx, n, streams * bps + 1, streams, &e);
+  if (rc != LRP_OK) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  cudaEventRecord(e->ev[0], st);
+  if (cudaMemcpyAsync(e->d_packed, in_dev, n, cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = LRP_E_CUDA;
+  if (rc == LRP_OK) rc = deflate_to_host(e, n, stream_bytes, st);
+  if (rc == LRP_OK) {
+    const size_t total = (size_t)e->h_stream_off[streams];
+    void *mem = malloc(total ? total : 1);
+    if (!mem) rc = LRP_E_OOM;
+    else {
+      memcpy(mem, e->h_compact, total);
+      for (size_t i = 0; i <= streams; ++i) offsets[i] = e->h_stream_off[i];
+      *out_bytes = mem;
+    }
+  }
+  encoder_free(e);
+  return rc;
 }
 
 int lrp_encoder_destroy(lrp_encoder *e) {

@@ -131,6 +131,7 @@ def lib():
         for f in (L.lrp_save_png_device, L.lrp_save_exr_device):
             f.argtypes = [vp, vp, i32, i32, i32, i32, i32, C.c_char_p, vp]
         L.lrp_free_bytes.argtypes = [vp]
+        L.lrp_debug_deflate.argtypes = [vp, vp, C.c_size_t, C.c_size_t, vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
         L.lrp_exr_info.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
         L.lrp_png_info.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(i32), C.POINTER(i32)]
         L.lrp_decoder_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
@@ -427,6 +428,20 @@ class Context:
         c, h, w = (int(v) for v in planar_t.shape)
         check(lib().lrp_save_exr_device(self.h, C.c_void_p(planar_t.data_ptr()), w, h, c, level, threads,
                                         os.fsencode(path), self._stream(stream)), "lrp_save_exr_device")
+
+    def debug_deflate(self, bytes_t, stream_bytes=None, stream=None):
+        """device deflate of a uint8 tensor -> list of zlib streams (bytes)"""
+        n = bytes_t.numel()
+        sb = n if stream_bytes is None else stream_bytes
+        ns = (n + sb - 1) // sb
+        out, offs = C.c_void_p(None), (C.c_uint64 * (ns + 1))()
+        check(lib().lrp_debug_deflate(self.h, C.c_void_p(bytes_t.data_ptr()), n, sb, self._stream(stream), C.byref(out), offs),
+              "lrp_debug_deflate")
+        try:
+            blob = C.string_at(out.value, offs[ns])
+        finally:
+            lib().lrp_free_bytes(out)
+        return [blob[offs[i]:offs[i + 1]] for i in range(ns)]
 
     # -- asynchronous host-buffer jobs on this context's worker streams --
     def submit(self, job):

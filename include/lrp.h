@@ -345,6 +345,12 @@ int lrp_debug_coords(lrp_ctx *ctx, const lrp_image *in_geom, const lrp_image *ou
 int lrp_debug_libm(lrp_ctx *ctx, int fn, const float *a_dev, const float *b_dev, float *out_dev,
                    size_t n, void *cuda_stream);
 
+/* the device deflate alone (csrc/lrp_deflate.cu): in_dev is cut into independent zlib streams of stream_bytes; they
+ * come back concatenated (release with lrp_free_bytes), stream i at [offsets[i], offsets[i + 1]); offsets holds
+ * ceil(n / stream_bytes) + 1 entries */
+int lrp_debug_deflate(lrp_ctx *ctx, const void *in_dev, size_t n, size_t stream_bytes, void *cuda_stream, void **out_bytes,
+                      uint64_t *offsets);
+
 /* the fused 8-bit sink quantiser (save_png arithmetic, src/image_formats.cpp:156-158) element-wise */
 int lrp_debug_encode_u8(lrp_ctx *ctx, const float *in_dev, uint8_t *out_dev, size_t n, void *cuda_stream);
 

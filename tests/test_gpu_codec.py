@@ -236,3 +236,47 @@ def test_device_deflate_ratio_on_a_reprojected_frame(lrp, ctx):
     assert (_decode_png(png) == dst.cpu().numpy()).all()
     stream = ctx.png_pack(dst, 3).cpu().numpy().tobytes()
     assert len(png) < 1.15 * len(zlib.compress(stream, 6))
+
+
+# ---- the device deflate alone, on byte distributions chosen to stress the Huffman construction ----
+
+def _distributions():
+    rng = np.random.default_rng(12)
+    fib = [1, 1]
+    while sum(fib) + fib[-1] + fib[-2] < 32768:
+        fib.append(fib[-1] + fib[-2])
+    fib_band = np.concatenate([np.full(c, s, np.uint8) for s, c in enumerate(fib)])  # unbounded Huffman depth = len(fib) - 1
+    rng.shuffle(fib_band)
+    geo = np.minimum(rng.geometric(0.5, 200000) - 1, 255).astype(np.uint8)            # 2^-k tail: many rare symbols
+    return {
+        "fibonacci_band": fib_band,
+        "fibonacci_x5": np.tile(fib_band, 5),
+        "geometric": geo,
+        "one_symbol": np.full(70000, 9, np.uint8),
+        "two_symbols": rng.integers(0, 2, 40000, dtype=np.uint8) * 255,
+        "uniform": rng.integers(0, 256, 100000, dtype=np.uint8),
+        "rare_255_of_256": np.concatenate([np.zeros(32768 - 255, np.uint8), np.arange(1, 256, dtype=np.uint8)]),
+        "len_1": np.array([200], np.uint8),
+        "len_2": np.array([0, 0], np.uint8),
+        "band_minus_1": rng.integers(0, 7, 32767, dtype=np.uint8),
+        "band_exact": rng.integers(0, 7, 32768, dtype=np.uint8),
+        "band_plus_1": rng.integers(0, 7, 32769, dtype=np.uint8),
+    }
+
+
+@pytest.mark.parametrize("name", sorted(_distributions()))
+def test_device_deflate_is_valid_zlib_for_any_distribution(lrp, ctx, name):
+    """zlib's inflate (strict about over-subscribed / incomplete codes, code lengths > 15 and the Adler-32) must return the
+    input; the Fibonacci band would need 21-bit codes without the weight floor."""
+    import torch
+    import zlib
+    data = _distributions()[name]
+    t = torch.from_numpy(data).cuda()
+    (z,) = ctx.debug_deflate(t)
+    assert zlib.decompress(z) == data.tobytes()
+    assert len(z) <= data.size + 5 * (data.size // 32768 + 1) + 8
+    if name in ("one_symbol", "two_symbols", "geometric", "fibonacci_band"):
+        assert len(z) < 0.5 * data.size
+    # the same bytes as independent streams of 50 000 bytes (the EXR layout: several bands + a short last stream)
+    parts = ctx.debug_deflate(t, 50000)
+    assert b"".join(zlib.decompress(p) for p in parts) == data.tobytes()
