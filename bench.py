@@ -72,14 +72,36 @@ def recorded_traffic(interp):
 
 # ---- clocks sampling --------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons of one GPU, sampled DURING the timed region: NVML in a thread every 2 ms (the timed
+    region of the default run lasts tens of milliseconds), `nvidia-smi -lms` as the fall-back."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+    def __init__(self, gpu_index, uuid=None):
+        self.gpu, self.uuid, self.proc, self.lines = gpu_index, uuid, None, []
+        self.nvml, self.samples, self.stop_flag, self.max_mhz = None, [], False, None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        if self.uuid:
+            try:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + self.uuid).encode())
+            except Exception:
+                pass
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.max_mhz = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -89,11 +111,32 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append((float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)),
+                                     int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            sm = [s for s, _ in self.samples]
+            reasons = set()
+            for _, r in self.samples:
+                for bit, name in self.BITS.items():
+                    if r & bit:
+                        reasons.add(name)
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                    "reasons": sorted(reasons), "source": "nvml, 2 ms period, timed region only"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -117,7 +160,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 # ---- the CPU arm ---------------------------------------------------------------------------------------
@@ -223,11 +266,15 @@ def run_gpu_arm(args, rank, world, local_rank):
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    try:
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local_rank, uuid)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if rank == 0:
+        sampler.start()
     ev0.record()
     for _ in range(args.steps):
         step()
