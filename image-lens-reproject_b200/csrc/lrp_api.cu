@@ -534,12 +534,19 @@ struct Pool {
   struct Item {
     lrp_job job;
     uint64_t ticket;
+    bool is_file = false;
+    lrp_file_job fjob;
   };
   struct Worker {
     lrp_ctx *ctx;
     Slot slot;
     std::thread th;
     int dev_index; // index into the pool's ctx list
+    // file jobs: codecs with grow-only workspaces, created on first use
+    lrp_decoder *dec = nullptr;
+    lrp_encoder *enc = nullptr;
+    size_t dec_px = 0, enc_px = 0;
+    int dec_c = 0, enc_c = 0;
   };
   std::vector<lrp_ctx *> ctxs;
   std::vector<Worker *> workers;
@@ -575,6 +582,59 @@ struct Pool {
     return LRP_OK;
   }
 
+  // One iteration of the reference's worker lambda (src/main.cpp:541-620) from file bytes to file bytes:
+  // read_png / read_exr -> reproject (+ post_process) -> save_png / save_exr, the image never leaving the device in between.
+  static int run_file_job(Worker *w, const lrp_file_job &j, const void **bytes, size_t *size) {
+    lrp_ctx *ctx = w->ctx;
+    LRP_CUDA(cudaSetDevice(ctx->phys_device));
+    if (!j.in_file || j.in_size == 0 || j.out_width <= 0 || j.out_height <= 0) return LRP_E_BAD_ARG;
+    int32_t iw = 0, ih = 0, ic = 3;
+    int rc = j.in_kind == LRP_FILE_PNG ? lrp_png_info(j.in_file, j.in_size, &iw, &ih)
+             : j.in_kind == LRP_FILE_EXR ? lrp_exr_info(j.in_file, j.in_size, &iw, &ih, &ic) : LRP_E_BAD_ARG;
+    if (rc != LRP_OK) return rc;
+    if (j.out_kind != LRP_FILE_PNG && j.out_kind != LRP_FILE_EXR) return LRP_E_BAD_ARG;
+    if (j.out_kind == LRP_FILE_PNG && ic > 4) return LRP_E_UNSUPPORTED_FORMAT; // save_png overruns its buffer (UB): refused
+    const size_t ipx = (size_t)iw * ih, opx = (size_t)j.out_width * j.out_height;
+    if (!w->dec || ipx > w->dec_px || ic > w->dec_c) {
+      if (w->dec) lrp_decoder_destroy(w->dec);
+      w->dec = nullptr;
+      rc = lrp_decoder_create(ctx, iw, ih, std::max(ic, 4), &w->dec);
+      if (rc != LRP_OK) return rc;
+      w->dec_px = ipx, w->dec_c = std::max(ic, 4);
+    }
+    if (!w->enc || opx > w->enc_px || ic > w->enc_c) {
+      if (w->enc) lrp_encoder_destroy(w->enc);
+      w->enc = nullptr;
+      rc = lrp_encoder_create(ctx, j.out_width, j.out_height, std::max(ic, 4), &w->enc);
+      if (rc != LRP_OK) return rc;
+      w->enc_px = opx, w->enc_c = std::max(ic, 4);
+    }
+    const bool in_png = j.in_kind == LRP_FILE_PNG, out_png = j.out_kind == LRP_FILE_PNG;
+    rc = slot_reserve(w->slot, in_png ? ipx * 4 : ipx * 2 * ic, out_png ? opx * 4 : opx * 2 * ic);
+    if (rc != LRP_OK) return rc;
+    rc = in_png ? lrp_decoder_png(w->dec, j.in_file, j.in_size, w->slot.d_in, w->slot.stream)
+                : lrp_decoder_exr(w->dec, j.in_file, j.in_size, j.decode_threads > 0 ? j.decode_threads : 1, w->slot.d_in,
+                                  w->slot.stream);
+    if (rc != LRP_OK) return rc;
+    ctx->h2d_bytes += in_png ? ipx * 4 : ipx * 2 * ic;
+    lrp_image din, dout;
+    memset(&din, 0, sizeof(din));
+    din.lens = j.in_lens, din.width = iw, din.height = ih, din.channels = ic;
+    din.layout = ic == 3 ? 0 : ic == 4 ? 2 : 3; // RGB / RGBZ / RGBAZ: informational, as in the reference
+    din.format = in_png ? LRP_FMT_U8_RGBA : LRP_FMT_F16_PLANAR;
+    din.data = w->slot.d_in;
+    dout = din;
+    dout.lens = j.out_lens, dout.width = j.out_width, dout.height = j.out_height;
+    dout.format = out_png ? LRP_FMT_U8_RGBA : LRP_FMT_F16_PLANAR;
+    dout.data = w->slot.d_out;
+    rc = launch_fused(ctx, &din, &dout, &j.params, nullptr, w->slot.stream);
+    if (rc != LRP_OK) return rc;
+    rc = out_png ? lrp_encoder_png(w->enc, w->slot.d_out, j.out_width, j.out_height, ic == 4 ? 4 : 3, w->slot.stream, bytes, size)
+                 : lrp_encoder_exr(w->enc, w->slot.d_out, j.out_width, j.out_height, ic, w->slot.stream, bytes, size);
+    if (rc == LRP_OK) ctx->d2h_bytes += *size;
+    return rc;
+  }
+
   void worker_main(Worker *w) {
     cudaSetDevice(w->ctx->phys_device);
     for (;;) {
@@ -586,8 +646,16 @@ struct Pool {
         it = queue.front();
         queue.pop_front();
       }
-      int rc = run_job(w, it.job);
-      if (it.job.on_done) it.job.on_done(it.job.user, rc);
+      int rc;
+      if (it.is_file) {
+        const void *bytes = nullptr;
+        size_t size = 0;
+        rc = run_file_job(w, it.fjob, &bytes, &size);
+        if (it.fjob.on_done) it.fjob.on_done(it.fjob.user, rc, rc == LRP_OK ? bytes : nullptr, rc == LRP_OK ? size : 0);
+      } else {
+        rc = run_job(w, it.job);
+        if (it.job.on_done) it.job.on_done(it.job.user, rc);
+      }
       {
         std::lock_guard<std::mutex> lk(mu);
         done[it.ticket] = rc;
@@ -618,7 +686,20 @@ struct Pool {
   uint64_t submit(const lrp_job &job) {
     std::lock_guard<std::mutex> lk(mu);
     uint64_t t = next_ticket++;
-    queue.push_back(Item{job, t});
+    Item it;
+    it.job = job, it.ticket = t;
+    queue.push_back(it);
+    in_flight++;
+    cv_work.notify_one();
+    return t;
+  }
+  uint64_t submit_file(const lrp_file_job &job) {
+    std::lock_guard<std::mutex> lk(mu);
+    uint64_t t = next_ticket++;
+    Item it;
+    memset(&it.job, 0, sizeof(it.job));
+    it.ticket = t, it.is_file = true, it.fjob = job;
+    queue.push_back(it);
     in_flight++;
     cv_work.notify_one();
     return t;
@@ -651,6 +732,8 @@ struct Pool {
     for (Worker *w : workers) {
       if (w->th.joinable()) w->th.join();
       cudaSetDevice(w->ctx->phys_device);
+      if (w->dec) lrp_decoder_destroy(w->dec);
+      if (w->enc) lrp_encoder_destroy(w->enc);
       slot_destroy(w->slot);
       delete w;
     }
@@ -1131,6 +1214,12 @@ int lrp_sched_create(const int *devices, int n_devices, int streams_per_device, 
 int lrp_sched_submit(lrp_sched *s, const lrp_job *job) {
   if (!s || !job) return LRP_E_BAD_ARG;
   s->pool.submit(*job);
+  return LRP_OK;
+}
+
+int lrp_sched_submit_file(lrp_sched *s, const lrp_file_job *job) {
+  if (!s || !job) return LRP_E_BAD_ARG;
+  s->pool.submit_file(*job);
   return LRP_OK;
 }
 

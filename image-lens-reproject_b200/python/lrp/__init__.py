@@ -58,6 +58,16 @@ class Job(C.Structure):
                 ("user", C.c_void_p)]
 
 
+FILE_PNG, FILE_EXR = 0, 1
+FILE_DONE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t)
+
+
+class FileJob(C.Structure):
+    _fields_ = [("in_file", C.c_void_p), ("in_size", C.c_size_t), ("in_kind", C.c_int32), ("out_kind", C.c_int32),
+                ("in_lens", Lens), ("out_lens", Lens), ("out_width", C.c_int32), ("out_height", C.c_int32),
+                ("params", Params), ("decode_threads", C.c_int32), ("on_done", FILE_DONE_FN), ("user", C.c_void_p)]
+
+
 _lib = None
 
 
@@ -112,6 +122,7 @@ def lib():
         L.lrp_wait_all.argtypes = [vp]
         L.lrp_sched_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(vp)]
         L.lrp_sched_submit.argtypes = [vp, C.POINTER(Job)]
+        L.lrp_sched_submit_file.argtypes = [vp, C.POINTER(FileJob)]
         L.lrp_sched_wait_all.argtypes = [vp]
         L.lrp_sched_destroy.argtypes = [vp]
         L.lrp_sched_num_devices.argtypes = [vp]
@@ -574,6 +585,22 @@ class Scheduler:
 
     def submit(self, job):
         check(lib().lrp_sched_submit(self.h, C.byref(job)), "lrp_sched_submit")
+
+    def submit_file(self, data, in_kind, in_lens, out_lens, W, H, out_kind, params, sink, decode_threads=2):
+        """file bytes -> file bytes on whichever GPU frees up first; `sink(status, bytes)` is called from a library thread.
+        The caller keeps `data` alive until then (the returned handle holds the references)."""
+        buf = C.create_string_buffer(data, len(data))
+
+        def _done(user, status, ptr, n):
+            sink(status, C.string_at(ptr, n) if status == OK and ptr else None)
+
+        cb = FILE_DONE_FN(_done)
+        j = FileJob()
+        j.in_file, j.in_size, j.in_kind, j.out_kind = C.cast(buf, C.c_void_p), len(data), in_kind, out_kind
+        j.in_lens, j.out_lens, j.out_width, j.out_height = in_lens, out_lens, W, H
+        j.params, j.decode_threads, j.on_done, j.user = params, decode_threads, cb, None
+        check(lib().lrp_sched_submit_file(self.h, C.byref(j)), "lrp_sched_submit_file")
+        return (buf, cb)
 
     def wait_all(self):
         check(lib().lrp_sched_wait_all(self.h), "lrp_sched_wait_all")

@@ -335,6 +335,29 @@ int lrp_decoder_exr(lrp_decoder *dec, const void *file, size_t n, int32_t thread
 /* RGBA8 as lodepng::decode delivers it (the kernel reads it as LRP_FMT_U8_RGBA with channels = 3) */
 int lrp_decoder_png(lrp_decoder *dec, const void *file, size_t n, void *out_rgba_dev, void *cuda_stream);
 
+/* ---- file jobs: one whole iteration of the reference's worker lambda (src/main.cpp:541-620): read_png / read_exr ->
+ * reproject (+ post_process when params.apply_post) -> save_png / save_exr, from the bytes of the input file to the
+ * bytes of the output file; the image stays on the device in between (decoder -> fused kernel -> device encoder).
+ * Submitted to the multi-GPU scheduler like lrp_job; on_done runs on a library thread, file_bytes is valid only
+ * during the call (write it out or copy it).  PNG input has 3 channels, EXR input 3..5 (R,G,B[,A][,Z]); the output
+ * keeps the channel count, as the reference (output.channels = input.channels). */
+typedef enum lrp_file_kind { LRP_FILE_PNG = 0, LRP_FILE_EXR = 1 } lrp_file_kind;
+typedef void (*lrp_file_done_fn)(void *user, int status, const void *file_bytes, size_t file_size);
+typedef struct lrp_file_job {
+  const void *in_file;    /* bytes of the input file; must stay valid until on_done */
+  size_t in_size;
+  int32_t in_kind;        /* lrp_file_kind */
+  int32_t out_kind;       /* lrp_file_kind */
+  lrp_lens in_lens;
+  lrp_lens out_lens;
+  int32_t out_width, out_height;
+  lrp_params params;
+  int32_t decode_threads; /* host threads inflating the blocks of an EXR input (>= 1) */
+  lrp_file_done_fn on_done;
+  void *user;
+} lrp_file_job;
+int lrp_sched_submit_file(lrp_sched *s, const lrp_file_job *job);
+
 /* ---- test hooks (Level-0 parity) -------------------------- */
 /* per-pixel (sx, sy) of sub-sample (0,0): out_sxy_dev = float[H*W*2] on device */
 int lrp_debug_coords(lrp_ctx *ctx, const lrp_image *in_geom, const lrp_image *out_geom,

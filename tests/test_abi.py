@@ -199,3 +199,15 @@ def test_cpp_host_mirror_compiles_and_links(lrp, tmp_path):
     subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(PKG, "host"), str(c), "-o", str(exe),
                     "-L", PKG, "-llrp", "-Wl,-rpath," + PKG], check=True)
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_file_job_layout_matches_the_compiled_header(lrp, tmp_path):
+    c = tmp_path / "fj.c"
+    c.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "lrp.h"\nint main(void){ printf("%zu %zu %zu %zu %zu\\n", '
+                 'sizeof(lrp_file_job), offsetof(lrp_file_job, in_lens), offsetof(lrp_file_job, params), '
+                 'offsetof(lrp_file_job, decode_threads), offsetof(lrp_file_job, on_done)); return 0; }\n')
+    exe = tmp_path / "fj"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.dirname(HDR), str(c), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    F = lrp.FileJob
+    assert got == [C.sizeof(F), F.in_lens.offset, F.params.offset, F.decode_threads.offset, F.on_done.offset]

@@ -144,3 +144,68 @@ def test_static_tile_stride_switch_gives_the_same_bits(lrp, monkeypatch):
         torch.cuda.synchronize()
         assert ol.same_bits(d.cpu().numpy(), want)
     ctx.close()
+
+
+# ---- file jobs: read -> reproject -> save, bytes to bytes, on the multi-GPU scheduler ----
+
+def test_file_jobs_on_the_scheduler_match_the_reference_chain(lrp, monkeypatch):
+    """lrp_sched_submit_file over 4 logical GPUs: PNG -> PNG, PNG -> EXR and EXR -> EXR jobs interleaved.  Every output
+    file, read back with independent readers, holds what the oracle's read -> reproject -> post_process -> save chain
+    computes (bit-exact)."""
+    import os
+    co = ol.codec_oracle()
+    monkeypatch.setenv("LRP_FAKE_GPUS", "4")
+    s = lrp.Scheduler([0, 1, 2, 3], streams_per_device=2)
+    w, h, W, H = 200, 100, 120, 68
+    il, olens = ol.erect(), ol.rect(18.0, 36.0, W, H)
+    rot = ORC.rotation_from_degrees(30, 20, 10)
+    p = lrp.make_params(1, lrp.BICUBIC, rot, (1.5, 4.0))
+    rng = np.random.default_rng(21)
+    results, keep, cases = {}, [], []
+    for k in range(18):
+        kind = k % 3
+        if kind < 2:  # PNG source
+            rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+            rgba[..., 3] = 255
+            data = lrp.png_assemble(co.png_filter_minsum(rgba[..., :3]), w, h, 3, 6, 1)
+            lin = ORC.post_process(ORC.reproject(ORC.png_decode(rgba), il, olens, W, H, 1, ol.BICUBIC, rot), 1.5, 4.0)
+            in_kind, out_kind = lrp.FILE_PNG, (lrp.FILE_PNG if kind == 0 else lrp.FILE_EXR)
+        else:  # EXR source, RGBZ
+            planes = (rng.random((4, h, w), dtype=np.float32) * 2).astype(np.float16)
+            data = lrp.exr_assemble(co.exr_pack(planes.view(np.uint16)), w, h, 4, 6, 1)
+            src = np.ascontiguousarray(planes.astype(np.float32).transpose(1, 2, 0))
+            lin = ORC.post_process(ORC.reproject(src, il, olens, W, H, 1, ol.BICUBIC, rot), 1.5, 4.0)
+            in_kind, out_kind = lrp.FILE_EXR, lrp.FILE_EXR
+        cases.append((out_kind, lin))
+        keep.append(s.submit_file(data, in_kind, lrp.lens_from(il), lrp.lens_from(olens), W, H, out_kind, p,
+                                  lambda status, b, k=k: results.__setitem__(k, (status, b))))
+    s.wait_all()
+    assert sum(s.stats()) == 18 and min(s.stats()) >= 1
+    s.close()
+    ref = ol.reference_lodepng()
+    for k, (out_kind, lin) in enumerate(cases):
+        status, data = results[k]
+        assert status == 0 and data
+        if out_kind == lrp.FILE_PNG:
+            got = ref.decode(data)[..., :3] if ref is not None else co.png_decode(data)
+            assert (got == ORC.png_encode(lin)[..., :3]).all()
+        else:
+            names, planes = co.exr_decode(data)
+            c = lin.shape[2]
+            got = co.exr_to_planes(names, planes, c)
+            want = lin.astype(np.float16).transpose(2, 0, 1).view(np.uint16)  # save_exr: float -> half, RNE
+            nan = np.isnan(lin.transpose(2, 0, 1))
+            assert ((got == want) | nan).all()
+
+
+def test_file_job_errors_are_reported_per_job(lrp):
+    s = lrp.Scheduler([0], streams_per_device=1)
+    out = {}
+    keep = s.submit_file(b"not a png at all, not even close" * 4, lrp.FILE_PNG, lrp.lens_from(ol.erect()),
+                         lrp.lens_from(ol.rect(18.0, 36.0, 8, 8)), 8, 8, lrp.FILE_PNG, lrp.make_params(1, lrp.BICUBIC, None, None),
+                         lambda status, b: out.__setitem__("r", (status, b)))
+    with pytest.raises(lrp.LrpError):
+        s.wait_all()  # first non-OK job status, like the other job kinds
+    assert out["r"][0] != 0 and out["r"][1] is None
+    s.close()
+    del keep
