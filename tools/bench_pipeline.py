@@ -11,7 +11,6 @@ usage: python tools/bench_pipeline.py [--threads T] [--frames N]
 import argparse
 import json
 import os
-import queue
 import sys
 import threading
 import time
@@ -50,51 +49,31 @@ def main():
         del pano
     enc0.close()
 
-    q = queue.Queue()
-    for i in range(args.frames):
-        q.put(files[i % 2])
-    out_bytes, lock = [0], threading.Lock()
-    stage_s = {"decode": 0.0, "gpu+encode": 0.0}
+    # the native pipeline: lrp_sched_submit_file, `threads` workers (streams) on this GPU, codecs inside the workers
+    sched = lrp.Scheduler([0], streams_per_device=args.threads)
+    out_bytes, lock, keep = [0, 0], threading.Lock(), []
 
-    ready = threading.Barrier(args.threads + 1)
+    def sink(status, data):
+        with lock:
+            out_bytes[0] += len(data) if data else 0
+            out_bytes[1] += 1 if status == 0 else 0
 
-    def worker():
-        torch.cuda.set_device(0)
-        st = torch.cuda.Stream()
-        dec, enc = lrp.Decoder(ctx, w, h, 4), lrp.Encoder(ctx, W, H, 4)  # pinned + device workspaces: set-up, not timed
-        dst = torch.empty((H, W, 4), dtype=torch.uint8, device=dev)
-        ready.wait()
-        while True:
-            try:
-                data = q.get_nowait()
-            except queue.Empty:
-                break
-            t0 = time.perf_counter()
-            src = dec.png(data, stream=st.cuda_stream)
-            t1 = time.perf_counter()
-            ctx.reproject(src, il, lrp.FMT_U8_RGBA, dst, olens, lrp.FMT_U8_RGBA, p, stream=st.cuda_stream)
-            png = enc.png(dst, 3, stream=st.cuda_stream)
-            t2 = time.perf_counter()
-            with lock:
-                out_bytes[0] += len(png)
-                stage_s["decode"] += t1 - t0
-                stage_s["gpu+encode"] += t2 - t1
-        dec.close()
-        enc.close()
+    def run(n):
+        for i in range(n):
+            keep.append(sched.submit_file(files[i % 2], lrp.FILE_PNG, il, olens, W, H, lrp.FILE_PNG, p, sink))
+        sched.wait_all()
 
-    ths = [threading.Thread(target=worker) for _ in range(args.threads)]
-    for t in ths:
-        t.start()
-    ready.wait()
+    run(args.threads)  # warm-up: every worker creates its decoder / encoder workspaces (pinned allocations)
+    del keep[:]
+    out_bytes[0] = out_bytes[1] = 0
     t0 = time.perf_counter()
-    for t in ths:
-        t.join()
-    torch.cuda.synchronize()
+    run(args.frames)
     dt = time.perf_counter() - t0
+    sched.close()
+    assert out_bytes[1] == args.frames
     res = {"frames": args.frames, "threads": args.threads, "seconds": dt, "frames_per_s": args.frames / dt,
            "output_gpix_per_s": args.frames * W * H / dt / 1e9, "in_file_bytes": len(files[0]),
-           "out_file_bytes_avg": out_bytes[0] / args.frames,
-           "per_frame_thread_s": {k: v / args.frames for k, v in stage_s.items()}}
+           "out_file_bytes_avg": out_bytes[0] / args.frames, "api": "lrp_sched_submit_file (C ABI, %d worker streams)" % args.threads}
 
     # the reference's chain, one frame, one core
     ref_png, ref = ol.reference_lodepng(), ol.reference()
