@@ -9,7 +9,7 @@
 //   * the stream is cut into bands of 32 KB; one CTA per band builds the band's own canonical Huffman code
 //     (histogram in shared memory -> bitonic sort -> two-queue Huffman merge -> code lengths) and emits ONE dynamic
 //     block of literals (no LZ77 matches: on filtered photographic scan lines a Huffman-only block is as small as
-//     zlib's level 6 output or smaller — tools/bench_encode.py prints both sizes);
+//     zlib's level 6 output or smaller — tests/perf/bench_encode.py prints both sizes);
 //   * the code is length-limited by construction: symbol weights are floored at total / 1024, which bounds the depth
 //     of a Huffman tree at log_phi(1280) < 15 (Katona–Nemetz), the limit of deflate;
 //   * every band ends with an empty stored block (the zlib "sync flush" marker), i.e. on a byte boundary, so bands

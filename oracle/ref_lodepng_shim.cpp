@@ -5,7 +5,7 @@
 // It gives the encode-side tests the reference's own PNG READER (lodepng::decode as read_png calls it,
 // src/image_formats.cpp:174-183) and WRITER (lodepng::encode as save_png calls it, :166-167): files produced by
 // liblrp must decode through the former to the samples the latter stores; the writer is also the CPU baseline of
-// tools/bench_encode.py.
+// tests/perf/bench_encode.py.
 #include "lodepng.cpp" // resolved through -I/root/reference/lib/lodepng
 
 #include <cstdint>

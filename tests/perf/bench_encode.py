@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Encode-side measurement: the device pack kernels against their byte roofline, the host
+"""(lives under tests/: it times the compiled reference from oracle/_ref next to the product, which only tests/ may load)
+Encode-side measurement: the device pack kernels against their byte roofline, the host
 assembly (parallel deflate) against the reference's own writer on the same frame.
 
   png_pack   reads 4 B/pixel (RGBA8 sink; the row above comes from L2), writes 3 B/pixel + 1 B/row
@@ -7,7 +8,7 @@ assembly (parallel deflate) against the reference's own writer on the same frame
   png e2e    sink on the device -> bytes of a .png in host memory (pack + D2H + deflate on T threads)
   reference  lodepng::encode on the same RGBA frame, one thread (what save_png costs per frame; -j N runs N frames)
 
-usage: python tools/bench_encode.py [--threads T] [--level L]
+usage: python tests/perf/bench_encode.py [--threads T] [--level L]
 """
 import argparse
 import json
@@ -15,7 +16,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "image-lens-reproject_b200", "python"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -1,12 +1,13 @@
 #!/usr/bin/env python
-"""File -> file pipeline on one B200 (north-star: "decode/encode pipelined against the GPU with pinned buffers and per-GPU
+"""(lives under tests/: it times the compiled reference from oracle/_ref next to the product, which only tests/ may load)
+File -> file pipeline on one B200 (north-star: "decode/encode pipelined against the GPU with pinned buffers and per-GPU
 CUDA streams"): T host threads, each with its own stream, lrp_decoder and lrp_encoder, pull PNG files (c2: 8192x4096
 equirect) from a queue: decode (host inflate + unfilter) -> upload -> fused reproject kernel -> PNG filter + deflate on the
 GPU -> file bytes.  Beside it, the reference's chain for ONE frame on ONE core, step by step, with the reference's own
 code where it compiled here (lodepng decode / encode, reproject()); the float conversions are numpy restatements of
 read_png's / save_png's loops (src/image_formats.cpp:189-199, 150-165).
 
-usage: python tools/bench_pipeline.py [--threads T] [--frames N]
+usage: python tests/perf/bench_pipeline.py [--threads T] [--frames N]
 """
 import argparse
 import json
@@ -15,7 +16,7 @@ import sys
 import threading
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "image-lens-reproject_b200", "python"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -1,7 +1,7 @@
 """debug helper: run one reproject case through both variants and print where they differ from the oracle"""
 import os, sys, math
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "image-lens-reproject_b200", "python")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_lib as ol, lrp
 ORC = ol.oracle()
