@@ -189,7 +189,9 @@ LRP_DEV void stage_group(const KParams &P, uint32_t lut, unsigned char *stage, c
       if (in) StageLoad<FMT, C>::decode(lut, raw[u], v);
       float nxt = 0.0f;
       if (Rec::LONE) nxt = __shfl_down_sync(0xffffffffu, v[C - 1], 1);
-      if (in && (!Rec::LONE || lane < 31 || t + 1u >= n)) {
+      // odd C: lane 31's texel is lane 0's texel of the next round (STEP = 31), which runs whenever t < n and
+      // knows the neighbour's value — lane 31 only supplies `nxt` to lane 30 and never writes
+      if (in && (!Rec::LONE || lane < 31)) {
         if (C == 3) recA[t] = make_float4(v[0], v[1], v[2], nxt);
         else recA[t] = make_float4(v[0], v[1], v[2], v[3 < C ? 3 : 0]);
         if (C == 5) recB[t] = make_float2(v[C - 1], nxt);
