@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 1200 compute-sanitizer --tool racecheck --racecheck-report analysis --error-exitcode 99 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "ragged or channels_rotations" 2>&1 | tail -25 > gpurun_out/racecheck_parity.log; tail -6 gpurun_out/racecheck_parity.log
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 > gpurun_out/pytest_gpu_r.log; tail -3 gpurun_out/pytest_gpu_r.log
+python bench.py > gpurun_out/bench_default_s.json 2> gpurun_out/bench_default_s.err; python -c "
+import json; d=json.loads(open('gpurun_out/bench_default_s.json').read().strip().splitlines()[-1]); print(d['value'], d['roofline']['frac'], d['remap_table_variant'], d['e2e']['value'], d['clocks'])"
+tail -2 gpurun_out/bench_default_s.err
