@@ -242,7 +242,8 @@ def run_gpu_arm(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     interp = INTERP[args.interp]
-    ctx = lrp.Context(local_rank, 4)
+    n_streams = int(os.environ.get("LRP_BENCH_STREAMS", "4"))  # worker streams of the e2e leg
+    ctx = lrp.Context(local_rank, n_streams)
     in_lens = lrp.lens_equirectangular()
     out_lens = lrp.lens_rectilinear(18.0, 36.0, OUT_W, OUT_H)
     rot = lrp.rotation_from_degrees(*ROTATION_DEG)
@@ -367,7 +368,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                              {"nn": "NEAREST", "bl": "BILINEAR", "bc": "BICUBIC"}[args.interp])},
             "e2e": {"value": e2e_value, "unit": "Gpix/s", "h2d_bytes_per_step": int(h2d_all),
                     "d2h_bytes_per_step": int(d2h_all), "steps": e2e_steps, "matches_device_path": e2e_ok,
-                    "api": "lrp_submit/lrp_wait_all (C ABI, pinned host buffers, 4 streams)",
+                    "api": "lrp_submit/lrp_wait_all (C ABI, pinned host buffers, %d streams)" % n_streams,
                     "upload": args.upload, "source_bytes_per_step": world * B * in_bytes,
                     "source_footprint_xxyy": list(roi),
                     "note": "upload=auto copies only the bounding box of the source texels the geometry can touch "
