@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-python bench.py > gpurun_out/bench_default_s.json 2> gpurun_out/bench_default_s.err; python -c "
-import json; d=json.loads(open('gpurun_out/bench_default_s.json').read().strip().splitlines()[-1]); print(d['value'], d['roofline']['frac'], d['remap_table_variant'], d['e2e']['value'], d['clocks'])"
-tail -2 gpurun_out/bench_default_s.err
+timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -3
+for v in "--interp bc" "--interp nn" "--interp bl"; do python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-steps 1 $v 2>/dev/null | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(d['config']['interp'], round(d['value'],2), round(d['roofline']['us_per_launch'],1), round(d['remap_table_variant']['us_per_launch'],1))"; done
+timeout 600 python tools/bench_configs.py --configs c3,c4t,c5e --variants staged 2>&1 | cut -c1-120
