@@ -363,7 +363,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                          "traffic": recorded_traffic(args.interp), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": balg, "us_per_launch": per_launch_s * 1e6,
                          "kernel": "lrp::%s<%s, %s, U8, 3>" % (
-                             "reproject_kernel" if args.variant == "gather" else "reproject_staged_kernel",
+                             "reproject_kernel" if (args.variant == "gather" or (args.variant == "auto" and args.interp != "bc"))
+                             else "reproject_staged_kernel",
                              "COORD_TABLE_WRAP" if args.coords == "table" else "COORD_ERECT_WRAP",
                              {"nn": "NEAREST", "bl": "BILINEAR", "bc": "BICUBIC"}[args.interp])},
             "e2e": {"value": e2e_value, "unit": "Gpix/s", "h2d_bytes_per_step": int(h2d_all),

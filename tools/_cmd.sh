@@ -1,6 +1,5 @@
 mkdir -p gpurun_out
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference_final.json 2>&1; tail -c 200 gpurun_out/bench_reference_final.json; echo
-python bench.py > gpurun_out/bench_default_final.json 2> gpurun_out/bench_default_final.err; python -c "
-import json; d=json.loads(open('gpurun_out/bench_default_final.json').read().strip().splitlines()[-1]); print(d['value'], d['roofline']['frac'], d['e2e']['value'], d['cpu_baseline']['value'], d['clocks']['samples'])"
+for i in nn bl; do
+ncu --set full --clock-control none --import-source on -k regex:reproject_ -s 26 -c 1 -f -o gpurun_out/prof_c2_$i python bench.py --interp $i --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/prof_$i.log 2>&1; tail -1 gpurun_out/prof_$i.log | cut -c1-80
+done
+ncu --set full --clock-control none --import-source on -k regex:deflate_band -s 1 -c 1 -f -o gpurun_out/prof_deflate python tests/perf/bench_encode.py --reps 1 > gpurun_out/prof_deflate.log 2>&1; tail -1 gpurun_out/prof_deflate.log | cut -c1-80
