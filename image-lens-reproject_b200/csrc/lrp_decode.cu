@@ -10,8 +10,9 @@
 //        independent).  device: exr_unpack_kernel undoes OpenEXR's predictor (a byte-wise prefix sum, scanned per
 //        warp) and byte-plane split (lib/openexr/src/lib/OpenEXRCore/internal_zip.c:47-160 "reconstruct" +
 //        "interleave") and scatters the channel-interleaved scan lines into the reference's plane order.
-//   PNG  host: chunks, one zlib inflate of the IDAT stream, scan-line un-filtering (inherently sequential along a
-//        line), expansion to RGBA8 as lodepng::decode delivers it; the pixels land in pinned memory and are uploaded.
+//   PNG  host: chunks, one zlib inflate of the IDAT stream (into pinned memory).  device: scan-line reconstruction as a
+//        wavefront over 1024 lines (png_unfilter_kernel) + expansion to RGBA8 as lodepng::decode delivers it, for RGB /
+//        RGBA files; grey / palette / colour-keyed files are reconstructed on the host and uploaded as RGBA8.
 // Scope: what the reference's pipeline reads — single-part scan-line EXR with HALF channels named from {R,G,B,A,Z},
 // NONE / ZIPS / ZIP compression; non-interlaced 8-bit PNG of colour type 0, 2, 3, 4 or 6.  Anything else returns
 // LRP_E_UNSUPPORTED_FORMAT (the reference would go through lodepng / OpenEXR's other code paths).
@@ -146,6 +147,67 @@ __global__ void __launch_bounds__(UNPACK_WARPS * 32) exr_unpack_kernel(const Exr
     }
     base_lo += __shfl_sync(0xffffffffu, il, 31);
     base_hi += __shfl_sync(0xffffffffu, ih, 31);
+  }
+}
+
+// ---- PNG: scan-line reconstruction on the device ------------------------------------------------------------
+//
+// Reconstruction (PNG specification section 9.2) of pixel (x, y) needs the reconstructed pixels to the left, above and
+// above-left, so a line is sequential in x and lines are sequential in y — but line y can run ONE pixel behind line
+// y - 1.  One CTA keeps 1024 consecutive lines in flight as a wavefront: thread r owns line row0 + r and at step s
+// reconstructs pixel x = s - r; it keeps its own left / upper-left pixels in registers and receives the pixel above
+// from thread r - 1 through a double-buffered shared-memory slot written one step (one barrier) earlier.  All byte
+// lanes of a pixel are reconstructed at once (the byte-lane Paeth predictor of the encoder, lrp_codec.cu).  A frame of
+// H lines takes ceil(H / 1024) launches of W + 1023 steps each on ONE SM (≈ 10 ms for 8192 x 4096) — frames of a
+// pipeline are reconstructed concurrently on different SMs, and the host core that would spend 0.15 s on it is free.
+constexpr int UNF_ROWS = 1024;
+
+__device__ __forceinline__ unsigned unf_paeth4(unsigned a, unsigned b, unsigned c) { // see paeth4 in lrp_codec.cu
+  const unsigned pa = __vabsdiffu4(b, c), pb = __vabsdiffu4(a, c);
+  const unsigned same = ~(__vcmpgeu4(a, c) ^ __vcmpgeu4(b, c));
+  const unsigned pc = __vabsdiffu4(pa, pb) | same;
+  const unsigned m1 = __vcmpleu4(pa, pb) & __vcmpleu4(pa, pc), m2 = __vcmpleu4(pb, pc);
+  return (a & m1) | (~m1 & ((b & m2) | (c & ~m2)));
+}
+
+template <int PC>
+__global__ void __launch_bounds__(UNF_ROWS) png_unfilter_kernel(const unsigned char *__restrict__ stream, int W, int H,
+                                                                 int row0, unsigned *out) {
+  __shared__ unsigned pub[2][UNF_ROWS];
+  const int r = threadIdx.x, y = row0 + r;
+  const int rows = min(UNF_ROWS, H - row0);
+  const bool active = r < rows;
+  const size_t pitch = (size_t)PC * W + 1;
+  const unsigned char *line = stream + (size_t)(active ? y : row0) * pitch;
+  const int ftype = active ? line[0] : 0;
+  constexpr unsigned LANES = PC == 3 ? 0x00FFFFFFu : 0xFFFFFFFFu;
+  auto fetch = [&](int x) -> unsigned {
+    const unsigned char *p = line + 1 + (size_t)PC * x;
+    unsigned v = (unsigned)__ldg(p) | ((unsigned)__ldg(p + 1) << 8) | ((unsigned)__ldg(p + 2) << 16);
+    if (PC == 4) v |= (unsigned)__ldg(p + 3) << 24;
+    return v;
+  };
+  unsigned a = 0, c = 0;                        // reconstructed left / upper-left pixels
+  unsigned f = (active && r == 0) ? fetch(0) : 0u; // the filtered bytes of this thread's next pixel, one step ahead
+  const int steps = W + rows - 1;
+  for (int s = 0; s < steps; ++s) {
+    const int x = s - r;
+    if (active && x >= 0 && x < W) {
+      unsigned b = 0;
+      if (y > 0) b = (r == 0 ? out[(size_t)(y - 1) * W + x] : pub[(s - 1) & 1][r - 1]) & LANES;
+      unsigned pred = 0;
+      if (ftype == 1) pred = a;
+      else if (ftype == 2) pred = b;
+      else if (ftype == 3) pred = __vhaddu4(a, b);
+      else if (ftype == 4) pred = unf_paeth4(a, b, c);
+      const unsigned v = __vadd4(f, pred) & LANES;
+      out[(size_t)y * W + x] = PC == 3 ? (v | 0xFF000000u) : v;
+      pub[s & 1][r] = v;
+      c = b;
+      a = v;
+    }
+    if (active && x + 1 >= 0 && x + 1 < W) f = fetch(x + 1);
+    __syncthreads();
   }
 }
 
@@ -449,6 +511,24 @@ int lrp_decoder_png(lrp_decoder *d, const void *file, size_t n, void *out_rgba_d
   const size_t row = (size_t)I.w * I.channels, px = (size_t)I.w * I.h;
   if (px * 4 > d->cap) return LRP_E_BAD_ARG;
   if (I.ctype == 3 && plte.size() < 3) return LRP_E_BAD_ARG;
+  const char *host_only = getenv("LRP_PNG_UNFILTER_ON_HOST"); // A/B switch
+  if ((I.ctype == 2 || I.ctype == 6) && trns.empty() && (row + 1) * I.h <= d->cap && !(host_only && host_only[0] == '1')) {
+    // RGB / RGBA: inflate straight into pinned memory, upload the FILTERED scan lines (3 or 4 bytes per pixel), reconstruct
+    // them on the device (png_unfilter_kernel) directly into the caller's RGBA8 buffer
+    uLongf got = (uLongf)((row + 1) * I.h);
+    if (uncompress(d->h_buf, &got, idat.data(), (uLong)idat.size()) != Z_OK || got != (row + 1) * I.h) return LRP_E_BAD_ARG;
+    for (uint32_t y = 0; y < I.h; ++y)
+      if (d->h_buf[(size_t)y * (row + 1)] > 4) return LRP_E_BAD_ARG; // filter type
+    if (cudaSetDevice(d->device) != cudaSuccess) return LRP_E_CUDA;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (cudaMemcpyAsync(d->d_buf, d->h_buf, (row + 1) * I.h, cudaMemcpyHostToDevice, st) != cudaSuccess) return LRP_E_CUDA;
+    for (uint32_t y0 = 0; y0 < I.h; y0 += UNF_ROWS) {
+      if (I.ctype == 2) png_unfilter_kernel<3><<<1, UNF_ROWS, 0, st>>>(d->d_buf, (int)I.w, (int)I.h, (int)y0, (unsigned *)out_rgba_dev);
+      else png_unfilter_kernel<4><<<1, UNF_ROWS, 0, st>>>(d->d_buf, (int)I.w, (int)I.h, (int)y0, (unsigned *)out_rgba_dev);
+    }
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return LRP_E_CUDA; // h_buf is reused
+    return LRP_OK;
+  }
   d->scratch.resize((row + 1) * I.h);
   uLongf got = (uLongf)d->scratch.size();
   if (uncompress(d->scratch.data(), &got, idat.data(), (uLong)idat.size()) != Z_OK || got != d->scratch.size())

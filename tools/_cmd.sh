@@ -1,5 +1,8 @@
 mkdir -p gpurun_out
-for i in nn bl; do
-ncu --set full --clock-control none --import-source on -k regex:reproject_ -s 26 -c 1 -f -o gpurun_out/prof_c2_$i python bench.py --interp $i --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/prof_$i.log 2>&1; tail -1 gpurun_out/prof_$i.log | cut -c1-80
-done
-ncu --set full --clock-control none --import-source on -k regex:deflate_band -s 1 -c 1 -f -o gpurun_out/prof_deflate python tests/perf/bench_encode.py --reps 1 > gpurun_out/prof_deflate.log 2>&1; tail -1 gpurun_out/prof_deflate.log | cut -c1-80
+timeout 1500 python -m pytest tests/test_gpu_decode.py tests/test_gpu_sched.py -m gpu -q -x 2>&1 | tail -12
+timeout 600 python tests/perf/bench_encode.py 2>&1 | tail -1 > gpurun_out/bench_encode_t.json; python -c "
+import json; e=json.load(open('gpurun_out/bench_encode_t.json'))
+for k in ('png_decoder','reference_lodepng_decode'): print(k, e.get(k))"
+LRP_PNG_UNFILTER_ON_HOST=1 timeout 600 python tests/perf/bench_encode.py 2>&1 | tail -1 | python -c "
+import json,sys; e=json.loads(sys.stdin.read()); print('host unfilter:', e.get('png_decoder'))"
+timeout 800 python tests/perf/bench_pipeline.py 2>&1 | tail -1 | tee gpurun_out/bench_pipeline_t.json | cut -c1-330
