@@ -321,7 +321,8 @@ int lrp_encoder_last_timing(const lrp_encoder *enc, double *ms3);
  * (src/image_formats.cpp:174-204: lodepng::decode + pow loop) and reproject::read_exr (:208-303: readPixels + half->float
  * loop with the name -> index mapping of :266-285); the pow / half->float arithmetic itself is fused into the kernel's
  * texel load.  EXR: blocks are inflated on `threads` host cores, the predictor / byte-plane / channel scatter runs on the
- * device.  PNG: inflate + un-filtering are sequential and stay on the host; the RGBA8 pixels go up from pinned memory.
+ * device.  PNG: the inflate is one sequential stream and stays on the host; RGB / RGBA scan lines are reconstructed on
+ * the device (a wavefront over 1024 lines), other colour types on the host.
  * Supported: single-part scan-line EXR, HALF channels R,G,B[,A][,Z], NONE / ZIPS / ZIP; non-interlaced 8-bit PNG of any
  * colour type.  Everything else: LRP_E_UNSUPPORTED_FORMAT.  A decoder owns pinned + device workspaces; one per thread. */
 typedef struct lrp_decoder lrp_decoder;
