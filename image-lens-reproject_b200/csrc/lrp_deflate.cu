@@ -344,6 +344,8 @@ __global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateP
 struct LayoutParams {
   const unsigned *band_len, *band_adler, *band_in;
   unsigned bands_per_stream, n_streams;
+  unsigned chunk_hdr;             // 0, or 8: every stream is preceded by an EXR chunk header {int32 y, int32 size}
+  unsigned lines_per_stream;      // scan lines per stream (the y of the chunk header)
   unsigned long long *band_off;   // n_bands: absolute byte offset of each band in the compact buffer
   unsigned long long *stream_off; // n_streams + 1
   unsigned *stream_adler;
@@ -374,7 +376,7 @@ __device__ unsigned long long block_exclusive_scan(unsigned long long v, unsigne
 __global__ void __launch_bounds__(LAYOUT_THREADS) deflate_layout_kernel(const LayoutParams P) {
   __shared__ unsigned long long ws[LAYOUT_THREADS / 32];
   const unsigned s = blockIdx.x, tid = threadIdx.x;
-  unsigned long long bytes = 2, asum = 0, bsum = 0; // running: offset in the stream, sum (a_j - 1), sum of b terms
+  unsigned long long bytes = P.chunk_hdr + 2, asum = 0, bsum = 0; // running: offset in the stream, sum (a_j - 1), sum of b terms
   for (unsigned k0 = 0; k0 < P.bands_per_stream; k0 += LAYOUT_THREADS) {
     const unsigned k = k0 + tid;
     const bool in = k < P.bands_per_stream;
@@ -431,6 +433,11 @@ __global__ void __launch_bounds__(256) deflate_gather_kernel(const LayoutParams 
   for (unsigned i = head + 16 * body + threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
   if (k == 0 && threadIdx.x == 0) { // stream framing
     unsigned char *st = out + sbase;
+    if (P.chunk_hdr) { // OpenEXR chunk header: first scan line, size of the data that follows
+      const unsigned yv = s * P.lines_per_stream, sz = (unsigned)(P.stream_off[s + 1] - sbase) - P.chunk_hdr;
+      for (int i = 0; i < 4; ++i) st[i] = (unsigned char)(yv >> (8 * i)), st[4 + i] = (unsigned char)(sz >> (8 * i));
+      st += P.chunk_hdr;
+    }
     st[0] = 0x78, st[1] = 0x01; // deflate / 32 KB window, check bits, "fastest" hint
     unsigned char *tail = out + P.stream_off[s + 1] - 6;
     const unsigned ad = P.stream_adler[s];
@@ -456,7 +463,10 @@ struct lrp_encoder {
   double last_ms[3] = {0, 0, 0}; // device (pack + deflate + layout), copy of the compressed body, container on the host
 };
 
-static size_t compact_bound(size_t n, size_t bands, size_t streams) { return n + 5 * bands + 16 * bands + 8 * streams + 64; }
+static size_t compact_bound(size_t n, size_t bands, size_t streams) { return n + 5 * bands + 16 * bands + 16 * streams + 64; }
+// bytes kept free in front of the compact stream in pinned memory: the container's leading bytes (PNG signature + IHDR +
+// IDAT header; EXR header + line offset table) are written there in place, so the file image needs no copy
+static size_t headroom(size_t streams) { return (4096 + 8 * streams + 63) & ~(size_t)63; }
 
 static void encoder_free(lrp_encoder *e) {
   if (!e) return;
@@ -472,8 +482,10 @@ static void encoder_free(lrp_encoder *e) {
 }
 
 // Runs pack output `d_packed` (n bytes, streams of stream_bytes) through the deflate kernels and brings the compact
-// result to the encoder's pinned buffer.  On return h_stream_off[0..n_streams] delimit the zlib streams in h_compact.
-static int deflate_to_host(lrp_encoder *e, size_t n, size_t stream_bytes, cudaStream_t st) {
+// result to the encoder's pinned buffer.  On return h_stream_off[0..n_streams] delimit the streams (each preceded by its
+// chunk header when chunk_hdr != 0) at h_compact + headroom(cap_streams).
+static int deflate_to_host(lrp_encoder *e, size_t n, size_t stream_bytes, cudaStream_t st, unsigned chunk_hdr = 0,
+                           unsigned lines_per_stream = 0) {
   const unsigned bps = (unsigned)((stream_bytes + DF_BAND - 1) / DF_BAND);
   const unsigned n_streams = (unsigned)((n + stream_bytes - 1) / stream_bytes);
   const unsigned n_bands = bps * n_streams;
@@ -492,6 +504,7 @@ static int deflate_to_host(lrp_encoder *e, size_t n, size_t stream_bytes, cudaSt
   LayoutParams L;
   L.band_len = e->d_band_len, L.band_adler = e->d_band_adler, L.band_in = e->d_band_in;
   L.bands_per_stream = bps, L.n_streams = n_streams;
+  L.chunk_hdr = chunk_hdr, L.lines_per_stream = lines_per_stream;
   L.band_off = e->d_band_off, L.stream_off = e->d_stream_off, L.stream_adler = e->d_stream_adler;
   deflate_layout_kernel<<<n_streams, LAYOUT_THREADS, 0, st>>>(L);
   deflate_offsets_kernel<<<1, 32, 0, st>>>(L);
@@ -501,7 +514,7 @@ static int deflate_to_host(lrp_encoder *e, size_t n, size_t stream_bytes, cudaSt
       cudaStreamSynchronize(st) != cudaSuccess)
     return LRP_E_CUDA;
   const size_t total = (size_t)e->h_stream_off[n_streams];
-  if (cudaMemcpyAsync(e->h_compact, e->d_compact, total, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+  if (cudaMemcpyAsync(e->h_compact + headroom(e->cap_streams), e->d_compact, total, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
       cudaEventRecord(e->ev[2], st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
     return LRP_E_CUDA;
   float a = 0, b = 0;
@@ -530,7 +543,8 @@ static int encoder_alloc(lrp_ctx *ctx, size_t cap_packed, size_t cap_bands, size
             cudaMalloc(&e->d_band_len, e->cap_bands * 4) == cudaSuccess && cudaMalloc(&e->d_band_adler, e->cap_bands * 4) == cudaSuccess &&
             cudaMalloc(&e->d_band_in, e->cap_bands * 4) == cudaSuccess && cudaMalloc(&e->d_stream_adler, e->cap_streams * 4) == cudaSuccess &&
             cudaMalloc(&e->d_band_off, e->cap_bands * 8) == cudaSuccess && cudaMalloc(&e->d_stream_off, (e->cap_streams + 1) * 8) == cudaSuccess &&
-            cudaMallocHost(&e->h_compact, cb) == cudaSuccess && cudaMallocHost(&e->h_stream_off, (e->cap_streams + 1) * 8) == cudaSuccess &&
+            cudaMallocHost(&e->h_compact, cb + headroom(e->cap_streams) + 64) == cudaSuccess &&
+            cudaMallocHost(&e->h_stream_off, (e->cap_streams + 1) * 8) == cudaSuccess &&
             cudaEventCreate(&e->ev[0]) == cudaSuccess && cudaEventCreate(&e->ev[1]) == cudaSuccess && cudaEventCreate(&e->ev[2]) == cudaSuccess;
   if (!ok) {
     cudaGetLastError();
@@ -569,7 +583,7 @@ int lrp_debug_deflate(lrp_ctx *ctx, const void *in_dev, size_t n, size_t stream_
     void *mem = malloc(total ? total : 1);
     if (!mem) rc = LRP_E_OOM;
     else {
-      memcpy(mem, e->h_compact, total);
+      memcpy(mem, e->h_compact + headroom(e->cap_streams), total);
       for (size_t i = 0; i <= streams; ++i) offsets[i] = e->h_stream_off[i];
       *out_bytes = mem;
     }
@@ -598,29 +612,46 @@ int lrp_encoder_png(lrp_encoder *e, const void *rgba_dev, int32_t width, int32_t
   if (rc != LRP_OK) return rc;
   const auto t_host = std::chrono::steady_clock::now();
   const size_t zn = (size_t)e->h_stream_off[1];
-  std::vector<unsigned char> &f = e->file;
-  f.clear();
-  f.reserve(zn + 128 + 12 * (zn / 0x7fffffffu + 1));
-  static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
-  f.insert(f.end(), sig, sig + 8);
-  auto chunk = [&f](const char *type, const unsigned char *data, size_t len) {
-    put32be(f, (uint32_t)len);
-    uLong c = crc32(0L, (const Bytef *)type, 4);
-    f.insert(f.end(), type, type + 4);
-    for (size_t p = 0; p < len; p += 1u << 30) c = crc32(c, data + p, (uInt)std::min<size_t>(len - p, 1u << 30));
-    if (len) f.insert(f.end(), data, data + len);
-    put32be(f, (uint32_t)c);
-  };
+  unsigned char *data = e->h_compact + headroom(e->cap_streams);
   unsigned char ihdr[13];
   const uint32_t wh[2] = {(uint32_t)width, (uint32_t)height};
   for (int i = 0; i < 2; ++i)
     for (int j = 0; j < 4; ++j) ihdr[4 * i + j] = (unsigned char)(wh[i] >> (24 - 8 * j));
   ihdr[8] = 8, ihdr[9] = png_channels == 3 ? 2 : 6, ihdr[10] = 0, ihdr[11] = 0, ihdr[12] = 0;
-  chunk("IHDR", ihdr, 13);
-  for (size_t p = 0; p < zn; p += 0x7fffffffu) chunk("IDAT", e->h_compact + p, std::min<size_t>(zn - p, 0x7fffffffu));
-  chunk("IEND", nullptr, 0);
-  *file_bytes = f.data();
-  *file_size = f.size();
+  static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+  auto be = [](unsigned char *p, uint32_t v) { p[0] = v >> 24, p[1] = v >> 16, p[2] = v >> 8, p[3] = v; };
+  if (zn <= 0x7fffffffu) { // one IDAT chunk: the container is written around the stream where it lies (no copy)
+    unsigned char *f = data - 41; // signature 8 + IHDR chunk 25 + IDAT length and type 8
+    memcpy(f, sig, 8);
+    be(f + 8, 13), memcpy(f + 12, "IHDR", 4), memcpy(f + 16, ihdr, 13);
+    be(f + 29, (uint32_t)crc32(0L, f + 12, 17));
+    be(f + 33, (uint32_t)zn), memcpy(f + 37, "IDAT", 4);
+    uLong c = crc32(0L, f + 37, 4);
+    for (size_t p = 0; p < zn; p += 1u << 30) c = crc32(c, data + p, (uInt)std::min<size_t>(zn - p, 1u << 30));
+    unsigned char *t = data + zn;
+    be(t, (uint32_t)c);
+    be(t + 4, 0), memcpy(t + 8, "IEND", 4), be(t + 12, (uint32_t)crc32(0L, t + 8, 4));
+    *file_bytes = f;
+    *file_size = 41 + zn + 16;
+  } else { // more than 2 GiB of compressed data: several IDAT chunks, assembled in a separate buffer
+    std::vector<unsigned char> &f = e->file;
+    f.clear();
+    f.reserve(zn + 128 + 12 * (zn / 0x7fffffffu + 1));
+    f.insert(f.end(), sig, sig + 8);
+    auto chunk = [&f](const char *type, const unsigned char *d, size_t len) {
+      put32be(f, (uint32_t)len);
+      uLong c = crc32(0L, (const Bytef *)type, 4);
+      f.insert(f.end(), type, type + 4);
+      for (size_t p = 0; p < len; p += 1u << 30) c = crc32(c, d + p, (uInt)std::min<size_t>(len - p, 1u << 30));
+      if (len) f.insert(f.end(), d, d + len);
+      put32be(f, (uint32_t)c);
+    };
+    chunk("IHDR", ihdr, 13);
+    for (size_t p = 0; p < zn; p += 0x7fffffffu) chunk("IDAT", data + p, std::min<size_t>(zn - p, 0x7fffffffu));
+    chunk("IEND", nullptr, 0);
+    *file_bytes = f.data();
+    *file_size = f.size();
+  }
   e->last_ms[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host).count();
   return LRP_OK;
 }
@@ -636,15 +667,17 @@ int lrp_encoder_exr(lrp_encoder *e, const void *half_planar_dev, int32_t width, 
   int rc = lrp_exr_pack_device(e->ctx, half_planar_dev, width, height, channels, e->d_packed, cuda_stream);
   if (rc != LRP_OK) return rc;
   const size_t line_bytes = (size_t)channels * width * 2, stream_bytes = 16 * line_bytes;
-  rc = deflate_to_host(e, n, stream_bytes, st);
+  rc = deflate_to_host(e, n, stream_bytes, st, 8, 16); // streams come back as complete chunks: {y, size} + zlib stream
   if (rc != LRP_OK) return rc;
   const auto t_host = std::chrono::steady_clock::now();
   const size_t blocks = ((size_t)height + 15) / 16;
+  unsigned char *chunks = e->h_compact + headroom(e->cap_streams);
   // blocks that did not shrink must be stored RAW (un-predicted, interleaved): fetch their packed bytes and invert
   std::vector<std::vector<unsigned char>> raw(blocks);
+  bool any_raw = false;
   for (size_t b = 0; b < blocks; ++b) {
     const size_t lines = std::min<size_t>(16, (size_t)height - 16 * b), raw_n = lines * line_bytes;
-    const size_t zn = (size_t)(e->h_stream_off[b + 1] - e->h_stream_off[b]);
+    const size_t zn = (size_t)(e->h_stream_off[b + 1] - e->h_stream_off[b]) - 8;
     if (zn < raw_n) continue;
     std::vector<unsigned char> t(raw_n);
     if (cudaMemcpyAsync(t.data(), e->d_packed + b * stream_bytes, raw_n, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
@@ -654,18 +687,18 @@ int lrp_encoder_exr(lrp_encoder *e, const void *half_planar_dev, int32_t width, 
     raw[b].resize(raw_n);
     const size_t h = (raw_n + 1) / 2;
     for (size_t i = 0; i < raw_n; ++i) raw[b][i] = (i & 1) ? t[h + i / 2] : t[i / 2];
+    any_raw = true;
   }
-  { // container: Imf::Header(width, height) defaults + channel list + ZIP_COMPRESSION, offset table, blocks
-    std::vector<unsigned char> &f = e->file;
-    f.clear();
-    f.reserve((size_t)e->h_stream_off[blocks] + 16 * blocks + 1024);
+  // header: Imf::Header(width, height) defaults + channel list + ZIP_COMPRESSION, attributes in name order
+  std::vector<unsigned char> hdr;
+  {
     const unsigned char magic[8] = {0x76, 0x2f, 0x31, 0x01, 2, 0, 0, 0};
-    f.insert(f.end(), magic, magic + 8);
-    auto attr = [&f](const char *name, const char *type, const void *data, uint32_t len) {
-      f.insert(f.end(), name, name + strlen(name) + 1);
-      f.insert(f.end(), type, type + strlen(type) + 1);
-      f.insert(f.end(), (const unsigned char *)&len, (const unsigned char *)&len + 4);
-      f.insert(f.end(), (const unsigned char *)data, (const unsigned char *)data + len);
+    hdr.insert(hdr.end(), magic, magic + 8);
+    auto attr = [&hdr](const char *name, const char *type, const void *data, uint32_t len) {
+      hdr.insert(hdr.end(), name, name + strlen(name) + 1);
+      hdr.insert(hdr.end(), type, type + strlen(type) + 1);
+      hdr.insert(hdr.end(), (const unsigned char *)&len, (const unsigned char *)&len + 4);
+      hdr.insert(hdr.end(), (const unsigned char *)data, (const unsigned char *)data + len);
     };
     static const char all[5] = {'R', 'G', 'B', 'A', 'Z'}; // save_exr names plane i "RGBAZ"[i]; the file lists them sorted
     int idx[5] = {0, 1, 2, 3, 4};
@@ -688,20 +721,38 @@ int lrp_encoder_exr(lrp_encoder *e, const void *half_planar_dev, int32_t width, 
     attr("pixelAspectRatio", "float", &one, 4);
     attr("screenWindowCenter", "v2f", v2, 8);
     attr("screenWindowWidth", "float", &one, 4);
-    f.push_back(0);
-    uint64_t off = f.size() + 8 * blocks;
+    hdr.push_back(0);
+  }
+  const size_t lead = hdr.size() + 8 * blocks; // header + line offset table
+  if (!any_raw && lead <= headroom(e->cap_streams)) {
+    // the chunks already lie back to back in pinned memory exactly as the file wants them: write the header and the
+    // offset table in front of them, in place
+    unsigned char *f = chunks - lead;
+    memcpy(f, hdr.data(), hdr.size());
+    for (size_t b = 0; b < blocks; ++b) {
+      const uint64_t off = lead + e->h_stream_off[b];
+      memcpy(f + hdr.size() + 8 * b, &off, 8);
+    }
+    *file_bytes = f;
+    *file_size = lead + (size_t)e->h_stream_off[blocks];
+  } else { // some block is stored raw (incompressible pixels): assemble in a separate buffer
+    std::vector<unsigned char> &f = e->file;
+    f.clear();
+    f.reserve((size_t)e->h_stream_off[blocks] + lead + 1024);
+    f.insert(f.end(), hdr.begin(), hdr.end());
+    uint64_t off = lead;
     for (size_t b = 0; b < blocks; ++b) {
       f.insert(f.end(), (const unsigned char *)&off, (const unsigned char *)&off + 8);
-      const size_t zn = raw[b].empty() ? (size_t)(e->h_stream_off[b + 1] - e->h_stream_off[b]) : raw[b].size();
-      off += 8 + zn;
+      off += raw[b].empty() ? (size_t)(e->h_stream_off[b + 1] - e->h_stream_off[b]) : 8 + raw[b].size();
     }
-    f.reserve((size_t)off);
     for (size_t b = 0; b < blocks; ++b) {
-      const unsigned char *data = raw[b].empty() ? e->h_compact + e->h_stream_off[b] : raw[b].data();
-      const size_t zn = raw[b].empty() ? (size_t)(e->h_stream_off[b + 1] - e->h_stream_off[b]) : raw[b].size();
-      const int32_t hdr[2] = {(int32_t)(16 * b), (int32_t)zn};
-      f.insert(f.end(), (const unsigned char *)hdr, (const unsigned char *)hdr + 8);
-      f.insert(f.end(), data, data + zn);
+      if (raw[b].empty()) {
+        f.insert(f.end(), chunks + e->h_stream_off[b], chunks + e->h_stream_off[b + 1]);
+      } else {
+        const int32_t ch[2] = {(int32_t)(16 * b), (int32_t)raw[b].size()};
+        f.insert(f.end(), (const unsigned char *)ch, (const unsigned char *)ch + 8);
+        f.insert(f.end(), raw[b].begin(), raw[b].end());
+      }
     }
     *file_bytes = f.data();
     *file_size = f.size();

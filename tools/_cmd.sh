@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 99 python -m pytest tests/test_gpu_decode.py -m gpu -q -x -k "not 1080" 2>&1 | tail -6 > gpurun_out/sanitizer_decode.log; tail -4 gpurun_out/sanitizer_decode.log
-timeout 1200 compute-sanitizer --tool racecheck --racecheck-report analysis --error-exitcode 99 python -m pytest tests/test_gpu_decode.py -m gpu -q -x -k "pillow or written_by_the_reference" 2>&1 | tail -8 > gpurun_out/racecheck_decode.log; tail -5 gpurun_out/racecheck_decode.log
+timeout 1500 python -m pytest tests/test_gpu_codec.py tests/test_gpu_decode.py tests/test_gpu_sched.py -m gpu -q -x 2>&1 | tail -8
+timeout 600 python tests/perf/bench_encode.py 2>&1 | tail -1 > gpurun_out/bench_encode_u.json; python -c "
+import json; e=json.load(open('gpurun_out/bench_encode_u.json'))
+for k in ('png_encoder_device','exr_encoder_device'): print(k, e.get(k))"
