@@ -575,3 +575,45 @@ def test_c2_full_size_png_path(lrp, variant):
     want = ORC.png_encode(ORC.reproject(ORC.png_decode(rgba), il, olens, W, H, 1, ol.BICUBIC, r))
     diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
     assert diff.max() == 0, "%d of %d samples differ (max %d LSB)" % ((diff > 0).sum(), diff.size, diff.max())
+
+
+FULL_SIZE_EXR = {
+    # BASELINE configs #3, #4 (reference-runnable twin) and #5 (the equator view 90,0,0) at full size
+    "c3": dict(il=lambda: ol.equidistant(3.14159), size=(4096, 4096), c=4, ol=lambda W, H: ol.erect(), out=(4096, 2048),
+               rot=None, post=(1.5, 4.0)),
+    "c4t": dict(il=lambda: ol.rect(36.0, 36.0, 3840, 2160), size=(3840, 2160), c=4, ol=lambda W, H: ol.equidistant(3.14159),
+                out=(3840, 2160), rot=None, post=None),
+    "c5e": dict(il=lambda: ol.erect(), size=(16384, 8192), c=3, ol=lambda W, H: ol.rect(18.0, 36.0, W, H), out=(4096, 4096),
+                rot=(90, 0, 0), post=None),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FULL_SIZE_EXR))
+def test_full_size_exr_configs_bit_exact(lrp, name):
+    """The EXR configurations of BASELINE.json at their full sizes through the synchronous C-ABI drop-in (host half
+    planes in, host half planes out, default variant): every half of the output equals the oracle's; the north star's 1e-5 relative
+    tolerance is asserted besides."""
+    cfg = FULL_SIZE_EXR[name]
+    (w, h), (W, H), c = cfg["size"], cfg["out"], cfg["c"]
+    rng = np.random.default_rng(len(name))
+    planes = (rng.random((c, h, w), dtype=np.float32) * 2).astype(np.float16).view(np.uint16)
+    if c == 4:  # depth plane: 1 + 0.001 x with 1 % of the samples at +inf (1e10 -> inf in half), SURVEY 8(d)
+        z = (1.0 + 0.001 * np.arange(w, dtype=np.float32))[None, :].repeat(h, 0).astype(np.float16)
+        z[rng.random((h, w)) < 0.01] = np.float16(np.inf)
+        planes[3] = z.view(np.uint16)
+    il, olens = cfg["il"](), cfg["ol"](W, H)
+    r = None if cfg["rot"] is None else ORC.rotation_from_degrees(*cfg["rot"])
+    got16 = lrp.reproject_host(planes, L(lrp, il), L(lrp, olens), W, H, 1, ol.BICUBIC, r, post=cfg["post"],
+                               in_fmt=lrp.FMT_F16_PLANAR, out_fmt=lrp.FMT_F16_PLANAR)
+    src_f = ORC.half_planar_to_f32(planes)
+    want = ORC.reproject(src_f, il, olens, W, H, 1, ol.BICUBIC, r)  # a few seconds on one core
+    del src_f
+    if cfg["post"]:
+        want = ORC.post_process(want, *cfg["post"])
+    want16 = ORC.f32_to_half_planar(want)
+    del want
+    same = (got16 == want16) | (((got16 & 0x7fff) > 0x7c00) & ((want16 & 0x7fff) > 0x7c00))
+    assert same.all(), "%s: half planes differ in %d of %d samples" % (name, (~same).sum(), same.size)
+    g, wv = got16.view(np.float16).astype(np.float64), want16.view(np.float16).astype(np.float64)
+    fin = np.isfinite(g) & np.isfinite(wv)
+    assert np.all(np.abs(g[fin] - wv[fin]) <= 1e-5 * np.abs(wv[fin]))
