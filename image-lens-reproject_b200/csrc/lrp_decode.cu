@@ -256,18 +256,21 @@ static int exr_parse(const unsigned char *f, size_t n, ExrInfo &I) {
       }
       have_ch = true;
     } else if (name == "compression") {
+      if (len < 1) return LRP_E_BAD_ARG;
       I.compression = d[0];
     } else if (name == "dataWindow") {
+      if (len < 16) return LRP_E_BAD_ARG;
       int32_t b[4];
       memcpy(b, d, 16);
       I.w = b[2] - b[0] + 1, I.h = b[3] - b[1] + 1;
       have_dw = true;
     } else if (name == "lineOrder") {
+      if (len < 1) return LRP_E_BAD_ARG;
       if (d[0] > 1) return LRP_E_UNSUPPORTED_FORMAT; // the offset table is in increasing y for both 0 and 1
     }
     pos += len;
   }
-  if (!have_ch || !have_dw || I.w <= 0 || I.h <= 0) return LRP_E_BAD_ARG;
+  if (!have_ch || !have_dw || I.w <= 0 || I.h <= 0 || (uint64_t)I.w * (uint64_t)I.h >= (1ull << 31)) return LRP_E_BAD_ARG;
   if (I.compression == 0 || I.compression == 2) I.lines_per_block = 1;
   else if (I.compression == 3) I.lines_per_block = 16;
   else return LRP_E_UNSUPPORTED_FORMAT; // RLE / PIZ / PXR24 / B44 / DWA
@@ -330,6 +333,7 @@ static int png_parse(const unsigned char *f, size_t n, PngInfo &I, std::vector<u
       if (data[12] != 0 || I.depth != 8) return LRP_E_UNSUPPORTED_FORMAT; // interlaced / other bit depths
       I.channels = I.ctype == 0 ? 1 : I.ctype == 2 ? 3 : I.ctype == 3 ? 1 : I.ctype == 4 ? 2 : I.ctype == 6 ? 4 : 0;
       if (!I.channels || I.w == 0 || I.h == 0) return LRP_E_UNSUPPORTED_FORMAT;
+      if ((uint64_t)I.w * (uint64_t)I.h >= (1ull << 31)) return LRP_E_BAD_ARG; // pixel indices are 32-bit on the device
       have_ihdr = true;
     } else if (!memcmp(type, "IDAT", 4)) {
       idat.insert(idat.end(), data, data + len);

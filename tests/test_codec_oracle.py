@@ -163,3 +163,26 @@ def test_exr_and_png_info(lrp):
             lrp.exr_info(bad)
         with pytest.raises(lrp.LrpError):
             lrp.png_info(bad)
+
+
+def test_container_parsers_survive_truncation_and_bit_flips(lrp):
+    """lrp_exr_info / lrp_png_info on every prefix of a valid file and on files with single corrupted bytes in the header
+    region: an error code or the right answer, never a crash (the parsers run on untrusted file bytes)."""
+    rng = np.random.default_rng(31)
+    exr = lrp.exr_assemble(co.exr_pack(half_planes(3, 20, 10)), 10, 20, 3, 6, 1)
+    img = images()["smooth"]
+    png = lrp.png_assemble(co.png_filter_minsum(img), img.shape[1], img.shape[0], 3, 6, 1)
+    for data, fn, want in ((exr, lrp.exr_info, (10, 20, 3)), (png, lrp.png_info, (img.shape[1], img.shape[0]))):
+        for n in list(range(0, 400, 7)) + [len(data) - 1]:
+            try:
+                fn(data[:n])
+            except lrp.LrpError:
+                pass
+        for _ in range(300):
+            b = bytearray(data)
+            b[int(rng.integers(0, min(len(b), 360)))] = int(rng.integers(0, 256))
+            try:
+                fn(bytes(b))
+            except lrp.LrpError:
+                pass
+        assert fn(data) == want
