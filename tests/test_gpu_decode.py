@@ -172,3 +172,36 @@ def test_file_to_file_png_pipeline_matches_the_reference_chain(lrp, ctx, dec):
     ref = ol.reference_lodepng()
     got = ref.decode(file_out) if ref is not None else np.dstack([co.png_decode(file_out), np.full((H, W), 255, np.uint8)])
     assert (got == want).all()
+
+
+def test_decoders_reject_or_survive_corrupted_files(lrp, ctx, dec):
+    """single corrupted bytes anywhere in a file (header, offset table, chunk headers, compressed body): the decoders
+    return an error or an image, and keep working afterwards"""
+    import torch
+    rng = np.random.default_rng(77)
+    img = rng.integers(0, 256, (60, 90, 4), dtype=np.uint8)
+    img[..., 3] = 255
+    png = lrp.png_assemble(co.png_filter_minsum(img[..., :3]), 90, 60, 3, 6, 1)
+    planes = _half_image(40, 33, 4, 5).transpose(2, 0, 1).copy().view(np.uint16)
+    exr = lrp.exr_assemble(co.exr_pack(planes), 33, 40, 4, 6, 1)
+    errors = 0
+    for data, fn in ((png, dec.png), (exr, lambda b: dec.exr(b, 2))):
+        for _ in range(150):
+            b = bytearray(data)
+            b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+            try:
+                fn(bytes(b))
+            except lrp.LrpError:
+                errors += 1
+        for n in (0, 1, 8, 30, len(data) // 2):
+            with pytest.raises(lrp.LrpError):
+                fn(data[:n])
+        try:  # a missing trailer byte (PNG: the IEND chunk's CRC) may be tolerated, but then the image must be right
+            out = fn(data[:len(data) - 1])
+            assert out is not None
+        except lrp.LrpError:
+            pass
+    assert errors > 100  # almost every flip breaks a checksum or a structure field
+    torch.cuda.synchronize()
+    assert (dec.png(png).cpu().numpy() == img).all()
+    assert (dec.exr(exr, 2).cpu().numpy().view(np.uint16) == planes).all()

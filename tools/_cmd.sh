@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "full_size" 2>&1 | tail -8
+timeout 1500 python -m pytest tests/test_gpu_decode.py -m gpu -q -x 2>&1 | tail -8
