@@ -446,9 +446,169 @@ __global__ void __launch_bounds__(256) deflate_gather_kernel(const LayoutParams 
   }
 }
 
+// ---- CRC-32 of the compact stream (PNG chunk check value) on the device -----------------------------------------
+// CRC-32 (IEEE, reflected, as PNG / zlib) is linear over GF(2): crc(A || B) = crc(A) * x^(8 |B|) mod P  xor  crc(B) for the
+// conditioned CRCs zlib's crc32_combine works with.  Every thread takes 64 bytes (table-driven), a CTA folds its 256
+// pieces in a tree (power-of-two lengths multiply by a tabulated x^(2^k) mod P), a second one-CTA kernel folds the CTAs.
+constexpr unsigned CRC_POLY = 0xEDB88320u;
+constexpr int CRC_THREADS = 256, CRC_PIECE = 64;
+
+__device__ unsigned crc_multmodp(unsigned a, unsigned b) { // a(x) * b(x) mod P, reflected bit order (bit 31 = x^0)
+  unsigned m = 1u << 31, p = 0;
+  for (;;) {
+    if (a & m) {
+      p ^= b;
+      if ((a & (m - 1)) == 0) break;
+    }
+    m >>= 1;
+    b = (b & 1u) ? (b >> 1) ^ CRC_POLY : b >> 1;
+  }
+  return p;
+}
+__device__ unsigned crc_x8n(unsigned long long n, const unsigned *x2n) { // x^(8 n) mod P; x2n[k] = x^(2^k) mod P
+  if (n && (n & (n - 1)) == 0) return x2n[(3 + (63 - __clzll((long long)n))) & 31];
+  unsigned p = 1u << 31, k = 3;
+  while (n) {
+    if (n & 1) p = crc_multmodp(x2n[k & 31], p);
+    n >>= 1;
+    ++k;
+  }
+  return p;
+}
+struct CrcNode {
+  unsigned crc;
+  unsigned long long len;
+};
+__device__ CrcNode crc_join(CrcNode l, CrcNode r, const unsigned *x2n) {
+  if (r.len == 0) return l;
+  if (l.len == 0) return r;
+  CrcNode o;
+  o.crc = crc_multmodp(crc_x8n(r.len, x2n), l.crc) ^ r.crc;
+  o.len = l.len + r.len;
+  return o;
+}
+struct CrcPowers { // x^(2^k) mod P for k < 32, computed once on the host (crc_powers())
+  unsigned v[32];
+};
+__device__ void crc_tables(unsigned *tab, unsigned *x2n, const CrcPowers &pw) { // 256-entry byte table + the powers
+  unsigned c = threadIdx.x;
+  for (int k = 0; k < 8; ++k) c = (c & 1u) ? CRC_POLY ^ (c >> 1) : c >> 1;
+  if (threadIdx.x < 256) tab[threadIdx.x] = c;
+  if (threadIdx.x < 32) x2n[threadIdx.x] = pw.v[threadIdx.x];
+  __syncthreads();
+}
+// folds nodes[0..CRC_THREADS) (shared memory) into nodes[0]
+__device__ void crc_fold(CrcNode *nodes, const unsigned *x2n) {
+  for (int s = 1; s < CRC_THREADS; s <<= 1) {
+    __syncthreads();
+    CrcNode o;
+    const bool act = (threadIdx.x % (2 * s)) == 0;
+    if (act) o = crc_join(nodes[threadIdx.x], nodes[threadIdx.x + s], x2n);
+    __syncthreads();
+    if (act) nodes[threadIdx.x] = o;
+  }
+  __syncthreads();
+}
+
+// total bytes = *total_ptr (known on the device only); CTA i covers bytes [i * 16384, ...)
+__global__ void __launch_bounds__(CRC_THREADS) crc_pieces_kernel(const unsigned char *data, const unsigned long long *total_ptr,
+                                                                  unsigned *cta_crc, unsigned long long *cta_len,
+                                                                  const CrcPowers pw) {
+  __shared__ unsigned tab[256], x2n[32];
+  __shared__ CrcNode nodes[CRC_THREADS];
+  const unsigned long long total = *total_ptr;
+  const unsigned long long begin = ((unsigned long long)blockIdx.x * CRC_THREADS + threadIdx.x) * CRC_PIECE;
+  if ((unsigned long long)blockIdx.x * CRC_THREADS * CRC_PIECE >= total) { // whole CTA beyond the data (grid is sized for the cap)
+    if (threadIdx.x == 0) cta_len[blockIdx.x] = 0, cta_crc[blockIdx.x] = 0;
+    return;
+  }
+  crc_tables(tab, x2n, pw);
+  CrcNode me;
+  me.crc = 0, me.len = 0;
+  if (begin < total) {
+    const unsigned n = (unsigned)(total - begin < (unsigned long long)CRC_PIECE ? total - begin : (unsigned long long)CRC_PIECE);
+    unsigned c = 0xFFFFFFFFu;
+    const unsigned char *p = data + begin;
+    if (n == CRC_PIECE && (((size_t)p) & 15) == 0) {
+#pragma unroll
+      for (int q = 0; q < CRC_PIECE / 16; ++q) {
+        const uint4 v = __ldg((const uint4 *)p + q);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int t = 0; t < 16; ++t) c = tab[(c ^ (w[t >> 2] >> (8 * (t & 3)))) & 255u] ^ (c >> 8);
+      }
+    } else {
+      for (unsigned i = 0; i < n; ++i) c = tab[(c ^ p[i]) & 255u] ^ (c >> 8);
+    }
+    me.crc = ~c, me.len = n;
+  }
+  // The one partial piece (the stream's last bytes) is kept out of the tree and joined at the end: a node whose length is
+  // not a power of two costs popcount(length) multiplications, and inside the tree it would do so on every level.
+  __shared__ CrcNode tail;
+  if (threadIdx.x == 0) tail.crc = 0, tail.len = 0;
+  __syncthreads();
+  if (me.len != 0 && me.len != CRC_PIECE) {
+    tail = me;
+    me.crc = 0, me.len = 0;
+  }
+  nodes[threadIdx.x] = me;
+  crc_fold(nodes, x2n);
+  if (threadIdx.x == 0) {
+    const CrcNode all = crc_join(nodes[0], tail, x2n);
+    cta_crc[blockIdx.x] = all.crc, cta_len[blockIdx.x] = all.len;
+  }
+}
+
+__global__ void __launch_bounds__(CRC_THREADS) crc_final_kernel(const unsigned *cta_crc, const unsigned long long *cta_len, unsigned n_ctas,
+                                                                 unsigned *out_crc, const CrcPowers pw) {
+  __shared__ unsigned tab[256], x2n[32];
+  __shared__ CrcNode nodes[CRC_THREADS];
+  crc_tables(tab, x2n, pw);
+  // every thread folds a contiguous run of CTAs serially, then the tree
+  unsigned per = 1; // a power of two, so that all but the last node span a power-of-two length (tabulated multiplier)
+  while (per * CRC_THREADS < n_ctas) per <<= 1;
+  __shared__ CrcNode tail; // the one partial CTA (see crc_pieces_kernel)
+  if (threadIdx.x == 0) tail.crc = 0, tail.len = 0;
+  __syncthreads();
+  CrcNode acc;
+  acc.crc = 0, acc.len = 0;
+  for (unsigned i = threadIdx.x * per; i < min(n_ctas, (threadIdx.x + 1) * per); ++i) {
+    CrcNode r;
+    r.crc = cta_crc[i], r.len = cta_len[i];
+    if (r.len != 0 && r.len != (unsigned long long)CRC_THREADS * CRC_PIECE) tail = r;
+    else acc = crc_join(acc, r, x2n);
+  }
+  nodes[threadIdx.x] = acc;
+  crc_fold(nodes, x2n);
+  if (threadIdx.x == 0) *out_crc = crc_join(nodes[0], tail, x2n).crc;
+}
+
 } // namespace lrp
 
 using namespace lrp;
+
+static const CrcPowers &crc_powers() {
+  static const CrcPowers pw = [] {
+    auto mul = [](unsigned a, unsigned b) {
+      unsigned m = 1u << 31, p = 0;
+      for (;;) {
+        if (a & m) {
+          p ^= b;
+          if ((a & (m - 1)) == 0) break;
+        }
+        m >>= 1;
+        b = (b & 1u) ? (b >> 1) ^ CRC_POLY : b >> 1;
+      }
+      return p;
+    };
+    CrcPowers t;
+    unsigned p = 1u << 30; // x^1
+    t.v[0] = p;
+    for (int k = 1; k < 32; ++k) t.v[k] = p = mul(p, p);
+    return t;
+  }();
+  return pw;
+}
 
 // ---- the encoder object: device + pinned workspaces for frames up to a maximum size ----
 struct lrp_encoder {
@@ -458,6 +618,10 @@ struct lrp_encoder {
   unsigned char *d_packed = nullptr, *d_slots = nullptr, *d_compact = nullptr, *h_compact = nullptr;
   unsigned *d_band_len = nullptr, *d_band_adler = nullptr, *d_band_in = nullptr, *d_stream_adler = nullptr;
   unsigned long long *d_band_off = nullptr, *d_stream_off = nullptr, *h_stream_off = nullptr;
+  unsigned *d_cta_crc = nullptr, *d_crc = nullptr;   // CRC-32 of the compact stream (PNG), folded on the device
+  unsigned long long *d_cta_len = nullptr;
+  size_t cap_crc_ctas = 0;
+  unsigned h_crc = 0;
   std::vector<unsigned char> file;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   double last_ms[3] = {0, 0, 0}; // device (pack + deflate + layout), copy of the compressed body, container on the host
@@ -474,6 +638,7 @@ static void encoder_free(lrp_encoder *e) {
   cudaFree(e->d_packed), cudaFree(e->d_slots), cudaFree(e->d_compact);
   cudaFree(e->d_band_len), cudaFree(e->d_band_adler), cudaFree(e->d_band_in), cudaFree(e->d_stream_adler);
   cudaFree(e->d_band_off), cudaFree(e->d_stream_off);
+  cudaFree(e->d_cta_crc), cudaFree(e->d_crc), cudaFree(e->d_cta_len);
   if (e->h_compact) cudaFreeHost(e->h_compact);
   if (e->h_stream_off) cudaFreeHost(e->h_stream_off);
   for (auto ev : e->ev)
@@ -485,7 +650,7 @@ static void encoder_free(lrp_encoder *e) {
 // result to the encoder's pinned buffer.  On return h_stream_off[0..n_streams] delimit the streams (each preceded by its
 // chunk header when chunk_hdr != 0) at h_compact + headroom(cap_streams).
 static int deflate_to_host(lrp_encoder *e, size_t n, size_t stream_bytes, cudaStream_t st, unsigned chunk_hdr = 0,
-                           unsigned lines_per_stream = 0) {
+                           unsigned lines_per_stream = 0, bool want_crc = false) {
   const unsigned bps = (unsigned)((stream_bytes + DF_BAND - 1) / DF_BAND);
   const unsigned n_streams = (unsigned)((n + stream_bytes - 1) / stream_bytes);
   const unsigned n_bands = bps * n_streams;
@@ -509,6 +674,13 @@ static int deflate_to_host(lrp_encoder *e, size_t n, size_t stream_bytes, cudaSt
   deflate_layout_kernel<<<n_streams, LAYOUT_THREADS, 0, st>>>(L);
   deflate_offsets_kernel<<<1, 32, 0, st>>>(L);
   deflate_gather_kernel<<<n_bands, 256, 0, st>>>(L, e->d_slots, e->d_compact);
+  if (want_crc) { // CRC-32 of everything just laid out (one stream: the IDAT payload)
+    const size_t bound = compact_bound(n, n_bands, n_streams);
+    const unsigned ctas = (unsigned)std::min(e->cap_crc_ctas, (bound + (size_t)CRC_THREADS * CRC_PIECE - 1) / ((size_t)CRC_THREADS * CRC_PIECE));
+    crc_pieces_kernel<<<ctas, CRC_THREADS, 0, st>>>(e->d_compact, e->d_stream_off + n_streams, e->d_cta_crc, e->d_cta_len, crc_powers());
+    crc_final_kernel<<<1, CRC_THREADS, 0, st>>>(e->d_cta_crc, e->d_cta_len, ctas, e->d_crc, crc_powers());
+    cudaMemcpyAsync(&e->h_crc, e->d_crc, 4, cudaMemcpyDeviceToHost, st);
+  }
   cudaEventRecord(e->ev[1], st);
   if (cudaMemcpyAsync(e->h_stream_off, e->d_stream_off, (n_streams + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
       cudaStreamSynchronize(st) != cudaSuccess)
@@ -538,7 +710,10 @@ static int encoder_alloc(lrp_ctx *ctx, size_t cap_packed, size_t cap_bands, size
   e->ctx = ctx, e->device = dev;
   e->cap_packed = cap_packed, e->cap_bands = cap_bands, e->cap_streams = cap_streams;
   const size_t cb = compact_bound(e->cap_packed, e->cap_bands, e->cap_streams);
+  e->cap_crc_ctas = (cb + (size_t)CRC_THREADS * CRC_PIECE - 1) / ((size_t)CRC_THREADS * CRC_PIECE);
   bool ok = cudaMalloc(&e->d_packed, e->cap_packed) == cudaSuccess &&
+            cudaMalloc(&e->d_cta_crc, e->cap_crc_ctas * 4) == cudaSuccess && cudaMalloc(&e->d_cta_len, e->cap_crc_ctas * 8) == cudaSuccess &&
+            cudaMalloc(&e->d_crc, 4) == cudaSuccess &&
             cudaMalloc(&e->d_slots, e->cap_bands * DF_SLOT) == cudaSuccess && cudaMalloc(&e->d_compact, cb) == cudaSuccess &&
             cudaMalloc(&e->d_band_len, e->cap_bands * 4) == cudaSuccess && cudaMalloc(&e->d_band_adler, e->cap_bands * 4) == cudaSuccess &&
             cudaMalloc(&e->d_band_in, e->cap_bands * 4) == cudaSuccess && cudaMalloc(&e->d_stream_adler, e->cap_streams * 4) == cudaSuccess &&
@@ -608,7 +783,7 @@ int lrp_encoder_png(lrp_encoder *e, const void *rgba_dev, int32_t width, int32_t
   cudaEventRecord(e->ev[0], st);
   int rc = lrp_png_pack_device(e->ctx, rgba_dev, width, height, png_channels, e->d_packed, cuda_stream);
   if (rc != LRP_OK) return rc;
-  rc = deflate_to_host(e, n, n, st);
+  rc = deflate_to_host(e, n, n, st, 0, 0, true);
   if (rc != LRP_OK) return rc;
   const auto t_host = std::chrono::steady_clock::now();
   const size_t zn = (size_t)e->h_stream_off[1];
@@ -626,8 +801,8 @@ int lrp_encoder_png(lrp_encoder *e, const void *rgba_dev, int32_t width, int32_t
     be(f + 8, 13), memcpy(f + 12, "IHDR", 4), memcpy(f + 16, ihdr, 13);
     be(f + 29, (uint32_t)crc32(0L, f + 12, 17));
     be(f + 33, (uint32_t)zn), memcpy(f + 37, "IDAT", 4);
-    uLong c = crc32(0L, f + 37, 4);
-    for (size_t p = 0; p < zn; p += 1u << 30) c = crc32(c, data + p, (uInt)std::min<size_t>(zn - p, 1u << 30));
+    // chunk CRC = CRC("IDAT" || stream): the stream's CRC was folded on the device, zlib joins the 4 type bytes
+    const uLong c = crc32_combine(crc32(0L, f + 37, 4), (uLong)e->h_crc, (z_off_t)zn);
     unsigned char *t = data + zn;
     be(t, (uint32_t)c);
     be(t + 4, 0), memcpy(t + 8, "IEND", 4), be(t + 12, (uint32_t)crc32(0L, t + 8, 4));
