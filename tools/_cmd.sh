@@ -1,7 +1,6 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_codec.py -m gpu -q -x -k "png" 2>&1 | tail -4
-timeout 600 python tests/perf/bench_encode.py 2>&1 | tail -1 > gpurun_out/bench_encode_v.json; python -c "
-import json; e=json.load(open('gpurun_out/bench_encode_v.json'))
-for k in ('png_encoder_device',): print(k, e.get(k))"
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"crc|deflate|pack" -c 24 --csv --log-file gpurun_out/encode_launches_v.csv python tests/perf/bench_encode.py --reps 1 > /dev/null 2>&1
-grep -E "crc|deflate|pack" gpurun_out/encode_launches_v.csv | awk -F'","' '{print $5, $NF}' | sed 's/(.*) / /; s/"$//' | awk '{n[$1]++; s[$1]+=$NF} END{for(k in n) printf "%-40s launches %3d  avg %.1f us\n", k, n[k], s[k]/n[k]/1000}' | sort | tee gpurun_out/encode_launches_summary_v.txt
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 99 python -m pytest tests/test_gpu_codec.py -m gpu -q -x -k "device_deflate_png and (7-33 or 100-109 or 300-500)" 2>&1 | tail -4
+timeout 800 python tests/perf/bench_pipeline.py 2>&1 | tail -1 > gpurun_out/bench_pipeline_w.json; python -c "
+import json; d=json.load(open('gpurun_out/bench_pipeline_w.json')); print(d['frames_per_s'], d['output_gpix_per_s'])"
