@@ -18,7 +18,10 @@
 //   * a second, small kernel lays the bands of every stream out back to back behind the 2-byte zlib header and
 //     appends the final empty block + the stream's Adler-32: PNG = one stream (the IDAT payload), EXR = one stream per
 //     block of 16 scan lines.
-// The host adds the container bytes only (PNG chunk framing + CRC-32, EXR header + offset table).
+//   * the CRC-32 of the PNG payload is folded on the device as well (crc_pieces_kernel / crc_final_kernel), and EXR chunks
+//     leave the device already framed ({y, size} headers).
+// The host adds the container's leading / trailing bytes only (PNG signature, IHDR, chunk framing; EXR header + offset
+// table), written in place around the compact stream in pinned memory: no pass over the data, no copy.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>

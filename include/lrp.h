@@ -300,8 +300,9 @@ int lrp_save_exr_device(lrp_ctx *ctx, const void *half_planar_dev, int32_t width
                         int32_t level, int32_t threads, const char *path, void *cuda_stream);
 
 /* The whole writer on the device: pack + DEFLATE on the GPU (one dynamic-Huffman block of literals per 32 KB band,
- * bands joined on byte boundaries with empty stored blocks, Adler-32 on the device: csrc/lrp_deflate.cu), so that
- * only the compressed file body crosses PCIe and the host adds the container bytes.  An encoder owns device and
+ * bands joined on byte boundaries with empty stored blocks, Adler-32 and the PNG chunk CRC-32 on the device:
+ * csrc/lrp_deflate.cu), so that only the compressed file body crosses PCIe and the host writes the few container
+ * bytes around it in place.  An encoder owns device and
  * pinned workspaces for frames up to the given size; use one per host thread.  *file_bytes points into the
  * encoder and stays valid until its next call.  The files are plain PNG / OpenEXR-ZIP files: any reader inflates
  * them (the reference's lodepng::decode and Imf::InputFile included) to the sink's samples. */
