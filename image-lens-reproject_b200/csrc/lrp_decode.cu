@@ -13,9 +13,12 @@
 //   PNG  host: chunks, one zlib inflate of the IDAT stream (into pinned memory).  device: scan-line reconstruction as a
 //        wavefront over 1024 lines (png_unfilter_kernel) + expansion to RGBA8 as lodepng::decode delivers it, for RGB /
 //        RGBA files; grey / palette / colour-keyed files are reconstructed on the host and uploaded as RGBA8.
-// Scope: what the reference's pipeline reads — single-part scan-line EXR with HALF channels named from {R,G,B,A,Z},
+// Scope: what the reference's pipeline reads — single-part scan-line EXR with channels named from {R,G,B,A,Z} of any
+// pixel type (HALF as save_exr writes them; FLOAT / UINT — e.g. Blender's full-float files or a float Z beside half
+// colour — are converted to half on the device exactly as OpenEXR converts them for read_exr's HALF slices),
 // NONE / ZIPS / ZIP compression; non-interlaced 8-bit PNG of colour type 0, 2, 3, 4 or 6.  Anything else returns
 // LRP_E_UNSUPPORTED_FORMAT (the reference would go through lodepng / OpenEXR's other code paths).
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -35,12 +38,15 @@ extern "C" int lrp_ctx_phys_device_(const lrp_ctx *ctx); // lrp_api.cu
 namespace lrp {
 
 // ---- EXR: predictor + byte planes + channel scatter on the device ---------------------------------------
+// A block of scan lines is a run of 16-bit UNITS: a HALF sample is one unit, a FLOAT / UINT sample two (low half first).
+// The predictor and the byte-plane split of OpenEXR's ZIP work on bytes and pair byte i of the low plane with byte i of
+// the high plane, i.e. on units, whatever the channel types are.
 struct ExrUnpackParams {
   const unsigned char *src;      // blocks back to back, each either predicted byte planes (inflate output) or raw
   const unsigned char *is_raw;   // per block
-  unsigned short *dst;           // planar half, plane stride W * H
+  unsigned short *dst[5];        // where the k-th channel (file order) goes: its half plane, or a 32-bit scratch plane
+  unsigned ustart[6];            // first unit of the k-th channel inside a scan line (ustart[C] = units per line)
   int W, H, C, lines_per_block;
-  int plane_of[5];               // destination plane of the k-th channel in file order
 };
 
 constexpr int UNPACK_WARPS = 32;
@@ -53,17 +59,23 @@ __global__ void __launch_bounds__(UNPACK_WARPS * 32) exr_unpack_kernel(const Exr
   __shared__ unsigned seg_lo[UNPACK_WARPS], seg_hi[UNPACK_WARPS];
   const int block = blockIdx.x, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const int y0 = block * P.lines_per_block, lines = min(P.lines_per_block, P.H - y0);
-  const unsigned W = (unsigned)P.W, C = (unsigned)P.C;
-  const unsigned halfs = (unsigned)lines * C * W;
-  const unsigned char *src = P.src + (size_t)y0 * C * W * 2;
-  const size_t plane = (size_t)W * P.H;
+  const unsigned C = (unsigned)P.C, UL = P.ustart[C]; // units per scan line
+  const unsigned halfs = (unsigned)lines * UL;         // units of this block
+  const unsigned char *src = P.src + (size_t)y0 * UL * 2;
   const bool raw = P.is_raw[block] != 0;
 
-  auto store8 = [&](unsigned i0, const unsigned short (&v)[8], unsigned m) { // halfs [i0, i0 + m) of the block's raw order
-    const unsigned rowc = i0 / W, x = i0 - rowc * W;
-    if (m == 8 && x + 8 <= W) {
-      const unsigned ly = rowc / C, k = rowc - ly * C;
-      unsigned short *d = P.dst + (size_t)P.plane_of[k] * plane + (size_t)(y0 + ly) * W + x;
+  // unit o of a scan line -> channel k (file order) and the unit's position inside the channel's run of the line
+  auto locate = [&](unsigned o, unsigned &k, unsigned &x, unsigned &run) {
+    k = 0;
+    while (k + 1 < C && o >= P.ustart[k + 1]) ++k;
+    x = o - P.ustart[k], run = P.ustart[k + 1] - P.ustart[k];
+  };
+  auto store8 = [&](unsigned i0, const unsigned short (&v)[8], unsigned m) { // units [i0, i0 + m) of the block's raw order
+    const unsigned ly = i0 / UL;
+    unsigned k, x, run;
+    locate(i0 - ly * UL, k, x, run);
+    if (m == 8 && x + 8 <= run) {
+      unsigned short *d = P.dst[k] + (size_t)(y0 + ly) * run + x;
       if ((((size_t)d) & 15) == 0) {
         uint4 q;
         q.x = v[0] | ((unsigned)v[1] << 16), q.y = v[2] | ((unsigned)v[3] << 16);
@@ -73,8 +85,9 @@ __global__ void __launch_bounds__(UNPACK_WARPS * 32) exr_unpack_kernel(const Exr
       }
     }
     for (unsigned j = 0; j < m; ++j) {
-      const unsigned i = i0 + j, rc = i / W, xx = i - rc * W, ly = rc / C, k = rc - ly * C;
-      P.dst[(size_t)P.plane_of[k] * plane + (size_t)(y0 + ly) * W + xx] = v[j];
+      const unsigned i = i0 + j, l = i / UL;
+      locate(i - l * UL, k, x, run);
+      P.dst[k][(size_t)(y0 + l) * run + x] = v[j];
     }
   };
 
@@ -150,6 +163,41 @@ __global__ void __launch_bounds__(UNPACK_WARPS * 32) exr_unpack_kernel(const Exr
   }
 }
 
+// FLOAT / UINT channels: read_exr hands OpenEXR HALF slices for every channel (src/image_formats.cpp:246-252), so the
+// library converts while it copies a line into the frame buffer (lib/openexr/src/lib/OpenEXR/ImfMisc.cpp:392, :412):
+//   floatToHalf (ImfConvert.cpp:104-115): finite values beyond +-HALF_MAX become +-infinity (so 65504 < f < 65520 does
+//     NOT round down to 65504), everything else is half(f) = imath_float_to_half (lib/Imath/src/Imath/half.h:368-437):
+//     round to nearest even, float denormals -> signed zero, NaN keeps its top 10 payload bits (at least one set);
+//   uintToHalf (ImfConvert.cpp:96-102): values above HALF_MAX -> +infinity, else half(float(ui)).
+__device__ __forceinline__ unsigned short exr_float_to_half(unsigned bits) {
+  const unsigned a = bits & 0x7fffffffu, s = (bits >> 16) & 0x8000u;
+  if (a > 0x7f800000u) { // NaN
+    const unsigned m = (a & 0x7fffffu) >> 13;
+    return (unsigned short)(s | 0x7c00u | m | (m == 0u ? 1u : 0u));
+  }
+  if (a > 0x477fe000u) return (unsigned short)(s | 0x7c00u); // |f| > 65504, infinity included
+  return __half_as_ushort(__float2half_rn(__uint_as_float(bits)));
+}
+__device__ __forceinline__ unsigned short exr_uint_to_half(unsigned ui) {
+  return ui > 65504u ? (unsigned short)0x7c00u : __half_as_ushort(__float2half_rn((float)ui));
+}
+
+__global__ void __launch_bounds__(256) exr_to_half_kernel(const unsigned *__restrict__ src, unsigned short *__restrict__ dst,
+                                                           size_t n, int is_uint) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 2;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += stride) {
+    if (i + 1 < n && ((((size_t)(src + i)) & 7) == 0) && ((((size_t)(dst + i)) & 3) == 0)) {
+      const uint2 v = *(const uint2 *)(src + i);
+      const unsigned a = is_uint ? exr_uint_to_half(v.x) : exr_float_to_half(v.x);
+      const unsigned b = is_uint ? exr_uint_to_half(v.y) : exr_float_to_half(v.y);
+      *(unsigned *)(dst + i) = a | (b << 16);
+    } else {
+      dst[i] = is_uint ? exr_uint_to_half(src[i]) : exr_float_to_half(src[i]);
+      if (i + 1 < n) dst[i + 1] = is_uint ? exr_uint_to_half(src[i + 1]) : exr_float_to_half(src[i + 1]);
+    }
+  }
+}
+
 // ---- PNG: scan-line reconstruction on the device ------------------------------------------------------------
 //
 // Reconstruction (PNG specification section 9.2) of pixel (x, y) needs the reconstructed pixels to the left, above and
@@ -215,6 +263,8 @@ __global__ void __launch_bounds__(UNF_ROWS) png_unfilter_kernel(const unsigned c
 struct ExrInfo {
   int w = 0, h = 0, c = 0, compression = 0, lines_per_block = 1;
   int plane_of[5] = {0, 0, 0, 0, 0}; // destination plane of the k-th channel in file order (read_exr's dstC)
+  int type_of[5] = {1, 1, 1, 1, 1};  // pixel type of the k-th channel in the file: 0 UINT, 1 HALF, 2 FLOAT
+  size_t sample_bytes = 0;           // bytes of one pixel over all channels as stored
   size_t table = 0;                  // offset of the line offset table
 };
 
@@ -226,6 +276,7 @@ static int exr_parse(const unsigned char *f, size_t n, ExrInfo &I) {
   size_t pos = 8;
   bool have_ch = false, have_dw = false;
   std::vector<std::string> names;
+  std::vector<int> types;
   while (pos < n && f[pos] != 0) {
     const void *e = memchr(f + pos, 0, n - pos);
     if (!e) return LRP_E_BAD_ARG;
@@ -251,7 +302,9 @@ static int exr_parse(const unsigned char *f, size_t n, ExrInfo &I) {
         if (p + 16 > (size_t)len) return LRP_E_BAD_ARG;
         int32_t rec[4];
         memcpy(rec, d + p, 16);
-        if (rec[0] != 1 || rec[2] != 1 || rec[3] != 1) return LRP_E_UNSUPPORTED_FORMAT; // HALF, no sub-sampling
+        if (rec[0] < 0 || rec[0] > 2) return LRP_E_BAD_ARG;                        // UINT / HALF / FLOAT
+        if (rec[2] != 1 || rec[3] != 1) return LRP_E_UNSUPPORTED_FORMAT;           // no sub-sampling
+        types.push_back(rec[0]);
         p += 16;
       }
       have_ch = true;
@@ -289,6 +342,8 @@ static int exr_parse(const unsigned char *f, size_t n, ExrInfo &I) {
   for (int k = 0; k < I.c; ++k) {
     const std::string &s = names[k];
     I.plane_of[k] = s == "R" ? 0 : s == "G" ? 1 : s == "B" ? 2 : s == "A" ? 3 : (hasA ? 4 : 3);
+    I.type_of[k] = types[k];
+    I.sample_bytes += types[k] == 1 ? 2 : 4;
   }
   return LRP_OK;
 }
@@ -385,10 +440,39 @@ using namespace lrp;
 struct lrp_decoder {
   lrp_ctx *ctx = nullptr;
   int device = 0;
-  size_t cap = 0, cap_blocks = 0;
+  size_t cap = 0, cap_out = 0, cap_blocks = 0, cap_wide = 0; // cap_out: the size limit given at creation
   unsigned char *h_buf = nullptr, *d_buf = nullptr, *h_raw = nullptr, *d_raw = nullptr;
+  unsigned char *d_wide = nullptr; // 32-bit planes of the FLOAT / UINT channels of an EXR file, before their conversion to half
   std::vector<unsigned char> scratch;
 };
+
+// Files with FLOAT / UINT channels store up to twice the bytes per pixel the decoder was sized for (it is sized for what
+// the reference's own save_exr writes: HALF): the staging buffers grow on first use.  No work is in flight between calls
+// (every decode ends with a stream synchronisation), so they can be replaced here.
+static int decoder_reserve(lrp_decoder *d, size_t stage_bytes, size_t wide_bytes) {
+  if (cudaSetDevice(d->device) != cudaSuccess) return LRP_E_CUDA;
+  if (stage_bytes > d->cap) {
+    cudaFreeHost(d->h_buf), cudaFree(d->d_buf);
+    d->h_buf = d->d_buf = nullptr, d->cap = 0;
+    if (cudaMallocHost(&d->h_buf, stage_bytes) != cudaSuccess || cudaMalloc(&d->d_buf, stage_bytes) != cudaSuccess) {
+      cudaGetLastError();
+      if (d->h_buf) cudaFreeHost(d->h_buf);
+      d->h_buf = nullptr;
+      return LRP_E_OOM;
+    }
+    d->cap = stage_bytes;
+  }
+  if (wide_bytes > d->cap_wide) {
+    cudaFree(d->d_wide);
+    d->d_wide = nullptr, d->cap_wide = 0;
+    if (cudaMalloc(&d->d_wide, wide_bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return LRP_E_OOM;
+    }
+    d->cap_wide = wide_bytes;
+  }
+  return LRP_OK;
+}
 
 extern "C" {
 
@@ -420,6 +504,7 @@ int lrp_decoder_create(lrp_ctx *ctx, int32_t max_width, int32_t max_height, int3
   lrp_decoder *d = new lrp_decoder();
   d->ctx = ctx, d->device = dev;
   d->cap = std::max((size_t)max_width * max_height * 4, (size_t)max_width * max_height * max_channels * 2);
+  d->cap_out = d->cap;
   d->cap_blocks = (size_t)max_height;
   const bool ok = cudaMallocHost(&d->h_buf, d->cap) == cudaSuccess && cudaMalloc(&d->d_buf, d->cap) == cudaSuccess &&
                   cudaMallocHost(&d->h_raw, d->cap_blocks) == cudaSuccess && cudaMalloc(&d->d_raw, d->cap_blocks) == cudaSuccess;
@@ -439,7 +524,7 @@ int lrp_decoder_destroy(lrp_decoder *d) {
   if (!d) return LRP_E_BAD_ARG;
   cudaSetDevice(d->device);
   cudaFreeHost(d->h_buf), cudaFreeHost(d->h_raw);
-  cudaFree(d->d_buf), cudaFree(d->d_raw);
+  cudaFree(d->d_buf), cudaFree(d->d_raw), cudaFree(d->d_wide);
   delete d;
   return LRP_OK;
 }
@@ -452,10 +537,15 @@ int lrp_decoder_exr(lrp_decoder *d, const void *file, size_t n, int32_t threads,
   ExrInfo I;
   int rc = exr_parse(f, n, I);
   if (rc != LRP_OK) return rc;
-  const size_t line_bytes = (size_t)I.c * I.w * 2, total = line_bytes * I.h;
+  const size_t line_bytes = I.sample_bytes * I.w, total = line_bytes * I.h, plane = (size_t)I.w * I.h;
   const size_t blocks = ((size_t)I.h + I.lines_per_block - 1) / I.lines_per_block;
-  if (total > d->cap || blocks > d->cap_blocks) return LRP_E_BAD_ARG;
+  int wide = 0; // channels stored as FLOAT / UINT
+  for (int k = 0; k < I.c; ++k) wide += I.type_of[k] != 1;
+  // the decoder's size limit is in pixels and channels of the OUTPUT (half planes), whatever the file's sample types
+  if (plane * I.c * 2 > d->cap_out || blocks > d->cap_blocks) return LRP_E_BAD_ARG;
   if (I.table + 8 * blocks > n) return LRP_E_BAD_ARG;
+  rc = decoder_reserve(d, total, (size_t)wide * plane * 4);
+  if (rc != LRP_OK) return rc;
   std::atomic<int> status{LRP_OK};
   parallel_for(blocks, threads, [&](size_t b) {
     uint64_t off;
@@ -497,10 +587,25 @@ int lrp_decoder_exr(lrp_decoder *d, const void *file, size_t n, int32_t threads,
       cudaMemcpyAsync(d->d_raw, d->h_raw, blocks, cudaMemcpyHostToDevice, st) != cudaSuccess)
     return LRP_E_CUDA;
   ExrUnpackParams P;
-  P.src = d->d_buf, P.is_raw = d->d_raw, P.dst = (unsigned short *)out_half_planar_dev;
+  P.src = d->d_buf, P.is_raw = d->d_raw;
   P.W = I.w, P.H = I.h, P.C = I.c, P.lines_per_block = I.lines_per_block;
-  for (int k = 0; k < 5; ++k) P.plane_of[k] = I.plane_of[k];
+  unsigned short *out = (unsigned short *)out_half_planar_dev;
+  unsigned u = 0;
+  for (int k = 0, wk = 0; k < 5; ++k) {
+    P.ustart[k] = u;
+    P.dst[k] = nullptr;
+    if (k >= I.c) continue;
+    P.dst[k] = I.type_of[k] == 1 ? out + (size_t)I.plane_of[k] * plane : (unsigned short *)(d->d_wide + (size_t)wk++ * plane * 4);
+    u += (unsigned)I.w * (I.type_of[k] == 1 ? 1u : 2u);
+  }
+  for (int k = I.c; k <= 5; ++k) P.ustart[k] = u;
   exr_unpack_kernel<<<(unsigned)blocks, UNPACK_WARPS * 32, 0, st>>>(P);
+  for (int k = 0; k < I.c; ++k)
+    if (I.type_of[k] != 1) {
+      const unsigned grid = (unsigned)std::min<size_t>((plane + 511) / 512, 148 * 8);
+      exr_to_half_kernel<<<grid, 256, 0, st>>>((const unsigned *)P.dst[k], out + (size_t)I.plane_of[k] * plane, plane,
+                                               I.type_of[k] == 0);
+    }
   if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return LRP_E_CUDA; // h_buf is reused
   return LRP_OK;
 }

@@ -324,8 +324,12 @@ int lrp_encoder_last_timing(const lrp_encoder *enc, double *ms3);
  * texel load.  EXR: blocks are inflated on `threads` host cores, the predictor / byte-plane / channel scatter runs on the
  * device.  PNG: the inflate is one sequential stream and stays on the host; RGB / RGBA scan lines are reconstructed on
  * the device (a wavefront over 1024 lines), other colour types on the host.
- * Supported: single-part scan-line EXR, HALF channels R,G,B[,A][,Z], NONE / ZIPS / ZIP; non-interlaced 8-bit PNG of any
- * colour type.  Everything else: LRP_E_UNSUPPORTED_FORMAT.  A decoder owns pinned + device workspaces; one per thread. */
+ * Supported: single-part scan-line EXR, channels R,G,B[,A][,Z] of any pixel type, NONE / ZIPS / ZIP; non-interlaced
+ * 8-bit PNG of any colour type.  Everything else: LRP_E_UNSUPPORTED_FORMAT.  FLOAT / UINT channels arrive as half, as
+ * they do in read_exr (which reads every channel through a HALF slice, :246-258): the device applies OpenEXR's
+ * Imf::floatToHalf / uintToHalf (lib/openexr/src/lib/OpenEXR/ImfConvert.cpp:96-115) bit for bit.
+ * A decoder owns pinned + device workspaces sized for max_width x max_height x max_channels HALF samples (they grow on
+ * the first file that stores wider samples); one per thread. */
 typedef struct lrp_decoder lrp_decoder;
 int lrp_exr_info(const void *file, size_t n, int32_t *width, int32_t *height, int32_t *channels);
 int lrp_png_info(const void *file, size_t n, int32_t *width, int32_t *height);

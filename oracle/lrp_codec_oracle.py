@@ -11,12 +11,17 @@ Restated algorithms (behaviour followed, no code copied):
   * OpenEXR scan-line ZIP pre-processing (reference lib/openexr/src/lib/OpenEXRCore/internal_zip.c:240-259):
     16 scan lines per block, channels in alphabetical order within a scan line, even bytes then odd bytes,
     then t[i] = t[i] - t[i-1] + 128 (mod 256) for i >= 1.
+  * OpenEXR's sample conversion for FLOAT / UINT channels read into read_exr's HALF slices (reference
+    src/image_formats.cpp:246-258; lib/openexr/src/lib/OpenEXR/ImfMisc.cpp:392,412 -> ImfConvert.cpp:96-115 on
+    top of lib/Imath/src/Imath/half.h:368-437): `exr_float_to_half`, `exr_uint_to_half`.
   * save_exr's channel naming (reference src/image_formats.cpp:309-325): plane i is "RGBAZ"[i].
 
 Pinning: `png_filter_minsum` is checked against the compiled reference lodepng (oracle/_ref/libref_lodepng.so:
 a PNG written by lodepng::encode is inflated and its filtered stream compared byte for byte — see
 tests/test_codec_oracle.py); the EXR restatement is checked against the OpenEXR library inside cv2 (an
-independent build of the same code the reference vendors): files assembled from it decode to the input samples.
+independent build of the same code the reference vendors): files assembled from it decode to the input samples;
+the float|uint -> half conversions are checked against the reference's own ImfConvert.cpp / half.h compiled into
+oracle/_ref/libref_half.so (tests/test_codec_oracle.py) and against tests/golden/exr_half_conversion.npz minted from it.
 """
 import struct
 import zlib
@@ -191,3 +196,86 @@ def exr_decode(exr):
 def exr_to_planes(names, data, channels):
     """file-order channels -> save_exr's plane order (plane i = "RGBAZ"[i])."""
     return np.stack([data[names.index(EXR_NAMES[i])] for i in range(channels)])
+
+
+# ---- EXR: FLOAT / UINT channels read through HALF slices ---------------------------------------------------
+def exr_float_to_half(f):
+    """Imf::floatToHalf (ImfConvert.cpp:104-115) over imath_float_to_half (half.h:368-437, the non-F16C path), on the
+    BIT PATTERNS: float32 array -> uint16 half bit patterns."""
+    ui = np.ascontiguousarray(f, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    sign = ((ui >> 16) & 0x8000).astype(np.uint32)
+    a = (ui & 0x7FFFFFFF).astype(np.uint32)
+    out = np.zeros(a.shape, dtype=np.uint32)
+    nan = a > 0x7F800000
+    m = (a & 0x7FFFFF) >> 13
+    out[nan] = (0x7C00 | m | (m == 0))[nan]                  # half.h:395-402: keep the top payload bits, at least one
+    big = ~nan & (a > 0x477FE000)                            # ImfConvert.cpp:108-112: finite beyond HALF_MAX (65504) -> inf;
+    out[big] = 0x7C00                                        #   infinity itself: half.h:398
+    normal = ~nan & ~big & (a >= 0x38800000)                 # half.h:392, :413-415: round to nearest even
+    u = a.astype(np.int64) - 0x38000000
+    out[normal] = ((u + 0x0FFF + ((u >> 13) & 1)) >> 13)[normal].astype(np.uint32)
+    den = ~nan & ~big & ~normal & (a >= 0x33000001)          # half.h:419-435: denormalised half
+    e = (a >> 23).astype(np.int64)
+    shift = np.where(den, 0x7E - e, 1)
+    mm = (0x800000 | (a & 0x7FFFFF)).astype(np.int64)
+    r = (mm << (32 - shift)) & 0xFFFFFFFF
+    d = mm >> shift
+    d = d + ((r > 0x80000000) | ((r == 0x80000000) & ((d & 1) != 0)))
+    out[den] = d[den].astype(np.uint32)
+    return (out | sign).astype(np.uint16)
+
+
+def exr_uint_to_half(u):
+    """Imf::uintToHalf (ImfConvert.cpp:96-102): above HALF_MAX -> +infinity, else half(float(ui))."""
+    u = np.ascontiguousarray(u, dtype=np.uint32)
+    out = exr_float_to_half(np.minimum(u, 65504).astype(np.float32))
+    out[u > 65504] = 0x7C00
+    return out
+
+
+EXR_TYPE = {np.dtype(np.uint32): 0, np.dtype(np.float16): 1, np.dtype(np.float32): 2}
+
+
+def exr_write_typed(channels, compression="zip", line_order=0):
+    """Test-side EXR writer with a pixel type PER CHANNEL (what Blender writes: e.g. half colour + float Z, or full float):
+    channels = {name: [H, W] array of float16 | float32 | uint32}; compression "none" | "zips" | "zip".
+    File layout: OpenEXR file layout document (scan-line, single part); block bytes per scan line = the channels in
+    alphabetical order, each W samples of its own type (internal_zip.c:240-259 for the ZIP pre-processing)."""
+    names = sorted(channels)
+    h, w = channels[names[0]].shape
+    comp = {"none": 0, "zips": 2, "zip": 3}[compression]
+    lpb = 16 if comp == 3 else 1
+
+    def attr(name, typ, data):
+        return name.encode() + b"\0" + typ.encode() + b"\0" + struct.pack("<i", len(data)) + data
+
+    chlist = b"".join(n.encode() + b"\0" + struct.pack("<iiii", EXR_TYPE[channels[n].dtype], 0, 1, 1) for n in names) + b"\0"
+    box = struct.pack("<iiii", 0, 0, w - 1, h - 1)
+    hdr = (b"\x76\x2f\x31\x01" + struct.pack("<I", 2) + attr("channels", "chlist", chlist) +
+           attr("compression", "compression", bytes([comp])) + attr("dataWindow", "box2i", box) +
+           attr("displayWindow", "box2i", box) + attr("lineOrder", "lineOrder", bytes([line_order])) +
+           attr("pixelAspectRatio", "float", struct.pack("<f", 1.0)) +
+           attr("screenWindowCenter", "v2f", struct.pack("<ff", 0.0, 0.0)) +
+           attr("screenWindowWidth", "float", struct.pack("<f", 1.0)) + b"\0")
+    blocks = []
+    for y0 in range(0, h, lpb):
+        raw = b"".join(np.ascontiguousarray(channels[n][y]).astype(channels[n].dtype.newbyteorder("<")).tobytes()
+                       for y in range(y0, min(h, y0 + lpb)) for n in names)
+        data = raw
+        if comp:
+            b = np.frombuffer(raw, dtype=np.uint8)
+            t = np.concatenate([b[0::2], b[1::2]]).astype(np.int32)
+            d = t.copy()
+            d[1:] = (t[1:] - t[:-1] + 128) & 255
+            z = zlib.compress(d.astype(np.uint8).tobytes(), 6)
+            data = z if len(z) < len(raw) else raw
+        blocks.append((y0, data))
+    order = blocks if line_order == 0 else blocks[::-1]  # DECREASING_Y: chunks stored from the bottom, table still by y
+    pos = len(hdr) + 8 * len(blocks)
+    offs = {}
+    body = b""
+    for y0, data in order:
+        offs[y0] = pos + len(body)
+        body += struct.pack("<ii", y0, len(data)) + data
+    table = b"".join(struct.pack("<Q", offs[y0]) for y0, _ in blocks)
+    return hdr + table + body

@@ -419,3 +419,32 @@ def reference_lodepng():
         if lib is not None:
             _ref_png = _RefLodepng(lib)
     return _ref_png
+
+
+_ref_half = None
+
+
+def reference_half():
+    """The reference's vendored Imf::floatToHalf / uintToHalf (oracle/_ref/libref_half.so), or None when oracle/_ref
+    was never built: .float_to_half(float32 array) / .uint_to_half(uint32 array) -> uint16 bit patterns."""
+    global _ref_half
+    if _ref_half is None:
+        path = os.path.join(ORACLE_DIR, "_ref", "libref_half.so")
+        if os.path.exists(path):
+            lib = C.CDLL(path)
+
+            class _RefHalf:
+                def _run(self, fn, a, dt):
+                    a = np.ascontiguousarray(a, dtype=dt).reshape(-1)
+                    out = np.empty(a.size, dtype=np.uint16)
+                    fn(a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_size_t(a.size))
+                    return out
+
+                def float_to_half(self, a):
+                    return self._run(lib.ref_float_to_half, a, np.float32)
+
+                def uint_to_half(self, a):
+                    return self._run(lib.ref_uint_to_half, a, np.uint32)
+
+            _ref_half = _RefHalf()
+    return _ref_half

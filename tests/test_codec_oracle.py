@@ -186,3 +186,75 @@ def test_container_parsers_survive_truncation_and_bit_flips(lrp):
             except lrp.LrpError:
                 pass
         assert fn(data) == want
+
+
+# ---- EXR files with FLOAT / UINT channels (read through read_exr's HALF slices) ----
+
+REF_HALF = ol.reference_half()
+GOLD_HALF = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "exr_half_conversion.npz"))
+
+
+def test_half_conversion_restatement_matches_the_golden_vectors():
+    """the committed outputs of the reference's Imf::floatToHalf / uintToHalf (tests/golden/make_half_golden.py)"""
+    assert (co.exr_float_to_half(GOLD_HALF["float_bits"].view(np.float32)) == GOLD_HALF["float_half"]).all()
+    assert (co.exr_uint_to_half(GOLD_HALF["uint"]) == GOLD_HALF["uint_half"]).all()
+    f = np.array([65504.0, 65505.0, 65519.99, 65520.0, -65512.0, np.inf, -np.inf, 1e-8, 6e-8], dtype=np.float32)
+    # finite values beyond HALF_MAX become infinity instead of rounding down to 65504 (ImfConvert.cpp:108-112)
+    assert co.exr_float_to_half(f).tolist() == [0x7BFF, 0x7C00, 0x7C00, 0x7C00, 0xFC00, 0x7C00, 0xFC00, 0x0000, 0x0001]
+
+
+@pytest.mark.skipif(REF_HALF is None, reason="oracle/_ref/libref_half.so not built")
+def test_half_conversion_restatement_matches_the_compiled_reference():
+    """every value of the upper 16 bits x the lower-bit patterns around the rounding points, both signs, + 1M random"""
+    rng = np.random.default_rng(0)
+    hi = np.arange(65536, dtype=np.uint32) << 16
+    low = np.array([0, 1, 0xfff, 0x1000, 0x1001, 0x1fff, 0x2000, 0x2001, 0x3000, 0xefff, 0xf000, 0xffff], dtype=np.uint32)
+    bits = np.concatenate([(hi[:, None] | low[None, :]).reshape(-1), rng.integers(0, 2 ** 32, 1_000_000, dtype=np.uint64).astype(np.uint32)])
+    f = bits.view(np.float32)
+    assert (co.exr_float_to_half(f) == REF_HALF.float_to_half(f)).all()
+    u = np.concatenate([np.arange(0, 70000, dtype=np.uint32), rng.integers(0, 2 ** 32, 100000, dtype=np.uint64).astype(np.uint32)])
+    assert (co.exr_uint_to_half(u) == REF_HALF.uint_to_half(u)).all()
+    # and the golden fixture is what the compiled reference gives today
+    assert (REF_HALF.float_to_half(GOLD_HALF["float_bits"].view(np.float32)) == GOLD_HALF["float_half"]).all()
+
+
+def typed_channels(h, w, types, seed=11, special=False):
+    """{name: [H, W] array} with the given dtype per channel name"""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, dt in types.items():
+        if dt == np.uint32:
+            v = rng.integers(0, 70000, (h, w), dtype=np.uint64).astype(np.uint32)
+        else:
+            v = (rng.random((h, w), dtype=np.float32) * 6 - 2).astype(dt)
+            v[::3, ::4] = dt(0.25)  # flat runs, so that blocks compress
+            if special and dt == np.float32 and h * w >= 12:
+                v.reshape(-1)[:12] = np.array([np.nan, np.inf, -np.inf, 65504.0, 65505.0, 65519.9, -65530.0, 1e10, 1e-8, 6e-8,
+                                               -0.0, 3.0e-5], dtype=np.float32)
+        out[name] = v
+    return out
+
+
+@pytest.mark.parametrize("comp", ["zip", "zips", "none"])
+def test_typed_exr_writer_is_read_by_openexr(tmp_path, comp):
+    """the test-side writer (mixed HALF / FLOAT channels) against the OpenEXR library inside cv2: samples come back exactly"""
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    cv2 = pytest.importorskip("cv2")
+    ch = typed_channels(37, 29, {"R": np.float32, "G": np.float16, "B": np.float16, "A": np.float32})
+    p = tmp_path / "t.exr"
+    p.write_bytes(co.exr_write_typed(ch, comp))
+    back = cv2.imread(str(p), cv2.IMREAD_UNCHANGED)
+    assert back is not None and back.shape == (37, 29, 4) and back.dtype == np.float32
+    for k, name in enumerate("BGRA"):
+        assert (back[..., k] == ch[name].astype(np.float32)).all()
+
+
+def test_exr_info_accepts_float_and_uint_channels(lrp):
+    ch = typed_channels(9, 21, {"R": np.float16, "G": np.float16, "B": np.float16, "Z": np.float32})
+    assert lrp.exr_info(co.exr_write_typed(ch, "zip")) == (21, 9, 4)
+    ch = typed_channels(5, 3, {"R": np.float32, "G": np.float32, "B": np.float32, "A": np.uint32, "Z": np.float32})
+    data = co.exr_write_typed(ch, "zips")
+    assert lrp.exr_info(data) == (3, 5, 5)
+    i = data.index(b"A\0") + 2  # the pixel type field of channel A
+    with pytest.raises(Exception):
+        lrp.exr_info(data[:i] + b"\x03" + data[i + 1:])  # no such pixel type

@@ -86,9 +86,6 @@ def test_exr_roundtrip_through_our_writers(lrp, ctx, dec, c, h, w, finite):
 def test_exr_unsupported_and_malformed(lrp, dec, tmp_path):
     import cv2
     p = str(tmp_path / "f.exr")
-    cv2.imwrite(p, np.zeros((8, 8, 3), np.float32), [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_FLOAT])
-    with pytest.raises(lrp.LrpError):  # FLOAT channels: read_exr asks OpenEXR to convert; not supported here
-        dec.exr(open(p, "rb").read())
     cv2.imwrite(p, np.zeros((8, 8, 3), np.float32), [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF,
                                                      cv2.IMWRITE_EXR_COMPRESSION, cv2.IMWRITE_EXR_COMPRESSION_PIZ])
     with pytest.raises(lrp.LrpError):
@@ -97,6 +94,86 @@ def test_exr_unsupported_and_malformed(lrp, dec, tmp_path):
     for bad in (good[:50], good[:-7], b"nope" + good[4:]):
         with pytest.raises(lrp.LrpError):
             dec.exr(bad)
+
+
+def _typed(h, w, types, seed=11, special=False):
+    import test_codec_oracle as tco
+    return tco.typed_channels(h, w, types, seed, special)
+
+
+def _want_half(v):
+    """what read_exr's HALF slice receives for a stored sample array"""
+    if v.dtype == np.float16:
+        return v.view(np.uint16)
+    return (co.exr_uint_to_half(v) if v.dtype == np.uint32 else co.exr_float_to_half(v)).reshape(v.shape)
+
+
+@pytest.mark.parametrize("h,w,c", [(1, 1, 3), (16, 8, 3), (17, 33, 4), (40, 1001, 3), (135, 240, 4), (1080, 1920, 4)])
+@pytest.mark.parametrize("comp", ["zip", "zips", "none"])
+def test_float_exr_written_by_openexr_is_converted_like_openexr(lrp, dec, tmp_path, h, w, c, comp):
+    """full-float files written by the OpenEXR library (inside cv2): read_exr reads them through HALF slices, so every
+    sample goes through Imf::floatToHalf — values beyond +-65504 become infinities, NaN payloads are kept"""
+    import cv2
+    rng = np.random.default_rng(h * w + c)
+    img = (rng.random((h, w, c), dtype=np.float32) * 3 - 1)
+    img[::4, ::3] = 0.5
+    flat = img.reshape(-1)
+    k = min(flat.size, 10)
+    flat[:k] = np.array([65504.0, 65505.0, -65519.9, 1e10, np.inf, -np.inf, 1e-8, 6e-8, 3e-5, -0.0], dtype=np.float32)[:k]
+    p = str(tmp_path / "t.exr")
+    flag = {"zip": cv2.IMWRITE_EXR_COMPRESSION_ZIP, "zips": cv2.IMWRITE_EXR_COMPRESSION_ZIPS,
+            "none": cv2.IMWRITE_EXR_COMPRESSION_NO}[comp]
+    assert cv2.imwrite(p, img, [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_FLOAT, cv2.IMWRITE_EXR_COMPRESSION, flag])
+    data = open(p, "rb").read()
+    assert lrp.exr_info(data) == (w, h, c)
+    got = dec.exr(data, 4).cpu().numpy().view(np.uint16)
+    order = [2, 1, 0] + ([3] if c == 4 else [])  # cv2 channel of plane R, G, B, A
+    for plane, k in enumerate(order):
+        assert (got[plane] == co.exr_float_to_half(img[..., k]).reshape(h, w)).all()
+
+
+@pytest.mark.parametrize("comp", ["zip", "zips", "none"])
+@pytest.mark.parametrize("h,w,types", [
+    (33, 50, {"R": np.float16, "G": np.float16, "B": np.float16, "Z": np.float32}),                   # half colour + float depth
+    (20, 31, {"R": np.float32, "G": np.float16, "B": np.float32, "A": np.float16, "Z": np.float32}),  # odd width: floats straddle chunks
+    (17, 7, {"R": np.float32, "G": np.float32, "B": np.float32, "A": np.uint32, "Z": np.float32}),
+    (3, 1, {"R": np.float32, "G": np.float16, "B": np.uint32}),
+    (64, 257, {"R": np.float32, "G": np.float32, "B": np.float32}),
+])
+def test_exr_with_mixed_channel_types(lrp, dec, comp, h, w, types):
+    """a pixel type per channel (Blender: half colour beside a float Z), NaN / infinities / out-of-range / denormal
+    samples included; planes come back in read_exr's order with OpenEXR's conversions applied"""
+    ch = _typed(h, w, types, seed=h * w, special=True)
+    data = co.exr_write_typed(ch, comp)
+    assert lrp.exr_info(data) == (w, h, len(types))
+    got = dec.exr(data, 3).cpu().numpy().view(np.uint16)
+    names = [n for n in "RGBAZ" if n in types]
+    for plane, n in enumerate(names):
+        assert (got[plane] == _want_half(ch[n])).all(), n
+
+
+def test_float_exr_golden_conversions_and_decoder_growth(lrp, ctx):
+    """the reference's own conversion outputs (tests/golden/exr_half_conversion.npz) through a file; the decoder was
+    created for a much smaller half image and grows its staging buffers; DECREASING_Y files; half files still decode"""
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "exr_half_conversion.npz"))
+    fb, fh, ub, uh = gold["float_bits"], gold["float_half"], gold["uint"], gold["uint_half"]
+    w = 211
+    h = min(fb.size, ub.size) // w
+    n = w * h
+    ch = {"R": fb[:n].view(np.float32).reshape(h, w), "G": fb[-n:].view(np.float32).reshape(h, w),
+          "B": ub[:n].reshape(h, w), "A": ub[-n:].reshape(h, w)}
+    d = lrp.Decoder(ctx, w, h, 4)  # sized for HALF samples: the file stores twice as many bytes
+    try:
+        for order in (0, 1):
+            got = d.exr(co.exr_write_typed(ch, "zip", order), 2).cpu().numpy().view(np.uint16)
+            assert (got[0] == fh[:n].reshape(h, w)).all() and (got[1] == fh[-n:].reshape(h, w)).all()
+            assert (got[2] == uh[:n].reshape(h, w)).all() and (got[3] == uh[-n:].reshape(h, w)).all()
+        planes = _half_image(h, w, 4, 9).transpose(2, 0, 1).copy().view(np.uint16)
+        assert (d.exr(lrp.exr_assemble(co.exr_pack(planes), w, h, 4, 6, 2), 2).cpu().numpy().view(np.uint16) == planes).all()
+        with pytest.raises(lrp.LrpError):  # the size limit given at creation still holds for the image itself
+            d.exr(co.exr_write_typed(_typed(h + 1, w, {"R": np.float32, "G": np.float32, "B": np.float32, "A": np.float32}), "zip"))
+    finally:
+        d.close()
 
 
 def _png_cases():
