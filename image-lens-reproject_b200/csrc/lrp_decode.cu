@@ -12,11 +12,12 @@
 //        "interleave") and scatters the channel-interleaved scan lines into the reference's plane order.
 //   PNG  host: chunks, one zlib inflate of the IDAT stream (into pinned memory).  device: scan-line reconstruction as a
 //        wavefront over 1024 lines (png_unfilter_kernel) + expansion to RGBA8 as lodepng::decode delivers it, for RGB /
-//        RGBA files; grey / palette / colour-keyed files are reconstructed on the host and uploaded as RGBA8.
+//        RGBA files; grey / palette / colour-keyed / 16-bit / 1-2-4-bit / Adam7 files are decoded on the host
+//        (png_decode_host) and uploaded as RGBA8.
 // Scope: what the reference's pipeline reads — single-part scan-line EXR with channels named from {R,G,B,A,Z} of any
 // pixel type (HALF as save_exr writes them; FLOAT / UINT — e.g. Blender's full-float files or a float Z beside half
 // colour — are converted to half on the device exactly as OpenEXR converts them for read_exr's HALF slices),
-// NONE / ZIPS / ZIP compression; non-interlaced 8-bit PNG of colour type 0, 2, 3, 4 or 6.  Anything else returns
+// NONE / ZIPS / ZIP compression; every PNG colour type, bit depth and interlace method.  Anything else returns
 // LRP_E_UNSUPPORTED_FORMAT (the reference would go through lodepng / OpenEXR's other code paths).
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -366,7 +367,8 @@ template <class F> static void parallel_for(size_t n, int threads, F fn) {
 // ---- host: PNG ---------------------------------------------------------------------------------------------
 struct PngInfo {
   uint32_t w = 0, h = 0;
-  int depth = 0, ctype = 0, channels = 0;
+  int depth = 0, ctype = 0, channels = 0, interlace = 0;
+  int bpp() const { return channels * depth; } // bits per complete pixel
 };
 
 static uint32_t be32(const unsigned char *p) { return ((uint32_t)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3]; }
@@ -384,10 +386,14 @@ static int png_parse(const unsigned char *f, size_t n, PngInfo &I, std::vector<u
     if (!memcmp(type, "IHDR", 4)) {
       if (len != 13) return LRP_E_BAD_ARG;
       I.w = be32(data), I.h = be32(data + 4), I.depth = data[8], I.ctype = data[9];
-      if (data[10] != 0 || data[11] != 0) return LRP_E_BAD_ARG;
-      if (data[12] != 0 || I.depth != 8) return LRP_E_UNSUPPORTED_FORMAT; // interlaced / other bit depths
+      if (data[10] != 0 || data[11] != 0 || data[12] > 1) return LRP_E_BAD_ARG;
+      I.interlace = data[12];
       I.channels = I.ctype == 0 ? 1 : I.ctype == 2 ? 3 : I.ctype == 3 ? 1 : I.ctype == 4 ? 2 : I.ctype == 6 ? 4 : 0;
-      if (!I.channels || I.w == 0 || I.h == 0) return LRP_E_UNSUPPORTED_FORMAT;
+      // PNG specification table 11.1: the bit depths each colour type allows
+      const bool depth_ok = I.ctype == 0   ? (I.depth == 1 || I.depth == 2 || I.depth == 4 || I.depth == 8 || I.depth == 16)
+                            : I.ctype == 3 ? (I.depth == 1 || I.depth == 2 || I.depth == 4 || I.depth == 8)
+                                           : (I.depth == 8 || I.depth == 16);
+      if (!I.channels || !depth_ok || I.w == 0 || I.h == 0) return LRP_E_BAD_ARG;
       if ((uint64_t)I.w * (uint64_t)I.h >= (1ull << 31)) return LRP_E_BAD_ARG; // pixel indices are 32-bit on the device
       have_ihdr = true;
     } else if (!memcmp(type, "IDAT", 4)) {
@@ -401,7 +407,16 @@ static int png_parse(const unsigned char *f, size_t n, PngInfo &I, std::vector<u
     }
     pos += 12 + len;
   }
-  return have_ihdr && !idat.empty() ? LRP_OK : LRP_E_BAD_ARG;
+  if (!have_ihdr || idat.empty()) return LRP_E_BAD_ARG;
+  // what lodepng refuses (readChunk_PLTE / readChunk_tRNS, lib/lodepng/lodepng.cpp:4380-4425): the reference stops there
+  if (I.ctype == 3 && (plte.size() < 3 || plte.size() / 3 > 256)) return LRP_E_BAD_ARG;
+  if (!trns.empty()) {
+    if (I.ctype == 4 || I.ctype == 6) return LRP_E_BAD_ARG;
+    if (I.ctype == 0 && trns.size() != 2) return LRP_E_BAD_ARG;
+    if (I.ctype == 2 && trns.size() != 6) return LRP_E_BAD_ARG;
+    if (I.ctype == 3 && trns.size() > plte.size() / 3) return LRP_E_BAD_ARG;
+  }
+  return LRP_OK;
 }
 
 // PNG specification section 9: reconstruction of one scan line in place (bpp = bytes per complete pixel)
@@ -431,6 +446,94 @@ static int png_unfilter_line(unsigned char *cur, const unsigned char *prev, size
   default: return LRP_E_BAD_ARG;
   }
   return LRP_OK;
+}
+
+// Every PNG the fast device path does not take (grey / palette / colour-keyed / 16-bit / 1-2-4-bit / Adam7 files) — rare
+// in the reference's pipeline, decoded on the host to the RGBA8 that lodepng::decode(image, w, h, file) delivers
+// (lib/lodepng/lodepng.cpp:3326-3420 getPixelColorsRGBA8): 16-bit samples keep their most significant byte, 1/2/4-bit
+// grey is scaled by 255 / (2^depth - 1) with integer division, a palette index beyond the palette is opaque black, the
+// tRNS colour key compares the full sample values.  Adam7 (PNG specification section 8.2): seven reduced images, each
+// filtered on its own; pixels are expanded straight to their place in the full image.
+static int png_decode_host(const PngInfo &I, std::vector<unsigned char> &stream, const std::vector<unsigned char> &plte,
+                           const std::vector<unsigned char> &trns, unsigned char *out) {
+  static const int IX[7] = {0, 4, 0, 2, 0, 1, 0}, IY[7] = {0, 0, 4, 0, 2, 0, 1}, DX[7] = {8, 8, 4, 4, 2, 2, 1},
+                   DY[7] = {8, 8, 8, 4, 4, 2, 2};
+  const int bpp = I.bpp(), bytewidth = std::max(1, bpp / 8), depth = I.depth;
+  const unsigned key[3] = {trns.size() >= 2 ? 256u * trns[0] + trns[1] : 0u, trns.size() >= 4 ? 256u * trns[2] + trns[3] : 0u,
+                           trns.size() >= 6 ? 256u * trns[4] + trns[5] : 0u};
+  const bool keyed = !trns.empty() && (I.ctype == 0 || I.ctype == 2);
+  const unsigned highest = (1u << depth) - 1u;
+  const size_t npal = plte.size() / 3;
+  size_t pos = 0;
+  for (int pass = 0; pass < (I.interlace ? 7 : 1); ++pass) {
+    const uint32_t ix = I.interlace ? IX[pass] : 0, iy = I.interlace ? IY[pass] : 0, dx = I.interlace ? DX[pass] : 1,
+                   dy = I.interlace ? DY[pass] : 1;
+    const uint32_t pw = (I.w + dx - ix - 1) / dx, ph = (I.h + dy - iy - 1) / dy;
+    if (pw == 0 || ph == 0) continue;
+    const size_t row = ((size_t)pw * bpp + 7) / 8;
+    const unsigned char *prev = nullptr;
+    for (uint32_t y = 0; y < ph; ++y) {
+      if (pos + row + 1 > stream.size()) return LRP_E_BAD_ARG;
+      unsigned char *line = stream.data() + pos;
+      const int rc = png_unfilter_line(line + 1, prev, row, bytewidth, line[0]);
+      if (rc != LRP_OK) return rc;
+      prev = line + 1;
+      pos += row + 1;
+      const unsigned char *s = line + 1;
+      unsigned char *orow = out + ((size_t)(iy + (size_t)y * dy) * I.w + ix) * 4;
+      for (uint32_t x = 0; x < pw; ++x) {
+        unsigned v[4]; // the pixel's samples as stored (full 16-bit values for depth 16)
+        if (depth == 8) {
+          for (int c = 0; c < I.channels; ++c) v[c] = s[(size_t)x * I.channels + c];
+        } else if (depth == 16) {
+          for (int c = 0; c < I.channels; ++c) v[c] = 256u * s[((size_t)x * I.channels + c) * 2] + s[((size_t)x * I.channels + c) * 2 + 1];
+        } else { // 1, 2, 4 bits, one channel, most significant bits first
+          const size_t bit = (size_t)x * depth;
+          v[0] = (s[bit >> 3] >> (8 - depth - (bit & 7))) & highest;
+        }
+        unsigned char *o = orow + (size_t)x * dx * 4;
+        const int sh = depth == 16 ? 8 : 0;
+        switch (I.ctype) {
+        case 0:
+          o[0] = o[1] = o[2] = (unsigned char)(depth < 8 ? (v[0] * 255u) / highest : v[0] >> sh);
+          o[3] = (keyed && v[0] == key[0]) ? 0 : 255;
+          break;
+        case 2:
+          o[0] = (unsigned char)(v[0] >> sh), o[1] = (unsigned char)(v[1] >> sh), o[2] = (unsigned char)(v[2] >> sh);
+          o[3] = (keyed && v[0] == key[0] && v[1] == key[1] && v[2] == key[2]) ? 0 : 255;
+          break;
+        case 3:
+          if (v[0] < npal) {
+            o[0] = plte[3 * v[0]], o[1] = plte[3 * v[0] + 1], o[2] = plte[3 * v[0] + 2];
+            o[3] = v[0] < trns.size() ? trns[v[0]] : 255;
+          } else {
+            o[0] = o[1] = o[2] = 0, o[3] = 255;
+          }
+          break;
+        case 4:
+          o[0] = o[1] = o[2] = (unsigned char)(v[0] >> sh), o[3] = (unsigned char)(v[1] >> sh);
+          break;
+        default: // 6
+          o[0] = (unsigned char)(v[0] >> sh), o[1] = (unsigned char)(v[1] >> sh), o[2] = (unsigned char)(v[2] >> sh),
+          o[3] = (unsigned char)(v[3] >> sh);
+        }
+      }
+    }
+  }
+  return pos == stream.size() ? LRP_OK : LRP_E_BAD_ARG;
+}
+
+// bytes of the inflated IDAT stream: a filter byte + the padded samples per line of each (reduced) image
+static size_t png_stream_bytes(const PngInfo &I) {
+  static const int IX[7] = {0, 4, 0, 2, 0, 1, 0}, IY[7] = {0, 0, 4, 0, 2, 0, 1}, DX[7] = {8, 8, 4, 4, 2, 2, 1},
+                   DY[7] = {8, 8, 8, 4, 4, 2, 2};
+  if (!I.interlace) return (size_t)I.h * (1 + ((size_t)I.w * I.bpp() + 7) / 8);
+  size_t n = 0;
+  for (int p = 0; p < 7; ++p) {
+    const size_t pw = ((size_t)I.w + DX[p] - IX[p] - 1) / DX[p], ph = ((size_t)I.h + DY[p] - IY[p] - 1) / DY[p];
+    if (pw && ph) n += ph * (1 + (pw * I.bpp() + 7) / 8);
+  }
+  return n;
 }
 
 } // namespace lrp
@@ -619,9 +722,8 @@ int lrp_decoder_png(lrp_decoder *d, const void *file, size_t n, void *out_rgba_d
   if (rc != LRP_OK) return rc;
   const size_t row = (size_t)I.w * I.channels, px = (size_t)I.w * I.h;
   if (px * 4 > d->cap) return LRP_E_BAD_ARG;
-  if (I.ctype == 3 && plte.size() < 3) return LRP_E_BAD_ARG;
   const char *host_only = getenv("LRP_PNG_UNFILTER_ON_HOST"); // A/B switch
-  if ((I.ctype == 2 || I.ctype == 6) && trns.empty() && (row + 1) * I.h <= d->cap && !(host_only && host_only[0] == '1')) {
+  if ((I.ctype == 2 || I.ctype == 6) && I.depth == 8 && !I.interlace && trns.empty() && (row + 1) * I.h <= d->cap && !(host_only && host_only[0] == '1')) {
     // RGB / RGBA: inflate straight into pinned memory, upload the FILTERED scan lines (3 or 4 bytes per pixel), reconstruct
     // them on the device (png_unfilter_kernel) directly into the caller's RGBA8 buffer
     uLongf got = (uLongf)((row + 1) * I.h);
@@ -638,51 +740,33 @@ int lrp_decoder_png(lrp_decoder *d, const void *file, size_t n, void *out_rgba_d
     if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return LRP_E_CUDA; // h_buf is reused
     return LRP_OK;
   }
-  d->scratch.resize((row + 1) * I.h);
+  d->scratch.resize(png_stream_bytes(I));
   uLongf got = (uLongf)d->scratch.size();
   if (uncompress(d->scratch.data(), &got, idat.data(), (uLong)idat.size()) != Z_OK || got != d->scratch.size())
     return LRP_E_BAD_ARG;
-  unsigned char *out = d->h_buf;
-  const unsigned char *prev = nullptr;
-  for (uint32_t y = 0; y < I.h; ++y) {
-    unsigned char *line = d->scratch.data() + (size_t)y * (row + 1);
-    rc = png_unfilter_line(line + 1, prev, row, I.channels, line[0]);
-    if (rc != LRP_OK) return rc;
-    prev = line + 1;
-    unsigned char *o = out + (size_t)y * I.w * 4;
-    const unsigned char *s = line + 1;
-    switch (I.ctype) { // to RGBA8, as lodepng::decode's default conversion
-    case 6: memcpy(o, s, (size_t)I.w * 4); break;
-    case 2:
-      for (uint32_t x = 0; x < I.w; ++x) {
-        o[4 * x] = s[3 * x], o[4 * x + 1] = s[3 * x + 1], o[4 * x + 2] = s[3 * x + 2];
-        o[4 * x + 3] = (trns.size() >= 6 && s[3 * x] == trns[1] && s[3 * x + 1] == trns[3] && s[3 * x + 2] == trns[5]) ? 0 : 255;
-      }
-      break;
-    case 0:
-      for (uint32_t x = 0; x < I.w; ++x) {
-        o[4 * x] = o[4 * x + 1] = o[4 * x + 2] = s[x];
-        o[4 * x + 3] = (trns.size() >= 2 && s[x] == trns[1]) ? 0 : 255;
-      }
-      break;
-    case 4:
-      for (uint32_t x = 0; x < I.w; ++x) o[4 * x] = o[4 * x + 1] = o[4 * x + 2] = s[2 * x], o[4 * x + 3] = s[2 * x + 1];
-      break;
-    default: // 3: palette
-      for (uint32_t x = 0; x < I.w; ++x) {
-        const size_t i = s[x];
-        if (3 * i + 2 >= plte.size()) return LRP_E_BAD_ARG;
-        o[4 * x] = plte[3 * i], o[4 * x + 1] = plte[3 * i + 1], o[4 * x + 2] = plte[3 * i + 2];
-        o[4 * x + 3] = i < trns.size() ? trns[i] : 255;
-      }
-    }
-  }
+  rc = png_decode_host(I, d->scratch, plte, trns, d->h_buf);
+  if (rc != LRP_OK) return rc;
   if (cudaSetDevice(d->device) != cudaSuccess) return LRP_E_CUDA;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   if (cudaMemcpyAsync(out_rgba_dev, d->h_buf, px * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
       cudaStreamSynchronize(st) != cudaSuccess)
     return LRP_E_CUDA;
   return LRP_OK;
+}
+
+// test hook: the host half of lrp_decoder_png alone (container + inflate + png_decode_host), for any PNG the library
+// accepts — lets `-m "not gpu"` tests compare it with the reference's lodepng::decode without a device
+int lrp_debug_png_decode_host(const void *file, size_t n, void *out_rgba_host, size_t out_bytes) {
+  if (!file || !out_rgba_host) return LRP_E_BAD_ARG;
+  PngInfo I;
+  std::vector<unsigned char> idat, plte, trns;
+  const int rc = png_parse((const unsigned char *)file, n, I, idat, plte, trns);
+  if (rc != LRP_OK) return rc;
+  if ((size_t)I.w * I.h * 4 != out_bytes) return LRP_E_BAD_ARG;
+  std::vector<unsigned char> stream(png_stream_bytes(I));
+  uLongf got = (uLongf)stream.size();
+  if (uncompress(stream.data(), &got, idat.data(), (uLong)idat.size()) != Z_OK || got != stream.size()) return LRP_E_BAD_ARG;
+  return png_decode_host(I, stream, plte, trns, (unsigned char *)out_rgba_host);
 }
 
 } // extern "C"

@@ -145,6 +145,7 @@ def lib():
         L.lrp_debug_deflate.argtypes = [vp, vp, C.c_size_t, C.c_size_t, vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
         L.lrp_exr_info.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
         L.lrp_png_info.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(i32), C.POINTER(i32)]
+        L.lrp_debug_png_decode_host.argtypes = [C.c_char_p, C.c_size_t, vp, C.c_size_t]
         L.lrp_decoder_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
         L.lrp_decoder_destroy.argtypes = [vp]
         L.lrp_decoder_exr.argtypes = [vp, C.c_char_p, C.c_size_t, i32, vp, vp]
@@ -509,6 +510,15 @@ def png_info(data):
     w, h = C.c_int32(0), C.c_int32(0)
     check(lib().lrp_png_info(data, len(data), C.byref(w), C.byref(h)), "lrp_png_info")
     return w.value, h.value
+
+
+def debug_png_decode_host(data):
+    """the host half of lrp_decoder_png (no device): bytes of a .png -> uint8 [H, W, 4] numpy array"""
+    import numpy as np
+    w, h = png_info(data)
+    out = np.empty((h, w, 4), dtype=np.uint8)
+    check(lib().lrp_debug_png_decode_host(data, len(data), out.ctypes.data_as(C.c_void_p), out.nbytes), "lrp_debug_png_decode_host")
+    return out
 
 
 class Decoder:

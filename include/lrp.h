@@ -322,10 +322,11 @@ int lrp_encoder_last_timing(const lrp_encoder *enc, double *ms3);
  * (src/image_formats.cpp:174-204: lodepng::decode + pow loop) and reproject::read_exr (:208-303: readPixels + half->float
  * loop with the name -> index mapping of :266-285); the pow / half->float arithmetic itself is fused into the kernel's
  * texel load.  EXR: blocks are inflated on `threads` host cores, the predictor / byte-plane / channel scatter runs on the
- * device.  PNG: the inflate is one sequential stream and stays on the host; RGB / RGBA scan lines are reconstructed on
- * the device (a wavefront over 1024 lines), other colour types on the host.
- * Supported: single-part scan-line EXR, channels R,G,B[,A][,Z] of any pixel type, NONE / ZIPS / ZIP; non-interlaced
- * 8-bit PNG of any colour type.  Everything else: LRP_E_UNSUPPORTED_FORMAT.  FLOAT / UINT channels arrive as half, as
+ * device.  PNG: the inflate is one sequential stream and stays on the host; 8-bit RGB / RGBA scan lines are reconstructed
+ * on the device (a wavefront over 1024 lines); the rare kinds (grey, palette, colour key, 16-bit, 1/2/4-bit, Adam7) are
+ * decoded on the host to the RGBA8 lodepng::decode delivers (16-bit samples keep their most significant byte).
+ * Supported: single-part scan-line EXR, channels R,G,B[,A][,Z] of any pixel type, NONE / ZIPS / ZIP; every PNG
+ * colour type, bit depth and interlace method.  Everything else: LRP_E_UNSUPPORTED_FORMAT.  FLOAT / UINT channels arrive as half, as
  * they do in read_exr (which reads every channel through a HALF slice, :246-258): the device applies OpenEXR's
  * Imf::floatToHalf / uintToHalf (lib/openexr/src/lib/OpenEXR/ImfConvert.cpp:96-115) bit for bit.
  * A decoder owns pinned + device workspaces sized for max_width x max_height x max_channels HALF samples (they grow on
@@ -379,6 +380,10 @@ int lrp_debug_libm(lrp_ctx *ctx, int fn, const float *a_dev, const float *b_dev,
  * ceil(n / stream_bytes) + 1 entries */
 int lrp_debug_deflate(lrp_ctx *ctx, const void *in_dev, size_t n, size_t stream_bytes, void *cuda_stream, void **out_bytes,
                       uint64_t *offsets);
+
+/* the host half of lrp_decoder_png alone (container, inflate, reconstruction + conversion to RGBA8 for every colour
+ * type / bit depth / interlace method), no device involved: out_rgba_host = uint8[H*W*4], out_bytes = H*W*4 */
+int lrp_debug_png_decode_host(const void *file, size_t n, void *out_rgba_host, size_t out_bytes);
 
 /* the fused 8-bit sink quantiser (save_png arithmetic, src/image_formats.cpp:156-158) element-wise */
 int lrp_debug_encode_u8(lrp_ctx *ctx, const float *in_dev, uint8_t *out_dev, size_t n, void *cuda_stream);

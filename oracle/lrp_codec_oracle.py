@@ -279,3 +279,75 @@ def exr_write_typed(channels, compression="zip", line_order=0):
         body += struct.pack("<ii", y0, len(data)) + data
     table = b"".join(struct.pack("<Q", offs[y0]) for y0, _ in blocks)
     return hdr + table + body
+
+
+# ---- PNG: test-side writer for every colour type / bit depth / interlace method ---------------------------------
+ADAM7 = ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2))  # ix, iy, dx, dy
+
+
+def _paeth_int(a, b, c):
+    p = a + b - c
+    pa, pb, pc = abs(p - a), abs(p - b), abs(p - c)
+    return a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)
+
+
+def _png_filter_line(cur, prev, bw, t):
+    """PNG specification section 9.2: filter one scan line (bytes) with type t; bw = bytes per complete pixel, >= 1"""
+    n = len(cur)
+    out = bytearray(n)
+    for i in range(n):
+        a = cur[i - bw] if i >= bw else 0
+        b = prev[i] if prev is not None else 0
+        c = prev[i - bw] if (prev is not None and i >= bw) else 0
+        pred = (0, a, b, (a + b) >> 1, _paeth_int(a, b, c))[t]
+        out[i] = (cur[i] - pred) & 255
+    return bytes(out)
+
+
+def png_write_any(samples, ctype, depth, interlace=0, plte=None, trns=None, seed=0, idat_split=3):
+    """samples: integer [H, W, channels] with values < 2**depth (channels = 1, 3, 1, 2, 4 for colour type 0, 2, 3, 4, 6).
+    Writes a PNG of exactly that colour type and bit depth, Adam7-interlaced on request, with a pseudo-random filter
+    type per scan line and the IDAT stream split over several chunks (PNG specification, sections 8.2, 9, 11)."""
+    h, w, ch = samples.shape
+    rng = np.random.default_rng(seed)
+
+    def pack(rows):  # [ph, pw, ch] -> list of packed scan lines
+        lines = []
+        for r in rows:
+            flat = r.reshape(-1).astype(np.uint32)
+            if depth == 16:
+                lines.append(flat.astype(">u2").tobytes())
+            elif depth == 8:
+                lines.append(flat.astype(np.uint8).tobytes())
+            else:
+                bits = ((flat[:, None] >> np.arange(depth - 1, -1, -1)) & 1).astype(np.uint8).reshape(-1)
+                lines.append(np.packbits(bits).tobytes())  # most significant bit first, zero padding at the end
+        return lines
+
+    bw = max(1, ch * depth // 8)
+    stream = b""
+    passes = ADAM7 if interlace else ((0, 0, 1, 1),)
+    for ix, iy, dx, dy in passes:
+        sub = samples[iy::dy, ix::dx]
+        if sub.shape[0] == 0 or sub.shape[1] == 0:
+            continue
+        prev = None
+        for line in pack(sub):
+            t = int(rng.integers(0, 5))
+            stream += bytes([t]) + _png_filter_line(line, prev, bw, t)
+            prev = line
+
+    def chunk(typ, data):
+        return struct.pack(">I", len(data)) + typ + data + struct.pack(">I", zlib.crc32(typ + data) & 0xFFFFFFFF)
+
+    z = zlib.compress(stream, 6)
+    cuts = [len(z) * k // idat_split for k in range(idat_split + 1)]
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, interlace))
+    if plte is not None:
+        out += chunk(b"PLTE", bytes(plte))
+    if trns is not None:
+        out += chunk(b"tRNS", bytes(trns))
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        if b > a:
+            out += chunk(b"IDAT", z[a:b])
+    return out + chunk(b"IEND", b"")

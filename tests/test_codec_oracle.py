@@ -258,3 +258,90 @@ def test_exr_info_accepts_float_and_uint_channels(lrp):
     i = data.index(b"A\0") + 2  # the pixel type field of channel A
     with pytest.raises(Exception):
         lrp.exr_info(data[:i] + b"\x03" + data[i + 1:])  # no such pixel type
+
+
+# ---- PNG: every colour type / bit depth / interlace method through the host half of lrp_decoder_png ----
+
+def png_kinds():
+    """(name, ctype, depth, channels, needs palette, tRNS kind)"""
+    out = []
+    for depth in (1, 2, 4, 8, 16):
+        out.append(("grey%d" % depth, 0, depth, 1, False, None))
+        out.append(("grey%d_key" % depth, 0, depth, 1, False, "key"))
+    for depth in (8, 16):
+        out += [("rgb%d" % depth, 2, depth, 3, False, None), ("rgb%d_key" % depth, 2, depth, 3, False, "key"),
+                ("ga%d" % depth, 4, depth, 2, False, None), ("rgba%d" % depth, 6, depth, 4, False, None)]
+    for depth in (1, 2, 4, 8):
+        out += [("pal%d" % depth, 3, depth, 1, True, None), ("pal%d_alpha" % depth, 3, depth, 1, True, "alpha")]
+    return out
+
+
+def make_png(kind, w, h, interlace, seed=1):
+    name, ctype, depth, ch, pal, tr = kind
+    rng = np.random.default_rng(seed + w * 131 + h)
+    samples = rng.integers(0, 1 << depth, (h, w, ch), dtype=np.uint64).astype(np.uint32)
+    if depth == 16:
+        samples[::2, ::3] &= 0xFF00  # so that the colour key below (a value with a zero low byte) has near misses
+    plte = trns = None
+    if pal:
+        n = max(2, (1 << depth) - (1 if depth > 1 else 0) - (3 if depth == 8 else 0))  # shorter than 2^depth: out-of-range indices occur
+        plte = rng.integers(0, 256, 3 * n, dtype=np.uint8).tobytes()
+        if tr == "alpha":
+            trns = rng.integers(0, 256, max(1, n // 2), dtype=np.uint8).tobytes()
+    elif tr == "key":
+        px = samples[h // 2, w // 2]  # an existing pixel is the transparent colour
+        trns = b"".join(int(v).to_bytes(2, "big") for v in px)
+    return co.png_write_any(samples, ctype, depth, interlace, plte, trns, seed)
+
+
+@pytest.mark.skipif(REF_PNG is None, reason="oracle/_ref/libref_lodepng.so not built")
+@pytest.mark.parametrize("interlace", [0, 1])
+@pytest.mark.parametrize("kind", png_kinds(), ids=lambda k: k[0])
+def test_png_host_decode_matches_the_reference_lodepng(lrp, kind, interlace):
+    """lodepng::decode(image, w, h, file) as read_png calls it (src/image_formats.cpp:178) is the authority: 16-bit samples
+    lose their low byte, small greys are scaled, colour keys compare full values, Adam7 passes with empty reduced images"""
+    for w, h in ((37, 23), (1, 1), (3, 2), (8, 9), (5, 1), (1, 6)):
+        data = make_png(kind, w, h, interlace)
+        want = REF_PNG.decode(data)
+        assert lrp.png_info(data) == (w, h)
+        got = lrp.debug_png_decode_host(data)
+        assert got.shape == want.shape and (got == want).all(), (kind[0], w, h)
+        if kind[5] is not None:
+            assert (want[..., 3] != 255).any() or w * h < 100  # the transparency path was exercised
+
+
+def test_png_host_decode_agrees_with_pillow_on_what_pillow_reads_alike(lrp):
+    """no reference library needed: for 8-bit kinds Pillow's RGBA conversion is lodepng's"""
+    from PIL import Image
+    for kind in png_kinds():
+        if kind[2] != 8 or kind[5] == "key":
+            continue
+        for interlace in (0, 1):
+            data = make_png(kind, 29, 17, interlace)
+            want = np.asarray(Image.open(io.BytesIO(data)).convert("RGBA"))
+            if kind[4]:
+                continue  # the test palettes are shorter than 2^depth: Pillow leaves out-of-range indices undefined
+            assert (lrp.debug_png_decode_host(data) == want).all(), kind[0]
+
+
+def test_png_host_decode_rejects_what_lodepng_rejects(lrp):
+    kinds = {k[0]: k for k in png_kinds()}
+    good = make_png(kinds["rgb8"], 9, 7, 0)
+    i = good.index(b"IHDR") + 4
+    for depth, ctype in ((4, 2), (16, 3), (3, 0), (8, 5), (2, 6)):  # combinations the PNG specification forbids
+        bad = bytearray(good)
+        bad[i + 8], bad[i + 9] = depth, ctype
+        with pytest.raises(Exception):
+            lrp.debug_png_decode_host(bytes(bad))
+    samples = np.zeros((4, 4, 4), dtype=np.uint32)
+    with pytest.raises(Exception):  # tRNS is not allowed beside an alpha channel (lodepng error 42)
+        lrp.debug_png_decode_host(co.png_write_any(samples, 6, 8, 0, None, b"\0\0"))
+    with pytest.raises(Exception):  # wrong key length (lodepng error 41)
+        lrp.debug_png_decode_host(co.png_write_any(samples[..., :3], 2, 8, 0, None, b"\0\0"))
+    with pytest.raises(Exception):  # more alpha entries than palette entries (lodepng error 39)
+        lrp.debug_png_decode_host(co.png_write_any(samples[..., :1], 3, 8, 0, bytes(6), bytes(3)))
+    with pytest.raises(Exception):  # truncated pixel data
+        s2 = np.zeros((6, 5, 3), dtype=np.uint32)
+        f = co.png_write_any(s2, 2, 8, 1)
+        j = f.index(b"IHDR") + 4
+        lrp.debug_png_decode_host(f[:j] + (9).to_bytes(4, "big") + f[j + 4:])  # claims a wider image than the data holds

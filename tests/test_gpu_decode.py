@@ -204,6 +204,39 @@ def test_png_written_by_pillow_decodes_like_lodepng(lrp, dec, name):
     assert got.shape == want.shape and (got == want).all()
 
 
+@pytest.mark.parametrize("interlace", [0, 1])
+def test_png_of_every_kind_decodes_like_lodepng(lrp, dec, interlace):
+    """16-bit, 1/2/4-bit, colour-keyed, palette and Adam7 files through lrp_decoder_png (host reconstruction + upload;
+    interlaced 8-bit RGB / RGBA must not take the device wavefront path)"""
+    import test_codec_oracle as tco
+    ref = ol.reference_lodepng()
+    for kind in tco.png_kinds():
+        data = tco.make_png(kind, 53, 31, interlace, seed=5)
+        want = ref.decode(data) if ref is not None else lrp.debug_png_decode_host(data)
+        got = dec.png(data).cpu().numpy()
+        assert got.shape == want.shape and (got == want).all(), kind[0]
+
+
+def test_16_bit_png_written_by_opencv(lrp, dec, tmp_path):
+    """an independent writer (libpng inside cv2) for the kind a renderer is most likely to produce besides 8-bit"""
+    import cv2
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    ref = ol.reference_lodepng()
+    for c in (1, 3, 4):
+        img = rng.integers(0, 65536, (120, 200, c), dtype=np.uint16)
+        p = str(tmp_path / ("t%d.png" % c))
+        assert cv2.imwrite(p, img)
+        data = open(p, "rb").read()
+        got = dec.png(data).cpu().numpy()
+        hi = (img >> 8).astype(np.uint8)  # lodepng keeps the most significant byte
+        want = np.dstack([hi[..., 0]] * 3 + [np.full(hi.shape[:2], 255, np.uint8)]) if c == 1 else \
+            np.dstack([hi[..., 2], hi[..., 1], hi[..., 0], hi[..., 3] if c == 4 else np.full(hi.shape[:2], 255, np.uint8)])
+        assert (got == want).all()
+        if ref is not None:
+            assert (got == ref.decode(data)).all()
+
+
 def test_png_written_by_the_reference_and_by_us(lrp, ctx, dec):
     import torch
     rng = np.random.default_rng(8)
