@@ -6,8 +6,8 @@
 // reproject::read_exr (:208-303) = Imf::InputFile::readPixels into HALF planes + a half->float interleaving loop that maps
 // channel names to indices (R, G, B -> 0, 1, 2; A / Z -> 3 or 4 by data layout, :266-285).  The pow() / half->float
 // arithmetic already lives in the kernel's texel load; what remains is the container + entropy decoding:
-//   EXR  host: header + offset table, one zlib inflate per block of scan lines on `threads` cores (blocks are
-//        independent).  device: exr_unpack_kernel undoes OpenEXR's predictor (a byte-wise prefix sum, scanned per
+//   EXR  host: header + offset table, one zlib inflate (or run-length expansion) per block of scan lines on `threads`
+//        cores (blocks are independent).  device: exr_unpack_kernel undoes OpenEXR's predictor (a byte-wise prefix sum, scanned per
 //        warp) and byte-plane split (lib/openexr/src/lib/OpenEXRCore/internal_zip.c:47-160 "reconstruct" +
 //        "interleave") and scatters the channel-interleaved scan lines into the reference's plane order.
 //   PNG  host: chunks, one zlib inflate of the IDAT stream (into pinned memory).  device: scan-line reconstruction as a
@@ -17,7 +17,7 @@
 // Scope: what the reference's pipeline reads — single-part scan-line EXR with channels named from {R,G,B,A,Z} of any
 // pixel type (HALF as save_exr writes them; FLOAT / UINT — e.g. Blender's full-float files or a float Z beside half
 // colour — are converted to half on the device exactly as OpenEXR converts them for read_exr's HALF slices),
-// NONE / ZIPS / ZIP compression; every PNG colour type, bit depth and interlace method.  Anything else returns
+// NONE / RLE / ZIPS / ZIP compression; every PNG colour type, bit depth and interlace method.  Anything else returns
 // LRP_E_UNSUPPORTED_FORMAT (the reference would go through lodepng / OpenEXR's other code paths).
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -325,9 +325,9 @@ static int exr_parse(const unsigned char *f, size_t n, ExrInfo &I) {
     pos += len;
   }
   if (!have_ch || !have_dw || I.w <= 0 || I.h <= 0 || (uint64_t)I.w * (uint64_t)I.h >= (1ull << 31)) return LRP_E_BAD_ARG;
-  if (I.compression == 0 || I.compression == 2) I.lines_per_block = 1;
+  if (I.compression == 0 || I.compression == 1 || I.compression == 2) I.lines_per_block = 1;
   else if (I.compression == 3) I.lines_per_block = 16;
-  else return LRP_E_UNSUPPORTED_FORMAT; // RLE / PIZ / PXR24 / B44 / DWA
+  else return LRP_E_UNSUPPORTED_FORMAT; // PIZ / PXR24 / B44 / DWA
   I.table = pos + 1;
   I.c = (int)names.size();
   if (I.c < 3 || I.c > 5) return LRP_E_UNSUPPORTED_FORMAT;
@@ -347,6 +347,27 @@ static int exr_parse(const unsigned char *f, size_t n, ExrInfo &I) {
     I.sample_bytes += types[k] == 1 ? 2 : 4;
   }
   return LRP_OK;
+}
+
+// OpenEXR's RLE_COMPRESSION (lib/openexr/src/lib/OpenEXRCore/internal_rle.c:127-170): a signed count byte n, then either
+// -n literal bytes (n < 0) or one byte to repeat n + 1 times; the bytes are the same predicted byte planes ZIP deflates.
+static bool exr_rle_decode(const unsigned char *in, size_t n, unsigned char *out, size_t want) {
+  size_t i = 0, o = 0;
+  while (i < n) {
+    const int c = (signed char)in[i++];
+    if (c < 0) {
+      const size_t m = (size_t)(-c);
+      if (i + m > n || o + m > want) return false;
+      memcpy(out + o, in + i, m);
+      i += m, o += m;
+    } else {
+      const size_t m = (size_t)c + 1;
+      if (i >= n || o + m > want) return false;
+      memset(out + o, in[i++], m);
+      o += m;
+    }
+  }
+  return o == want;
 }
 
 template <class F> static void parallel_for(size_t n, int threads, F fn) {
@@ -674,6 +695,12 @@ int lrp_decoder_exr(lrp_decoder *d, const void *file, size_t n, int32_t threads,
       }
       memcpy(dst, f + off + 8, raw_n);
       d->h_raw[b] = 1;
+    } else if (I.compression == 1) {
+      if (!exr_rle_decode(f + off + 8, (size_t)hdr[1], dst, raw_n)) {
+        status = LRP_E_BAD_ARG;
+        return;
+      }
+      d->h_raw[b] = 0;
     } else {
       uLongf got = (uLongf)raw_n;
       if (uncompress(dst, &got, f + off + 8, (uLong)hdr[1]) != Z_OK || got != raw_n) {

@@ -43,7 +43,7 @@ def _half_image(h, w, c, seed):
 
 
 @pytest.mark.parametrize("h,w,c", [(1, 1, 3), (16, 8, 3), (17, 33, 4), (40, 1001, 3), (135, 240, 4), (1080, 1920, 4)])
-@pytest.mark.parametrize("comp", ["zip", "zips", "none"])
+@pytest.mark.parametrize("comp", ["zip", "zips", "none", "rle"])
 def test_exr_written_by_openexr_decodes_like_openexr(lrp, dec, tmp_path, h, w, c, comp):
     """cv2 writes with the OpenEXR library (B,G,R[,A] order, HALF); our planes must hold the same bit patterns in the
     reference's R,G,B[,A] order — and equal what OpenEXR's own reader returns."""
@@ -51,7 +51,7 @@ def test_exr_written_by_openexr_decodes_like_openexr(lrp, dec, tmp_path, h, w, c
     img = _half_image(h, w, c, h * w + c)
     p = str(tmp_path / "t.exr")
     flag = {"zip": cv2.IMWRITE_EXR_COMPRESSION_ZIP, "zips": cv2.IMWRITE_EXR_COMPRESSION_ZIPS,
-            "none": cv2.IMWRITE_EXR_COMPRESSION_NO}[comp]
+            "none": cv2.IMWRITE_EXR_COMPRESSION_NO, "rle": cv2.IMWRITE_EXR_COMPRESSION_RLE}[comp]
     assert cv2.imwrite(p, img.astype(np.float32), [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF,
                                                    cv2.IMWRITE_EXR_COMPRESSION, flag])
     data = open(p, "rb").read()
@@ -62,6 +62,32 @@ def test_exr_written_by_openexr_decodes_like_openexr(lrp, dec, tmp_path, h, w, c
     for plane, k in enumerate(order):
         assert (got[plane] == img[..., k].view(np.uint16)).all()
         assert (got[plane] == back[..., k].view(np.uint16)).all()
+
+
+@pytest.mark.parametrize("typ", ["half", "float"])
+def test_rle_exr_with_long_runs_written_by_openexr(lrp, dec, tmp_path, typ):
+    """flat areas so that the run-length coder emits repeat runs (up to 128 bytes) as well as literal runs, and lines that
+    do not shrink are stored raw"""
+    import cv2
+    h, w = 90, 300
+    rng = np.random.default_rng(12)
+    img = np.zeros((h, w, 3), dtype=np.float32)
+    img[:30] = 0.5                                                   # whole lines of one value
+    img[30:60, :150] = rng.random((30, 1, 3), dtype=np.float32)      # half a line flat, half noise
+    img[30:60, 150:] = rng.random((30, 150, 3), dtype=np.float32)
+    img[60:] = rng.random((30, w, 3), dtype=np.float32)              # incompressible: stored raw
+    img = img.astype(np.float16).astype(np.float32)
+    p = str(tmp_path / "r.exr")
+    t = cv2.IMWRITE_EXR_TYPE_HALF if typ == "half" else cv2.IMWRITE_EXR_TYPE_FLOAT
+    assert cv2.imwrite(p, img, [cv2.IMWRITE_EXR_TYPE, t, cv2.IMWRITE_EXR_COMPRESSION, cv2.IMWRITE_EXR_COMPRESSION_RLE])
+    data = open(p, "rb").read()
+    assert len(data) < img.size * (2 if typ == "half" else 4) * 0.9  # the runs were coded
+    got = dec.exr(data, 3).cpu().numpy().view(np.uint16)
+    for plane, k in enumerate([2, 1, 0]):
+        assert (got[plane] == img[..., k].astype(np.float16).view(np.uint16)).all()
+    for cut in (len(data) - 1, len(data) - 40):
+        with pytest.raises(lrp.LrpError):
+            dec.exr(data[:cut], 2)
 
 
 @pytest.mark.parametrize("c,h,w,finite", [(3, 40, 33, True), (4, 100, 64, True), (5, 17, 7, True), (4, 33, 50, False)])
@@ -109,7 +135,7 @@ def _want_half(v):
 
 
 @pytest.mark.parametrize("h,w,c", [(1, 1, 3), (16, 8, 3), (17, 33, 4), (40, 1001, 3), (135, 240, 4), (1080, 1920, 4)])
-@pytest.mark.parametrize("comp", ["zip", "zips", "none"])
+@pytest.mark.parametrize("comp", ["zip", "zips", "none", "rle"])
 def test_float_exr_written_by_openexr_is_converted_like_openexr(lrp, dec, tmp_path, h, w, c, comp):
     """full-float files written by the OpenEXR library (inside cv2): read_exr reads them through HALF slices, so every
     sample goes through Imf::floatToHalf — values beyond +-65504 become infinities, NaN payloads are kept"""
@@ -122,7 +148,7 @@ def test_float_exr_written_by_openexr_is_converted_like_openexr(lrp, dec, tmp_pa
     flat[:k] = np.array([65504.0, 65505.0, -65519.9, 1e10, np.inf, -np.inf, 1e-8, 6e-8, 3e-5, -0.0], dtype=np.float32)[:k]
     p = str(tmp_path / "t.exr")
     flag = {"zip": cv2.IMWRITE_EXR_COMPRESSION_ZIP, "zips": cv2.IMWRITE_EXR_COMPRESSION_ZIPS,
-            "none": cv2.IMWRITE_EXR_COMPRESSION_NO}[comp]
+            "none": cv2.IMWRITE_EXR_COMPRESSION_NO, "rle": cv2.IMWRITE_EXR_COMPRESSION_RLE}[comp]
     assert cv2.imwrite(p, img, [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_FLOAT, cv2.IMWRITE_EXR_COMPRESSION, flag])
     data = open(p, "rb").read()
     assert lrp.exr_info(data) == (w, h, c)

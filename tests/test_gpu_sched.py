@@ -173,6 +173,11 @@ def test_file_jobs_on_the_scheduler_match_the_reference_chain(lrp, monkeypatch):
         else:  # EXR source, RGBZ
             planes = (rng.random((4, h, w), dtype=np.float32) * 2).astype(np.float16)
             data = lrp.exr_assemble(co.exr_pack(planes.view(np.uint16)), w, h, 4, 6, 1)
+            if k % 6 == 5:  # half colour + a FLOAT depth channel, as Blender writes it: read through a HALF slice
+                zf = rng.random((h, w), dtype=np.float32) * 2
+                zf[::7, ::5] = 1e10  # beyond HALF_MAX: infinity after OpenEXR's conversion
+                planes[3] = co.exr_float_to_half(zf).reshape(h, w).view(np.float16)
+                data = co.exr_write_typed({"R": planes[0], "G": planes[1], "B": planes[2], "Z": zf}, "zip")
             src = np.ascontiguousarray(planes.astype(np.float32).transpose(1, 2, 0))
             lin = ORC.post_process(ORC.reproject(src, il, olens, W, H, 1, ol.BICUBIC, rot), 1.5, 4.0)
             in_kind, out_kind = lrp.FILE_EXR, lrp.FILE_EXR
