@@ -17,7 +17,7 @@
 // Scope: what the reference's pipeline reads — single-part scan-line EXR with channels named from {R,G,B,A,Z} of any
 // pixel type (HALF as save_exr writes them; FLOAT / UINT — e.g. Blender's full-float files or a float Z beside half
 // colour — are converted to half on the device exactly as OpenEXR converts them for read_exr's HALF slices),
-// NONE / RLE / ZIPS / ZIP compression; every PNG colour type, bit depth and interlace method.  Anything else returns
+// NONE / RLE / ZIPS / ZIP / PXR24 compression; every PNG colour type, bit depth and interlace method.  Anything else returns
 // LRP_E_UNSUPPORTED_FORMAT (the reference would go through lodepng / OpenEXR's other code paths).
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -326,8 +326,8 @@ static int exr_parse(const unsigned char *f, size_t n, ExrInfo &I) {
   }
   if (!have_ch || !have_dw || I.w <= 0 || I.h <= 0 || (uint64_t)I.w * (uint64_t)I.h >= (1ull << 31)) return LRP_E_BAD_ARG;
   if (I.compression == 0 || I.compression == 1 || I.compression == 2) I.lines_per_block = 1;
-  else if (I.compression == 3) I.lines_per_block = 16;
-  else return LRP_E_UNSUPPORTED_FORMAT; // PIZ / PXR24 / B44 / DWA
+  else if (I.compression == 3 || I.compression == 5) I.lines_per_block = 16;
+  else return LRP_E_UNSUPPORTED_FORMAT; // PIZ / B44 / DWA
   I.table = pos + 1;
   I.c = (int)names.size();
   if (I.c < 3 || I.c > 5) return LRP_E_UNSUPPORTED_FORMAT;
@@ -368,6 +368,36 @@ static bool exr_rle_decode(const unsigned char *in, size_t n, unsigned char *out
     }
   }
   return o == want;
+}
+
+// OpenEXR's PXR24_COMPRESSION (lib/openexr/src/lib/OpenEXRCore/internal_pxr24.c:256-390): the block is one zlib stream
+// of byte planes — per scan line and channel, the most significant bytes of all samples, then the next bytes, ... (HALF 2
+// planes, UINT 4, FLOAT 3: the low byte of a float is dropped by the writer and comes back as zero) — and each sample is
+// the running sum of the values so assembled, restarting at every line and channel.  Rebuilds the block's raw scan lines
+// (little-endian samples, channels in file order), which the device scatters like a stored block.
+static bool exr_pxr24_decode(const unsigned char *in, size_t n, unsigned char *out, size_t lines, size_t w, int channels,
+                             const int *type_of) {
+  size_t i = 0;
+  for (size_t y = 0; y < lines; ++y)
+    for (int c = 0; c < channels; ++c) {
+      const int planes = type_of[c] == 1 ? 2 : type_of[c] == 2 ? 3 : 4, bytes = type_of[c] == 1 ? 2 : 4;
+      if (i + w * planes > n) return false;
+      const unsigned char *p0 = in + i, *p1 = p0 + w, *p2 = p1 + w, *p3 = p2 + w;
+      uint32_t pixel = 0;
+      for (size_t x = 0; x < w; ++x) {
+        if (planes == 2) {
+          pixel += ((uint32_t)p0[x] << 8) | p1[x];
+          out[0] = (unsigned char)pixel, out[1] = (unsigned char)(pixel >> 8);
+        } else {
+          pixel += ((uint32_t)p0[x] << 24) | ((uint32_t)p1[x] << 16) | ((uint32_t)p2[x] << 8) | (planes == 4 ? p3[x] : 0u);
+          out[0] = (unsigned char)pixel, out[1] = (unsigned char)(pixel >> 8), out[2] = (unsigned char)(pixel >> 16),
+          out[3] = (unsigned char)(pixel >> 24);
+        }
+        out += bytes;
+      }
+      i += w * planes;
+    }
+  return i == n;
 }
 
 template <class F> static void parallel_for(size_t n, int threads, F fn) {
@@ -694,6 +724,15 @@ int lrp_decoder_exr(lrp_decoder *d, const void *file, size_t n, int32_t threads,
         return;
       }
       memcpy(dst, f + off + 8, raw_n);
+      d->h_raw[b] = 1;
+    } else if (I.compression == 5) {
+      std::vector<unsigned char> planes(raw_n);
+      uLongf got = (uLongf)raw_n;
+      if (uncompress(planes.data(), &got, f + off + 8, (uLong)hdr[1]) != Z_OK ||
+          !exr_pxr24_decode(planes.data(), (size_t)got, dst, lines, (size_t)I.w, I.c, I.type_of)) {
+        status = LRP_E_BAD_ARG;
+        return;
+      }
       d->h_raw[b] = 1;
     } else if (I.compression == 1) {
       if (!exr_rle_decode(f + off + 8, (size_t)hdr[1], dst, raw_n)) {

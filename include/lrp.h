@@ -325,7 +325,7 @@ int lrp_encoder_last_timing(const lrp_encoder *enc, double *ms3);
  * device.  PNG: the inflate is one sequential stream and stays on the host; 8-bit RGB / RGBA scan lines are reconstructed
  * on the device (a wavefront over 1024 lines); the rare kinds (grey, palette, colour key, 16-bit, 1/2/4-bit, Adam7) are
  * decoded on the host to the RGBA8 lodepng::decode delivers (16-bit samples keep their most significant byte).
- * Supported: single-part scan-line EXR, channels R,G,B[,A][,Z] of any pixel type, NONE / RLE / ZIPS / ZIP; every PNG
+ * Supported: single-part scan-line EXR, channels R,G,B[,A][,Z] of any pixel type, NONE / RLE / ZIPS / ZIP / PXR24; every PNG
  * colour type, bit depth and interlace method.  Everything else: LRP_E_UNSUPPORTED_FORMAT.  FLOAT / UINT channels arrive as half, as
  * they do in read_exr (which reads every channel through a HALF slice, :246-258): the device applies OpenEXR's
  * Imf::floatToHalf / uintToHalf (lib/openexr/src/lib/OpenEXR/ImfConvert.cpp:96-115) bit for bit.

@@ -43,7 +43,7 @@ def _half_image(h, w, c, seed):
 
 
 @pytest.mark.parametrize("h,w,c", [(1, 1, 3), (16, 8, 3), (17, 33, 4), (40, 1001, 3), (135, 240, 4), (1080, 1920, 4)])
-@pytest.mark.parametrize("comp", ["zip", "zips", "none", "rle"])
+@pytest.mark.parametrize("comp", ["zip", "zips", "none", "rle", "pxr24"])
 def test_exr_written_by_openexr_decodes_like_openexr(lrp, dec, tmp_path, h, w, c, comp):
     """cv2 writes with the OpenEXR library (B,G,R[,A] order, HALF); our planes must hold the same bit patterns in the
     reference's R,G,B[,A] order — and equal what OpenEXR's own reader returns."""
@@ -51,7 +51,8 @@ def test_exr_written_by_openexr_decodes_like_openexr(lrp, dec, tmp_path, h, w, c
     img = _half_image(h, w, c, h * w + c)
     p = str(tmp_path / "t.exr")
     flag = {"zip": cv2.IMWRITE_EXR_COMPRESSION_ZIP, "zips": cv2.IMWRITE_EXR_COMPRESSION_ZIPS,
-            "none": cv2.IMWRITE_EXR_COMPRESSION_NO, "rle": cv2.IMWRITE_EXR_COMPRESSION_RLE}[comp]
+            "none": cv2.IMWRITE_EXR_COMPRESSION_NO, "rle": cv2.IMWRITE_EXR_COMPRESSION_RLE,
+            "pxr24": cv2.IMWRITE_EXR_COMPRESSION_PXR24}[comp]
     assert cv2.imwrite(p, img.astype(np.float32), [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF,
                                                    cv2.IMWRITE_EXR_COMPRESSION, flag])
     data = open(p, "rb").read()
@@ -62,6 +63,27 @@ def test_exr_written_by_openexr_decodes_like_openexr(lrp, dec, tmp_path, h, w, c
     for plane, k in enumerate(order):
         assert (got[plane] == img[..., k].view(np.uint16)).all()
         assert (got[plane] == back[..., k].view(np.uint16)).all()
+
+
+@pytest.mark.parametrize("h,w,c", [(1, 1, 3), (17, 33, 4), (40, 1001, 3), (135, 240, 4)])
+def test_pxr24_float_exr_written_by_openexr(lrp, dec, tmp_path, h, w, c):
+    """PXR24 keeps 24 bits of a FLOAT sample: the decoder must rebuild exactly the floats OpenEXR's own reader returns
+    (cv2.imread), and then convert them to half as read_exr's HALF slices do"""
+    import cv2
+    rng = np.random.default_rng(h * w)
+    img = (rng.random((h, w, c), dtype=np.float32) * 300 - 100)
+    img[::4, ::3] = 0.5
+    img.reshape(-1)[:3] = np.array([70000.0, -1e10, 3e-6], dtype=np.float32)[:min(3, img.size)]
+    p = str(tmp_path / "p.exr")
+    assert cv2.imwrite(p, img, [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_FLOAT,
+                                cv2.IMWRITE_EXR_COMPRESSION, cv2.IMWRITE_EXR_COMPRESSION_PXR24])
+    back = cv2.imread(p, cv2.IMREAD_UNCHANGED).reshape(h, w, c)  # the 24-bit floats
+    assert back.dtype == np.float32
+    assert h * w < 16 or (back.view(np.uint32) & 0xFF == 0).all()  # (a block that does not shrink is stored with full floats)
+    got = dec.exr(open(p, "rb").read(), 4).cpu().numpy().view(np.uint16)
+    order = [2, 1, 0] + ([3] if c == 4 else [])
+    for plane, k in enumerate(order):
+        assert (got[plane] == co.exr_float_to_half(back[..., k]).reshape(h, w)).all()
 
 
 @pytest.mark.parametrize("typ", ["half", "float"])
