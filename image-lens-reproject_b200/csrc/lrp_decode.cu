@@ -704,7 +704,7 @@ int lrp_decoder_exr(lrp_decoder *d, const void *file, size_t n, int32_t threads,
   parallel_for(blocks, threads, [&](size_t b) {
     uint64_t off;
     memcpy(&off, f + I.table + 8 * b, 8);
-    if (off + 8 > n) {
+    if (off > n || n - off < 8) { // (no wrap-around for offsets near 2^64)
       status = LRP_E_BAD_ARG;
       return;
     }

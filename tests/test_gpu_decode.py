@@ -139,7 +139,10 @@ def test_exr_unsupported_and_malformed(lrp, dec, tmp_path):
     with pytest.raises(lrp.LrpError):
         dec.exr(open(p, "rb").read())
     good = lrp.exr_assemble(co.exr_pack(np.zeros((3, 20, 10), np.uint16)), 10, 20, 3, 6, 1)
-    for bad in (good[:50], good[:-7], b"nope" + good[4:]):
+    import struct
+    table = next(p for p in range(8, len(good) - 16) if struct.unpack_from("<Q", good, p)[0] == p + 16)  # 2 blocks
+    wrap = good[:table] + struct.pack("<Q", 2 ** 64 - 3) + good[table + 8:]  # an offset that wraps around when 8 is added
+    for bad in (good[:50], good[:-7], b"nope" + good[4:], wrap):
         with pytest.raises(lrp.LrpError):
             dec.exr(bad)
 
