@@ -633,7 +633,7 @@ struct Pool {
     rc = slot_reserve(w->slot, in_png ? ipx * 4 : ipx * 2 * ic, out_png ? opx * 4 : opx * 2 * ic);
     if (rc != LRP_OK) return rc;
     rc = in_png ? lrp_decoder_png(w->dec, j.in_file, j.in_size, w->slot.d_in, w->slot.stream)
-                : lrp_decoder_exr(w->dec, j.in_file, j.in_size, j.decode_threads > 0 ? j.decode_threads : 1, w->slot.d_in,
+                : lrp_decoder_exr(w->dec, j.in_file, j.in_size, j.decode_threads > 0 || j.decode_threads == LRP_DECODE_ON_DEVICE ? j.decode_threads : 1, w->slot.d_in,
                                   w->slot.stream);
     if (rc != LRP_OK) return rc;
     ctx->h2d_bytes += in_png ? ipx * 4 : ipx * 2 * ic;

@@ -33,6 +33,7 @@
 #include <vector>
 
 #include "../../include/lrp.h"
+#include "lrp_inflate.cuh"
 
 extern "C" int lrp_ctx_phys_device_(const lrp_ctx *ctx); // lrp_api.cu
 
@@ -162,6 +163,46 @@ __global__ void __launch_bounds__(UNPACK_WARPS * 32) exr_unpack_kernel(const Exr
     base_lo += __shfl_sync(0xffffffffu, il, 31);
     base_hi += __shfl_sync(0xffffffffu, ih, 31);
   }
+}
+
+// ---- EXR: the zlib streams of the blocks inflated on the device (lrp_inflate.cuh) -----------------------------
+// One warp per block of scan lines: lane 0 walks the bit stream with the Huffman tables in shared memory, then all
+// lanes verify the Adler-32 of what was written; stored blocks are copied by all lanes.  A frame has H / 16 independent
+// streams and a pipeline keeps tens of frames in flight, so thousands of decoders run concurrently while the host
+// only reads the chunk table — the compressed file is what crosses PCIe.
+struct InflateJob {
+  unsigned long long src_off, dst_off; // into the file bytes / into the staging buffer of the unpack kernel
+  unsigned src_len, dst_len;
+  unsigned stored, pad;
+};
+
+__global__ void __launch_bounds__(32) exr_inflate_kernel(const unsigned char *__restrict__ file, const InflateJob *__restrict__ jobs,
+                                                          unsigned char *out, int *status) {
+  __shared__ InflateTables T;
+  const InflateJob J = jobs[blockIdx.x];
+  const unsigned lane = threadIdx.x;
+  const unsigned char *in = file + J.src_off;
+  unsigned char *dst = out + J.dst_off;
+  if (J.stored) {
+    for (unsigned i = lane; i < J.dst_len; i += 32) dst[i] = in[i];
+    if (lane == 0) status[blockIdx.x] = INF_OK;
+    return;
+  }
+  int rc = 0;
+  unsigned stored_adler = 0;
+  if (lane == 0) rc = inflate_zlib(in, J.src_len, dst, J.dst_len, T, &stored_adler);
+  rc = __shfl_sync(0xffffffffu, rc, 0);
+  if (rc == INF_OK) {
+    __syncwarp();
+    uint64_t a, b;
+    inf_adler_partial(dst, J.dst_len, lane, 32, a, b);
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0 && inf_adler_finish(a, b, J.dst_len) != stored_adler) rc = INF_E_ADLER;
+  }
+  if (lane == 0) status[blockIdx.x] = rc;
 }
 
 // FLOAT / UINT channels: read_exr hands OpenEXR HALF slices for every channel (src/image_formats.cpp:246-252), so the
@@ -596,6 +637,10 @@ struct lrp_decoder {
   int device = 0;
   size_t cap = 0, cap_out = 0, cap_blocks = 0, cap_wide = 0; // cap_out: the size limit given at creation
   unsigned char *h_buf = nullptr, *d_buf = nullptr, *h_raw = nullptr, *d_raw = nullptr;
+  unsigned char *d_file = nullptr;  // device inflate: the file's bytes
+  size_t cap_file = 0;
+  InflateJob *h_jobs = nullptr, *d_jobs = nullptr; // cap_blocks entries
+  int *h_status = nullptr, *d_status = nullptr;
   unsigned char *d_wide = nullptr; // 32-bit planes of the FLOAT / UINT channels of an EXR file, before their conversion to half
   std::vector<unsigned char> scratch;
 };
@@ -603,8 +648,17 @@ struct lrp_decoder {
 // Files with FLOAT / UINT channels store up to twice the bytes per pixel the decoder was sized for (it is sized for what
 // the reference's own save_exr writes: HALF): the staging buffers grow on first use.  No work is in flight between calls
 // (every decode ends with a stream synchronisation), so they can be replaced here.
-static int decoder_reserve(lrp_decoder *d, size_t stage_bytes, size_t wide_bytes) {
+static int decoder_reserve(lrp_decoder *d, size_t stage_bytes, size_t wide_bytes, size_t file_bytes = 0) {
   if (cudaSetDevice(d->device) != cudaSuccess) return LRP_E_CUDA;
+  if (file_bytes > d->cap_file) {
+    cudaFree(d->d_file);
+    d->d_file = nullptr, d->cap_file = 0;
+    if (cudaMalloc(&d->d_file, file_bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return LRP_E_OOM;
+    }
+    d->cap_file = file_bytes;
+  }
   if (stage_bytes > d->cap) {
     cudaFreeHost(d->h_buf), cudaFree(d->d_buf);
     d->h_buf = d->d_buf = nullptr, d->cap = 0;
@@ -661,12 +715,18 @@ int lrp_decoder_create(lrp_ctx *ctx, int32_t max_width, int32_t max_height, int3
   d->cap_out = d->cap;
   d->cap_blocks = (size_t)max_height;
   const bool ok = cudaMallocHost(&d->h_buf, d->cap) == cudaSuccess && cudaMalloc(&d->d_buf, d->cap) == cudaSuccess &&
-                  cudaMallocHost(&d->h_raw, d->cap_blocks) == cudaSuccess && cudaMalloc(&d->d_raw, d->cap_blocks) == cudaSuccess;
+                  cudaMallocHost(&d->h_raw, d->cap_blocks) == cudaSuccess && cudaMalloc(&d->d_raw, d->cap_blocks) == cudaSuccess &&
+                  cudaMallocHost(&d->h_jobs, d->cap_blocks * sizeof(InflateJob)) == cudaSuccess &&
+                  cudaMalloc(&d->d_jobs, d->cap_blocks * sizeof(InflateJob)) == cudaSuccess &&
+                  cudaMallocHost(&d->h_status, d->cap_blocks * sizeof(int)) == cudaSuccess &&
+                  cudaMalloc(&d->d_status, d->cap_blocks * sizeof(int)) == cudaSuccess;
   if (!ok) {
     cudaGetLastError();
     if (d->h_buf) cudaFreeHost(d->h_buf);
     if (d->h_raw) cudaFreeHost(d->h_raw);
-    cudaFree(d->d_buf), cudaFree(d->d_raw);
+    if (d->h_jobs) cudaFreeHost(d->h_jobs);
+    if (d->h_status) cudaFreeHost(d->h_status);
+    cudaFree(d->d_buf), cudaFree(d->d_raw), cudaFree(d->d_jobs), cudaFree(d->d_status);
     delete d;
     return LRP_E_OOM;
   }
@@ -677,8 +737,8 @@ int lrp_decoder_create(lrp_ctx *ctx, int32_t max_width, int32_t max_height, int3
 int lrp_decoder_destroy(lrp_decoder *d) {
   if (!d) return LRP_E_BAD_ARG;
   cudaSetDevice(d->device);
-  cudaFreeHost(d->h_buf), cudaFreeHost(d->h_raw);
-  cudaFree(d->d_buf), cudaFree(d->d_raw), cudaFree(d->d_wide);
+  cudaFreeHost(d->h_buf), cudaFreeHost(d->h_raw), cudaFreeHost(d->h_jobs), cudaFreeHost(d->h_status);
+  cudaFree(d->d_buf), cudaFree(d->d_raw), cudaFree(d->d_wide), cudaFree(d->d_file), cudaFree(d->d_jobs), cudaFree(d->d_status);
   delete d;
   return LRP_OK;
 }
@@ -698,9 +758,36 @@ int lrp_decoder_exr(lrp_decoder *d, const void *file, size_t n, int32_t threads,
   // the decoder's size limit is in pixels and channels of the OUTPUT (half planes), whatever the file's sample types
   if (plane * I.c * 2 > d->cap_out || blocks > d->cap_blocks) return LRP_E_BAD_ARG;
   if (I.table + 8 * blocks > n) return LRP_E_BAD_ARG;
-  rc = decoder_reserve(d, total, (size_t)wide * plane * 4);
+  const bool on_device = threads == LRP_DECODE_ON_DEVICE && (I.compression == 0 || I.compression == 2 || I.compression == 3);
+  rc = decoder_reserve(d, on_device ? std::max(total, n) : total, (size_t)wide * plane * 4, on_device ? n : 0);
   if (rc != LRP_OK) return rc;
   std::atomic<int> status{LRP_OK};
+  if (on_device) { // the host only walks the chunk table; the file's bytes go to the device as they are
+    for (size_t b = 0; b < blocks; ++b) {
+      uint64_t off;
+      memcpy(&off, f + I.table + 8 * b, 8);
+      if (off > n || n - off < 8) return LRP_E_BAD_ARG;
+      int32_t hdr[2];
+      memcpy(hdr, f + off, 8);
+      const size_t lines = std::min<size_t>(I.lines_per_block, (size_t)I.h - b * I.lines_per_block), raw_n = lines * line_bytes;
+      if (hdr[1] < 0 || (size_t)hdr[1] > n - off - 8) return LRP_E_BAD_ARG;
+      const bool stored = (size_t)hdr[1] == raw_n || I.compression == 0;
+      if (stored && (size_t)hdr[1] != raw_n) return LRP_E_BAD_ARG;
+      InflateJob &J = d->h_jobs[b];
+      J.src_off = off + 8, J.dst_off = b * I.lines_per_block * line_bytes;
+      J.src_len = (unsigned)hdr[1], J.dst_len = (unsigned)raw_n, J.stored = stored ? 1u : 0u, J.pad = 0;
+      d->h_raw[b] = stored ? 1 : 0;
+    }
+    memcpy(d->h_buf, f, n); // pinned staging: the copy below is asynchronous and the caller's buffer may be pageable
+    if (cudaSetDevice(d->device) != cudaSuccess) return LRP_E_CUDA;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (cudaMemcpyAsync(d->d_file, d->h_buf, n, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(d->d_jobs, d->h_jobs, blocks * sizeof(InflateJob), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(d->d_raw, d->h_raw, blocks, cudaMemcpyHostToDevice, st) != cudaSuccess)
+      return LRP_E_CUDA;
+    exr_inflate_kernel<<<(unsigned)blocks, 32, 0, st>>>(d->d_file, d->d_jobs, d->d_buf, d->d_status);
+    if (cudaMemcpyAsync(d->h_status, d->d_status, blocks * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return LRP_E_CUDA;
+  } else
   parallel_for(blocks, threads, [&](size_t b) {
     uint64_t off;
     memcpy(&off, f + I.table + 8 * b, 8);
@@ -752,8 +839,8 @@ int lrp_decoder_exr(lrp_decoder *d, const void *file, size_t n, int32_t threads,
   if (status != LRP_OK) return status;
   if (cudaSetDevice(d->device) != cudaSuccess) return LRP_E_CUDA;
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  if (cudaMemcpyAsync(d->d_buf, d->h_buf, total, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-      cudaMemcpyAsync(d->d_raw, d->h_raw, blocks, cudaMemcpyHostToDevice, st) != cudaSuccess)
+  if (!on_device && (cudaMemcpyAsync(d->d_buf, d->h_buf, total, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                     cudaMemcpyAsync(d->d_raw, d->h_raw, blocks, cudaMemcpyHostToDevice, st) != cudaSuccess))
     return LRP_E_CUDA;
   ExrUnpackParams P;
   P.src = d->d_buf, P.is_raw = d->d_raw;
@@ -776,6 +863,9 @@ int lrp_decoder_exr(lrp_decoder *d, const void *file, size_t n, int32_t threads,
                                                I.type_of[k] == 0);
     }
   if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return LRP_E_CUDA; // h_buf is reused
+  if (on_device)
+    for (size_t b = 0; b < blocks; ++b)
+      if (d->h_status[b] != INF_OK) return LRP_E_BAD_ARG; // a block that does not inflate (the planes then hold garbage)
   return LRP_OK;
 }
 

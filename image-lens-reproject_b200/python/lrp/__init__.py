@@ -500,6 +500,9 @@ class Encoder:
         return self._run(lib().lrp_encoder_exr, planar_t, w, h, c, stream)
 
 
+DECODE_ON_DEVICE = -1  # lrp_decoder_exr: inflate the blocks on the device
+
+
 def exr_info(data):
     w, h, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
     check(lib().lrp_exr_info(data, len(data), C.byref(w), C.byref(h), C.byref(c)), "lrp_exr_info")

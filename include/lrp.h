@@ -336,7 +336,12 @@ int lrp_exr_info(const void *file, size_t n, int32_t *width, int32_t *height, in
 int lrp_png_info(const void *file, size_t n, int32_t *width, int32_t *height);
 int lrp_decoder_create(lrp_ctx *ctx, int32_t max_width, int32_t max_height, int32_t max_channels, lrp_decoder **out);
 int lrp_decoder_destroy(lrp_decoder *dec);
-/* planes R, G, B, [A], [Z] (the reference's channel order) of IEEE half, plane stride width * height */
+/* planes R, G, B, [A], [Z] (the reference's channel order) of IEEE half, plane stride width * height.
+ * threads > 0: the blocks' zlib streams are inflated on that many host cores (lowest latency for one frame);
+ * threads == LRP_DECODE_ON_DEVICE: the compressed file crosses PCIe and every block is inflated by its own warp on the
+ * device (csrc/lrp_inflate.cuh) — the host only walks the chunk table, so a pipeline's decode rate no longer depends on
+ * host cores (NONE / ZIPS / ZIP files; RLE and PXR24 blocks are always expanded on the host). */
+#define LRP_DECODE_ON_DEVICE (-1)
 int lrp_decoder_exr(lrp_decoder *dec, const void *file, size_t n, int32_t threads, void *out_half_planar_dev,
                     void *cuda_stream);
 /* RGBA8 as lodepng::decode delivers it (the kernel reads it as LRP_FMT_U8_RGBA with channels = 3) */
@@ -359,7 +364,7 @@ typedef struct lrp_file_job {
   lrp_lens out_lens;
   int32_t out_width, out_height;
   lrp_params params;
-  int32_t decode_threads; /* host threads inflating the blocks of an EXR input (>= 1) */
+  int32_t decode_threads; /* host threads inflating the blocks of an EXR input (>= 1), or LRP_DECODE_ON_DEVICE */
   lrp_file_done_fn on_done;
   void *user;
 } lrp_file_job;

@@ -86,6 +86,62 @@ def test_pxr24_float_exr_written_by_openexr(lrp, dec, tmp_path, h, w, c):
         assert (got[plane] == co.exr_float_to_half(back[..., k]).reshape(h, w)).all()
 
 
+@pytest.mark.parametrize("h,w,c", [(1, 1, 3), (16, 8, 3), (17, 33, 4), (40, 1001, 3), (135, 240, 4), (1080, 1920, 4)])
+@pytest.mark.parametrize("comp", ["zip", "zips", "none"])
+@pytest.mark.parametrize("typ", ["half", "float"])
+def test_exr_blocks_inflated_on_the_device(lrp, dec, tmp_path, h, w, c, comp, typ):
+    """LRP_DECODE_ON_DEVICE: the zlib streams OpenEXR wrote (dynamic + fixed + stored deflate blocks, raw EXR blocks) are
+    inflated by exr_inflate_kernel; the planes equal those of the host-inflate path and OpenEXR's samples"""
+    import cv2
+    rng = np.random.default_rng(h + w + c)
+    img = (rng.random((h, w, c), dtype=np.float32) * 3 - 1)
+    img[::4, ::3] = 0.5
+    img[h // 2:] = np.round(img[h // 2:] * 8) / 8  # long matches in the lower half, near-noise above
+    if typ == "half":
+        img = img.astype(np.float16).astype(np.float32)
+    p = str(tmp_path / "t.exr")
+    flag = {"zip": cv2.IMWRITE_EXR_COMPRESSION_ZIP, "zips": cv2.IMWRITE_EXR_COMPRESSION_ZIPS,
+            "none": cv2.IMWRITE_EXR_COMPRESSION_NO}[comp]
+    t = cv2.IMWRITE_EXR_TYPE_HALF if typ == "half" else cv2.IMWRITE_EXR_TYPE_FLOAT
+    assert cv2.imwrite(p, img, [cv2.IMWRITE_EXR_TYPE, t, cv2.IMWRITE_EXR_COMPRESSION, flag])
+    data = open(p, "rb").read()
+    got = dec.exr(data, lrp.DECODE_ON_DEVICE).cpu().numpy().view(np.uint16)
+    assert (got == dec.exr(data, 3).cpu().numpy().view(np.uint16)).all()
+    order = [2, 1, 0] + ([3] if c == 4 else [])
+    for plane, k in enumerate(order):
+        assert (got[plane] == co.exr_float_to_half(img[..., k]).reshape(h, w)).all()
+
+
+def test_device_inflate_of_every_deflate_flavour_and_of_corrupted_files(lrp, dec):
+    """files whose blocks were deflated by zlib at every level / strategy (stored, fixed-Huffman, RLE, filtered ...), our
+    own device-deflated files, and corrupted files: an error or the right image, and the decoder keeps working"""
+    import zlib
+    rng = np.random.default_rng(9)
+    h, w = 70, 129
+    planes = _half_image(h, w, 4, 5).transpose(2, 0, 1).copy().view(np.uint16)
+    planes[:, 40:] = planes[:, 40:41]  # repeated lines: long matches
+    packed = co.exr_pack(planes)
+    ch = {n: planes[i].view(np.float16) for i, n in enumerate("RGBA")}
+    files = [lrp.exr_assemble(packed, w, h, 4, level, 2) for level in (1, 6, 9)] + [co.exr_write_typed(ch, "zips")]
+    for data in files:
+        assert (dec.exr(data, lrp.DECODE_ON_DEVICE).cpu().numpy().view(np.uint16) == planes).all()
+    good = files[1]
+    errors = 0
+    for _ in range(200):
+        b = bytearray(good)
+        b[int(rng.integers(400, len(b)))] ^= 1 << int(rng.integers(0, 8))  # inside the chunks (header is parsed on the host)
+        try:
+            out = dec.exr(bytes(b), lrp.DECODE_ON_DEVICE)
+            assert (out.cpu().numpy().view(np.uint16) == planes).all()  # accepted only when the samples are right
+        except lrp.LrpError:
+            errors += 1
+    assert errors > 150
+    for n in (len(good) - 1, len(good) - 30, len(good) // 2):
+        with pytest.raises(lrp.LrpError):
+            dec.exr(good[:n], lrp.DECODE_ON_DEVICE)
+    assert (dec.exr(good, lrp.DECODE_ON_DEVICE).cpu().numpy().view(np.uint16) == planes).all()
+
+
 @pytest.mark.parametrize("typ", ["half", "float"])
 def test_rle_exr_with_long_runs_written_by_openexr(lrp, dec, tmp_path, typ):
     """flat areas so that the run-length coder emits repeat runs (up to 128 bytes) as well as literal runs, and lines that
