@@ -44,6 +44,14 @@ struct InflateBits {
 };
 
 LRP_HD void inf_refill(InflateBits &b) {
+  // four bytes per step while they last: the loads are independent of each other, so their latencies overlap (a decoder
+  // is one dependent chain; a byte-at-a-time loop would pay one memory latency per byte)
+  if (b.cnt <= 32 && b.end - b.p >= 4) {
+    const uint32_t v = (uint32_t)b.p[0] | ((uint32_t)b.p[1] << 8) | ((uint32_t)b.p[2] << 16) | ((uint32_t)b.p[3] << 24);
+    b.buf |= (uint64_t)v << b.cnt;
+    b.cnt += 32, b.p += 4;
+    return;
+  }
   while (b.cnt <= 56 && b.p < b.end) {
     b.buf |= (uint64_t)(*b.p++) << b.cnt;
     b.cnt += 8;
@@ -214,8 +222,28 @@ LRP_HD int inflate_zlib(const uint8_t *in, size_t n, uint8_t *out, size_t out_n,
       const unsigned dist = DBASE[d] + inf_take(b, DEXT[d]);
       if (dist > o) return INF_E_DISTANCE;
       if (out_n - o < len) return INF_E_OUTPUT;
+      // LZ77 copy (bytes may overlap: the pattern repeats).  A byte-by-byte loop is one load latency per byte on the
+      // device, so: distances >= 8 move eight bytes per step (independent loads, then the stores), shorter distances
+      // read their pattern once into a register and only store.
       const uint8_t *from = out + o - dist;
-      for (unsigned k = 0; k < len; ++k) out[o + k] = from[k]; // byte by byte: overlapping copies repeat the pattern
+      uint8_t *to = out + o;
+      unsigned k = 0;
+      if (dist >= 8) {
+        for (; k + 8 <= len; k += 8) {
+          const uint8_t b0 = from[k], b1 = from[k + 1], b2 = from[k + 2], b3 = from[k + 3], b4 = from[k + 4], b5 = from[k + 5],
+                        b6 = from[k + 6], b7 = from[k + 7];
+          to[k] = b0, to[k + 1] = b1, to[k + 2] = b2, to[k + 3] = b3, to[k + 4] = b4, to[k + 5] = b5, to[k + 6] = b6, to[k + 7] = b7;
+        }
+        for (; k < len; ++k) to[k] = from[k];
+      } else {
+        uint64_t pat = 0;
+        for (unsigned j = 0; j < dist; ++j) pat |= (uint64_t)from[j] << (8 * j);
+        unsigned j = 0;
+        for (; k < len; ++k) {
+          to[k] = (uint8_t)(pat >> (8 * j));
+          j = (j + 1 == dist) ? 0 : j + 1;
+        }
+      }
       o += len;
     }
     if (b.overrun) return INF_E_INPUT;

@@ -7,8 +7,11 @@ Decode-side measurement of lrp_decoder_exr on 4K frames, 
                exr_to_half_kernel (Imf::floatToHalf)
   float_rgba   full float, ZIP
 
-Reports wall milliseconds per frame of the whole call (host inflate on T threads + H2D + device kernels); run it under
-`ncu --metrics gpu__time_duration.sum` for the device share (exr_unpack_kernel, exr_to_half_kernel).
+Reports, per kind: wall milliseconds per frame of one call with the blocks inflated on T host threads and with the blocks
+inflated on the device (LRP_DECODE_ON_DEVICE), and the frames per second of K concurrent decoders (one per Python thread,
+each on its own stream — what the file pipeline does) in both modes: host mode with one inflate thread per decoder.
+Run it under `ncu --metrics gpu__time_duration.sum` for the device share (exr_inflate_kernel, exr_unpack_kernel,
+exr_to_half_kernel).
 
 usage: python tests/perf/bench_decode_exr.py [--threads T] [--reps N] [--cache DIR]
 """
@@ -27,6 +30,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--threads", type=int, default=len(os.sched_getaffinity(0)))
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--decoders", type=int, default=16, help="concurrent decoders of the throughput leg (0: skip it)")
     ap.add_argument("--cache", default="", help="directory to keep the generated files in (a second run reuses them)")
     args = ap.parse_args()
     import numpy as np
@@ -69,7 +73,41 @@ def main():
             dec.exr(data, args.threads)
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) * 1e3 / args.reps
-        out["kinds"][name] = {"file_mb": round(len(data) / 1e6, 1), "ms_per_frame": round(ms, 2), "bit_exact": ok}
+        got_d = dec.exr(data, lrp.DECODE_ON_DEVICE)
+        torch.cuda.synchronize()
+        ok_d = bool((got_d.cpu().numpy().view(np.uint16) == want).all())
+        t0 = time.perf_counter()
+        for _ in range(args.reps):
+            dec.exr(data, lrp.DECODE_ON_DEVICE)
+        torch.cuda.synchronize()
+        ms_d = (time.perf_counter() - t0) * 1e3 / args.reps
+        rec = {"file_mb": round(len(data) / 1e6, 1), "ms_per_frame": round(ms, 2), "bit_exact": ok,
+               "device_inflate_ms_per_frame": round(ms_d, 2), "device_inflate_bit_exact": ok_d}
+        if args.decoders > 0:
+            import threading
+            decs = [lrp.Decoder(ctx, W, H, 4) for _ in range(args.decoders)]
+            streams = [torch.cuda.Stream() for _ in range(args.decoders)]
+            outs = [torch.empty((len(names), H, W), dtype=torch.float16, device="cuda:0") for _ in range(args.decoders)]
+
+            def work(i, mode, reps):
+                for _ in range(reps):
+                    lrp.check(lrp.lib().lrp_decoder_exr(decs[i].h, data, len(data), mode, outs[i].data_ptr(), streams[i].cuda_stream), "exr")
+
+            for mode, key in ((1, "host_inflate_fps"), (lrp.DECODE_ON_DEVICE, "device_inflate_fps")):
+                for reps in (1, args.reps):  # first round: warm-up and buffer growth
+                    ts = [threading.Thread(target=work, args=(i, mode, reps)) for i in range(args.decoders)]
+                    t0 = time.perf_counter()
+                    for t in ts:
+                        t.start()
+                    for t in ts:
+                        t.join()
+                    torch.cuda.synchronize()
+                    dt = time.perf_counter() - t0
+                rec[key] = round(args.decoders * args.reps / dt, 1)
+            rec["decoders"] = args.decoders
+            for x in decs:
+                x.close()
+        out["kinds"][name] = rec
     dec.close()
     ctx.close()
     print(json.dumps(out))
