@@ -183,7 +183,8 @@ def test_file_jobs_on_the_scheduler_match_the_reference_chain(lrp, monkeypatch):
             in_kind, out_kind = lrp.FILE_EXR, lrp.FILE_EXR
         cases.append((out_kind, lin))
         keep.append(s.submit_file(data, in_kind, lrp.lens_from(il), lrp.lens_from(olens), W, H, out_kind, p,
-                                  lambda status, b, k=k: results.__setitem__(k, (status, b))))
+                                  lambda status, b, k=k: results.__setitem__(k, (status, b)),
+                                  decode_threads=lrp.DECODE_ON_DEVICE if k % 6 == 2 else 2))  # some EXR inputs inflated on the device
     s.wait_all()
     assert sum(s.stats()) == 18 and min(s.stats()) >= 1
     s.close()
