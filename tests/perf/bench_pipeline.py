@@ -7,7 +7,11 @@ GPU -> file bytes.  Beside it, the reference's chain for ONE frame on ONE core, 
 code where it compiled here (lodepng decode / encode, reproject()); the float conversions are numpy restatements of
 read_png's / save_png's loops (src/image_formats.cpp:189-199, 150-165).
 
-usage: python tests/perf/bench_pipeline.py [--threads T] [--frames N]
+`--exr` runs the c4' shape instead (3840x2160 RGBZ half EXR, rectilinear f=36 -> equidistant(pi), EXR
+out; input files deflated by zlib level 4 as OpenEXR 3.2 writes them) twice: blocks inflated on 2 host threads per job,
+and blocks inflated on the device (LRP_DECODE_ON_DEVICE).
+
+usage: python tests/perf/bench_pipeline.py [--threads T] [--frames N] [--exr]
 """
 import argparse
 import json
@@ -25,7 +29,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--threads", type=int, default=len(os.sched_getaffinity(0)))
     ap.add_argument("--frames", type=int, default=64)
+    ap.add_argument("--exr", action="store_true")
     args = ap.parse_args()
+    if args.exr:
+        return main_exr(args)
     import numpy as np
     import torch
     import lrp
@@ -101,6 +108,53 @@ def main():
         res["reference_frames_per_s_if_all_%d_cores_scale" % args.threads] = args.threads / tot
     print(json.dumps(res))
     ctx.close()
+
+
+def main_exr(args):
+    import numpy as np
+    import lrp
+    import oracle_lib as ol
+    co = ol.codec_oracle()
+    lrp.lib()
+    W = w = 3840
+    H = h = 2160
+    il, olens = lrp.lens_rectilinear(36.0, 36.0, w, h), lrp.lens_equidistant(3.14159)
+    p = lrp.make_params(1, lrp.BICUBIC, None, (1.5, 4.0))
+    y, x = np.mgrid[0:h, 0:w].astype(np.float32)
+    files = []
+    for k in range(2):
+        rng = np.random.default_rng(k)
+        col = [(0.5 + 0.4 * np.sin(0.01 * x + c + k) * np.cos(0.013 * y) + rng.normal(0, 0.01, (h, w))).astype(np.float16) for c in range(3)]
+        z = (1.0 + 0.001 * x + rng.normal(0, 1e-4, (h, w))).astype(np.float16)
+        planes = np.stack(col + [z]).view(np.uint16)
+        files.append(lrp.exr_assemble(co.exr_pack(planes), w, h, 4, 4, args.threads))
+    res = {"workload": "c4': %dx%d RGBZ half EXR rect(36,36) -> equidistant(pi) %dx%d, bicubic, exposure + reinhard, EXR out" % (w, h, W, H),
+           "frames": args.frames, "threads": args.threads, "in_file_bytes": len(files[0])}
+    for key, mode in (("host_inflate", 2), ("device_inflate", lrp.DECODE_ON_DEVICE)):
+        sched = lrp.Scheduler([0], streams_per_device=args.threads)
+        done, lock, keep = [0, 0], threading.Lock(), []
+
+        def sink(status, data):
+            with lock:
+                done[0] += len(data) if data else 0
+                done[1] += 1 if status == 0 else 0
+
+        def run(n):
+            for i in range(n):
+                keep.append(sched.submit_file(files[i % 2], lrp.FILE_EXR, il, olens, W, H, lrp.FILE_EXR, p, sink, decode_threads=mode))
+            sched.wait_all()
+
+        run(args.threads)  # warm-up: workspaces
+        del keep[:]
+        done[0] = done[1] = 0
+        t0 = time.perf_counter()
+        run(args.frames)
+        dt = time.perf_counter() - t0
+        sched.close()
+        assert done[1] == args.frames
+        res[key] = {"frames_per_s": round(args.frames / dt, 2), "output_gpix_per_s": round(args.frames * W * H / dt / 1e9, 3),
+                    "out_file_bytes_avg": done[0] // args.frames}
+    print(json.dumps(res))
 
 
 if __name__ == "__main__":
