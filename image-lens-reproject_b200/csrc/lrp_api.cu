@@ -1209,7 +1209,7 @@ int lrp_wait_all(lrp_ctx *ctx) {
 // ---- multi-GPU scheduler ----
 
 int lrp_sched_create(const int *devices, int n_devices, int streams_per_device, lrp_sched **out) {
-  if (!out || n_devices < 1 || streams_per_device < 1 || streams_per_device > 16) return LRP_E_BAD_ARG;
+  if (!out || n_devices < 1 || streams_per_device < 1 || streams_per_device > 64) return LRP_E_BAD_ARG;
   *out = nullptr;
   lrp_sched *s = new lrp_sched();
   for (int i = 0; i < n_devices; ++i) {

@@ -252,6 +252,7 @@ int lrp_wait_all(lrp_ctx *ctx);
  * pool.push(job) + pool.stop(true) (src/main.cpp:538-541, 657).  Images are
  * independent, so jobs are handed to whichever GPU stream frees up first; no
  * collective is involved. */
+/* streams_per_device: 1..64 workers per GPU, each with its own stream and codec workspaces */
 int lrp_sched_create(const int *devices, int n_devices, int streams_per_device, lrp_sched **out);
 int lrp_sched_submit(lrp_sched *s, const lrp_job *job);
 int lrp_sched_wait_all(lrp_sched *s); /* returns first non-OK job status, else LRP_OK */

@@ -130,22 +130,29 @@ def main_exr(args):
         files.append(lrp.exr_assemble(co.exr_pack(planes), w, h, 4, 4, args.threads))
     res = {"workload": "c4': %dx%d RGBZ half EXR rect(36,36) -> equidistant(pi) %dx%d, bicubic, exposure + reinhard, EXR out" % (w, h, W, H),
            "frames": args.frames, "threads": args.threads, "in_file_bytes": len(files[0])}
+    import ctypes as C
+    bufs = [C.create_string_buffer(f, len(f)) for f in files]  # jobs point at these: no per-job copies on the Python side
     for key, mode in (("host_inflate", 2), ("device_inflate", lrp.DECODE_ON_DEVICE)):
         sched = lrp.Scheduler([0], streams_per_device=args.threads)
-        done, lock, keep = [0, 0], threading.Lock(), []
+        done, lock = [0, 0], threading.Lock()
 
-        def sink(status, data):
+        def _done(user, status, ptr, n):  # the file bytes are valid during the call; a real sink would write them out
             with lock:
-                done[0] += len(data) if data else 0
+                done[0] += n
                 done[1] += 1 if status == 0 else 0
+
+        cb = lrp.FILE_DONE_FN(_done)
 
         def run(n):
             for i in range(n):
-                keep.append(sched.submit_file(files[i % 2], lrp.FILE_EXR, il, olens, W, H, lrp.FILE_EXR, p, sink, decode_threads=mode))
+                j = lrp.FileJob()
+                j.in_file, j.in_size, j.in_kind, j.out_kind = C.cast(bufs[i % 2], C.c_void_p), len(files[i % 2]), lrp.FILE_EXR, lrp.FILE_EXR
+                j.in_lens, j.out_lens, j.out_width, j.out_height = il, olens, W, H
+                j.params, j.decode_threads, j.on_done, j.user = p, mode, cb, None
+                lrp.check(lrp.lib().lrp_sched_submit_file(sched.h, C.byref(j)), "lrp_sched_submit_file")
             sched.wait_all()
 
         run(args.threads)  # warm-up: workspaces
-        del keep[:]
         done[0] = done[1] = 0
         t0 = time.perf_counter()
         run(args.frames)
