@@ -260,6 +260,20 @@ def test_exr_info_accepts_float_and_uint_channels(lrp):
         lrp.exr_info(data[:i] + b"\x03" + data[i + 1:])  # no such pixel type
 
 
+def test_exr_info_compression_ids(lrp):
+    """NONE 0, RLE 1, ZIPS 2, ZIP 3, PXR24 5 are decoded; PIZ 4, B44 6/7, DWA 8/9 are refused as unsupported"""
+    ch = typed_channels(20, 11, {"R": np.float16, "G": np.float16, "B": np.float16})
+    data = co.exr_write_typed(ch, "zip")
+    i = data.index(b"compression\0compression\0") + 24 + 4
+    assert data[i] == 3
+    for comp in (0, 1, 2, 3, 5):
+        assert lrp.exr_info(data[:i] + bytes([comp]) + data[i + 1:]) == (11, 20, 3)
+    for comp in (4, 6, 7, 8, 9, 200):
+        with pytest.raises(lrp.LrpError) as e:
+            lrp.exr_info(data[:i] + bytes([comp]) + data[i + 1:])
+        assert e.value.status == lrp.E_UNSUPPORTED_FORMAT
+
+
 # ---- PNG: every colour type / bit depth / interlace method through the host half of lrp_decoder_png ----
 
 def png_kinds():
