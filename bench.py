@@ -8,11 +8,17 @@ A "step" = one pass of the hot path over one batch of FRAMES_PER_STEP distinct s
 (one fused kernel launch per frame).  The batch's sources (8 x 134 MB) are much larger than the
 126 MB L2, so every launch reads its taps from HBM, not from a warm L2.
 
-  value  whole-job output Gpix/s with inputs resident in HBM (CUDA events, max over ranks)
+  value  whole-job output Gpix/s with inputs resident in HBM (CUDA events, max over ranks), library defaults: the
+         frames of a batch share their geometry, so from the second frame on the coordinates come from the context's
+         remap table (lrp_coords AUTO); `coords_legs` prints the forced on-the-fly and table figures next to it
   e2e    the same metric through the C ABI with HOST (pinned) buffers: H2D + kernel + D2H inside
-         the timed region (lrp_submit on the context's streams)
+         the timed region (lrp_submit: one engine thread per GPU, completion callbacks)
+  sched  rank 0 alone drives ALL N GPUs through the product's scheduler (lrp_sched_*): the c2 batch, a c4' batch
+         (3840x2160 RGBZ half frames) and the six c5 views, each next to its copy-only ceiling (same bytes through the
+         same slots, no kernel)
   roofline  achieved = algorithmic bytes per launch / average launch duration, against the measured
          HBM copy bandwidth of MEASURED_PEAKS.json
+  configs / interp_legs  the other BASELINE configurations and samplers, device-resident (N = 1 only)
   cpu_baseline  the reference's own CPU code (oracle/_ref, else the oracle port) on the host cores
 
 `--impl reference` times the reference's CPU implementation instead (same metric/config).
@@ -212,7 +218,7 @@ def run_reference_arm(args, rank, world):
     line = {"impl": "reference", "metric": "output_gpix_per_s", "value": value, "unit": "Gpix/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "interp": args.interp, "frames_per_step": T},
+            "config": shared_config(args.interp, args.gpus), "run": {"frames_per_step": T},
             "cpu_baseline": {"value": value, "unit": "Gpix/s", "cores": T, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -220,6 +226,147 @@ def run_reference_arm(args, rank, world):
 
 
 # ---- the GPU arm ----------------------------------------------------------------------------------------
+def shared_config(interp, n_gpus):
+    """`config` of BOTH arms (the driver compares them): the workload, nothing arm-specific."""
+    return {"workload": WORKLOAD, "interp": interp,
+            "l2": "inputs larger than L2: the GPU arm walks %d distinct 134 MB sources (%.2f GB) and %d distinct 33 MB "
+                  "sinks per step and GPU" % (FRAMES_PER_STEP, FRAMES_PER_STEP * SRC_W * SRC_H * 4 / 1e9, FRAMES_PER_STEP),
+            "parallelism": "images sharded over %d GPU(s), no collective" % n_gpus}
+
+
+def timed(torch, fn, reps, barrier):
+    """CUDA events on the current stream around `reps` calls of fn, barrier + synchronize on both sides -> ms"""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def device_leg(torch, lrp, ctx, name, interp, coords, variant, steps, barrier=None):
+    """Kernel-level timing of one BASELINE configuration with device-resident frames (B distinct frames per pass,
+    working set >> L2) -> dict(us, gpix_per_s, alg_gb_per_s)"""
+    from lrp import workloads as wl
+    il_k, (w, h), ol_k, (W, H), fmt, c, rotdeg, post, n_touched, B = wl.CONFIGS[name]
+    dev = torch.device("cuda", ctx.device)
+    il, olens = wl.lens(lrp, il_k, w, h), wl.lens(lrp, ol_k, W, H)
+    rot = None if rotdeg is None else lrp.rotation_from_degrees(*rotdeg)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    if fmt == "u8":
+        srcs = [torch.randint(0, 256, (h, w, 4), dtype=torch.uint8, device=dev, generator=g) for _ in range(B)]
+        dsts = [torch.empty((H, W, 4), dtype=torch.uint8, device=dev) for _ in range(B)]
+        f = lrp.FMT_U8_RGBA
+    else:
+        srcs = [torch.rand((c, h, w), device=dev, generator=g).to(torch.float16) for _ in range(B)]
+        dsts = [torch.empty((c, H, W), dtype=torch.float16, device=dev) for _ in range(B)]
+        f = lrp.FMT_F16_PLANAR
+    p = lrp.make_params(1, interp, rot, post, variant=variant, coords=coords, ext=lrp.EXT_FISHEYE_MODELS)
+
+    def step():
+        for s, d in zip(srcs, dsts):
+            ctx.reproject(s, il, f, d, olens, f, p)
+    for _ in range(3):
+        step()
+    sync = barrier or torch.cuda.synchronize
+    ms = timed(torch, step, steps, sync)
+    us = ms * 1e3 / (steps * B)
+    del srcs, dsts
+    torch.cuda.empty_cache()
+    return {"us": round(us, 2), "gpix_per_s": round(W * H / us / 1e3, 2), "alg_gb_per_s": round(wl.algorithmic_bytes(name) / us / 1e3, 1)}
+
+
+def sched_leg(lrp, sched, jobs, n_out_pixels, reps, ctxs_stats=None):
+    """jobs through lrp_sched_submit / wait_all, then the same jobs copy-only -> dict"""
+    def run():
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            for j in jobs:
+                sched.submit(j)
+        sched.wait_all()
+        return time.perf_counter() - t0
+    run()  # warm-up: slot buffers, footprints, remap tables
+    before = sched.stats()
+    dt = run()
+    after = sched.stats()
+    sched.copy_only(True)
+    run()
+    dt_copy = run()
+    sched.copy_only(False)
+    n = reps * len(jobs)
+    return {"frames_per_s": round(n / dt, 2), "gpix_per_s": round(n * n_out_pixels / dt / 1e9, 3),
+            "jobs": n, "jobs_per_device": [a - b for a, b in zip(after, before)],
+            "copy_ceiling_frames_per_s": round(n / dt_copy, 2),
+            "copy_ceiling_gpix_per_s": round(n * n_out_pixels / dt_copy / 1e9, 3), "of_ceiling": round(dt_copy / dt, 3)}
+
+
+def run_sched_legs(lrp, world, params_c2, quick):
+    """Rank 0 drives GPUs 0..world-1 through the product's multi-GPU scheduler (the replacement of the reference's
+    ctpl pool, src/main.cpp:536-657) with host pinned buffers: (a) the c2 batch of the e2e leg, (b) a c4' batch
+    (3840x2160 RGBZ half -> equidistant), (c) the six c5 views of one 16384x8192 RGB half panorama."""
+    from lrp import workloads as wl
+    out, handles = {}, []
+    streams = int(os.environ.get("LRP_BENCH_SCHED_STREAMS", "3"))
+    sched = lrp.Scheduler(list(range(world)), streams_per_device=streams)
+    rng = np.random.default_rng(7)
+
+    def pinned(shape, dtype, fill=True):
+        a, h = lrp.pinned_empty(shape, dtype)
+        handles.append(h)
+        if fill:
+            flat = a.reshape(-1).view(np.uint8)
+            block = rng.integers(0, 256, 1 << 22, dtype=np.uint8)  # a 4 MB random block repeated (fast to fill; frames differ by phase)
+            for o in range(0, flat.size, block.size):
+                n = min(block.size, flat.size - o)
+                flat[o:o + n] = block[:n]
+        return a
+
+    try:
+        # (a) c2: 8 sources, 8 sinks per GPU in flight
+        il, olens = lrp.lens_equirectangular(), lrp.lens_rectilinear(18.0, 36.0, OUT_W, OUT_H)
+        n_src = 4 if quick else 8
+        srcs = [pinned((SRC_H, SRC_W, 4), np.uint8) for _ in range(n_src)]
+        sinks = [pinned((OUT_H, OUT_W, 4), np.uint8, fill=False) for _ in range(max(8, 4 * world))]
+        jobs = [lrp.make_job(srcs[k % n_src].ctypes.data, il, SRC_W, SRC_H, 3, lrp.FMT_U8_RGBA, sinks[k].ctypes.data, olens,
+                             OUT_W, OUT_H, lrp.FMT_U8_RGBA, params_c2) for k in range(len(sinks))]
+        out["c2"] = sched_leg(lrp, sched, jobs, N_OUT, 4 if quick else 8)
+        out["c2"]["streams_per_device"] = streams
+        del srcs, sinks, jobs
+        # (b) c4': >= 256 frames of 3840x2160 RGBZ half (16 distinct pinned sources, one sink per job in flight)
+        il_k, (w, h), ol_k, (W, H), fmt, c, rotdeg, post, _, _ = wl.CONFIGS["c4t"]
+        il, olens = wl.lens(lrp, il_k, w, h), wl.lens(lrp, ol_k, W, H)
+        p4 = lrp.make_params(1, lrp.BICUBIC, None, None)
+        n_src = 4 if quick else 16
+        srcs = [pinned((c, h, w), np.uint16) for _ in range(n_src)]
+        for a in srcs:  # random bytes are not sane halves: keep the exponent below infinity / NaN
+            a &= 0x3BFF
+        sinks = [pinned((c, H, W), np.uint16, fill=False) for _ in range(max(8, 4 * world))]
+        jobs = [lrp.make_job(srcs[k % n_src].ctypes.data, il, w, h, c, lrp.FMT_F16_PLANAR, sinks[k].ctypes.data, olens, W, H,
+                             lrp.FMT_F16_PLANAR, p4) for k in range(len(sinks))]
+        reps = max(1, (32 if quick else 256) // len(jobs))
+        out["c4t"] = sched_leg(lrp, sched, jobs, W * H, reps)
+        del srcs, sinks, jobs
+        # (c) c5: six views of one panorama, the set repeated (a batch of panoramas)
+        il_k, (w, h), ol_k, (W, H), fmt, c, _, _, _, _ = wl.CONFIGS["c5e"]
+        il, olens = wl.lens(lrp, il_k, w, h), wl.lens(lrp, ol_k, W, H)
+        pano = pinned((c, h, w), np.uint16)
+        pano &= 0x3BFF
+        sinks = [pinned((c, H, W), np.uint16, fill=False) for _ in range(6)]
+        jobs = [lrp.make_job(pano.ctypes.data, il, w, h, c, lrp.FMT_F16_PLANAR, sinks[k].ctypes.data, olens, W, H,
+                             lrp.FMT_F16_PLANAR, lrp.make_params(1, lrp.BICUBIC, lrp.rotation_from_degrees(*wl.C5_VIEWS[k]), None))
+                for k in range(6)]
+        out["c5"] = sched_leg(lrp, sched, jobs, W * H, 2 if quick else 4)
+        out["c5"]["note"] = "one 16384x8192 RGB half panorama in pinned memory, six rect(18,36) 4096x4096 views per pass"
+    finally:
+        sched.close()
+        for hnd in handles:
+            lrp.free_pinned(hnd)
+    return out
+
+
 def run_gpu_arm(args, rank, world, local_rank):
     import torch
     import lrp
@@ -230,11 +377,12 @@ def run_gpu_arm(args, rank, world, local_rank):
     lrp.lib()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    dist = None
+    dist, host_group = None, None
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        host_group = dist.new_group(backend="gloo")  # a barrier that sleeps on a socket: used while rank 0 drives all GPUs
 
     def barrier():
         if dist is not None:
@@ -242,14 +390,15 @@ def run_gpu_arm(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     interp = INTERP[args.interp]
-    n_streams = int(os.environ.get("LRP_BENCH_STREAMS", "4"))  # worker streams of the e2e leg
+    n_streams = int(os.environ.get("LRP_BENCH_STREAMS", "3"))  # jobs in flight per GPU in the e2e leg
     ctx = lrp.Context(local_rank, n_streams)
     in_lens = lrp.lens_equirectangular()
     out_lens = lrp.lens_rectilinear(18.0, 36.0, OUT_W, OUT_H)
     rot = lrp.rotation_from_degrees(*ROTATION_DEG)
     variant = {"auto": lrp.VARIANT_AUTO, "gather": lrp.VARIANT_GATHER, "staged": lrp.VARIANT_STAGED}[args.variant]
     upload = {"auto": lrp.UPLOAD_AUTO, "full": lrp.UPLOAD_FULL}[args.upload]
-    params = lrp.make_params(1, interp, rot, None, variant=variant, upload=upload)
+    coords = {"auto": lrp.COORDS_AUTO, "fly": lrp.COORDS_FLY, "table": lrp.COORDS_TABLE}[args.coords]
+    params = lrp.make_params(1, interp, rot, None, variant=variant, upload=upload, coords=coords)
 
     B = FRAMES_PER_STEP
     g = torch.Generator(device=dev)
@@ -258,13 +407,16 @@ def run_gpu_arm(args, rank, world, local_rank):
         g.manual_seed(1234 + frame)
         srcs.append(torch.randint(0, 256, (SRC_H, SRC_W, 4), dtype=torch.uint8, device=dev, generator=g))
     dsts = [torch.empty((OUT_H, OUT_W, 4), dtype=torch.uint8, device=dev) for _ in range(B)]
-    remap = ctx.build_remap(in_lens, SRC_W, SRC_H, out_lens, OUT_W, OUT_H, params) if args.coords == "table" else None
 
-    def step():
-        for s, d in zip(srcs, dsts):
-            ctx.reproject(s, in_lens, lrp.FMT_U8_RGBA, d, out_lens, lrp.FMT_U8_RGBA, params, remap=remap)
+    def make_step(p):
+        def step():
+            for s, d in zip(srcs, dsts):
+                ctx.reproject(s, in_lens, lrp.FMT_U8_RGBA, d, out_lens, lrp.FMT_U8_RGBA, p)
+        return step
 
-    for _ in range(max(3, args.warmup)):
+    step = make_step(params)
+    warm = max(3, args.warmup)
+    for _ in range(warm):
         step()
     barrier()
     try:
@@ -284,30 +436,18 @@ def run_gpu_arm(args, rank, world, local_rank):
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     launches = args.steps * B
+    remap_tables = ctx.remap_stats()
 
-    # informational second leg: the same steps with the per-batch remap table (north-star item 3 asks for both);
-    # `value` above stays the on-the-fly figure unless --coords table was requested
-    alt = None
-    if args.coords == "fly":
-        table = ctx.build_remap(in_lens, SRC_W, SRC_H, out_lens, OUT_W, OUT_H, params)
-
-        def step_table():
-            for s, d in zip(srcs, dsts):
-                ctx.reproject(s, in_lens, lrp.FMT_U8_RGBA, d, out_lens, lrp.FMT_U8_RGBA, params, remap=table)
+    # ---- the same steps with the coordinate source forced (north-star item 3 asks for both figures) ----
+    leg_ms = {}
+    for name, cm in (("fly", lrp.COORDS_FLY), ("table", lrp.COORDS_TABLE)):
+        st = make_step(lrp.make_params(1, interp, rot, None, variant=variant, coords=cm))
         for _ in range(3):
-            step_table()
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(args.steps):
-            step_table()
-        a1.record()
-        barrier()
-        alt = a0.elapsed_time(a1)
-        del table
+            st()
+        leg_ms[name] = timed(torch, st, args.steps, barrier)
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_steps = max(1, args.e2e_steps)
     in_bytes, out_bytes = SRC_W * SRC_H * 4, OUT_W * OUT_H * 4
     hsrc, hdst, handles = [], [], []
     for k in range(B):
@@ -317,31 +457,82 @@ def run_gpu_arm(args, rank, world, local_rank):
         hsrc.append(a)
         hdst.append(o)
         handles += [ha, ho]
-    jobs = [lrp.make_job(a.ctypes.data, in_lens, SRC_W, SRC_H, 3, lrp.FMT_U8_RGBA, o.ctypes.data, out_lens, OUT_W,
-                         OUT_H, lrp.FMT_U8_RGBA, params) for a, o in zip(hsrc, hdst)]
 
-    def e2e_step():
-        for j in jobs:
-            ctx.submit(j)
-        ctx.wait_all()
+    def e2e_run(p, steps):
+        jobs = [lrp.make_job(a.ctypes.data, in_lens, SRC_W, SRC_H, 3, lrp.FMT_U8_RGBA, o.ctypes.data, out_lens, OUT_W,
+                             OUT_H, lrp.FMT_U8_RGBA, p) for a, o in zip(hsrc, hdst)]
 
-    e2e_step()  # warm-up: allocates the per-stream staging buffers, computes the geometry's source footprint
-    barrier()
-    moved0 = ctx.transfer_stats()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    moved1 = ctx.transfer_stats()
-    h2d_per_step = (moved1[0] - moved0[0]) // e2e_steps  # counted by the library from the copies it enqueued
-    d2h_per_step = (moved1[1] - moved0[1]) // e2e_steps
-    roi = ctx.source_footprint(in_lens, SRC_W, SRC_H, out_lens, OUT_W, OUT_H, params)
+        def one():
+            for j in jobs:
+                ctx.submit(j)
+            ctx.wait_all()
+        for _ in range(3):  # warm-up: per-slot staging buffers, the geometry's source footprint and remap table
+            one()
+        barrier()
+        moved0 = ctx.transfer_stats()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        moved1 = ctx.transfer_stats()
+        return dt, (moved1[0] - moved0[0]) // steps, (moved1[1] - moved0[1]) // steps
+
+    e2e_s, h2d_per_step, d2h_per_step = e2e_run(params, e2e_steps)
     e2e_ok = bool((torch.from_numpy(hdst[0]).to(dev) == dsts[0]).all().item())
+    roi = ctx.source_footprint(in_lens, SRC_W, SRC_H, out_lens, OUT_W, OUT_H, params)
+    full_s, full_h2d, _ = e2e_run(lrp.make_params(1, interp, rot, None, variant=variant, upload=lrp.UPLOAD_FULL, coords=coords),
+                                  max(1, e2e_steps // 4))
+    full_steps = max(1, e2e_steps // 4)
 
-    ms, e2e_ms, alt_ms = sharding.max_over_ranks([ms, e2e_s * 1e3, alt if alt is not None else 0.0], dist, dev)  # the slowest rank defines the job's time
-    launches_all, e2e_frames_all, h2d_all, d2h_all = sharding.sum_over_ranks(
-        [launches, e2e_steps * B, h2d_per_step, d2h_per_step], dist, dev)
+    red = sharding.max_over_ranks([ms, e2e_s * 1e3, leg_ms["fly"], leg_ms["table"], full_s * 1e3], dist, dev)
+    ms, e2e_ms, fly_ms, table_ms, full_ms = red  # the slowest rank defines the job's time
+    launches_all, e2e_frames_all, h2d_all, d2h_all, full_h2d_all = sharding.sum_over_ranks(
+        [launches, e2e_steps * B, h2d_per_step, d2h_per_step, full_h2d], dist, dev)
+
+    # ---- N = 1 extras on rank 0: the other samplers and the other BASELINE configurations, device resident ----
+    interp_legs, configs = None, None
+    if world == 1 and not args.quick:
+        interp_legs = {}
+        for nm in ("nn", "bl", "bc"):
+            if nm == args.interp:
+                continue
+            interp_legs[nm] = {}
+            for cn, cm in (("fly", lrp.COORDS_FLY), ("auto", lrp.COORDS_AUTO)):
+                st = make_step(lrp.make_params(1, INTERP[nm], rot, None, coords=cm))
+                for _ in range(3):
+                    st()
+                t = timed(torch, st, args.steps, barrier)
+                us = t * 1e3 / launches
+                interp_legs[nm][cn] = {"us": round(us, 2), "gpix_per_s": round(N_OUT / us / 1e3, 2),
+                                       "frac": round(algorithmic_bytes(nm) / us / 1e3 / measured_peak()[0], 4)}
+    del srcs
+    torch.cuda.empty_cache()
+    if world == 1 and not args.quick:
+        from lrp import workloads as wl
+        configs = {}
+        for name in ("c1t", "c3", "c4t", "c5e", "c5p"):
+            d = device_leg(torch, lrp, ctx, name, lrp.BICUBIC, lrp.COORDS_AUTO, lrp.VARIANT_AUTO, 5)
+            d["frac"] = round(d["alg_gb_per_s"] / measured_peak()[0], 4)
+            d["fly_us"] = device_leg(torch, lrp, ctx, name, lrp.BICUBIC, lrp.COORDS_FLY, lrp.VARIANT_AUTO, 5)["us"]
+            configs[name] = d
+
+    for hnd in handles:
+        lrp.free_pinned(hnd)
+    del hsrc, hdst, dsts
+    ctx.close()
+    torch.cuda.empty_cache()
+
+    # ---- the product's multi-GPU scheduler, driven by rank 0 alone; the other ranks sleep at a socket barrier ----
+    sched = None
+    if not args.no_sched:
+        if rank == 0:
+            try:
+                sched = run_sched_legs(lrp, world, params, args.quick)
+            except Exception as e:  # the headline line must still be printed
+                sched = {"error": repr(e)}
+        if host_group is not None:
+            dist.barrier(group=host_group)
 
     if rank == 0:
         value = sharding.whole_job_rate(launches_all * N_OUT, ms * 1e-3) / 1e9
@@ -350,51 +541,65 @@ def run_gpu_arm(args, rank, world, local_rank):
         per_launch_s = ms * 1e-3 / launches
         achieved = balg / per_launch_s / 1e9
         peak, peak_src = measured_peak()
+        table_used = remap_tables[0] > 0
+        kname = "lrp::%s<%s, %s, U8, 3>" % (
+            "reproject_kernel" if (args.variant == "gather" or (args.variant == "auto" and args.interp != "bc"))
+            else "reproject_staged_kernel", "COORD_TABLE_WRAP" if table_used else "COORD_ERECT_WRAP",
+            {"nn": "NEAREST", "bl": "BILINEAR", "bc": "BICUBIC"}[args.interp])
+        if args.interp == "nn" and table_used and args.variant != "staged":
+            kname = "lrp::nn_table_u8_kernel<identity>"
+
+        def leg(t_ms):
+            us = t_ms * 1e3 / launches
+            return {"us_per_launch": round(us, 2), "gpix_per_s": round(world * N_OUT / us / 1e3, 2),
+                    "frac": round(balg / us / 1e3 / peak, 4)}
+        cfg = shared_config(args.interp, world)
         line = {
             "metric": "output_gpix_per_s", "value": value, "unit": "Gpix/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "interp": args.interp, "variant": args.variant, "coords": args.coords,
-                       "frames_per_step": world * B, "frames_per_gpu": B,
-                       "l2": "inputs larger than L2: each step walks %d distinct 134 MB sources (%.2f GB) and "
-                             "%d distinct 33 MB sinks per GPU" % (B, B * in_bytes / 1e9, B),
-                       "parallelism": "images sharded over %d GPU(s), no collective" % world},
+            "config": cfg,
+            "run": {"variant": args.variant, "coords": args.coords, "frames_per_step": world * B, "frames_per_gpu": B,
+                    "coords_note": "auto = library default: a context computes a geometry's coordinates on the fly the first "
+                                   "time it meets it and keeps a remap table from the second frame on (bit-identical; "
+                                   "one run of the reference shares one geometry across its images)",
+                    "remap_tables_held": remap_tables[0], "remap_table_bytes": remap_tables[1]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(args.interp), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": balg, "us_per_launch": per_launch_s * 1e6,
-                         "kernel": "lrp::%s<%s, %s, U8, 3>" % (
-                             "reproject_kernel" if (args.variant == "gather" or (args.variant == "auto" and args.interp != "bc"))
-                             else "reproject_staged_kernel",
-                             "COORD_TABLE_WRAP" if args.coords == "table" else "COORD_ERECT_WRAP",
-                             {"nn": "NEAREST", "bl": "BILINEAR", "bc": "BICUBIC"}[args.interp])},
+                         "algorithmic_bytes_per_launch": balg, "us_per_launch": per_launch_s * 1e6, "kernel": kname},
+            "coords_legs": {"fly": leg(fly_ms), "table": leg(table_ms),
+                            "note": "the timed steps again with lrp_params.coords forced; table = +8 B (nearest: +4 B) per "
+                                    "output pixel of reads, kept in L2 across frames"},
             "e2e": {"value": e2e_value, "unit": "Gpix/s", "h2d_bytes_per_step": int(h2d_all),
-                    "d2h_bytes_per_step": int(d2h_all), "steps": e2e_steps, "matches_device_path": e2e_ok,
-                    "api": "lrp_submit/lrp_wait_all (C ABI, pinned host buffers, %d streams)" % n_streams,
+                    "d2h_bytes_per_step": int(d2h_all), "steps": e2e_steps, "warmup": 3, "matches_device_path": e2e_ok,
+                    "api": "lrp_submit/lrp_wait_all (C ABI, pinned host buffers, %d jobs in flight per GPU, one engine "
+                           "thread per GPU)" % n_streams,
                     "upload": args.upload, "source_bytes_per_step": world * B * in_bytes,
                     "source_footprint_xxyy": list(roi),
                     "note": "upload=auto copies only the bounding box of the source texels the geometry can touch "
                             "(lrp_source_footprint, cached per geometry); results are bit-identical to a full upload"},
-            "remap_table_variant": None if alt is None else {
-                "value": sharding.whole_job_rate(launches_all * N_OUT, alt_ms * 1e-3) / 1e9, "unit": "Gpix/s",
-                "us_per_launch": alt_ms * 1e3 / launches,
-                "note": "same steps with coordinates read from a table built once per batch (+8 B per output pixel of "
-                        "HBM reads, bit-identical results); not part of `value`"},
+            "e2e_full_upload": {"value": sharding.whole_job_rate(world * full_steps * B * N_OUT, full_ms * 1e-3) / 1e9,
+                                "unit": "Gpix/s", "h2d_bytes_per_step": int(full_h2d_all), "steps": full_steps,
+                                "note": "the same leg with lrp_params.upload = FULL: the whole 134 MB source crosses PCIe per frame"},
+            "sched": sched, "interp_legs": interp_legs, "configs": configs,
             "gpu_launches": int(launches_all), "clocks": clocks,
             "host_libm_fma": lrp.host_libm_uses_fma(),
         }
         if world == 1 and not args.no_cpu_baseline:
             T = max(1, min(host_threads(), 64))
-            v, dt, kind = cpu_reference_run(args.interp, T, T)
-            line["cpu_baseline"] = {"value": v, "unit": "Gpix/s", "cores": T, "kind": kind,
-                                    "sample": "%d frames of c2 (one per thread), %.1f s wall, float32 RGB source, "
-                                              "reproject() only (no codecs)" % (T, dt)}
+            reps = 0
+            t_all, kind = 0.0, "reference"
+            while t_all < 10.0 and reps < 16:  # ~10-30 s of CPU work
+                v, dt, kind = cpu_reference_run(args.interp, T, T)
+                t_all += dt
+                reps += 1
+            line["cpu_baseline"] = {"value": reps * T * N_OUT / t_all / 1e9, "unit": "Gpix/s", "cores": T, "kind": kind,
+                                    "sample": "%d x %d frames of c2 (one per thread), %.1f s wall, float32 RGB source, "
+                                              "reproject() only (no codecs)" % (reps, T, t_all)}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
 
-    for hnd in handles:
-        lrp.free_pinned(hnd)
-    ctx.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -408,12 +613,14 @@ def main():
     ap.add_argument("--interp", default="bc", choices=["nn", "bl", "bc"])
     ap.add_argument("--variant", default="auto", choices=["auto", "gather", "staged"],
                     help="source access: footprint staging in shared memory (auto = the library default) or per-tap gather")
-    ap.add_argument("--coords", default="fly", choices=["fly", "table"],
-                    help="source coordinates computed on the fly, or read from a per-batch remap table")
+    ap.add_argument("--coords", default="auto", choices=["auto", "fly", "table"],
+                    help="source coordinates: library default (table once a geometry repeats), always on the fly, always table")
     ap.add_argument("--upload", default="auto", choices=["auto", "full"],
                     help="e2e leg: upload the source footprint's bounding box (library default) or the whole source")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sched", action="store_true", help="skip the scheduler legs (rank 0 driving all GPUs)")
+    ap.add_argument("--quick", action="store_true", help="development runs: skip the N = 1 extras, short scheduler legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

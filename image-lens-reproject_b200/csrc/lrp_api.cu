@@ -43,6 +43,8 @@ int launch_footprint(const KParams &P, int coord, int interp, int wrap, void *st
 int launch_post_process(float *data, size_t n_pixels, int channels, float exposure, float reinhard, void *stream);
 int launch_libm(int fn, const float *a, const float *b, float *out, size_t n, int use_fma, void *stream);
 int launch_encode_u8(const float *in, unsigned char *out, size_t n, const float *thr, void *stream);
+int launch_nn_index(const KParams &P, int coord, void *stream);
+int launch_nn_table(const KParams &P, int fc, void *stream);
 
 static LaunchFn get_launcher(int coord, int interp, int fc, bool staged) {
   typedef LaunchFn (*Getter)(int);
@@ -231,6 +233,20 @@ struct lrp_ctx {
   cudaStream_t fp_stream = nullptr;
   int *d_bbox = nullptr, *h_bbox = nullptr;
   std::atomic<uint64_t> h2d_bytes{0}, d2h_bytes{0}; // moved by the host-buffer paths (lrp_ctx_transfer_stats)
+  // remap tables per geometry (lrp_coords): LRU over LRP_REMAP_CACHE_MB of device memory
+  struct RemapEntry {
+    void *table = nullptr;       // device: [ns*ns][H][W] float2 (kind 0) or [H][W] packed u16 x | u16 y << 16 (kind 1)
+    size_t bytes = 0;
+    cudaEvent_t ready = nullptr; // recorded behind the kernel that writes the table
+    cudaStream_t built_on = nullptr;
+    uint64_t last_use = 0;
+    int seen = 0;                // launches of this geometry so far
+  };
+  std::mutex remap_mu;
+  std::map<std::string, RemapEntry> remap_cache;
+  size_t remap_total = 0, remap_budget = (size_t)4096 << 20;
+  uint64_t remap_clock = 0;
+  std::atomic<uint64_t> remap_hits{0};
   // tile scheduler counters (lrp_kernel.cuh): one self-resetting {tickets, retired} pair per stream ever launched on —
   // launches of one stream run in order, so they can share a pair; launches of different streams may overlap
   static constexpr int SCHED_PAIRS = 1024;
@@ -325,6 +341,7 @@ int prepare(const lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const
   if (p->interpolation < 0 || p->interpolation > 2) return LRP_E_UNSUPPORTED_INTERP; // :364-366
   if (p->variant < LRP_VARIANT_AUTO || p->variant > LRP_VARIANT_STAGED) return LRP_E_BAD_ARG;
   if (p->upload < LRP_UPLOAD_AUTO || p->upload > LRP_UPLOAD_FULL) return LRP_E_BAD_ARG;
+  if (p->coords < LRP_COORDS_AUTO || p->coords > LRP_COORDS_TABLE) return LRP_E_BAD_ARG;
   if (need_data) {
     if (!in->data || !out->data) return LRP_E_BAD_ARG;
     if (in->channels != out->channels) return LRP_E_BAD_ARG; // reference: output.channels = input.channels
@@ -411,6 +428,137 @@ struct DeviceGuard {
   }
 };
 
+std::string geometry_key(const lrp_image *in, const lrp_image *out, const lrp_params *p, bool with_sampler = true) {
+  std::string k;
+  auto put = [&k](const void *d, size_t n) { k.append((const char *)d, n); };
+  put(&in->lens, sizeof(in->lens));
+  put(&in->width, 4);
+  put(&in->height, 4);
+  put(&out->lens, sizeof(out->lens));
+  put(&out->width, 4);
+  put(&out->height, 4);
+  put(&p->num_samples, 4);
+  if (with_sampler) put(&p->interpolation, 4);
+  const int32_t hr = p->has_rotation ? 1 : 0;
+  put(&hr, 4);
+  if (hr) put(p->rotation, sizeof(p->rotation));
+  return k;
+}
+
+// ---- remap tables (lrp_coords) ---------------------------------------------------------------------------
+// kind 0: float2 (sx, sy) per sub-sample and pixel — what every sampler can consume;
+// kind 1: the RESOLVED nearest tap (x | y << 16) per pixel — 4 B instead of 8 B for the one-tap sampler.
+enum { REMAP_F2 = 0, REMAP_NN = 1 };
+
+// Hands out the geometry's table for a launch on `stream` (building it there when this launch is the one that
+// crosses the policy's threshold), or nullptr: compute on the fly.  Tables are written by the same device functions
+// the on-the-fly kernels run (coords_kernel / nn_index_kernel), so the results cannot differ.
+const void *acquire_remap(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const lrp_params *p, const KParams &K,
+                          int coord, int kind, cudaStream_t stream) {
+  int mode = p->coords;
+  if (const char *e = getenv("LRP_COORDS")) { // A/B switch for unmodified callers: fly | table | auto
+    if (mode == LRP_COORDS_AUTO) mode = e[0] == 'f' ? LRP_COORDS_FLY : e[0] == 't' ? LRP_COORDS_TABLE : LRP_COORDS_AUTO;
+  }
+  if (mode == LRP_COORDS_FLY) return nullptr;
+  const size_t px = (size_t)K.W * (size_t)K.H;
+  const size_t bytes = kind == REMAP_NN ? px * 4 : px * (size_t)K.ns * (size_t)K.ns * 8;
+  std::string key = geometry_key(in, out, p, false);
+  key.push_back((char)kind);
+  if (kind == REMAP_NN) key.push_back((char)(coord == COORD_ERECT_WRAP)); // resolved indices depend on the wrap
+  std::lock_guard<std::mutex> lk(ctx->remap_mu);
+  if (const char *mb = getenv("LRP_REMAP_CACHE_MB")) ctx->remap_budget = (size_t)atoll(mb) << 20;
+  lrp_ctx::RemapEntry &e = ctx->remap_cache[key];
+  e.seen++;
+  e.last_use = ++ctx->remap_clock;
+  if (e.table) {
+    if (e.built_on != stream && cudaStreamWaitEvent(stream, e.ready, 0) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    ctx->remap_hits++;
+    return e.table;
+  }
+  // AUTO: the second launch of a geometry pays for the table (one extra pass of the coordinate kernel), every later
+  // one reads it.  A single image (the reference's --single) never builds one.
+  if (mode == LRP_COORDS_AUTO && e.seen < 2) return nullptr;
+  if (bytes > ctx->remap_budget) return nullptr;
+  while (ctx->remap_total + bytes > ctx->remap_budget) { // evict the least recently used table
+    auto victim = ctx->remap_cache.end();
+    for (auto it = ctx->remap_cache.begin(); it != ctx->remap_cache.end(); ++it)
+      if (it->second.table && &it->second != &e && (victim == ctx->remap_cache.end() || it->second.last_use < victim->second.last_use))
+        victim = it;
+    if (victim == ctx->remap_cache.end()) return nullptr;
+    cudaFree(victim->second.table); // waits for the launches that still read it
+    cudaEventDestroy(victim->second.ready);
+    ctx->remap_total -= victim->second.bytes;
+    ctx->remap_cache.erase(victim);
+  }
+  void *tab = nullptr;
+  if (cudaMalloc(&tab, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  cudaEvent_t ev = nullptr;
+  KParams B = K;
+  int rc;
+  if (kind == REMAP_NN) {
+    B.nn_index_out = (unsigned *)tab;
+    rc = launch_nn_index(B, coord, stream);
+  } else {
+    B.coords_out = (float2 *)tab;
+    B.coords_planes = K.ns * K.ns;
+    rc = launch_coords(B, coord == COORD_ERECT_WRAP ? COORD_ERECT_CLAMP : coord, stream);
+  }
+  if (rc != 0 || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventRecord(ev, stream) != cudaSuccess) {
+    cudaGetLastError();
+    if (ev) cudaEventDestroy(ev);
+    cudaFree(tab);
+    return nullptr;
+  }
+  e.table = tab;
+  e.bytes = bytes;
+  e.ready = ev;
+  e.built_on = stream;
+  ctx->remap_total += bytes;
+  ctx->remap_hits++;
+  return tab;
+}
+
+void remap_cache_clear(lrp_ctx *ctx) {
+  std::lock_guard<std::mutex> lk(ctx->remap_mu);
+  for (auto &kv : ctx->remap_cache)
+    if (kv.second.table) {
+      cudaFree(kv.second.table);
+      cudaEventDestroy(kv.second.ready);
+    }
+  ctx->remap_cache.clear();
+  ctx->remap_total = 0;
+}
+
+// The whole per-sample function of an 8-bit source behind an 8-bit sink with one tap per pixel is a map from the
+// source byte to the sink byte:  encode_u8(post_process(0.0f + lut[p]) * 1.0f)  (reference src/image_formats.cpp:195-197,
+// src/reproject.cpp:334-341, 428-431, src/image_formats.cpp:156-158).  256 values, evaluated here with the host's own
+// powf — the same arithmetic, operation by operation, the kernels' generic tail performs per pixel.
+void build_composite_table(const HostTables &T, const KParams &K, unsigned char *ctab, int *identity) {
+  bool ident = true;
+  for (int v = 0; v < 256; ++v) {
+    volatile float s = 0.0f + T.lut[v]; // acc = 0 + sample (:334-336)
+    s = s * K.normalize;                // ns == 1: * 1.0f (:338-341)
+    if (K.post) {                       // post_process, :428-431
+      volatile float e = s * K.exposure;
+      volatile float q = e / K.r2;
+      volatile float n = e * (1.0f + q);
+      s = n / (1.0f + e);
+    }
+    float c = s;
+    c = (c != c) ? 1.0f : (c < 0.0f ? 0.0f : (c > 1.0f ? 1.0f : c)); // std::max(0, std::min(1, s)), NaN -> 1
+    ctab[v] = gamma_q(c);
+    ident = ident && ctab[v] == v;
+  }
+  *identity = ident ? 1 : 0;
+}
+
 // `win` (host-buffer paths): in->data holds only the texels of that region of the source, rows of win->width()
 // texels (planes of width x height for planar formats).  The kernels keep addressing texel (x, y) of the whole
 // image: the source pointer is moved to where texel (0, 0) would be and the row pitch becomes the region's width.
@@ -427,10 +575,6 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
     K.src_plane = (long long)win->width() * win->height();
     K.src = (const char *)in->data - ((size_t)win->y0 * K.src_pitch + (size_t)win->x0) * K.src_px_bytes;
   }
-  if (remap) {
-    K.remap = (const float2 *)remap;
-    coord = (coord == COORD_ERECT_WRAP) ? COORD_TABLE_WRAP : COORD_TABLE_CLAMP;
-  }
   {
     const char *ss = getenv("LRP_STATIC_TILES"); // A/B switch: static tile stride instead of the ticket counter
     K.sched = (ss && ss[0] == '1') ? nullptr : ctx->sched_for(stream);
@@ -439,32 +583,37 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
   const char *force = getenv("LRP_FORCE_VARIANT"); // A/B runs of unmodified callers: "gather" | "staged"
   int variant = p->variant;
   if (force && variant == LRP_VARIANT_AUTO) variant = force[0] == 'g' ? LRP_VARIANT_GATHER : LRP_VARIANT_STAGED;
+
+  // ---- nearest, one sample per pixel, codec-native 8-bit in and out: the byte-map path (lrp_nearest.cu) ----
+  const bool nn1 = p->interpolation == LRP_NEAREST && p->num_samples == 1 && variant != LRP_VARIANT_STAGED;
+  const char *no_nn = getenv("LRP_NO_NN_FAST"); // A/B switch: nearest through the generic float tail
+  const bool nn_fast = nn1 && !(no_nn && no_nn[0] == '1');
+  if (nn_fast && in->format == LRP_FMT_U8_RGBA && out->format == LRP_FMT_U8_RGBA) {
+    build_composite_table(host_tables(), K, K.ctab, &K.ctab_identity);
+    K.nn_composite = 1;
+  }
+  const bool nn_copy = nn_fast && !K.post && in->format == out->format && in->format != LRP_FMT_U8_RGBA; // pure texel copy
+  if (!remap && (K.nn_composite || nn_copy) && K.w <= 65536 && K.h <= 65536 && ((uintptr_t)out->data & 31) == 0) {
+    if (const void *idx = acquire_remap(ctx, in, out, p, K, coord, REMAP_NN, stream)) {
+      K.nn_index = (const unsigned *)idx;
+      return map_cuda((cudaError_t)launch_nn_table(K, fc, stream));
+    }
+  }
+  if (!remap) remap = acquire_remap(ctx, in, out, p, K, coord, REMAP_F2, stream);
+  if (remap) {
+    K.remap = (const float2 *)remap;
+    coord = (coord == COORD_ERECT_WRAP) ? COORD_TABLE_WRAP : COORD_TABLE_CLAMP;
+  }
   // AUTO follows the measurements (profiles/r1_bench_configs_s6*.jsonl): footprint staging pays for the 16 taps of
   // bicubic on every config (c2 185 vs 209 us, c4t 249 vs 340 us); the 1 / 4 taps of nearest / bilinear are cheaper
   // gathered through L1 (c2 nn 107 vs 179 us, bl 124 vs 139 us; c3 bl 137 vs 235 us)
   const bool want_staged = (variant == LRP_VARIANT_STAGED) ||
                            (variant == LRP_VARIANT_AUTO && p->interpolation == LRP_BICUBIC);
   const bool staged = want_staged && p->num_samples == 1;
+  if (staged) K.nn_composite = 0; // the staged sampler keeps the float tail
   LaunchFn fn = get_launcher(coord, p->interpolation, fc, staged);
   if (!fn) return LRP_E_UNSUPPORTED_FORMAT;
   return map_cuda((cudaError_t)fn(K, stream));
-}
-
-std::string geometry_key(const lrp_image *in, const lrp_image *out, const lrp_params *p) {
-  std::string k;
-  auto put = [&k](const void *d, size_t n) { k.append((const char *)d, n); };
-  put(&in->lens, sizeof(in->lens));
-  put(&in->width, 4);
-  put(&in->height, 4);
-  put(&out->lens, sizeof(out->lens));
-  put(&out->width, 4);
-  put(&out->height, 4);
-  put(&p->num_samples, 4);
-  put(&p->interpolation, 4);
-  const int32_t hr = p->has_rotation ? 1 : 0;
-  put(&hr, 4);
-  if (hr) put(p->rotation, sizeof(p->rotation));
-  return k;
 }
 
 // lrp_source_footprint: cached per geometry; the first request of a geometry runs the footprint kernel
@@ -547,59 +696,185 @@ int upload_source(lrp_ctx *ctx, Slot &slot, const lrp_image *in, const lrp_image
 
 } // namespace
 
-// ---- asynchronous worker pool (also the multi-GPU scheduler) ---------------------------------
-
+// ---- asynchronous job engine + file-job workers (also the multi-GPU scheduler) ----------------------------
+//
+// Replaces ctpl::thread_pool + pool.push + pool.stop(true) (reference src/main.cpp:538-541, 657).
+//
+// Pixel jobs (lrp_job: host buffers in, host buffers out) never block a host thread per job: ONE engine thread per GPU
+// takes jobs from the scheduler's queue whenever one of its S slots (stream + device buffers) is free, enqueues
+// H2D -> fused kernel -> D2H -> completion callback on the slot's stream and goes back to sleep; the callback
+// (cudaLaunchHostFunc, run by the driver behind the D2H) marks the slot done and wakes the engine, which reaps it (user
+// callback, statistics) and refills it.  S jobs per GPU are in flight, so uploads, kernels and downloads of
+// neighbouring jobs overlap on the copy engines, and an 8-GPU box runs 8 sleeping threads instead of 8 x S pollers.
+//
+// File jobs (lrp_file_job: decode -> kernel -> encode) keep host work in the loop (inflate of the input on host
+// cores, container assembly), so they run on worker threads: `workers` per GPU, started by the first file job.
 struct Pool {
   struct Item {
     lrp_job job;
-    uint64_t ticket;
+    uint64_t ticket = 0;
+    bool tracked = false; // lrp_submit handed the ticket out: its status waits in `done` for lrp_wait
     bool is_file = false;
     lrp_file_job fjob;
   };
-  struct Worker {
+  struct Engine;
+  struct JobSlot {
+    Slot slot;
+    Engine *eng = nullptr;
+    int index = 0;
+    bool busy = false;
+    Item item;
+    size_t out_bytes = 0;
+  };
+  struct Engine {
+    Pool *pool = nullptr;
+    lrp_ctx *ctx = nullptr;
+    int dev_index = 0;
+    std::thread th;
+    std::condition_variable cv; // new work for this engine, or one of its slots completed
+    std::vector<JobSlot *> slots;
+    std::deque<int> completed;  // slot indices, pushed by the stream callbacks
+    int busy = 0;
+  };
+  struct Worker { // file jobs
     lrp_ctx *ctx;
     Slot slot;
     std::thread th;
     int dev_index; // index into the pool's ctx list
-    // file jobs: codecs with grow-only workspaces, created on first use
+    // codecs with grow-only workspaces, created on first use, rebuilt when a job exceeds them in either dimension
     lrp_decoder *dec = nullptr;
     lrp_encoder *enc = nullptr;
-    size_t dec_px = 0, enc_px = 0;
-    int dec_c = 0, enc_c = 0;
+    int dec_w = 0, dec_h = 0, dec_c = 0, enc_w = 0, enc_h = 0, enc_c = 0;
   };
   std::vector<lrp_ctx *> ctxs;
+  std::vector<Engine *> engines;
   std::vector<Worker *> workers;
-  std::deque<Item> queue;
-  std::map<uint64_t, int> done; // ticket -> status
+  int workers_per_ctx = 1;
+  bool workers_started = false;
+  std::deque<Item> queue;  // pixel jobs
+  std::deque<Item> fqueue; // file jobs
+  std::map<uint64_t, int> done; // tracked tickets -> status, until lrp_wait / lrp_wait_all collects them
   std::vector<int64_t> per_device;
   std::mutex mu;
-  std::condition_variable cv_work, cv_done;
+  std::condition_variable cv_file, cv_done;
   uint64_t next_ticket = 1;
   uint64_t in_flight = 0;
   int first_error = LRP_OK;
   bool stopping = false;
+  bool copy_only = false; // lrp_sched_debug_copy_only: the same traffic without the kernel (the copy ceiling)
 
-  static int run_job(Worker *w, const lrp_job &job) {
-    lrp_ctx *ctx = w->ctx;
-    LRP_CUDA(cudaSetDevice(ctx->phys_device));
+  // ---- pixel jobs: enqueue on a slot's stream, no waiting ----
+  static void CUDART_CB on_stream_done(void *p) {
+    JobSlot *js = (JobSlot *)p;
+    Engine *e = js->eng;
+    {
+      std::lock_guard<std::mutex> lk(e->pool->mu);
+      e->completed.push_back(js->index);
+    }
+    e->cv.notify_one();
+  }
+
+  int enqueue_job(JobSlot *js) {
+    lrp_ctx *ctx = js->eng->ctx;
+    const lrp_job &job = js->item.job;
     const size_t in_bytes = lrp_image_bytes(&job.in), out_bytes = lrp_image_bytes(&job.out);
     if (!in_bytes || !out_bytes || !job.in.data || !job.out.data) return LRP_E_BAD_ARG;
+    { // validate before anything is enqueued, so that errors mirror the reference's early exits
+      KParams K;
+      int coord, fc;
+      int rc = prepare(ctx, &job.in, &job.out, &job.params, true, K, coord, fc);
+      if (rc != LRP_OK) return rc;
+    }
     Roi win;
     bool use_win = false;
     size_t h2d = 0;
-    int rc = upload_source(ctx, w->slot, &job.in, &job.out, &job.params, out_bytes, win, use_win, &h2d);
+    int rc = upload_source(ctx, js->slot, &job.in, &job.out, &job.params, out_bytes, win, use_win, &h2d);
     if (rc != LRP_OK) return rc;
-    ctx->h2d_bytes += h2d;
     lrp_image din = job.in, dout = job.out;
-    din.data = w->slot.d_in;
-    dout.data = w->slot.d_out;
-    rc = launch_fused(ctx, &din, &dout, &job.params, nullptr, w->slot.stream, use_win ? &win : nullptr);
-    if (rc != LRP_OK) return rc;
-    LRP_CUDA(cudaMemcpyAsync(job.out.data, w->slot.d_out, out_bytes, cudaMemcpyDeviceToHost, w->slot.stream));
-    rc = slot_wait(w->slot);
-    if (rc != LRP_OK) return rc;
-    ctx->d2h_bytes += out_bytes;
+    din.data = js->slot.d_in;
+    dout.data = js->slot.d_out;
+    if (!copy_only) {
+      rc = launch_fused(ctx, &din, &dout, &job.params, nullptr, js->slot.stream, use_win ? &win : nullptr);
+      if (rc != LRP_OK) return rc;
+    }
+    LRP_CUDA(cudaMemcpyAsync(job.out.data, js->slot.d_out, out_bytes, cudaMemcpyDeviceToHost, js->slot.stream));
+    LRP_CUDA(cudaLaunchHostFunc(js->slot.stream, on_stream_done, js));
+    ctx->h2d_bytes += h2d;
+    js->out_bytes = out_bytes;
     return LRP_OK;
+  }
+
+  void finish(Engine *e, const Item &it, int rc) { // engine thread, `mu` not held
+    if (it.job.on_done) it.job.on_done(it.job.user, rc);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (it.tracked) done[it.ticket] = rc;
+      per_device[e->dev_index]++;
+      if (rc != LRP_OK && first_error == LRP_OK) first_error = rc;
+      in_flight--;
+    }
+    cv_done.notify_all();
+  }
+
+  void engine_main(Engine *e) {
+    cudaSetDevice(e->ctx->phys_device);
+    std::unique_lock<std::mutex> lk(mu);
+    for (;;) {
+      if (!e->completed.empty()) { // reap: the slot's stream has run its D2H
+        JobSlot *js = e->slots[e->completed.front()];
+        e->completed.pop_front();
+        lk.unlock();
+        int rc = map_cuda(cudaStreamQuery(js->slot.stream)); // surfaces an asynchronous error of the job's work
+        if (rc == LRP_OK) e->ctx->d2h_bytes += js->out_bytes;
+        finish(e, js->item, rc);
+        lk.lock();
+        js->busy = false;
+        e->busy--;
+        continue;
+      }
+      // level filling: the least loaded GPU takes the next job (6 views on 8 GPUs land on 6 GPUs, not on the
+      // first one's S slots); whoever takes one passes the word on while jobs remain
+      if (e->busy < (int)e->slots.size() && !queue.empty() && e->busy <= min_busy_locked()) {
+        JobSlot *js = nullptr;
+        for (JobSlot *c : e->slots)
+          if (!c->busy) {
+            js = c;
+            break;
+          }
+        js->item = queue.front();
+        queue.pop_front();
+        js->busy = true;
+        e->busy++;
+        const bool more = !queue.empty();
+        lk.unlock();
+        if (more) wake_engines(e);
+        int rc = enqueue_job(js);
+        if (rc != LRP_OK) { // nothing (or only part) of the job is on the stream: drain it and report
+          cudaStreamSynchronize(js->slot.stream);
+          cudaGetLastError();
+          finish(e, js->item, rc);
+          lk.lock();
+          js->busy = false;
+          e->busy--;
+          continue;
+        }
+        lk.lock();
+        continue;
+      }
+      if (stopping && queue.empty() && e->busy == 0) return;
+      e->cv.wait(lk);
+    }
+  }
+
+  int min_busy_locked() const { // over the engines that could take a job
+    int m = 1 << 30;
+    for (const Engine *o : engines)
+      if (o->busy < (int)o->slots.size() && o->busy < m) m = o->busy;
+    return m;
+  }
+  void wake_engines(const Engine *except) {
+    for (Engine *o : engines)
+      if (o != except) o->cv.notify_one();
   }
 
   // One iteration of the reference's worker lambda (src/main.cpp:541-620) from file bytes to file bytes:
@@ -615,19 +890,28 @@ struct Pool {
     if (j.out_kind != LRP_FILE_PNG && j.out_kind != LRP_FILE_EXR) return LRP_E_BAD_ARG;
     if (j.out_kind == LRP_FILE_PNG && ic > 4) return LRP_E_UNSUPPORTED_FORMAT; // save_png overruns its buffer (UB): refused
     const size_t ipx = (size_t)iw * ih, opx = (size_t)j.out_width * j.out_height;
-    if (!w->dec || ipx > w->dec_px || ic > w->dec_c) {
+    // the codecs size some workspaces per dimension (blocks per height, streams per 16 rows), so a job that is taller
+    // OR wider OR deeper than anything seen rebuilds them for the per-dimension maxima
+    if (!w->dec || iw > w->dec_w || ih > w->dec_h || ic > w->dec_c) {
       if (w->dec) lrp_decoder_destroy(w->dec);
       w->dec = nullptr;
-      rc = lrp_decoder_create(ctx, iw, ih, std::max(ic, 4), &w->dec);
-      if (rc != LRP_OK) return rc;
-      w->dec_px = ipx, w->dec_c = std::max(ic, 4);
+      w->dec_w = std::max(w->dec_w, iw), w->dec_h = std::max(w->dec_h, ih), w->dec_c = std::max(w->dec_c, std::max(ic, 4));
+      rc = lrp_decoder_create(ctx, w->dec_w, w->dec_h, w->dec_c, &w->dec);
+      if (rc != LRP_OK) {
+        w->dec_w = w->dec_h = w->dec_c = 0;
+        return rc;
+      }
     }
-    if (!w->enc || opx > w->enc_px || ic > w->enc_c) {
+    if (!w->enc || j.out_width > w->enc_w || j.out_height > w->enc_h || ic > w->enc_c) {
       if (w->enc) lrp_encoder_destroy(w->enc);
       w->enc = nullptr;
-      rc = lrp_encoder_create(ctx, j.out_width, j.out_height, std::max(ic, 4), &w->enc);
-      if (rc != LRP_OK) return rc;
-      w->enc_px = opx, w->enc_c = std::max(ic, 4);
+      w->enc_w = std::max(w->enc_w, j.out_width), w->enc_h = std::max(w->enc_h, j.out_height);
+      w->enc_c = std::max(w->enc_c, std::max(ic, 4));
+      rc = lrp_encoder_create(ctx, w->enc_w, w->enc_h, w->enc_c, &w->enc);
+      if (rc != LRP_OK) {
+        w->enc_w = w->enc_h = w->enc_c = 0;
+        return rc;
+      }
     }
     const bool in_png = j.in_kind == LRP_FILE_PNG, out_png = j.out_kind == LRP_FILE_PNG;
     rc = slot_reserve(w->slot, in_png ? ipx * 4 : ipx * 2 * ic, out_png ? opx * 4 : opx * 2 * ic);
@@ -657,28 +941,26 @@ struct Pool {
 
   void worker_main(Worker *w) {
     cudaSetDevice(w->ctx->phys_device);
+    const bool have_stream = cudaStreamCreateWithFlags(&w->slot.stream, cudaStreamNonBlocking) == cudaSuccess;
     for (;;) {
       Item it;
       {
         std::unique_lock<std::mutex> lk(mu);
-        cv_work.wait(lk, [&] { return stopping || !queue.empty(); });
-        if (queue.empty()) return; // stopping and drained
-        it = queue.front();
-        queue.pop_front();
+        cv_file.wait(lk, [&] { return stopping || !fqueue.empty(); });
+        if (fqueue.empty()) return; // stopping and drained
+        it = fqueue.front();
+        fqueue.pop_front();
       }
-      int rc;
-      if (it.is_file) {
-        const void *bytes = nullptr;
-        size_t size = 0;
-        rc = run_file_job(w, it.fjob, &bytes, &size);
-        if (it.fjob.on_done) it.fjob.on_done(it.fjob.user, rc, rc == LRP_OK ? bytes : nullptr, rc == LRP_OK ? size : 0);
-      } else {
-        rc = run_job(w, it.job);
-        if (it.job.on_done) it.job.on_done(it.job.user, rc);
+      const void *bytes = nullptr;
+      size_t size = 0;
+      int rc = have_stream ? run_file_job(w, it.fjob, &bytes, &size) : LRP_E_CUDA;
+      if (rc != LRP_OK && have_stream) { // work may still be queued on the stream behind the failing call
+        cudaStreamSynchronize(w->slot.stream);
+        cudaGetLastError();
       }
+      if (it.fjob.on_done) it.fjob.on_done(it.fjob.user, rc, rc == LRP_OK ? bytes : nullptr, rc == LRP_OK ? size : 0);
       {
         std::lock_guard<std::mutex> lk(mu);
-        done[it.ticket] = rc;
         per_device[w->dev_index]++;
         if (rc != LRP_OK && first_error == LRP_OK) first_error = rc;
         in_flight--;
@@ -687,51 +969,92 @@ struct Pool {
     }
   }
 
-  int start(const std::vector<lrp_ctx *> &cs, int workers_per_ctx) {
+  int start(const std::vector<lrp_ctx *> &cs, int slots_per_ctx) {
     ctxs = cs;
+    workers_per_ctx = slots_per_ctx;
     per_device.assign(cs.size(), 0);
-    for (size_t d = 0; d < cs.size(); ++d)
+    for (size_t d = 0; d < cs.size(); ++d) {
+      Engine *e = new Engine();
+      e->pool = this, e->ctx = cs[d], e->dev_index = (int)d;
+      engines.push_back(e);
+      LRP_CUDA(cudaSetDevice(cs[d]->phys_device));
+      for (int k = 0; k < slots_per_ctx; ++k) {
+        JobSlot *js = new JobSlot();
+        js->eng = e, js->index = k;
+        e->slots.push_back(js);
+        LRP_CUDA(cudaStreamCreateWithFlags(&js->slot.stream, cudaStreamNonBlocking));
+      }
+    }
+    for (Engine *e : engines) e->th = std::thread([this, e] { engine_main(e); });
+    return LRP_OK;
+  }
+
+  int start_workers_locked() { // `mu` held
+    if (workers_started) return LRP_OK;
+    workers_started = true;
+    for (size_t d = 0; d < ctxs.size(); ++d)
       for (int k = 0; k < workers_per_ctx; ++k) {
         Worker *w = new Worker();
-        w->ctx = cs[d];
+        w->ctx = ctxs[d];
         w->dev_index = (int)d;
-        LRP_CUDA(cudaSetDevice(cs[d]->phys_device));
-        LRP_CUDA(cudaStreamCreateWithFlags(&w->slot.stream, cudaStreamNonBlocking));
         workers.push_back(w);
       }
     for (Worker *w : workers) w->th = std::thread([this, w] { worker_main(w); });
     return LRP_OK;
   }
 
-  uint64_t submit(const lrp_job &job) {
-    std::lock_guard<std::mutex> lk(mu);
-    uint64_t t = next_ticket++;
-    Item it;
-    it.job = job, it.ticket = t;
-    queue.push_back(it);
-    in_flight++;
-    cv_work.notify_one();
+  uint64_t submit(const lrp_job &job, bool tracked) {
+    uint64_t t;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      t = next_ticket++;
+      Item it;
+      it.job = job, it.ticket = t, it.tracked = tracked;
+      memset(&it.fjob, 0, sizeof(it.fjob));
+      queue.push_back(it);
+      in_flight++;
+    }
+    wake_engines(nullptr); // the least loaded one takes it (engine_main)
     return t;
   }
-  uint64_t submit_file(const lrp_file_job &job) {
-    std::lock_guard<std::mutex> lk(mu);
-    uint64_t t = next_ticket++;
-    Item it;
-    memset(&it.job, 0, sizeof(it.job));
-    it.ticket = t, it.is_file = true, it.fjob = job;
-    queue.push_back(it);
-    in_flight++;
-    cv_work.notify_one();
-    return t;
+  int submit_file(const lrp_file_job &job) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      int rc = start_workers_locked();
+      if (rc != LRP_OK) return rc;
+      Item it;
+      memset(&it.job, 0, sizeof(it.job));
+      it.ticket = next_ticket++, it.is_file = true, it.fjob = job;
+      fqueue.push_back(it);
+      in_flight++;
+    }
+    cv_file.notify_one();
+    return LRP_OK;
   }
 
   int wait(uint64_t ticket) {
     std::unique_lock<std::mutex> lk(mu);
     if (ticket == 0 || ticket >= next_ticket) return LRP_E_BAD_ARG;
-    cv_done.wait(lk, [&] { return done.count(ticket) != 0; });
-    int rc = done[ticket];
-    done.erase(ticket);
-    return rc;
+    // a ticket is either still on its way (in_flight > 0 and it will land in `done`) or was collected before: the
+    // latter can never complete again, so it is an error rather than a wait forever
+    for (;;) {
+      auto it = done.find(ticket);
+      if (it != done.end()) {
+        int rc = it->second;
+        done.erase(it);
+        return rc;
+      }
+      if (!ticket_pending_locked(ticket)) return LRP_E_BAD_ARG;
+      cv_done.wait(lk);
+    }
+  }
+  bool ticket_pending_locked(uint64_t ticket) {
+    for (const Item &it : queue)
+      if (it.ticket == ticket) return true;
+    for (Engine *e : engines)
+      for (JobSlot *js : e->slots)
+        if (js->busy && js->item.ticket == ticket) return true;
+    return false;
   }
 
   int wait_all() {
@@ -748,7 +1071,18 @@ struct Pool {
       std::lock_guard<std::mutex> lk(mu);
       stopping = true;
     }
-    cv_work.notify_all();
+    cv_file.notify_all();
+    for (Engine *e : engines) e->cv.notify_all();
+    for (Engine *e : engines) {
+      if (e->th.joinable()) e->th.join();
+      cudaSetDevice(e->ctx->phys_device);
+      for (JobSlot *js : e->slots) {
+        slot_destroy(js->slot);
+        delete js;
+      }
+      delete e;
+    }
+    engines.clear();
     for (Worker *w : workers) {
       if (w->th.joinable()) w->th.join();
       cudaSetDevice(w->ctx->phys_device);
@@ -927,6 +1261,7 @@ int lrp_ctx_destroy(lrp_ctx *c) {
     delete c->pool;
   }
   cudaSetDevice(c->phys_device);
+  remap_cache_clear(c);
   for (auto s : c->streams) cudaStreamDestroy(s);
   for (auto &s : c->slots) slot_destroy(s);
   if (c->d_lut) cudaFree(c->d_lut);
@@ -996,6 +1331,18 @@ int lrp_source_footprint(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out
   roi[1] = r.x1;
   roi[2] = r.y0;
   roi[3] = r.y1;
+  return LRP_OK;
+}
+
+int lrp_ctx_remap_stats(const lrp_ctx *ctx, int32_t *tables, uint64_t *bytes, uint64_t *hits) {
+  if (!ctx) return LRP_E_BAD_ARG;
+  lrp_ctx *c = const_cast<lrp_ctx *>(ctx);
+  std::lock_guard<std::mutex> lk(c->remap_mu);
+  int32_t n = 0;
+  for (auto &kv : c->remap_cache) n += kv.second.table ? 1 : 0;
+  if (tables) *tables = n;
+  if (bytes) *bytes = c->remap_total;
+  if (hits) *hits = c->remap_hits.load();
   return LRP_OK;
 }
 
@@ -1190,7 +1537,7 @@ int lrp_submit(lrp_ctx *ctx, const lrp_job *job, uint64_t *ticket) {
       ctx->pool = p;
     }
   }
-  uint64_t t = ctx->pool->submit(*job);
+  uint64_t t = ctx->pool->submit(*job, ticket != nullptr);
   if (ticket) *ticket = t;
   return LRP_OK;
 }
@@ -1233,19 +1580,25 @@ int lrp_sched_create(const int *devices, int n_devices, int streams_per_device, 
 
 int lrp_sched_submit(lrp_sched *s, const lrp_job *job) {
   if (!s || !job) return LRP_E_BAD_ARG;
-  s->pool.submit(*job);
+  s->pool.submit(*job, false);
   return LRP_OK;
 }
 
 int lrp_sched_submit_file(lrp_sched *s, const lrp_file_job *job) {
   if (!s || !job) return LRP_E_BAD_ARG;
-  s->pool.submit_file(*job);
-  return LRP_OK;
+  return s->pool.submit_file(*job);
 }
 
 int lrp_sched_wait_all(lrp_sched *s) {
   if (!s) return LRP_E_BAD_ARG;
   return s->pool.wait_all();
+}
+
+int lrp_sched_debug_copy_only(lrp_sched *s, int on) {
+  if (!s) return LRP_E_BAD_ARG;
+  std::lock_guard<std::mutex> lk(s->pool.mu);
+  s->pool.copy_only = on != 0;
+  return LRP_OK;
 }
 
 int lrp_sched_num_devices(const lrp_sched *s) { return s ? (int)s->ctxs.size() : 0; }

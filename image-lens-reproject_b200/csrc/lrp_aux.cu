@@ -4,15 +4,6 @@
 
 namespace lrp {
 
-// runtime dispatch over the input-lens projection (the wrap variants only differ in the sampler)
-LRP_DEV void source_coord_rt(const KParams &P, int coord, float scx, float scy, float &sx, float &sy) {
-  if (coord == COORD_RECT) source_coord<COORD_RECT>(P, scx, scy, sx, sy);
-  else if (coord == COORD_EQUIDISTANT) source_coord<COORD_EQUIDISTANT>(P, scx, scy, sx, sy);
-  else if (coord == COORD_EQUISOLID) source_coord<COORD_EQUISOLID>(P, scx, scy, sx, sy);
-  else if (coord == COORD_STEREO) source_coord<COORD_STEREO>(P, scx, scy, sx, sy);
-  else source_coord<COORD_ERECT_CLAMP>(P, scx, scy, sx, sy);
-}
-
 // Writes (sx, sy) of every output pixel for the first `coords_planes` sub-samples
 // ([ssx*ns + ssy][H][W] float2).  Serves lrp_build_remap (all ns*ns planes) and
 // lrp_debug_coords (plane 0).  Same device functions as the fused kernel, so a remap

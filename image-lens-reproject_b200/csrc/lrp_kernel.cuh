@@ -197,6 +197,15 @@ LRP_DEV void source_coord(const KParams &P, float scx, float scy, float &sx, flo
   ray_to_source<COORD>(P, vx, vy, vz, sx, sy);
 }
 
+// runtime dispatch over the input-lens projection (the wrap variants only differ in the sampler)
+LRP_DEV void source_coord_rt(const KParams &P, int coord, float scx, float scy, float &sx, float &sy) {
+  if (coord == COORD_RECT) source_coord<COORD_RECT>(P, scx, scy, sx, sy);
+  else if (coord == COORD_EQUIDISTANT) source_coord<COORD_EQUIDISTANT>(P, scx, scy, sx, sy);
+  else if (coord == COORD_EQUISOLID) source_coord<COORD_EQUISOLID>(P, scx, scy, sx, sy);
+  else if (coord == COORD_STEREO) source_coord<COORD_STEREO>(P, scx, scy, sx, sy);
+  else source_coord<COORD_ERECT_CLAMP>(P, scx, scy, sx, sy);
+}
+
 // ---- source texel access -------------------------------------------------------------------
 
 // Per-thread view of the source: parameters + this lane's base address into the
@@ -551,8 +560,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) reproject_kernel(const __grid_con
   if (FMT == FMT_U8) {
     const uint32_t low_end = shared_addr(s_thr + THR_FLOATS);
     const uint32_t lut_base = (low_end + 0xFFFFu) & ~0xFFFFu;
-    for (int i = tid; i < 256 * 32; i += NTHREADS) {
-      const float g = __ldg(P.lut + (i >> 5));
+    const bool composite = (INTERP == INTERP_NN) && P.nn_composite; // the table then holds sink bytes, not floats
+    for (int i = tid; i < 256 * 32 && !(composite && P.ctab_identity); i += NTHREADS) {
+      const float g = composite ? __uint_as_float((unsigned)P.ctab[i >> 5]) : __ldg(P.lut + (i >> 5));
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(lut_base + ((uint32_t)(i >> 5) << 8) + ((uint32_t)(i & 31) << 2)), "f"(g));
     }
     lut_lane = lut_base | ((uint32_t)lane << 2);
@@ -630,6 +640,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) reproject_kernel(const __grid_con
             }
             ray_to_source<COORD>(P, vx, vy, vz, sx, sy);
           }
+          if (INTERP == INTERP_NN && FMT == FMT_U8 && P.nn_composite) {
+            // 8-bit source and sink, one tap, one sample: the texel's bytes go through the byte map (KParams::ctab,
+            // == encode_u8(post(0 + lut[p]) * 1) for every p) — no float arithmetic behind the coordinates
+            const float off[1] = {0.5f};
+            int xs[1], ys[1];
+            tap_indices<WRAP, 1>(sx, sy, off, P.w, P.h, xs, ys); // :43-47
+            const uint32_t t = __ldg((const unsigned int *)byte_offset_rt(Texel<FMT, C>::row(S, ys[0]), (unsigned)xs[0], 4u));
+            uint32_t o = t | 0xFF000000u; // identity map: copy R, G, B; alpha = 255 (src/image_formats.cpp:159-161)
+            if (!P.ctab_identity) {
+              o = __float_as_uint(Texel<FMT_U8, 3>::lut(__byte_perm(t, S.lut_lane, 0x7604))) |
+                  (__float_as_uint(Texel<FMT_U8, 3>::lut(__byte_perm(t, S.lut_lane, 0x7614))) << 8) |
+                  (__float_as_uint(Texel<FMT_U8, 3>::lut(__byte_perm(t, S.lut_lane, 0x7624))) << 16) | 0xFF000000u;
+            }
+            ((unsigned *)P.dst)[(size_t)((unsigned)y * (unsigned)P.W + (unsigned)x)] = o;
+            continue; // ns == 1: the pixel is done (the tail below is skipped)
+          }
           float smp[C];
           if (INTERP == INTERP_NN) sample_nearest<WRAP, FMT, C>(S, sx, sy, smp);
           else if (INTERP == INTERP_BL) sample_bilinear<WRAP, FMT, C>(S, sx, sy, smp);
@@ -639,6 +665,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) reproject_kernel(const __grid_con
         }
       }
 
+      if (INTERP == INTERP_NN && FMT == FMT_U8 && P.nn_composite) continue; // stored above
       float v[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) v[c] = fmul(acc[c], P.normalize); // :338-341

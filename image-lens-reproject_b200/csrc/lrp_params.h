@@ -63,6 +63,12 @@ struct KParams {
   int stage_gain;               // staged kernel: issue slots per step (2 x 16 pixels) that staged taps save over gathered ones
   int *sched;                   // tile scheduler counters {tickets, retired warps} of this launch's stream, or nullptr
   int fast_lens;                // input-lens divisors are normal numbers in [2^-20, 2^20]: unguarded divisions apply
+  // nearest, one sample per pixel, 8-bit source and sink: the whole per-sample function as a byte map (lrp_api.cu
+  // build_composite_table); ctab_identity: the map is the identity (no post-process), the texel is copied
+  int nn_composite, ctab_identity;
+  unsigned char ctab[256];
+  const unsigned *nn_index;     // nearest tap per output pixel, resolved: x | y << 16  (lrp_nearest.cu)
+  unsigned *nn_index_out;       // nn_index_kernel output
 };
 
 typedef int (*LaunchFn)(const KParams &P, void *stream);

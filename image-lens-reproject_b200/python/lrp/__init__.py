@@ -24,6 +24,7 @@ NEAREST, BILINEAR, BICUBIC = range(3)
 FMT_F32, FMT_U8_RGBA, FMT_F16_PLANAR = range(3)
 VARIANT_AUTO, VARIANT_GATHER, VARIANT_STAGED = range(3)
 UPLOAD_AUTO, UPLOAD_FULL = range(2)
+COORDS_AUTO, COORDS_FLY, COORDS_TABLE = range(3)
 EXT_FISHEYE_MODELS = 1
 
 
@@ -47,7 +48,7 @@ class Params(C.Structure):
     _fields_ = [("num_samples", C.c_int32), ("interpolation", C.c_int32), ("has_rotation", C.c_int32),
                 ("rotation", C.c_float * 9), ("apply_post", C.c_int32), ("exposure", C.c_float),
                 ("reinhard", C.c_float), ("variant", C.c_int32), ("upload", C.c_int32),
-                ("extensions", C.c_int32)]
+                ("extensions", C.c_int32), ("coords", C.c_int32)]
 
 
 DONE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int)
@@ -127,9 +128,11 @@ def lib():
         L.lrp_sched_destroy.argtypes = [vp]
         L.lrp_sched_num_devices.argtypes = [vp]
         L.lrp_sched_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+        L.lrp_sched_debug_copy_only.argtypes = [vp, C.c_int]
         L.lrp_debug_coords.argtypes = [vp, ip, ip, pp, vp, vp]
         L.lrp_source_footprint.argtypes = [vp, ip, ip, pp, C.POINTER(C.c_int32)]
         L.lrp_ctx_transfer_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.lrp_ctx_remap_stats.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.lrp_debug_libm.argtypes = [vp, C.c_int, vp, vp, vp, C.c_size_t, vp]
         L.lrp_debug_encode_u8.argtypes = [vp, vp, vp, C.c_size_t, vp]
         i32 = C.c_int32
@@ -237,7 +240,8 @@ def rotation_matrix(pan, pitch, roll):
     return np.array(m, dtype=np.float32)
 
 
-def make_params(ns=1, interp=BICUBIC, rot=None, post=None, variant=VARIANT_AUTO, upload=UPLOAD_AUTO, ext=0):
+def make_params(ns=1, interp=BICUBIC, rot=None, post=None, variant=VARIANT_AUTO, upload=UPLOAD_AUTO, ext=0,
+                coords=COORDS_AUTO):
     """post = (exposure, reinhard) or None — main() calls post_process only when either differs
     from 1.0 (reference src/main.cpp:601)."""
     p = Params()
@@ -254,6 +258,7 @@ def make_params(ns=1, interp=BICUBIC, rot=None, post=None, variant=VARIANT_AUTO,
     p.variant = variant
     p.upload = upload
     p.extensions = ext
+    p.coords = coords
     return p
 
 
@@ -289,7 +294,8 @@ def _describe(arr, fmt):
 # ---- synchronous host drop-in --------------------------------------------------------------------
 
 def reproject_host(src, in_lens, out_lens, W, H, ns=1, interp=BICUBIC, rot=None, post=None,
-                   in_fmt=FMT_F32, out_fmt=None, device=0, channels=None, upload=UPLOAD_AUTO, ext=0):
+                   in_fmt=FMT_F32, out_fmt=None, device=0, channels=None, upload=UPLOAD_AUTO, ext=0,
+                   variant=VARIANT_AUTO, coords=COORDS_AUTO):
     """reproject::reproject() (+ post_process) on HOST numpy buffers through lrp_reproject_host."""
     out_fmt = in_fmt if out_fmt is None else out_fmt
     _, dt = _shape_of(in_fmt, 1, 1, 1)
@@ -301,7 +307,7 @@ def reproject_host(src, in_lens, out_lens, W, H, ns=1, interp=BICUBIC, rot=None,
     out = np.empty(oshape, dtype=odt)
     iim = make_image(in_lens, w, h, c, in_fmt, src.ctypes.data)
     oim = make_image(out_lens, W, H, c, out_fmt, out.ctypes.data)
-    p = make_params(ns, interp, rot, post, upload=upload, ext=ext)
+    p = make_params(ns, interp, rot, post, variant=variant, upload=upload, ext=ext, coords=coords)
     check(lib().lrp_reproject_host(C.byref(iim), C.byref(oim), C.byref(p), device), "lrp_reproject_host")
     return out
 
@@ -395,6 +401,12 @@ class Context:
         a, b = C.c_uint64(0), C.c_uint64(0)
         check(lib().lrp_ctx_transfer_stats(self.h, C.byref(a), C.byref(b)), "lrp_ctx_transfer_stats")
         return a.value, b.value
+
+    def remap_stats(self):
+        """(tables held, device bytes, launches served from a table)"""
+        n, b, h = C.c_int32(0), C.c_uint64(0), C.c_uint64(0)
+        check(lib().lrp_ctx_remap_stats(self.h, C.byref(n), C.byref(b), C.byref(h)), "lrp_ctx_remap_stats")
+        return n.value, b.value, h.value
 
     def debug_libm(self, fn, a_t, b_t=None, stream=None):
         import torch
@@ -595,28 +607,57 @@ class Scheduler:
         check(lib().lrp_sched_create(arr, len(devices), streams_per_device, C.byref(h)), "lrp_sched_create")
         self.h = h
         self.n = len(devices)
+        import threading
+        self._lock = threading.Lock()
+        self._live, self._retired, self._next_id = {}, [], 0
 
     def submit(self, job):
         check(lib().lrp_sched_submit(self.h, C.byref(job)), "lrp_sched_submit")
 
     def submit_file(self, data, in_kind, in_lens, out_lens, W, H, out_kind, params, sink, decode_threads=2):
         """file bytes -> file bytes on whichever GPU frees up first; `sink(status, bytes)` is called from a library thread.
-        The caller keeps `data` alive until then (the returned handle holds the references)."""
+        The scheduler object keeps the input bytes and the callback thunk alive until the job has completed."""
         buf = C.create_string_buffer(data, len(data))
+        with self._lock:
+            job_id = self._next_id
+            self._next_id += 1
 
         def _done(user, status, ptr, n):
-            sink(status, C.string_at(ptr, n) if status == OK and ptr else None)
+            try:
+                sink(status, C.string_at(ptr, n) if status == OK and ptr else None)
+            finally:
+                with self._lock:
+                    self._retired.append(job_id)  # dropped by the next submit / wait_all, never from inside the thunk
 
         cb = FILE_DONE_FN(_done)
+        with self._lock:
+            for k in self._retired:
+                self._live.pop(k, None)
+            self._retired = []
+            self._live[job_id] = (buf, cb)
         j = FileJob()
         j.in_file, j.in_size, j.in_kind, j.out_kind = C.cast(buf, C.c_void_p), len(data), in_kind, out_kind
         j.in_lens, j.out_lens, j.out_width, j.out_height = in_lens, out_lens, W, H
         j.params, j.decode_threads, j.on_done, j.user = params, decode_threads, cb, None
-        check(lib().lrp_sched_submit_file(self.h, C.byref(j)), "lrp_sched_submit_file")
-        return (buf, cb)
+        try:
+            check(lib().lrp_sched_submit_file(self.h, C.byref(j)), "lrp_sched_submit_file")
+        except Exception:
+            with self._lock:
+                self._live.pop(job_id, None)
+            raise
+        return job_id
+
+    def copy_only(self, on):
+        """measurement hook: pixel jobs move their bytes but launch no kernel (lrp_sched_debug_copy_only)"""
+        check(lib().lrp_sched_debug_copy_only(self.h, 1 if on else 0), "lrp_sched_debug_copy_only")
 
     def wait_all(self):
-        check(lib().lrp_sched_wait_all(self.h), "lrp_sched_wait_all")
+        try:
+            check(lib().lrp_sched_wait_all(self.h), "lrp_sched_wait_all")
+        finally:
+            with self._lock:  # every callback has returned
+                self._live.clear()
+                self._retired = []
 
     def stats(self):
         a = (C.c_int64 * self.n)()
@@ -625,8 +666,9 @@ class Scheduler:
 
     def close(self):
         if self.h:
-            lib().lrp_sched_destroy(self.h)
+            lib().lrp_sched_destroy(self.h)  # waits for every job
             self.h = None
+            self._live.clear()
 
     def __del__(self):
         try:

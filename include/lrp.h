@@ -107,7 +107,20 @@ typedef struct lrp_params {
   int32_t variant;       /* lrp_variant: source-access strategy; 0 = library default        */
   int32_t upload;        /* lrp_upload: what the HOST-buffer entry points copy to the GPU   */
   int32_t extensions;    /* LRP_EXT_* bits; 0 = exactly the reference's behaviour           */
+  int32_t coords;        /* lrp_coords: where source coordinates come from; 0 = library default */
 } lrp_params;
+
+/* Where a launch takes its source coordinates from (north-star item 3: "a per-batch precomputed remap
+ * table is also benchmarked against on-the-fly recompute").  The coordinates depend on the geometry only
+ * (lenses, sizes, rotation, num_samples) and one run of the reference shares ONE geometry across all its
+ * images (a single set of CLI lens flags, src/main.cpp:257-492), so a context keeps the tables of the
+ * geometries it meets (LRU, LRP_REMAP_CACHE_MB of device memory, default 4096): the table is written by the
+ * same device functions the on-the-fly kernels evaluate, so results are bit-identical either way. */
+typedef enum lrp_coords {
+  LRP_COORDS_AUTO = 0, /* on the fly the first time a context meets a geometry, from its table afterwards */
+  LRP_COORDS_FLY = 1,  /* always recomputed per pixel                                                      */
+  LRP_COORDS_TABLE = 2 /* from the table, built on first use                                               */
+} lrp_coords;
 
 /* Opt-in behaviour beyond the reference.
  *
@@ -220,6 +233,9 @@ int lrp_reproject_device_remap(lrp_ctx *ctx, const lrp_image *in_dev, const lrp_
 int lrp_source_footprint(lrp_ctx *ctx, const lrp_image *in_geom, const lrp_image *out_geom,
                          const lrp_params *p, int32_t roi[4]);
 
+/* Remap tables the context currently holds: count, device bytes, and how many launches read one so far. */
+int lrp_ctx_remap_stats(const lrp_ctx *ctx, int32_t *tables, uint64_t *bytes, uint64_t *hits);
+
 /* Bytes the host-buffer entry points have moved over PCIe through this context so far
  * (lrp_reproject_host on its default context is not visible here; lrp_submit / lrp_sched_* are). */
 int lrp_ctx_transfer_stats(const lrp_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
@@ -252,7 +268,9 @@ int lrp_wait_all(lrp_ctx *ctx);
  * pool.push(job) + pool.stop(true) (src/main.cpp:538-541, 657).  Images are
  * independent, so jobs are handed to whichever GPU stream frees up first; no
  * collective is involved. */
-/* streams_per_device: 1..64 workers per GPU, each with its own stream and codec workspaces */
+/* streams_per_device: 1..64 jobs in flight per GPU, each on its own stream with its own device buffers.  Pixel jobs
+ * are driven by one engine thread per GPU (enqueue + completion callbacks, no thread blocks on a job); file jobs by
+ * that many worker threads per GPU with their own codec workspaces. */
 int lrp_sched_create(const int *devices, int n_devices, int streams_per_device, lrp_sched **out);
 int lrp_sched_submit(lrp_sched *s, const lrp_job *job);
 int lrp_sched_wait_all(lrp_sched *s); /* returns first non-OK job status, else LRP_OK */
@@ -260,6 +278,10 @@ int lrp_sched_destroy(lrp_sched *s);
 int lrp_sched_num_devices(const lrp_sched *s);
 /* jobs completed per device so far (array of n_devices) — for tests / stats */
 int lrp_sched_stats(const lrp_sched *s, int64_t *jobs_per_device);
+/* Measurement hook: while on, pixel jobs move exactly the bytes they would (H2D of the source region, D2H of the
+ * sink) through the same slots, streams and callbacks but launch no kernel — the copy-only ceiling of the host path
+ * that bench.py prints next to the scheduler's throughput.  The sinks then hold undefined bytes. */
+int lrp_sched_debug_copy_only(lrp_sched *s, int on);
 
 /* ---- encode side --------------------------------------------------------
  * Replaces what follows the kernel in the reference's writers: reproject::save_png

@@ -57,7 +57,7 @@ def test_struct_layouts_match_header(lrp):
     assert C.sizeof(lrp.Lens) == 28  # == sizeof(reproject::LensInfo), reference src/config.hpp:15-37
     assert C.sizeof(ol.Lens) == 28
     assert lrp.Image.data.offset == 48 and C.sizeof(lrp.Image) == 56
-    assert C.sizeof(lrp.Params) == 12 + 36 + 24  # ... variant, upload, extensions
+    assert C.sizeof(lrp.Params) == 12 + 36 + 28  # ... variant, upload, extensions, coords
     assert lrp.Params.variant.offset == 60 and lrp.Params.upload.offset == 64
 
 
