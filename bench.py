@@ -395,7 +395,8 @@ def run_gpu_arm(args, rank, world, local_rank):
     in_lens = lrp.lens_equirectangular()
     out_lens = lrp.lens_rectilinear(18.0, 36.0, OUT_W, OUT_H)
     rot = lrp.rotation_from_degrees(*ROTATION_DEG)
-    variant = {"auto": lrp.VARIANT_AUTO, "gather": lrp.VARIANT_GATHER, "staged": lrp.VARIANT_STAGED}[args.variant]
+    variant = {"auto": lrp.VARIANT_AUTO, "gather": lrp.VARIANT_GATHER, "staged": lrp.VARIANT_STAGED,
+               "tiled": lrp.VARIANT_TILED}[args.variant]
     upload = {"auto": lrp.UPLOAD_AUTO, "full": lrp.UPLOAD_FULL}[args.upload]
     coords = {"auto": lrp.COORDS_AUTO, "fly": lrp.COORDS_FLY, "table": lrp.COORDS_TABLE}[args.coords]
     params = lrp.make_params(1, interp, rot, None, variant=variant, upload=upload, coords=coords)
@@ -611,7 +612,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lrp", choices=["lrp", "reference"])
     ap.add_argument("--interp", default="bc", choices=["nn", "bl", "bc"])
-    ap.add_argument("--variant", default="auto", choices=["auto", "gather", "staged"],
+    ap.add_argument("--variant", default="auto", choices=["auto", "gather", "staged", "tiled"],
                     help="source access: footprint staging in shared memory (auto = the library default) or per-tap gather")
     ap.add_argument("--coords", default="auto", choices=["auto", "fly", "table"],
                     help="source coordinates: library default (table once a geometry repeats), always on the fly, always table")

@@ -38,6 +38,9 @@ LRP_DECL(2, 0) LRP_DECL(2, 1) LRP_DECL(2, 2) LRP_DECL(3, 0) LRP_DECL(3, 1) LRP_D
 LRP_DECL(4, 0) LRP_DECL(4, 1) LRP_DECL(4, 2) LRP_DECL(5, 0) LRP_DECL(5, 1) LRP_DECL(5, 2)
 LRP_DECL(6, 0) LRP_DECL(6, 1) LRP_DECL(6, 2) LRP_DECL(7, 0) LRP_DECL(7, 1) LRP_DECL(7, 2)
 #undef LRP_DECL
+#define LRP_DECL(c) LaunchFn get_tiled_launcher_c##c(int fc);
+LRP_DECL(0) LRP_DECL(1) LRP_DECL(2) LRP_DECL(3) LRP_DECL(4) LRP_DECL(5)
+#undef LRP_DECL
 int launch_coords(const KParams &P, int coord, void *stream);
 int launch_footprint(const KParams &P, int coord, int interp, int wrap, void *stream);
 int launch_post_process(float *data, size_t n_pixels, int channels, float exposure, float reinhard, void *stream);
@@ -45,6 +48,13 @@ int launch_libm(int fn, const float *a, const float *b, float *out, size_t n, in
 int launch_encode_u8(const float *in, unsigned char *out, size_t n, const float *thr, void *stream);
 int launch_nn_index(const KParams &P, int coord, void *stream);
 int launch_nn_table(const KParams &P, int fc, void *stream);
+
+static LaunchFn get_tiled_launcher(int coord, int fc) {
+  typedef LaunchFn (*Getter)(int);
+  static const Getter table[6] = {get_tiled_launcher_c0, get_tiled_launcher_c1, get_tiled_launcher_c2,
+                                  get_tiled_launcher_c3, get_tiled_launcher_c4, get_tiled_launcher_c5};
+  return (coord >= 0 && coord < 6) ? table[coord](fc) : nullptr;
+}
 
 static LaunchFn get_launcher(int coord, int interp, int fc, bool staged) {
   typedef LaunchFn (*Getter)(int);
@@ -339,7 +349,7 @@ int prepare(const lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const
   if (!lens_supported(out->lens.type, p->extensions)) return LRP_E_UNSUPPORTED_OUTPUT_LENS; // reference :415-417
   if (!lens_supported(in->lens.type, p->extensions)) return LRP_E_UNSUPPORTED_INPUT_LENS;   // reference :395-397
   if (p->interpolation < 0 || p->interpolation > 2) return LRP_E_UNSUPPORTED_INTERP; // :364-366
-  if (p->variant < LRP_VARIANT_AUTO || p->variant > LRP_VARIANT_STAGED) return LRP_E_BAD_ARG;
+  if (p->variant < LRP_VARIANT_AUTO || p->variant > LRP_VARIANT_TILED) return LRP_E_BAD_ARG;
   if (p->upload < LRP_UPLOAD_AUTO || p->upload > LRP_UPLOAD_FULL) return LRP_E_BAD_ARG;
   if (p->coords < LRP_COORDS_AUTO || p->coords > LRP_COORDS_TABLE) return LRP_E_BAD_ARG;
   if (need_data) {
@@ -582,10 +592,11 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
   // source access: the staged kernel handles one sample per pixel; supersampled launches gather
   const char *force = getenv("LRP_FORCE_VARIANT"); // A/B runs of unmodified callers: "gather" | "staged"
   int variant = p->variant;
-  if (force && variant == LRP_VARIANT_AUTO) variant = force[0] == 'g' ? LRP_VARIANT_GATHER : LRP_VARIANT_STAGED;
+  if (force && variant == LRP_VARIANT_AUTO)
+    variant = force[0] == 'g' ? LRP_VARIANT_GATHER : force[0] == 't' ? LRP_VARIANT_TILED : LRP_VARIANT_STAGED;
 
   // ---- nearest, one sample per pixel, codec-native 8-bit in and out: the byte-map path (lrp_nearest.cu) ----
-  const bool nn1 = p->interpolation == LRP_NEAREST && p->num_samples == 1 && variant != LRP_VARIANT_STAGED;
+  const bool nn1 = p->interpolation == LRP_NEAREST && p->num_samples == 1 && variant != LRP_VARIANT_STAGED && variant != LRP_VARIANT_TILED;
   const char *no_nn = getenv("LRP_NO_NN_FAST"); // A/B switch: nearest through the generic float tail
   const bool nn_fast = nn1 && !(no_nn && no_nn[0] == '1');
   if (nn_fast && in->format == LRP_FMT_U8_RGBA && out->format == LRP_FMT_U8_RGBA) {
@@ -607,6 +618,14 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
   // AUTO follows the measurements (profiles/r1_bench_configs_s6*.jsonl): footprint staging pays for the 16 taps of
   // bicubic on every config (c2 185 vs 209 us, c4t 249 vs 340 us); the 1 / 4 taps of nearest / bilinear are cheaper
   // gathered through L1 (c2 nn 107 vs 179 us, bl 124 vs 139 us; c3 bl 137 vs 235 us)
+  {
+    const char *tc = getenv("LRP_TL_CTAS"); // A/B switch: resident CTAs per SM of the tiled kernel
+    K.tiled_ctas = tc ? atoi(tc) : (in->format == LRP_FMT_U8_RGBA ? 3 : 2);
+  }
+  if (variant == LRP_VARIANT_TILED && p->interpolation == LRP_BICUBIC && p->num_samples == 1) {
+    if (LaunchFn tf = get_tiled_launcher(coord, fc)) return map_cuda((cudaError_t)tf(K, stream));
+  }
+  if (variant == LRP_VARIANT_TILED) variant = LRP_VARIANT_STAGED; // formats / samplers the tiled kernel does not cover
   const bool want_staged = (variant == LRP_VARIANT_STAGED) ||
                            (variant == LRP_VARIANT_AUTO && p->interpolation == LRP_BICUBIC);
   const bool staged = want_staged && p->num_samples == 1;

@@ -156,8 +156,11 @@ typedef enum lrp_upload {
 typedef enum lrp_variant {
   LRP_VARIANT_AUTO = 0,   /* by measurement: STAGED for bicubic with num_samples == 1, else GATHER */
   LRP_VARIANT_GATHER = 1, /* every tap is a global load through L1/L2                            */
-  LRP_VARIANT_STAGED = 2  /* each warp stages + decodes the bounding box of its tile's taps in
+  LRP_VARIANT_STAGED = 2, /* each warp stages + decodes the bounding box of its tile's taps in
                              shared memory once; rows whose box does not fit are gathered      */
+  LRP_VARIANT_TILED = 3   /* bicubic, PNG / EXR formats with 3-4 channels: a CTA stages the box of a 32 x 32 tile
+                             once and shares the per-texel coefficients of the column interpolations between
+                             the pixels that use them (csrc/lrp_tiled.cuh); other launches fall back to STAGED */
 } lrp_variant;
 
 typedef struct lrp_ctx lrp_ctx;     /* one per GPU; thread-safe                          */

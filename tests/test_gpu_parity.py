@@ -36,10 +36,11 @@ def ctx(lrp):
     c.close()
 
 
-@pytest.fixture(params=["staged", "gather"])
+@pytest.fixture(params=["staged", "gather", "tiled"])
 def variant(request, monkeypatch):
     """Runs a pixel test once per source-access variant (liblrp reads LRP_FORCE_VARIANT at every launch when the
-    caller leaves lrp_params.variant at AUTO): the footprint-staging kernel and the per-tap gather kernel."""
+    caller leaves lrp_params.variant at AUTO): the footprint-staging kernel, the per-tap gather kernel and the
+    CTA-tiled shared-coefficient kernel (bicubic on the codec formats; it falls back to staged elsewhere)."""
     monkeypatch.setenv("LRP_FORCE_VARIANT", request.param)
     return request.param
 

@@ -253,7 +253,7 @@ def test_c1t_full_size_png_border_clamped(lrp):
     rgba = np.random.default_rng(11).integers(0, 256, (h, w, 4), dtype=np.uint8)
     il, olens = ol.rect(36.0, 36.0, w, h), ol.equidistant(3.14159)
     want = ORC.png_encode(ORC.reproject(ORC.png_decode(rgba), il, olens, W, H, 1, ol.BICUBIC, None))
-    for v in (lrp.VARIANT_STAGED, lrp.VARIANT_GATHER):
+    for v in (lrp.VARIANT_STAGED, lrp.VARIANT_GATHER, lrp.VARIANT_TILED):
         for cm in (lrp.COORDS_FLY, lrp.COORDS_TABLE):
             got = lrp.reproject_host(rgba, L(lrp, il), L(lrp, olens), W, H, 1, ol.BICUBIC, None, in_fmt=lrp.FMT_U8_RGBA,
                                      out_fmt=lrp.FMT_U8_RGBA, variant=v, coords=cm)
@@ -265,16 +265,17 @@ def test_c5_pole_views_full_size(lrp, pitch):
     """c5 pole views: 16384x8192 RGB half equirect -> rect(18,36) 4096x4096, rotation 0,+-90,0 — tap boxes as wide as the
     source around the pole (the staged kernel's gathered fall-back rows)"""
     w, h, W, H, c = 16384, 8192, 4096, 4096, 3
-    rng = np.random.default_rng(50 + pitch)
+    rng = np.random.default_rng(150 + pitch)
     planes = (rng.random((c, h, w), dtype=np.float32) * 2).astype(np.float16).view(np.uint16)
     il, olens, r = ol.erect(), ol.rect(18.0, 36.0, W, H), rotd(0, pitch, 0)
-    got16 = lrp.reproject_host(planes, L(lrp, il), L(lrp, olens), W, H, 1, ol.BICUBIC, r, in_fmt=lrp.FMT_F16_PLANAR,
-                               out_fmt=lrp.FMT_F16_PLANAR)
     src_f = ORC.half_planar_to_f32(planes)
     want16 = ORC.f32_to_half_planar(ORC.reproject(src_f, il, olens, W, H, 1, ol.BICUBIC, r))
     del src_f
-    sm = same_half(got16, want16)
-    assert sm.all(), "c5 pole %d: %d of %d differ" % (pitch, (~sm).sum(), sm.size)
+    for v in (lrp.VARIANT_STAGED, lrp.VARIANT_TILED):
+        got16 = lrp.reproject_host(planes, L(lrp, il), L(lrp, olens), W, H, 1, ol.BICUBIC, r, in_fmt=lrp.FMT_F16_PLANAR,
+                                   out_fmt=lrp.FMT_F16_PLANAR, variant=v)
+        sm = same_half(got16, want16)
+        assert sm.all(), "c5 pole %d variant %d: %d of %d differ" % (pitch, v, (~sm).sum(), sm.size)
 
 
 def test_c3_full_size_through_each_variant(lrp):
@@ -288,7 +289,7 @@ def test_c3_full_size_through_each_variant(lrp):
     want = ORC.post_process(ORC.reproject(ORC.half_planar_to_f32(planes), il, olens, W, H, 1, ol.BICUBIC, None), 1.5, 4.0)
     want16 = ORC.f32_to_half_planar(want)
     del want
-    for v in (lrp.VARIANT_STAGED, lrp.VARIANT_GATHER):
+    for v in (lrp.VARIANT_STAGED, lrp.VARIANT_GATHER, lrp.VARIANT_TILED):
         for cm in (lrp.COORDS_FLY, lrp.COORDS_TABLE):
             got16 = lrp.reproject_host(planes, L(lrp, il), L(lrp, olens), W, H, 1, ol.BICUBIC, None, post=(1.5, 4.0),
                                        in_fmt=lrp.FMT_F16_PLANAR, out_fmt=lrp.FMT_F16_PLANAR, variant=v, coords=cm)
@@ -321,3 +322,34 @@ def test_codec_formats_against_the_compiled_reference(lrp):
                 got16 = lrp.reproject_host(planes, L(lrp, il), L(lrp, olens), W, H, 1, interp, r, in_fmt=lrp.FMT_F16_PLANAR,
                                            out_fmt=lrp.FMT_F16_PLANAR, coords=cm)
                 assert same_half(got16, want16).all(), "ref exr interp %d" % interp
+
+
+# ---- the CTA-tiled shared-coefficient kernel (lrp_tiled.cuh) ---------------------------------------------------------
+
+@pytest.mark.parametrize("ctas", ["2", "3"])
+def test_tiled_kernel_both_occupancies(lrp, ctas, monkeypatch):
+    """2 and 3 resident CTAs per SM are separate instantiations with different record capacities (block splits differ)"""
+    monkeypatch.setenv("LRP_TL_CTAS", ctas)
+    rng = np.random.default_rng(int(ctas))
+    for (W, H, w, h, il, olens, r) in (
+            (517, 301, 1024, 512, ol.erect(), lambda W, H: ol.rect(18.0, 36.0, W, H), rotd(30, 20, 10)),   # magnified, wrap
+            (300, 280, 300, 280, ol.rect(36.0, 36.0, 300, 280), lambda W, H: ol.rect(36.0, 36.0, W, H), None),  # 1:1, kink at 0
+            (256, 128, 2048, 2048, ol.equidistant(math.pi), lambda W, H: ol.erect(), None),                 # minified: boxes split
+            (333, 333, 512, 256, ol.erect(), lambda W, H: ol.rect(18.0, 36.0, W, H), rotd(0, 90, 0))):      # pole
+        rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        f4 = (rng.random((h, w, 4), dtype=np.float32) * 2.0).astype(np.float32)
+        f4[::13, ::11, 3] = 1e10
+        planes = ORC.f32_to_half_planar(f4)
+        for cm in (lrp.COORDS_FLY, lrp.COORDS_TABLE):
+            want8 = ORC.png_encode(ORC.reproject(ORC.png_decode(rgba), il, olens(W, H), W, H, 1, ol.BICUBIC, r))
+            got8 = lrp.reproject_host(rgba, L(lrp, il), L(lrp, olens(W, H)), W, H, 1, ol.BICUBIC, r, in_fmt=lrp.FMT_U8_RGBA,
+                                      out_fmt=lrp.FMT_U8_RGBA, variant=lrp.VARIANT_TILED, coords=cm)
+            assert (got8 == want8).all(), "tiled u8 %r: %d differ" % ((W, H, w, h), (got8 != want8).sum())
+            for c in (3, 4):
+                pl = np.ascontiguousarray(planes[:c])
+                want16 = ORC.f32_to_half_planar(ORC.post_process(
+                    ORC.reproject(ORC.half_planar_to_f32(pl), il, olens(W, H), W, H, 1, ol.BICUBIC, r), 1.5, 4.0))
+                got16 = lrp.reproject_host(pl, L(lrp, il), L(lrp, olens(W, H)), W, H, 1, ol.BICUBIC, r, post=(1.5, 4.0),
+                                           in_fmt=lrp.FMT_F16_PLANAR, out_fmt=lrp.FMT_F16_PLANAR, variant=lrp.VARIANT_TILED,
+                                           coords=cm)
+                assert same_half(got16, want16).all(), "tiled f16 c%d %r: %d differ" % (c, (W, H, w, h), (~same_half(got16, want16)).sum())

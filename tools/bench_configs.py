@@ -23,17 +23,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "image-lens-reproject_b200", "python"))
 
-CONFIGS = {
-    # name: (in lens ctor, (w, h), out lens ctor, (W, H), fmt, channels, rotation deg, post, N_touched bc, frames)
-    "c1": ("rect36", (1920, 1080), "equisolid", (1920, 1080), "u8", 3, None, None, 2073600, 16),
-    "c4": ("rect36", (3840, 2160), "equisolid", (3840, 2160), "f16", 4, None, None, 8294400, 8),
-    "c1t": ("rect36", (1920, 1080), "equidistant", (1920, 1080), "u8", 3, None, None, 2073600, 16),
-    "c2": ("erect", (8192, 4096), "rect18", (3840, 2160), "u8", 3, (30, 20, 10), None, 2673058, 8),
-    "c3": ("equidistant", (4096, 4096), "erect", (4096, 2048), "f16", 4, None, (1.5, 4.0), 9023406, 8),
-    "c4t": ("rect36", (3840, 2160), "equidistant", (3840, 2160), "f16", 4, None, None, 8294400, 8),
-    "c5e": ("erect", (16384, 8192), "rect18", (4096, 4096), "f16", 3, (90, 0, 0), None, 15641012, 2),
-    "c5p": ("erect", (16384, 8192), "rect18", (4096, 4096), "f16", 3, (0, 90, 0), None, 32782266, 2),
-}
+from lrp import workloads as _wl  # noqa: E402
+
+CONFIGS = _wl.CONFIGS
 
 
 def main():
@@ -79,9 +71,10 @@ def main():
         balg = W * H * bpp + n_touched * bpp
         for variant in args.variants.split(","):
             for coords in args.coords.split(","):
-                v = {"staged": lrp.VARIANT_STAGED, "gather": lrp.VARIANT_GATHER}[variant]
-                p = lrp.make_params(1, interp, rot, post, variant=v, ext=lrp.EXT_FISHEYE_MODELS)
-                remap = ctx.build_remap(il, w, h, ol, W, H, p) if coords == "table" else None
+                v = {"staged": lrp.VARIANT_STAGED, "gather": lrp.VARIANT_GATHER, "tiled": lrp.VARIANT_TILED, "auto": lrp.VARIANT_AUTO}[variant]
+                p = lrp.make_params(1, interp, rot, post, variant=v, ext=lrp.EXT_FISHEYE_MODELS,
+                                    coords={"fly": lrp.COORDS_FLY, "table": lrp.COORDS_TABLE, "auto": lrp.COORDS_AUTO}[coords])
+                remap = None
 
                 def step():
                     for s, d in zip(srcs, dsts):
