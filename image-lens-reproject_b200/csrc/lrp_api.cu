@@ -32,11 +32,8 @@ LRP_DECL(2, 0) LRP_DECL(2, 1) LRP_DECL(2, 2) LRP_DECL(3, 0) LRP_DECL(3, 1) LRP_D
 LRP_DECL(4, 0) LRP_DECL(4, 1) LRP_DECL(4, 2) LRP_DECL(5, 0) LRP_DECL(5, 1) LRP_DECL(5, 2)
 LRP_DECL(6, 0) LRP_DECL(6, 1) LRP_DECL(6, 2) LRP_DECL(7, 0) LRP_DECL(7, 1) LRP_DECL(7, 2)
 #undef LRP_DECL
-#define LRP_DECL(c, i) LaunchFn get_staged_launcher_c##c##_i##i(int fc);
-LRP_DECL(0, 0) LRP_DECL(0, 1) LRP_DECL(0, 2) LRP_DECL(1, 0) LRP_DECL(1, 1) LRP_DECL(1, 2)
-LRP_DECL(2, 0) LRP_DECL(2, 1) LRP_DECL(2, 2) LRP_DECL(3, 0) LRP_DECL(3, 1) LRP_DECL(3, 2)
-LRP_DECL(4, 0) LRP_DECL(4, 1) LRP_DECL(4, 2) LRP_DECL(5, 0) LRP_DECL(5, 1) LRP_DECL(5, 2)
-LRP_DECL(6, 0) LRP_DECL(6, 1) LRP_DECL(6, 2) LRP_DECL(7, 0) LRP_DECL(7, 1) LRP_DECL(7, 2)
+#define LRP_DECL(c) LaunchFn get_staged_launcher_c##c##_i2(int fc);
+LRP_DECL(0) LRP_DECL(1) LRP_DECL(2) LRP_DECL(3) LRP_DECL(4) LRP_DECL(5)
 #undef LRP_DECL
 #define LRP_DECL(c) LaunchFn get_tiled_launcher_c##c(int fc);
 LRP_DECL(0) LRP_DECL(1) LRP_DECL(2) LRP_DECL(3) LRP_DECL(4) LRP_DECL(5)
@@ -58,17 +55,11 @@ static LaunchFn get_tiled_launcher(int coord, int fc) {
 
 static LaunchFn get_launcher(int coord, int interp, int fc, bool staged) {
   typedef LaunchFn (*Getter)(int);
-  static const Getter staged_table[COORD_COUNT][3] = {
-      {get_staged_launcher_c0_i0, get_staged_launcher_c0_i1, get_staged_launcher_c0_i2},
-      {get_staged_launcher_c1_i0, get_staged_launcher_c1_i1, get_staged_launcher_c1_i2},
-      {get_staged_launcher_c2_i0, get_staged_launcher_c2_i1, get_staged_launcher_c2_i2},
-      {get_staged_launcher_c3_i0, get_staged_launcher_c3_i1, get_staged_launcher_c3_i2},
-      {get_staged_launcher_c4_i0, get_staged_launcher_c4_i1, get_staged_launcher_c4_i2},
-      {get_staged_launcher_c5_i0, get_staged_launcher_c5_i1, get_staged_launcher_c5_i2},
-      {get_staged_launcher_c6_i0, get_staged_launcher_c6_i1, get_staged_launcher_c6_i2},
-      {get_staged_launcher_c7_i0, get_staged_launcher_c7_i1, get_staged_launcher_c7_i2},
-  };
-  if (staged) return staged_table[coord][interp](fc);
+  // footprint staging: bicubic on the reference's lenses and the table modes (the extension lenses always take the
+  // guarded projections and the 1 / 4 taps of nearest / bilinear are cheaper gathered: both run the gather kernel)
+  static const Getter staged_table[6] = {get_staged_launcher_c0_i2, get_staged_launcher_c1_i2, get_staged_launcher_c2_i2,
+                                         get_staged_launcher_c3_i2, get_staged_launcher_c4_i2, get_staged_launcher_c5_i2};
+  if (staged && interp == INTERP_BC && coord >= 0 && coord < 6) return staged_table[coord](fc);
   static const Getter table[COORD_COUNT][3] = {
       {get_launcher_c0_i0, get_launcher_c0_i1, get_launcher_c0_i2},
       {get_launcher_c1_i0, get_launcher_c1_i1, get_launcher_c1_i2},
@@ -604,7 +595,7 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
     K.nn_composite = 1;
   }
   const bool nn_copy = nn_fast && !K.post && in->format == out->format && in->format != LRP_FMT_U8_RGBA; // pure texel copy
-  if (!remap && (K.nn_composite || nn_copy) && K.w <= 65536 && K.h <= 65536 && ((uintptr_t)out->data & 31) == 0) {
+  if (!remap && (K.nn_composite || nn_copy) && K.w <= 65536 && K.h <= 65536) {
     if (const void *idx = acquire_remap(ctx, in, out, p, K, coord, REMAP_NN, stream)) {
       K.nn_index = (const unsigned *)idx;
       return map_cuda((cudaError_t)launch_nn_table(K, fc, stream));
@@ -619,10 +610,14 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
   // bicubic on every config (c2 185 vs 209 us, c4t 249 vs 340 us); the 1 / 4 taps of nearest / bilinear are cheaper
   // gathered through L1 (c2 nn 107 vs 179 us, bl 124 vs 139 us; c3 bl 137 vs 235 us)
   {
-    const char *tc = getenv("LRP_TL_CTAS"); // A/B switch: resident CTAs per SM of the tiled kernel
-    K.tiled_ctas = tc ? atoi(tc) : (in->format == LRP_FMT_U8_RGBA ? 3 : 2);
+    const char *rp = getenv("LRP_REC_PAD"); // A/B switch: padded record rows in the staged kernel
+    K.rec_pad = rp ? atoi(rp) : 1;
   }
-  if (variant == LRP_VARIANT_TILED && p->interpolation == LRP_BICUBIC && p->num_samples == 1) {
+  {
+    const char *tc = getenv("LRP_TL_CTAS"); // A/B switch: resident CTAs per SM of the tiled kernel
+    K.tiled_ctas = tc ? atoi(tc) : (in->format == LRP_FMT_U8_RGBA ? 1 : 0); // 1: the higher of the two instantiated counts
+  }
+  if (variant == LRP_VARIANT_TILED && p->interpolation == LRP_BICUBIC && p->num_samples == 1 && out->format == in->format) {
     if (LaunchFn tf = get_tiled_launcher(coord, fc)) return map_cuda((cudaError_t)tf(K, stream));
   }
   if (variant == LRP_VARIANT_TILED) variant = LRP_VARIANT_STAGED; // formats / samplers the tiled kernel does not cover

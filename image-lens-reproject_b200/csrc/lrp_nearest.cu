@@ -7,8 +7,9 @@
 //   nn_index_kernel   once per geometry: the same device functions as the fused kernels (source_coord + tap_indices)
 //                     -> the RESOLVED tap (after the reference's wrap / clamp, :43-47) of every output pixel,
 //                     4 bytes per pixel:  x | y << 16
-//   nn_table_kernel   per frame: index (one 256-bit load per 8 pixels, kept in L2 across the frames of the batch with
-//                     evict-last) -> 8 gathered texels -> the per-sample function -> one 256-bit streaming store.
+//   nn_table_kernel   per frame: index (kept in L2 across the frames of the batch with an evict-last policy) -> gathered
+//                     texel -> the per-sample function -> streaming store; every warp-wide access covers 32 consecutive
+//                     output pixels, 8 of them in flight per thread.
 //
 // The per-sample function of an 8-bit source behind an 8-bit sink,  encode_u8(post(0 + lut[p]) * 1),  is a map from byte
 // to byte (KParams::ctab, built by the host with its own powf: lrp_api.cu build_composite_table) — exact by
@@ -46,20 +47,29 @@ int launch_nn_index(const KParams &P, int coord, void *stream) {
   return (int)cudaGetLastError();
 }
 
-// 256-bit global accesses with L2 eviction priorities (sm_100): the index table is re-read by every frame of the batch
-// (evict last), the sink is written once and not read again by this library (evict first)
-LRP_DEV void ld_index8(const unsigned *p, unsigned (&v)[8]) {
-  asm volatile("ld.global.nc.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "l"(p));
+// L2 eviction priorities (sm_100): the index table is re-read by every frame of the batch (evict last), the sink is
+// written once and not read again by this library (evict first)
+LRP_DEV unsigned long long policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
-LRP_DEV void st_stream8(unsigned *p, const unsigned (&v)[8]) {
-  asm volatile("st.global.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]),
-               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
+LRP_DEV unsigned long long policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+LRP_DEV unsigned ld_index(const unsigned *p, unsigned long long pol) {
+  unsigned v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+LRP_DEV void st_stream(unsigned *p, unsigned v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
 
 constexpr int NN_THREADS = 512;
+constexpr int NN_PER_THREAD = 8; // a warp owns 256 consecutive pixels: pixel = base + 32 k + lane, k = 0..7
 
 // byte map through the lane-replicated table: address = table | value << 7 | lane << 2 (bank = lane: no conflicts)
 LRP_DEV unsigned map_rgba(unsigned t, uint32_t tab_lane) {
@@ -71,6 +81,9 @@ LRP_DEV unsigned map_rgba(unsigned t, uint32_t tab_lane) {
 }
 
 // RGBA8 -> RGBA8.  IDENT: the byte map is the identity (no post-process): copy R, G, B, force alpha.
+// Every warp-wide access covers 32 CONSECUTIVE output pixels: index loads and sink stores are one 128-byte line, and a
+// gather touches the one or two lines that hold the ~32 / magnification source texels of that run (a thread that owned 8
+// consecutive pixels instead spread each gather instruction over 256 pixels = a dozen lines: 13 us of L1 tag cycles on c2).
 template <bool IDENT>
 __global__ void __launch_bounds__(NN_THREADS, 4) nn_table_u8_kernel(const __grid_constant__ KParams P) {
   __shared__ __align__(128) unsigned s_tab[IDENT ? 32 : 256 * 32];
@@ -80,28 +93,31 @@ __global__ void __launch_bounds__(NN_THREADS, 4) nn_table_u8_kernel(const __grid
     __syncthreads();
     tab_lane = shared_addr(s_tab) + ((threadIdx.x & 31u) << 2);
   }
-  const unsigned n = (unsigned)P.W * (unsigned)P.H, n8 = n >> 3; // W * H < 2^31 (checked on the host)
+  const unsigned n = (unsigned)P.W * (unsigned)P.H; // W * H < 2^31 (checked on the host)
   const unsigned *idx = P.nn_index;
   const char *src = (const char *)P.src;
   unsigned *dst = (unsigned *)P.dst;
   const unsigned pitch = P.src_pitch;
+  const unsigned long long keep = policy_evict_last(), stream = policy_evict_first();
+  const unsigned lane = threadIdx.x & 31u, warp = (blockIdx.x * NN_THREADS + threadIdx.x) >> 5;
+  const unsigned warps = (gridDim.x * NN_THREADS) >> 5;
+  constexpr unsigned CHUNK = 32 * NN_PER_THREAD;
 #pragma unroll 1
-  for (unsigned i = blockIdx.x * NN_THREADS + threadIdx.x; i < n8; i += gridDim.x * NN_THREADS) {
-    unsigned e[8], t[8];
-    ld_index8(idx + 8 * (size_t)i, e);
+  for (unsigned base = warp * CHUNK; base < n; base += warps * CHUNK) {
+    unsigned e[NN_PER_THREAD], t[NN_PER_THREAD];
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
+    for (int k = 0; k < NN_PER_THREAD; ++k) {
+      const unsigned i = base + 32u * k + lane;
+      e[k] = i < n ? ld_index(idx + i, keep) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < NN_PER_THREAD; ++k)
       t[k] = __ldg((const unsigned *)byte_offset_rt(src, (e[k] >> 16) * pitch + (e[k] & 0xFFFFu), 4u));
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t[k] = IDENT ? (t[k] | 0xFF000000u) : map_rgba(t[k], tab_lane);
-    st_stream8(dst + 8 * (size_t)i, t);
-  }
-  // the last n % 8 pixels
-  const unsigned tail = (n8 << 3) + blockIdx.x * NN_THREADS + threadIdx.x;
-  if (tail < n) {
-    const unsigned e = __ldg(idx + tail);
-    const unsigned t = __ldg((const unsigned *)byte_offset_rt(src, (e >> 16) * pitch + (e & 0xFFFFu), 4u));
-    dst[tail] = IDENT ? (t | 0xFF000000u) : map_rgba(t, tab_lane);
+    for (int k = 0; k < NN_PER_THREAD; ++k) {
+      const unsigned i = base + 32u * k + lane;
+      if (i < n) st_stream(dst + i, IDENT ? (t[k] | 0xFF000000u) : map_rgba(t[k], tab_lane), stream);
+    }
   }
 }
 
@@ -112,37 +128,38 @@ LRP_DEV unsigned short copy_half(unsigned short h) {
 }
 
 template <int C> __global__ void __launch_bounds__(NN_THREADS, 4) nn_table_f16_kernel(const __grid_constant__ KParams P) {
-  const size_t n = (size_t)P.W * (size_t)P.H;
+  const unsigned n = (unsigned)P.W * (unsigned)P.H;
   const unsigned *idx = P.nn_index;
   const unsigned short *src = (const unsigned short *)P.src;
   unsigned short *dst = (unsigned short *)P.dst;
   const unsigned pitch = P.src_pitch;
-  const bool vec = (n & 3) == 0; // every plane starts 8-byte aligned
-  if (vec) {
-    for (size_t i = (size_t)blockIdx.x * NN_THREADS + threadIdx.x; i < (n >> 2); i += (size_t)gridDim.x * NN_THREADS) {
-      const uint4 e = __ldg((const uint4 *)idx + i);
-      const unsigned ee[4] = {e.x, e.y, e.z, e.w};
-      unsigned short h[C][4];
+  const unsigned long long keep = policy_evict_last();
+  const unsigned lane = threadIdx.x & 31u, warp = (blockIdx.x * NN_THREADS + threadIdx.x) >> 5;
+  const unsigned warps = (gridDim.x * NN_THREADS) >> 5;
+  constexpr int PER = 4;
+  constexpr unsigned CHUNK = 32 * PER;
+#pragma unroll 1
+  for (unsigned base = warp * CHUNK; base < n; base += warps * CHUNK) {
+    unsigned e[PER];
+    unsigned short h[PER][C];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const unsigned short *p = src + (size_t)((ee[k] >> 16) * pitch + (ee[k] & 0xFFFFu));
-#pragma unroll
-        for (int c = 0; c < C; ++c) h[c][k] = __ldg(p + (size_t)c * (size_t)P.src_plane);
-      }
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        uint2 o;
-        o.x = (unsigned)copy_half(h[c][0]) | ((unsigned)copy_half(h[c][1]) << 16);
-        o.y = (unsigned)copy_half(h[c][2]) | ((unsigned)copy_half(h[c][3]) << 16);
-        __stcs((uint2 *)(dst + (size_t)c * (size_t)P.dst_plane) + i, o);
-      }
+    for (int k = 0; k < PER; ++k) {
+      const unsigned i = base + 32u * k + lane;
+      e[k] = i < n ? ld_index(idx + i, keep) : 0u;
     }
-  } else {
-    for (size_t i = (size_t)blockIdx.x * NN_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * NN_THREADS) {
-      const unsigned e = __ldg(idx + i);
-      const unsigned short *p = src + (size_t)((e >> 16) * pitch + (e & 0xFFFFu));
 #pragma unroll
-      for (int c = 0; c < C; ++c) dst[(size_t)c * (size_t)P.dst_plane + i] = copy_half(__ldg(p + (size_t)c * (size_t)P.src_plane));
+    for (int k = 0; k < PER; ++k) {
+      const unsigned short *p = src + (size_t)((e[k] >> 16) * pitch + (e[k] & 0xFFFFu));
+#pragma unroll
+      for (int c = 0; c < C; ++c) h[k][c] = __ldg(p + (size_t)c * (size_t)P.src_plane);
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const unsigned i = base + 32u * k + lane;
+      if (i < n) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) __stcs(dst + (size_t)c * (size_t)P.dst_plane + i, copy_half(h[k][c]));
+      }
     }
   }
 }
@@ -176,7 +193,7 @@ template <int C> __global__ void __launch_bounds__(NN_THREADS, 4) nn_table_f32_k
 
 int launch_nn_table(const KParams &P, int fc, void *stream) {
   const size_t n = (size_t)P.W * (size_t)P.H;
-  const size_t per_thread = (fc == FC_U8_3) ? 8 : (fc == FC_F16_3 || fc == FC_F16_4 || fc == FC_F16_5) ? 4 : 1;
+  const size_t per_thread = (fc == FC_U8_3) ? NN_PER_THREAD : (fc == FC_F16_3 || fc == FC_F16_4 || fc == FC_F16_5) ? 4 : 1;
   size_t ctas = (n / per_thread + NN_THREADS - 1) / NN_THREADS + 1;
   const size_t persistent = (size_t)P.num_sms * 4; // 4 resident CTAs per SM; grid-stride beyond
   if (ctas > persistent) ctas = persistent;

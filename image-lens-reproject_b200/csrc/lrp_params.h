@@ -62,6 +62,7 @@ struct KParams {
   int num_sms;                  // persistent grid size (SM count of the context's device)
   int stage_gain;               // staged kernel: issue slots per step (2 x 16 pixels) that staged taps save over gathered ones
   int *sched;                   // tile scheduler counters {tickets, retired warps} of this launch's stream, or nullptr
+  int rec_pad;                  // staged kernel: pad the rows of staged records to a pitch of 4 (mod 8) records (bank groups)
   int tiled_ctas;               // tiled kernel: resident CTAs per SM (2 or 3), chosen by the host per format
   int fast_lens;                // input-lens divisors are normal numbers in [2^-20, 2^20]: unguarded divisions apply
   // nearest, one sample per pixel, 8-bit source and sink: the whole per-sample function as a byte map (lrp_api.cu

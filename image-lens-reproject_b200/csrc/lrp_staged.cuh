@@ -53,12 +53,18 @@ constexpr int ST_COORD_BYTES = ST_STEPS * 32 * 8;
 constexpr int ST_SMEM_BYTES = 232448;     // 227 KB: the opt-in maximum of dynamic shared memory per CTA
 constexpr int ST_FIXED_BYTES = 1088 + 1024 + 1024; // thresholds + 1 KB alignment slack + gamma table
 
-// staging record: C <= 4 -> one float4 (c0, c1, c2, c3|next c2); C == 5 -> float4 + float2 (c4, next c4)
+// staging records (shared-memory wavefronts bound this kernel: profiles/r2_c2_bc_table_staged_wavefronts.txt):
+//   C == 3   two planes of 8-byte records: A = (c0, c1), B = (c2, c2 of the next column) — every load is a 64-bit load of
+//            densely packed records (2.1 wavefronts per warp; the former float4 record cost 5.45 per 128-bit load and
+//            4.27 per 64-bit load of half a record, 78 -> 50 wavefronts per 32 pixels)
+//   C == 4   one float4 (c0, c1, c2, c3)
+//   C == 5   float4 + float2 (c4, c4 of the next column)
 // NW = warps per CTA: a warp's staging area is its share of the dynamic shared memory
 template <int C, int NW> struct StageRec {
   static constexpr int STAGE_BYTES = (((ST_SMEM_BYTES - ST_FIXED_BYTES) / NW) - ST_COORD_BYTES) & ~15;
-  static constexpr int A_BYTES = 16;
-  static constexpr int B_BYTES = (C == 5) ? 8 : 0;
+  static constexpr bool SPLIT = (C == 3);
+  static constexpr int A_BYTES = SPLIT ? 8 : 16;
+  static constexpr int B_BYTES = (C == 5 || SPLIT) ? 8 : 0;
   static constexpr int CAP = STAGE_BYTES / (A_BYTES + B_BYTES); // texels per warp
   static constexpr bool LONE = (C & 1) != 0; // odd channel count: the last channel travels as (value, value of the next column)
 };
@@ -75,9 +81,14 @@ struct BBox {
 struct GroupPlan {
   BBox eff;
   unsigned bw, bh;
+  unsigned pitch; // records per staged row: bw, padded to 4 (mod 8) when P.rec_pad — see below
   bool clamped;
 };
-template <bool WRAP> LRP_DEV bool plan_group(const BBox &raw, int w, int h, unsigned cap, GroupPlan &g) {
+// Shared-memory bank groups: a record is 16 bytes, a quarter-warp (8 lanes) is served per wavefront of a 128-bit load when
+// its records fall into 8 different 16-byte bank groups, i.e. have different indices mod 8.  The 8 pixels of a quarter
+// touch 3-4 consecutive records of one source row and, when the mapping is rotated, as many of the next row: with a row
+// pitch of 4 (mod 8) the two runs land in disjoint residues whatever the box width is (measured: profiles/r2_*pad*).
+template <bool WRAP> LRP_DEV bool plan_group(const BBox &raw, int w, int h, unsigned cap, GroupPlan &g, int rec_pad = 0) {
   // out-of-image tests on the RAW box (unsigned compare: negative indices are huge)
   const bool cut_y = ((unsigned)raw.y0 >= (unsigned)h) || ((unsigned)raw.y1 >= (unsigned)h);
   const bool cut_x = !WRAP && (((unsigned)raw.x0 >= (unsigned)w) || ((unsigned)raw.x1 >= (unsigned)w));
@@ -94,7 +105,8 @@ template <bool WRAP> LRP_DEV bool plan_group(const BBox &raw, int w, int h, unsi
   g.clamped = cut_x || cut_y;
   g.bw = (unsigned)g.eff.x1 - (unsigned)g.eff.x0 + 1u;
   g.bh = (unsigned)g.eff.y1 - (unsigned)g.eff.y0 + 1u;
-  return ok && g.bw <= 4096u && g.bh <= 4096u && g.bw * g.bh <= cap;
+  g.pitch = rec_pad ? (((g.bw + 3u) & ~7u) + 4u) : g.bw;
+  return ok && g.bw <= 4096u && g.bh <= 4096u && g.pitch * g.bh <= cap;
 }
 
 // (i + w) % w / clamp exactly as the gather path applies them to a raw tap index (reference :43-47, :60-67,
@@ -158,7 +170,7 @@ template <int C> struct StageLoad<FMT_F16, C> {
 // width), U x 32 at a time with all the global loads of a round issued before the first decode.
 template <bool WRAP, int FMT, int C, int NW>
 LRP_DEV void stage_group(const KParams &P, uint32_t lut, unsigned char *stage, const BBox &b, unsigned bw, unsigned bh,
-                         int lane) {
+                         unsigned pitch, int lane) {
   typedef StageRec<C, NW> Rec;
   constexpr unsigned STEP = Rec::LONE ? 31u : 32u; // odd C: lane k needs lane k+1's texel, so rounds overlap by one record
   constexpr int U = 4;
@@ -183,6 +195,10 @@ LRP_DEV void stage_group(const KParams &P, uint32_t lut, unsigned char *stage, c
       if (t0 + (unsigned)u * STEP >= n) break; // warp-uniform
       const unsigned t = t0 + (unsigned)u * STEP + (unsigned)lane;
       const bool in = t < n;
+      // record slot: row * pitch + column (pitch == bw unless the rows are padded; a lone channel's right-hand neighbour is
+      // the next slot of the same row, and the last column's neighbour value is never read)
+      const unsigned tyr = (bw == 1u) ? t : __umulhi(t, magic);
+      const unsigned slot = t + tyr * (pitch - bw);
       float v[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) v[c] = 0.0f;
@@ -192,9 +208,9 @@ LRP_DEV void stage_group(const KParams &P, uint32_t lut, unsigned char *stage, c
       // odd C: lane 31's texel is lane 0's texel of the next round (STEP = 31), which runs whenever t < n and
       // knows the neighbour's value — lane 31 only supplies `nxt` to lane 30 and never writes
       if (in && (!Rec::LONE || lane < 31)) {
-        if (C == 3) recA[t] = make_float4(v[0], v[1], v[2], nxt);
-        else recA[t] = make_float4(v[0], v[1], v[2], v[3 < C ? 3 : 0]);
-        if (C == 5) recB[t] = make_float2(v[C - 1], nxt);
+        if (Rec::SPLIT) ((float2 *)stage)[slot] = make_float2(v[0], v[1]);
+        else recA[slot] = make_float4(v[0], v[1], v[2], v[3 < C ? 3 : 0]);
+        if (Rec::LONE) recB[slot] = make_float2(v[C - 1], nxt);
       }
     }
   }
@@ -205,7 +221,7 @@ LRP_DEV void stage_group(const KParams &P, uint32_t lut, unsigned char *stage, c
 struct StageView {
   const unsigned char *stage; // this warp's records
   int bx0, by0;               // tap index of record (0, 0)
-  unsigned bw;                // records per row
+  unsigned bw;                // records per row (the plan's pitch)
   bool clamped;               // warp-uniform: resolve indices before addressing (border groups)
   float frac_max;             // warp-uniform: largest fraction for which indices are provably consecutive
 };
@@ -278,61 +294,6 @@ LRP_DEV void staged_indices(const KParams &P, const StageView &V, float sx, floa
   }
 }
 
-template <int C> LRP_DEV void unpack_rec(const float4 a, float (&out)[C]) {
-  out[0] = a.x;
-  if (C > 1) out[1 < C ? 1 : 0] = a.y;
-  if (C > 2) out[2 < C ? 2 : 0] = a.z;
-  if (C > 3) out[3 < C ? 3 : 0] = a.w;
-}
-
-template <bool WRAP, int C, int NW>
-LRP_DEV void staged_nearest(const KParams &P, const StageView &V, float sx, float sy, float (&out)[C]) {
-  typedef StageRec<C, NW> Rec;
-  const float off[1] = {0.5f};
-  int ix[1], iy[1];
-  staged_indices<WRAP, 1>(P, V, sx, sy, off, ix, iy); // :43-47
-  const unsigned t = (unsigned)(iy[0] - V.by0) * V.bw + (unsigned)(ix[0] - V.bx0);
-  unpack_rec<C>(((const float4 *)V.stage)[t], out);
-  if (C == 5) out[C - 1] = ((const float2 *)(V.stage + Rec::CAP * Rec::A_BYTES))[t].x;
-}
-
-template <bool WRAP, int C, int NW>
-LRP_DEV void staged_bilinear(const KParams &P, const StageView &V, float sx, float sy, float (&out)[C]) {
-  typedef StageRec<C, NW> Rec;
-  const float off[2] = {0.0f, 1.0f};
-  int ix[2], iy[2];
-  staged_indices<WRAP, 2>(P, V, sx, sy, off, ix, iy); // :60-67
-  const float fx = clamp01_std(fsub(sx, (float)resolve_x<WRAP>(ix[0], P.w))); // post-wrap/clamp lx, :70
-  const float fy = clamp01_std(fsub(sy, (float)clampi(iy[0], P.h)));
-  const float cfx = fsub(1.0f, fx), cfy = fsub(1.0f, fy);
-  const unsigned r0 = (unsigned)(iy[0] - V.by0) * V.bw, r1 = (unsigned)(iy[1] - V.by0) * V.bw;
-  const unsigned c0 = (unsigned)(ix[0] - V.bx0), c1 = (unsigned)(ix[1] - V.bx0);
-  const ulonglong2 *recA = (const ulonglong2 *)V.stage;
-  const ulonglong2 ll = recA[r0 + c0], lu = recA[r0 + c1], ul = recA[r1 + c0], uu = recA[r1 + c1];
-  const f2 fx2 = pack2(fx, fx), cfx2 = pack2(cfx, cfx), fy2 = pack2(fy, fy), cfy2 = pack2(cfy, cfy);
-  const unsigned long long nz = P.neg_zero2;
-  { // channels 0, 1
-    const f2 l = add2(mul2(fx2, as_f2(lu.x), nz), mul2(cfx2, as_f2(ll.x), nz)); // :83
-    const f2 u = add2(mul2(fx2, as_f2(uu.x), nz), mul2(cfx2, as_f2(ul.x), nz)); // :84
-    unpack2(add2(mul2(fy2, u, nz), mul2(cfy2, l, nz)), out[0], out[1]);         // :87
-  }
-  { // channels 2, 3 (the upper lane is a spare when C == 3)
-    const f2 l = add2(mul2(fx2, as_f2(lu.y), nz), mul2(cfx2, as_f2(ll.y), nz));
-    const f2 u = add2(mul2(fx2, as_f2(uu.y), nz), mul2(cfx2, as_f2(ul.y), nz));
-    float a, b;
-    unpack2(add2(mul2(fy2, u, nz), mul2(cfy2, l, nz)), a, b);
-    out[2] = a;
-    if (C >= 4) out[3 < C ? 3 : 0] = b;
-  }
-  if (C == 5) {
-    const float2 *recB = (const float2 *)(V.stage + Rec::CAP * Rec::A_BYTES);
-    const float vll = recB[r0 + c0].x, vlu = recB[r0 + c1].x, vul = recB[r1 + c0].x, vuu = recB[r1 + c1].x;
-    const float l = fadd(fmul(fx, vlu), fmul(cfx, vll));
-    const float u = fadd(fmul(fx, vuu), fmul(cfx, vul));
-    out[C - 1] = fadd(fmul(fy, u), fmul(cfy, l));
-  }
-}
-
 template <bool WRAP, int C, bool X2, int NW>
 LRP_DEV void staged_bicubic(const KParams &P, const StageView &V, float sx, float sy, float (&out)[C]) {
   typedef StageRec<C, NW> Rec;
@@ -352,9 +313,9 @@ LRP_DEV void staged_bicubic(const KParams &P, const StageView &V, float sx, floa
   f2 P0[4][4], P1[4][4], L[2][4];
   const unsigned rowrec = V.bw;
   const bool regular = !V.clamped && (sx >= 1.0f) && (sy >= 1.0f) && (fx <= V.frac_max) && (fy <= V.frac_max);
-  const ulonglong2 *recA = (const ulonglong2 *)V.stage;
-  const unsigned long long *recA64 = (const unsigned long long *)V.stage;
-  const unsigned long long *recB = (const unsigned long long *)(V.stage + Rec::CAP * Rec::A_BYTES);
+  const ulonglong2 *recA = (const ulonglong2 *)V.stage;                  // C >= 4: float4 records
+  const unsigned long long *recA64 = (const unsigned long long *)V.stage; // C == 3: (c0, c1) records
+  const unsigned long long *recB = (const unsigned long long *)(V.stage + Rec::CAP * Rec::A_BYTES); // odd C: lone channel
   if (regular) { // consecutive records: row base + immediate offsets
     const unsigned t00 = (unsigned)(y1 - 1 - V.by0) * rowrec + (unsigned)(x1 - 1 - V.bx0);
 #pragma unroll
@@ -362,16 +323,15 @@ LRP_DEV void staged_bicubic(const KParams &P, const StageView &V, float sx, floa
       const unsigned t = t00 + (unsigned)yi * rowrec;
 #pragma unroll
       for (int xi = 0; xi < 4; ++xi) {
-        if (C == 3 && (xi & 1)) {
-          P0[xi][yi] = as_f2(recA64[2 * (t + xi)]); // (c0, c1) only: c2 came with the column to the left
+        if (Rec::SPLIT) {
+          P0[xi][yi] = as_f2(recA64[t + xi]);
         } else {
           const ulonglong2 q = recA[t + xi];
           P0[xi][yi] = as_f2(q.x);
-          if (C == 3) L[xi >> 1][yi] = as_f2(q.y); // (c2 of this column, c2 of the next)
-          else P1[xi][yi] = as_f2(q.y);
+          P1[xi][yi] = as_f2(q.y);
         }
       }
-      if (C == 5) {
+      if (Rec::LONE) { // (value of this column, value of the next)
         L[0][yi] = as_f2(recB[t]);
         L[1][yi] = as_f2(recB[t + 2]);
       }
@@ -391,11 +351,14 @@ LRP_DEV void staged_bicubic(const KParams &P, const StageView &V, float sx, floa
       float lone[4];
 #pragma unroll
       for (int xi = 0; xi < 4; ++xi) {
-        const ulonglong2 q = recA[ry[yi] + cx[xi]];
-        P0[xi][yi] = as_f2(q.x);
-        if (C == 3) lone[xi] = f2_lo(as_f2(q.y));
-        else P1[xi][yi] = as_f2(q.y);
-        if (C == 5) lone[xi] = f2_lo(as_f2(recB[ry[yi] + cx[xi]]));
+        if (Rec::SPLIT) {
+          P0[xi][yi] = as_f2(recA64[ry[yi] + cx[xi]]);
+        } else {
+          const ulonglong2 q = recA[ry[yi] + cx[xi]];
+          P0[xi][yi] = as_f2(q.x);
+          P1[xi][yi] = as_f2(q.y);
+        }
+        if (Rec::LONE) lone[xi] = f2_lo(as_f2(recB[ry[yi] + cx[xi]]));
       }
       if (Rec::LONE) {
         L[0][yi] = pack2(lone[0], lone[1]);
@@ -441,6 +404,7 @@ LRP_DEV void staged_bicubic(const KParams &P, const StageView &V, float sx, floa
 //   + NW x Rec::STAGE_BYTES              per-warp staging records
 template <int COORD, int INTERP, int FMT, int C>
 __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_kernel(const __grid_constant__ KParams P) {
+  static_assert(INTERP == INTERP_BC, "the 1 / 4 taps of nearest / bilinear are cheaper gathered through L1 (measured, round 1)");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool WRAP = (COORD == COORD_ERECT_WRAP || COORD == COORD_TABLE_WRAP);
   constexpr bool TABLE = (COORD == COORD_TABLE_CLAMP || COORD == COORD_TABLE_WRAP);
@@ -591,20 +555,20 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
         const bool any_bad = __any_sync(0xffffffffu, bad);
         // worth it: the records fit, and staging them (about one issue slot per record) costs less than the
         // per-tap global loads + decodes it replaces (P.stage_gain issue slots per step, set by the host per format)
-        staged = plan_group<WRAP>(raw, P.w, P.h, Rec::CAP, plan) && !any_bad &&
+        staged = plan_group<WRAP>(raw, P.w, P.h, Rec::CAP, plan, P.rec_pad) && !any_bad &&
                  plan.bw * plan.bh <= (unsigned)(P.stage_gain * (end - start));
         if (staged || len == 1) break;
         len >>= 1;
       }
       const int end = min(start + len, R);
       if (staged) {
-        stage_group<WRAP, FMT, C, NW>(P, lut_addr, s_stage, plan.eff, plan.bw, plan.bh, lane);
+        stage_group<WRAP, FMT, C, NW>(P, lut_addr, s_stage, plan.eff, plan.bw, plan.bh, plan.pitch, lane);
         __syncwarp();
       }
       // fraction bound of the sampler's consecutive-index shortcut: rounding error of s + 2.0f <= ulp / 2,
       // ulp(M) <= M * 2^-23; the bound leaves twice that
       const float big = (float)(max(plan.eff.x1, plan.eff.y1) + 4);
-      const StageView V{s_stage, plan.eff.x0, plan.eff.y0, plan.bw, plan.clamped,
+      const StageView V{s_stage, plan.eff.x0, plan.eff.y0, plan.pitch, plan.clamped,
                         fsub(1.0f, fmul(big, 1.1920929e-7f))};
       for (int rr = start; rr < end; ++rr) {
         const int y = y0 + 2 * rr + ly;
@@ -612,9 +576,7 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
         const float2 s = s_coord[rr * 32 + lane];
         float v[C];
         if (staged) {
-          if (INTERP == INTERP_NN) staged_nearest<WRAP, C, NW>(P, V, s.x, s.y, v);
-          else if (INTERP == INTERP_BL) staged_bilinear<WRAP, C, NW>(P, V, s.x, s.y, v);
-          else staged_bicubic<WRAP, C, X2, NW>(P, V, s.x, s.y, v);
+          staged_bicubic<WRAP, C, X2, NW>(P, V, s.x, s.y, v);
         } else {
           if (INTERP == INTERP_NN) sample_nearest<WRAP, FMT, C>(S, s.x, s.y, v);
           else if (INTERP == INTERP_BL) sample_bilinear<WRAP, FMT, C>(S, s.x, s.y, v);

@@ -30,13 +30,21 @@
 
 namespace lrp {
 
-constexpr int TL_W = 32, TL_H = 32;
-constexpr int TL_WARPS = 8, TL_THREADS = TL_WARPS * 32;
-constexpr int TL_ROWS = TL_H / TL_WARPS; // pixels per thread
-// resident CTAs per SM (NCTA): 3 x 74 KB (80 registers per thread) or 2 x 112 KB (128 registers) — both instantiated, the
-// launcher picks per format by measurement (LRP_TL_CTAS overrides)
-__host__ __device__ constexpr int tl_smem_bytes(int ncta) { return ncta == 3 ? 74 * 1024 : ncta == 2 ? 112 * 1024 : 226 * 1024; }
-constexpr int TL_FIXED_BYTES = 1088 + 1024 + 1024 + 256; // thresholds, alignment slack, gamma table, per-warp boxes + ticket
+// tile shape: TL_WARPS warps x TL_ROWS rows each, 32 columns (-D overrides for A/B builds)
+#ifndef LRP_TL_WARPS
+#define LRP_TL_WARPS 8
+#endif
+#ifndef LRP_TL_ROWS
+#define LRP_TL_ROWS 4
+#endif
+constexpr int TL_WARPS = LRP_TL_WARPS, TL_THREADS = TL_WARPS * 32;
+constexpr int TL_ROWS = LRP_TL_ROWS; // pixels per thread
+constexpr int TL_W = 32, TL_H = TL_WARPS * TL_ROWS;
+// resident CTAs per SM (NCTA): two choices are instantiated (more CTAs = more independent phases but fewer registers and
+// less record space each); the launcher picks per format by measurement (LRP_TL_CTAS = 0 / 1 overrides)
+constexpr int TL_NCTA_LO = (TL_WARPS == 8) ? 2 : 4, TL_NCTA_HI = (TL_WARPS == 8) ? 3 : 6; // 128 / 80 registers per thread
+__host__ __device__ constexpr int tl_smem_bytes(int ncta) { return ((227 * 1024) / ncta - 1024) & ~1023; }
+constexpr int TL_FIXED_BYTES = 1088 + 1024 + 1024 + 32 * TL_WARPS; // thresholds, alignment slack, gamma table, per-warp boxes
 
 // records: C == 3: 48 B  q0 = [p.c0 p.c1 | D.c0 D.c1]  q1 = [A.c0 A.c1 | B.c0 B.c1]  q2 = [p.c2 D.c2 A.c2 B.c2]
 //          C == 4: 80 B  q0, q1 as above for (c0, c1), q2, q3 the same for (c2, c3), 16 B of padding: eight consecutive
@@ -259,8 +267,10 @@ __global__ void __launch_bounds__(TL_THREADS, NCTA) reproject_tiled_kernel(const
   WarpBox *s_box = (WarpBox *)(smem_raw + (lut_addr - win0) + 1024u);
   unsigned char *s_rec = (unsigned char *)(s_box + TL_WARPS);
 
-  if (P.dst_fmt == FMT_U8 && tid <= 256) s_thr[tid] = (tid < 256) ? P.thr[tid] : __int_as_float(0x7f800000);
-  if (FMT == FMT_U8 && tid < 256) ((float *)(smem_raw + (lut_addr - win0)))[tid] = __ldg(P.lut + tid);
+  if (P.dst_fmt == FMT_U8) // 257 entries: thr[256] = +inf closes the last bin
+    for (int i = tid; i <= 256; i += TL_THREADS) s_thr[i] = (i < 256) ? P.thr[i] : __int_as_float(0x7f800000);
+  if (FMT == FMT_U8)
+    for (int i = tid; i < 256; i += TL_THREADS) ((float *)(smem_raw + (lut_addr - win0)))[i] = __ldg(P.lut + i);
   __syncthreads();
 
   const bool separable = !TABLE && (P.ol.type == LENS_RECT || P.ol.type == LENS_ERECT);
@@ -306,7 +316,7 @@ __global__ void __launch_bounds__(TL_THREADS, NCTA) reproject_tiled_kernel(const
       float rvx[3] = {0.0f, 0.0f, 0.0f}, rvz[3] = {0.0f, 0.0f, 0.0f};
       if (separable) { // rect / equirect output lenses: column part per lane, row part of row yw + lane by lanes 0..3
         const float scx = fsub(fadd(cx, q), 0.5f);
-        const float cyl = fsub(fadd((float)(yw + (lane & (TL_ROWS - 1))), 0.5f), half_H);
+        const float cyl = fsub(fadd((float)(yw + (lane % TL_ROWS)), 0.5f), half_H);
         const float scyl = fsub(fadd(cyl, q), 0.5f);
         if (out_rect) {
           col_vx = fdiv(fmul(fdiv(scx, Wf), P.ol.sw), P.ol.p0);
@@ -393,24 +403,23 @@ __global__ void __launch_bounds__(TL_THREADS, NCTA) reproject_tiled_kernel(const
       int len = (start | TL_WARPS) & -(start | TL_WARPS);
       GroupPlan plan;
       bool staged;
-      for (;;) { // every thread evaluates the same plan from the same shared boxes
-        BBox raw;
-        raw.x0 = raw.y0 = 0x7fffffff;
-        raw.x1 = raw.y1 = (int)0x80000000;
-        bool any_bad = false;
+      for (;;) { // every warp evaluates the same plan from the same shared boxes: lane i reads box start + i
         const int end = min(start + len, warps_live);
-        for (int w2 = start; w2 < end; ++w2) {
-          const WarpBox wb = s_box[w2];
-          raw.x0 = min(raw.x0, wb.x0);
-          raw.x1 = max(raw.x1, wb.x1);
-          raw.y0 = min(raw.y0, wb.y0);
-          raw.y1 = max(raw.y1, wb.y1);
-          any_bad = any_bad || wb.bad != 0;
-        }
+        WarpBox wb;
+        wb.x0 = wb.y0 = 0x7fffffff;
+        wb.x1 = wb.y1 = (int)0x80000000;
+        wb.bad = 0;
+        if (start + lane < end) wb = s_box[start + lane];
+        BBox raw;
+        raw.x0 = __reduce_min_sync(0xffffffffu, wb.x0);
+        raw.x1 = __reduce_max_sync(0xffffffffu, wb.x1);
+        raw.y0 = __reduce_min_sync(0xffffffffu, wb.y0);
+        raw.y1 = __reduce_max_sync(0xffffffffu, wb.y1);
+        const bool any_bad = __any_sync(0xffffffffu, wb.bad != 0);
         // worth staging: the records fit, and cost less than the per-tap gathers they replace (P.stage_gain issue
-        // slots per 32-pixel row step, as in lrp_staged.cuh; a block of `len` warps holds 4 * len such steps)
+        // slots per 32-pixel row step, as in lrp_staged.cuh; a block of `len` warps holds TL_ROWS * len such steps)
         staged = !any_bad && plan_group<WRAP>(raw, P.w, P.h, (unsigned)Rec::cap(NCTA), plan) &&
-                 plan.bw * plan.bh <= (unsigned)(P.stage_gain * 2 * TL_ROWS * (end - start));
+                 plan.bw * plan.bh <= (unsigned)(P.stage_gain * TL_ROWS * (end - start));
         if (staged || len == 1) break;
         len >>= 1;
       }
@@ -477,8 +486,8 @@ int launch_reproject_tiled_n(const KParams &P, void *stream) {
 
 template <int COORD, int FMT, int C>
 int launch_reproject_tiled(const KParams &P, void *stream) {
-  return P.tiled_ctas == 2 ? launch_reproject_tiled_n<COORD, FMT, C, 2>(P, stream)
-                           : launch_reproject_tiled_n<COORD, FMT, C, 3>(P, stream);
+  return P.tiled_ctas == 0 ? launch_reproject_tiled_n<COORD, FMT, C, TL_NCTA_LO>(P, stream)
+                           : launch_reproject_tiled_n<COORD, FMT, C, TL_NCTA_HI>(P, stream);
 }
 
 } // namespace lrp

@@ -326,9 +326,9 @@ def test_codec_formats_against_the_compiled_reference(lrp):
 
 # ---- the CTA-tiled shared-coefficient kernel (lrp_tiled.cuh) ---------------------------------------------------------
 
-@pytest.mark.parametrize("ctas", ["2", "3"])
+@pytest.mark.parametrize("ctas", ["0", "1"])
 def test_tiled_kernel_both_occupancies(lrp, ctas, monkeypatch):
-    """2 and 3 resident CTAs per SM are separate instantiations with different record capacities (block splits differ)"""
+    """the two instantiated residencies (LRP_TL_CTAS 0 / 1: 2 / 3 CTAs per SM) have different record capacities (block splits differ)"""
     monkeypatch.setenv("LRP_TL_CTAS", ctas)
     rng = np.random.default_rng(int(ctas))
     for (W, H, w, h, il, olens, r) in (
