@@ -812,6 +812,9 @@ struct Pool {
       if (rc != LRP_OK) return rc;
     }
     LRP_CUDA(cudaMemcpyAsync(job.out.data, js->slot.d_out, out_bytes, cudaMemcpyDeviceToHost, js->slot.stream));
+    // the event carries the job's status to the reaper (the stream itself still counts as busy while the callback runs)
+    if (!js->slot.done) LRP_CUDA(cudaEventCreateWithFlags(&js->slot.done, cudaEventDisableTiming));
+    LRP_CUDA(cudaEventRecord(js->slot.done, js->slot.stream));
     LRP_CUDA(cudaLaunchHostFunc(js->slot.stream, on_stream_done, js));
     ctx->h2d_bytes += h2d;
     js->out_bytes = out_bytes;
@@ -838,7 +841,7 @@ struct Pool {
         JobSlot *js = e->slots[e->completed.front()];
         e->completed.pop_front();
         lk.unlock();
-        int rc = map_cuda(cudaStreamQuery(js->slot.stream)); // surfaces an asynchronous error of the job's work
+        int rc = map_cuda(cudaEventQuery(js->slot.done)); // complete by stream order; surfaces an asynchronous error
         if (rc == LRP_OK) e->ctx->d2h_bytes += js->out_bytes;
         finish(e, js->item, rc);
         lk.lock();
