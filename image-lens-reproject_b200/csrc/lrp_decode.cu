@@ -358,7 +358,10 @@ static int exr_parse(const unsigned char *f, size_t n, ExrInfo &I) {
       if (len < 16) return LRP_E_BAD_ARG;
       int32_t b[4];
       memcpy(b, d, 16);
-      I.w = b[2] - b[0] + 1, I.h = b[3] - b[1] + 1;
+      // attacker-controlled corners: the extent in 64 bits, range-checked before it narrows
+      const int64_t ww = (int64_t)b[2] - (int64_t)b[0] + 1, hh = (int64_t)b[3] - (int64_t)b[1] + 1;
+      if (ww <= 0 || hh <= 0 || ww > 0x7fffffff || hh > 0x7fffffff) return LRP_E_BAD_ARG;
+      I.w = (int)ww, I.h = (int)hh;
       have_dw = true;
     } else if (name == "lineOrder") {
       if (len < 1) return LRP_E_BAD_ARG;
@@ -425,6 +428,9 @@ static int png_parse(const unsigned char *f, size_t n, PngInfo &I, std::vector<u
     const uint32_t len = be32(f + pos);
     if (pos + 12 + (size_t)len > n) return LRP_E_BAD_ARG;
     const unsigned char *type = f + pos + 4, *data = f + pos + 8;
+    // lodepng verifies every chunk's CRC (ignore_crc = 0, lib/lodepng/lodepng.cpp: error 57): a corrupted file the
+    // reference refuses is refused here too
+    if ((uint32_t)crc32(0L, type, 4 + len) != be32(data + len)) return LRP_E_BAD_ARG;
     if (!memcmp(type, "IHDR", 4)) {
       if (len != 13) return LRP_E_BAD_ARG;
       I.w = be32(data), I.h = be32(data + 4), I.depth = data[8], I.ctype = data[9];
@@ -721,22 +727,30 @@ int lrp_decoder_exr(lrp_decoder *d, const void *file, size_t n, int32_t threads,
       memcpy(hdr, f + off, 8);
       const size_t lines = std::min<size_t>(I.lines_per_block, (size_t)I.h - b * I.lines_per_block), raw_n = lines * line_bytes;
       if (hdr[1] < 0 || (size_t)hdr[1] > n - off - 8) return LRP_E_BAD_ARG;
-      const bool stored = (size_t)hdr[1] == raw_n || I.compression == 0;
-      if (stored && (size_t)hdr[1] != raw_n) return LRP_E_BAD_ARG;
+      // a block whose data size is not below its raw size is stored raw (OpenEXR's reader: dataSize >= uncompressedSize)
+      const bool stored = (size_t)hdr[1] >= raw_n || I.compression == 0;
+      if (stored && (size_t)hdr[1] < raw_n) return LRP_E_BAD_ARG;
       InflateJob &J = d->h_jobs[b];
       J.src_off = off + 8, J.dst_off = b * I.lines_per_block * line_bytes;
-      J.src_len = (unsigned)hdr[1], J.dst_len = (unsigned)raw_n, J.stored = stored ? 1u : 0u, J.pad = 0;
+      J.src_len = stored ? (unsigned)raw_n : (unsigned)hdr[1], J.dst_len = (unsigned)raw_n, J.stored = stored ? 1u : 0u, J.pad = 0;
       d->h_raw[b] = stored ? 1 : 0;
     }
     memcpy(d->h_buf, f, n); // pinned staging: the copy below is asynchronous and the caller's buffer may be pageable
     if (cudaSetDevice(d->device) != cudaSuccess) return LRP_E_CUDA;
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    // (copies out of the decoder's pinned buffers may already be queued when a later call fails: drain the stream before
+    // the error returns, the caller is free to reuse the decoder at once)
+    auto fail = [st]() {
+      cudaStreamSynchronize(st);
+      cudaGetLastError();
+      return (int)LRP_E_CUDA;
+    };
     if (cudaMemcpyAsync(d->d_file, d->h_buf, n, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(d->d_jobs, d->h_jobs, blocks * sizeof(InflateJob), cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(d->d_raw, d->h_raw, blocks, cudaMemcpyHostToDevice, st) != cudaSuccess)
-      return LRP_E_CUDA;
+      return fail();
     exr_inflate_kernel<<<(unsigned)blocks, 32, 0, st>>>(d->d_file, d->d_jobs, d->d_buf, d->d_status);
-    if (cudaMemcpyAsync(d->h_status, d->d_status, blocks * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return LRP_E_CUDA;
+    if (cudaMemcpyAsync(d->h_status, d->d_status, blocks * sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail();
   } else
   parallel_for(blocks, threads, [&](size_t b) {
     uint64_t off;
@@ -755,8 +769,8 @@ int lrp_decoder_exr(lrp_decoder *d, const void *file, size_t n, int32_t threads,
       return;
     }
     unsigned char *dst = d->h_buf + b * I.lines_per_block * line_bytes;
-    if ((size_t)hdr[1] == raw_n || I.compression == 0) { // stored (NO_COMPRESSION, or a block that did not shrink)
-      if ((size_t)hdr[1] != raw_n) {
+    if ((size_t)hdr[1] >= raw_n || I.compression == 0) { // stored (NO_COMPRESSION, or a block that did not shrink:
+      if ((size_t)hdr[1] < raw_n) {                       // OpenEXR's reader takes dataSize >= uncompressedSize as raw)
         status = LRP_E_BAD_ARG;
         return;
       }
@@ -790,8 +804,11 @@ int lrp_decoder_exr(lrp_decoder *d, const void *file, size_t n, int32_t threads,
   if (cudaSetDevice(d->device) != cudaSuccess) return LRP_E_CUDA;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   if (!on_device && (cudaMemcpyAsync(d->d_buf, d->h_buf, total, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-                     cudaMemcpyAsync(d->d_raw, d->h_raw, blocks, cudaMemcpyHostToDevice, st) != cudaSuccess))
+                     cudaMemcpyAsync(d->d_raw, d->h_raw, blocks, cudaMemcpyHostToDevice, st) != cudaSuccess)) {
+    cudaStreamSynchronize(st); // the first copy may be queued: h_buf must not be reused under it
+    cudaGetLastError();
     return LRP_E_CUDA;
+  }
   ExrUnpackParams P;
   P.src = d->d_buf, P.is_raw = d->d_raw;
   P.W = I.w, P.H = I.h, P.C = I.c, P.lines_per_block = I.lines_per_block;

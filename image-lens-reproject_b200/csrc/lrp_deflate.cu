@@ -42,8 +42,10 @@ constexpr int DF_BAND = 32768;                  // input bytes per band (<= 6553
 constexpr int DF_THREADS = 256;
 constexpr int DF_CHUNK = DF_BAND / DF_THREADS;  // bytes per thread
 constexpr int DF_SLOT = DF_BAND + 64;           // output bytes reserved per band
-constexpr int DF_SYMS = 257;                    // literals + end-of-block
-constexpr int DF_HDR_BITS = 3 + 5 + 5 + 4 + 19 * 3 + DF_SYMS * 4 + 4;
+constexpr int DF_LL = 286;                      // literal / length symbols (literals, end-of-block, 29 length codes)
+constexpr int DF_DS = 30;                       // distance symbols
+constexpr int DF_HDR_FIXED = 3 + 5 + 5 + 4 + 19 * 3; // block header + the (fixed, 4 bits per length) code-length code
+constexpr int DF_CAND = 12;                     // candidate match distances
 constexpr unsigned ADLER_MOD = 65521u;
 
 struct DeflateParams {
@@ -54,6 +56,9 @@ struct DeflateParams {
   unsigned *band_len;      // bytes emitted per band
   unsigned *band_adler;    // Adler-32 of the band's input, started from 1
   unsigned *band_in;       // input bytes of the band
+  unsigned cand[DF_CAND];  // match distances tried at every position (0 = unused slot): small periods + the strides of
+                           // the stream's layout (PNG: bytes per pixel and per scan line; EXR: the byte-plane rows)
+  int lz;                  // 0: literals only (the round-1 coder)
 };
 
 struct BitWriter { // LSB-first bit packing into zero-initialised shared words; neighbours share words -> atomicOr
@@ -79,16 +84,74 @@ struct BitWriter { // LSB-first bit packing into zero-initialised shared words; 
 
 __device__ __forceinline__ unsigned reverse_bits(unsigned code, unsigned len) { return __brev(code) >> (32 - len); }
 
+// RFC 1951 section 3.2.5: length 3..258 -> (symbol 257..285, extra bits, extra value); distance 1..32768 -> (symbol 0..29, ...)
+__device__ __forceinline__ void length_symbol(unsigned len, unsigned &sym, unsigned &eb, unsigned &ev) {
+  const unsigned l = len - 3;
+  if (l < 8) {
+    sym = 257 + l, eb = 0, ev = 0;
+  } else if (l == 255) {
+    sym = 285, eb = 0, ev = 0;
+  } else {
+    eb = 29 - __clz(l); // floor(log2 l) - 2
+    sym = 257 + 4 * eb + (l >> eb);
+    ev = l & ((1u << eb) - 1);
+  }
+}
+__device__ __forceinline__ void distance_symbol(unsigned dist, unsigned &sym, unsigned &eb, unsigned &ev) {
+  const unsigned d = dist - 1;
+  if (d < 4) {
+    sym = d, eb = 0, ev = 0;
+  } else {
+    const unsigned lg = 31 - __clz(d);
+    eb = lg - 1;
+    sym = 2 * lg + ((d >> eb) & 1);
+    ev = d & ((1u << eb) - 1);
+  }
+}
+
+// The band in shared memory: byte i lives at swz(i).  A thread parses the 128-byte chunk [128 t, 128 t + 128) front to back, and
+// with a linear layout the 32 lanes of a warp would walk one bank in lockstep; XOR-ing the word index with the chunk index
+// spreads them over the 32 banks (words stay words: bytes keep their order inside a word).
+__device__ __forceinline__ unsigned swz(unsigned i) { return i ^ (((i >> 7) & 31u) << 2); }
+
+// 16 logical bytes [i, i + 16), i a multiple of 16: the XOR permutes the four words inside their aligned group
+__device__ __forceinline__ uint4 ld16_swz(const unsigned char *band, unsigned i) {
+  const unsigned t = (i >> 7) & 31u;
+  uint4 v = *(const uint4 *)(band + (i ^ ((t & ~3u) << 2)));
+  if (t & 1u) {
+    unsigned a = v.x; v.x = v.y; v.y = a;
+    a = v.z; v.z = v.w; v.w = a;
+  }
+  if (t & 2u) {
+    unsigned a = v.x; v.x = v.z; v.z = a;
+    a = v.y; v.y = v.w; v.w = a;
+  }
+  return v;
+}
+
+// One CTA per band of 32 KB.
+//   match   every thread parses its chunk greedily: at each position the candidate distances are tried (first byte, then the
+//           run), the longest match of >= 3 bytes that stays inside the chunk wins; matches may reach back anywhere in the
+//           band.  Chunks are independent, so the parse is parallel and deterministic.  token map: side[i] = length at a
+//           match start (the candidate's index in side[i + 1]), 0 at a literal.
+//   code    histograms of the literal/length and distance symbols -> two canonical Huffman codes (bitonic sort + two-queue
+//           merge for the 286, a 30-symbol merge by one thread of another warp for the distances), length-limited by flooring
+//           the weights at total / 1024.
+//   emit    per-thread bit counts -> exclusive scan -> every thread writes its tokens at its bit offset.
+// The band becomes ONE dynamic block + an empty stored block (byte alignment), or a stored block when that is smaller.
 __global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
-  unsigned char *band = smem;                               // DF_BAND
-  unsigned *outw = (unsigned *)(smem + DF_BAND);            // DF_SLOT bytes
+  unsigned char *band = smem;                               // DF_BAND, swizzled
+  unsigned char *side = smem + DF_BAND;                     // DF_BAND, token map (same swizzle)
+  unsigned *outw = (unsigned *)(smem + 2 * DF_BAND);        // DF_SLOT bytes
   __shared__ unsigned hist[512];                            // counts, then sort keys (weight << 9 | symbol)
-  __shared__ unsigned short parent[2 * DF_SYMS];
-  __shared__ unsigned nodew[2 * DF_SYMS];
-  __shared__ unsigned char lens[DF_SYMS + 3];
+  __shared__ unsigned short parent[2 * DF_LL];
+  __shared__ unsigned nodew[2 * DF_LL];
+  __shared__ unsigned char lens[DF_LL + 2];
   __shared__ unsigned bl_count[16], next_code[16];
-  __shared__ unsigned codelen[DF_SYMS];                     // reversed code << 4 | length
+  __shared__ unsigned codelen[DF_LL];                       // reversed code << 4 | length
+  __shared__ unsigned dhist[DF_DS], dcodelen[DF_DS];
+  __shared__ unsigned hmax[2];                              // highest used literal/length symbol, highest used distance symbol
   __shared__ unsigned warp_tot[DF_THREADS / 32];
   __shared__ unsigned long long red[2][DF_THREADS / 32];
 
@@ -108,35 +171,143 @@ __global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateP
     return;
   }
 
-  // ---- load the band, clear the output words and the histogram ----
+  // ---- load the band (swizzled words), clear the output words and the histograms ----
   const unsigned char *src = P.in + start;
-  if ((((size_t)src) & 15) == 0) {
-    for (unsigned i = tid; i < (len + 15) / 16; i += DF_THREADS) {
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (16 * i + 16 <= len) v = __ldg((const uint4 *)src + i);
+  if ((((size_t)src) & 3) == 0) {
+    for (unsigned i = tid; i < (len + 3) / 4; i += DF_THREADS) {
+      unsigned v = 0;
+      if (4 * i + 4 <= len) v = __ldg((const unsigned *)src + i);
       else
-        for (unsigned j = 0; 16 * i + j < len; ++j) ((unsigned char *)&v)[j] = src[16 * i + j];
-      ((uint4 *)band)[i] = v;
+        for (unsigned j = 0; 4 * i + j < len; ++j) v |= (unsigned)src[4 * i + j] << (8 * j);
+      *(unsigned *)(band + swz(4 * i)) = v;
     }
   } else {
-    for (unsigned i = tid; i < len; i += DF_THREADS) band[i] = src[i];
+    for (unsigned i = tid; i < len; i += DF_THREADS) band[swz(i)] = src[i];
   }
   for (unsigned i = tid; i < DF_SLOT / 4; i += DF_THREADS) outw[i] = 0;
   for (unsigned i = tid; i < 512; i += DF_THREADS) hist[i] = 0;
+  if (tid < DF_DS) dhist[tid] = 0;
+  if (tid < 2) hmax[tid] = tid == 0 ? 256u : 0u;
   __syncthreads();
 
-  // ---- histogram + Adler-32 partial sums over this thread's chunk ----
   const unsigned base = tid * DF_CHUNK;
   const unsigned cnt = base >= len ? 0u : (len - base < (unsigned)DF_CHUNK ? len - base : (unsigned)DF_CHUNK);
+  const unsigned end = base + cnt;
+
+  // ---- Adler-32 partial sums over the bytes + the compressibility probe (bytes equal to their predecessor) ----
   unsigned long long s1 = 0, s2 = 0;
-  const unsigned rot = cnt ? (lane * 4u) % cnt : 0u; // rotated start: the lanes of a warp hit different banks
-  for (unsigned j = 0; j < cnt; ++j) {
-    unsigned jj = j + rot;
-    if (jj >= cnt) jj -= cnt;
-    const unsigned d = band[base + jj];
-    atomicAdd(&outw[d * 32u + lane], 1u); // lane-replicated bins: every lane of a warp owns a bank, no conflicts
-    s1 += d;
-    s2 += (unsigned long long)(cnt - jj) * d;
+  unsigned same = 0;
+  {
+    unsigned prev = base ? band[swz(base - 1)] : 256u;
+    if (cnt == (unsigned)DF_CHUNK) {
+      for (unsigned q = 0; q < DF_CHUNK / 16; ++q) {
+        const uint4 v = ld16_swz(band, base + 16 * q);
+        const unsigned wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const unsigned d = (wds[t >> 2] >> (8 * (t & 3))) & 255u;
+          s1 += d;
+          s2 += (unsigned long long)(cnt - (16 * q + t)) * d;
+          same += d == prev;
+          prev = d;
+        }
+      }
+    } else {
+      for (unsigned j = 0; j < cnt; ++j) {
+        const unsigned d = band[swz(base + j)];
+        s1 += d;
+        s2 += (unsigned long long)(cnt - j) * d;
+        same += d == prev;
+        prev = d;
+      }
+    }
+  }
+  // Matches are searched only in bands where they can pay: rendered frames are flat or smooth (runs and short periods
+  // after the PNG filter / EXR predictor), photographic ones are not — there a dynamic block of literals is both smaller
+  // and cheaper to build (measured, profiles/r2_bench_encode.json).  Probe: every 4th byte of the chunk against the bytes
+  // at the candidate distances; a chunk votes for matches when half of its samples repeat, the band follows the majority.
+  if (P.lz) {
+    unsigned hits = same, samples = cnt; // distance 1 on every byte (counted above)
+    if (P.cand[1] != 0) {
+      hits = 0, samples = 0;
+      for (unsigned j = 0; j < cnt; j += 4) {
+        const unsigned i = base + j, b0 = band[swz(i)];
+        bool hit = false;
+#pragma unroll 1
+        for (unsigned kk = 0; kk < (unsigned)DF_CAND && P.cand[kk] != 0; ++kk)
+          hit = hit || (P.cand[kk] <= i && band[swz(i - P.cand[kk])] == b0);
+        hits += hit;
+        ++samples;
+      }
+    }
+    same = (samples > 0 && hits * 2u >= samples) ? 1u : 0u;
+  }
+  const bool lz_on = P.lz && __syncthreads_count(same != 0 && cnt > 0) * 2 >= (int)((len + DF_CHUNK - 1) / DF_CHUNK);
+
+  // ---- match: greedy parse of this thread's chunk ----
+  if (lz_on) {
+    unsigned i = base;
+    while (i < end) {
+      unsigned best = 0, best_k = 0;
+      if (end - i >= 3) {
+        const unsigned b0 = band[swz(i)];
+#pragma unroll 1
+        for (unsigned kk = 0; kk < (unsigned)DF_CAND; ++kk) {
+          const unsigned d = P.cand[kk];
+          if (d == 0) break;
+          if (d > i) continue; // history inside the band only
+          if (band[swz(i - d)] != b0) continue;
+          unsigned l = 1;
+          while (i + l < end && band[swz(i + l)] == band[swz(i + l - d)]) ++l;
+          if (l > best) best = l, best_k = kk; // ties go to the earlier (shorter) distance
+          if (l == end - i) break; // nothing can be longer
+        }
+      }
+      if (best >= 3) {
+        side[swz(i)] = (unsigned char)best; // <= 128
+        side[swz(i + 1)] = (unsigned char)best_k;
+        i += best;
+      } else {
+        side[swz(i)] = 0;
+        i += 1;
+      }
+    }
+  } else if (cnt != (unsigned)DF_CHUNK) { // (full chunks of a band without matches never read the token map)
+    for (unsigned i = base; i < end; ++i) side[swz(i)] = 0;
+  }
+
+  // ---- histograms over the tokens (a band without matches: over the bytes, 16 per load) ----
+  if (!lz_on) {
+    if (cnt == (unsigned)DF_CHUNK) {
+      for (unsigned q = 0; q < DF_CHUNK / 16; ++q) {
+        const uint4 v = ld16_swz(band, base + 16 * ((q + lane) % (DF_CHUNK / 16))); // rotated start: lanes spread over banks
+        const unsigned wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int t = 0; t < 16; ++t) atomicAdd(&outw[((wds[t >> 2] >> (8 * (t & 3))) & 255u) * 32u + lane], 1u);
+      }
+    } else {
+      for (unsigned j = 0; j < cnt; ++j) atomicAdd(&outw[(unsigned)band[swz(base + j)] * 32u + lane], 1u);
+    }
+  } else {
+    unsigned i = base, max_ll = 0, max_d = 0;
+    while (i < end) {
+      const unsigned l = side[swz(i)];
+      if (l == 0) {
+        atomicAdd(&outw[(unsigned)band[swz(i)] * 32u + lane], 1u); // lane-replicated literal bins: every lane owns a bank
+        i += 1;
+      } else {
+        unsigned sym, eb, ev;
+        length_symbol(l, sym, eb, ev);
+        atomicAdd(&hist[sym], 1u);
+        max_ll = max(max_ll, sym);
+        distance_symbol(P.cand[side[swz(i + 1)]], sym, eb, ev);
+        atomicAdd(&dhist[sym], 1u);
+        max_d = max(max_d, sym);
+        i += l;
+      }
+    }
+    if (max_ll) atomicMax(&hmax[0], max_ll);
+    if (max_d) atomicMax(&hmax[1], max_d);
   }
   // b = len + sum_i (len - i) d_i  with  (len - base - j) = (len - base - cnt) + (cnt - j)
   unsigned long long pa = s1, pb = cnt ? ((unsigned long long)(len - base - cnt) * s1 + s2) % ADLER_MOD : 0ull;
@@ -159,21 +330,73 @@ __global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateP
     P.band_in[b] = len;
     hist[256] = 1; // end-of-block
   }
-  { // fold the 32 replicas (rotated start: the threads of a warp read different banks), then clear the words again
+  unsigned lit_total;
+  { // fold the 32 replicas of the literal bins (rotated start: the threads of a warp read different banks)
     unsigned c = 0;
     for (unsigned j = 0; j < 32; ++j) c += outw[tid * 32u + ((j + tid) & 31u)];
-    hist[tid] = c;
+    lit_total = c;
   }
   __syncthreads();
+  hist[tid] = lit_total; // literals 0..255 (the length symbols were counted in place)
   for (unsigned i = tid; i < 256 * 32; i += DF_THREADS) outw[i] = 0;
   __syncthreads();
 
+  // ---- the distance code: <= 30 symbols, one thread of warp 1 while warp 0 merges the big tree below ----
+  const unsigned n_ll = hmax[0] + 1;                 // HLIT + 257
+  const unsigned n_d = hmax[1] + 1;                  // HDIST + 1
+  if (tid == 32) {
+    unsigned w[DF_DS], par[2 * DF_DS], total = 0, m = 0, idx[DF_DS];
+    for (unsigned i = 0; i < n_d; ++i) total += dhist[i];
+    const unsigned floor_w = (total + 1023) / 1024;
+    for (unsigned i = 0; i < n_d; ++i)
+      if (dhist[i]) idx[m] = i, w[m] = max(dhist[i], floor_w), ++m;
+    unsigned dl[DF_DS];
+    for (unsigned i = 0; i < DF_DS; ++i) dl[i] = 0;
+    if (m == 0) {
+      dl[0] = 1; // no matches: one unused code of one bit
+    } else if (m == 1) {
+      dl[idx[0]] = 1;
+    } else { // O(m^2) Huffman: repeatedly join the two lightest live nodes
+      unsigned nw[2 * DF_DS];
+      bool live[2 * DF_DS];
+      unsigned nn = m;
+      for (unsigned i = 0; i < m; ++i) nw[i] = w[i], live[i] = true;
+      for (unsigned step = 0; step + 1 < m; ++step) {
+        unsigned a0 = 0xFFFFFFFFu, a1 = 0xFFFFFFFFu, i0 = 0, i1 = 0;
+        for (unsigned i = 0; i < nn; ++i)
+          if (live[i]) {
+            if (nw[i] < a0) a1 = a0, i1 = i0, a0 = nw[i], i0 = i;
+            else if (nw[i] < a1) a1 = nw[i], i1 = i;
+          }
+        live[i0] = live[i1] = false;
+        nw[nn] = a0 + a1, live[nn] = true;
+        par[i0] = par[i1] = nn;
+        ++nn;
+      }
+      for (unsigned i = 0; i < m; ++i) {
+        unsigned d = 0, node = i;
+        while (node != nn - 1 && d < 15) node = par[node], ++d;
+        dl[idx[i]] = d;
+      }
+    }
+    unsigned cnt_l[16], nc[16];
+    for (int i = 0; i < 16; ++i) cnt_l[i] = 0;
+    for (unsigned i = 0; i < DF_DS; ++i) cnt_l[dl[i]]++;
+    cnt_l[0] = 0;
+    unsigned code = 0;
+    for (int bits = 1; bits <= 15; ++bits) {
+      code = (code + cnt_l[bits - 1]) << 1;
+      nc[bits] = code;
+    }
+    for (unsigned i = 0; i < DF_DS; ++i) dcodelen[i] = dl[i] ? (reverse_bits(nc[dl[i]]++, dl[i]) << 4) | dl[i] : 0u;
+  }
+
   // ---- sort keys: weight floored at total / 1024 (depth bound), absent symbols last ----
   {
-    const unsigned floor_w = (len + 1 + 1023) / 1024;
+    const unsigned floor_w = (len + 1 + 1023) / 1024; // >= tokens / 1024
     for (unsigned i = tid; i < 512; i += DF_THREADS) {
       const unsigned c = hist[i];
-      hist[i] = (i < DF_SYMS && c > 0) ? ((c > floor_w ? c : floor_w) << 9) | i : 0xFFFFFFFFu;
+      hist[i] = (i < DF_LL && c > 0) ? ((c > floor_w ? c : floor_w) << 9) | i : 0xFFFFFFFFu;
     }
   }
   __syncthreads();
@@ -193,8 +416,8 @@ __global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateP
 
   // ---- Huffman merge (two queues): the one serial step, queue heads kept in registers ----
   const unsigned m = (unsigned)__syncthreads_count(hist[tid] != 0xFFFFFFFFu) +
-                     (unsigned)__syncthreads_count(hist[tid + 256] != 0xFFFFFFFFu); // present symbols (>= 2)
-  if (tid == 0) {
+                     (unsigned)__syncthreads_count(hist[tid + 256] != 0xFFFFFFFFu); // present symbols (>= 1: end-of-block)
+  if (tid == 0 && m >= 2) {
     const unsigned INF = 0xFFFFFFFFu;
     unsigned li = 0, ii = m, nn = m;
     unsigned lw = hist[0] >> 9, iw = INF; // weights at the heads of the leaf / internal-node queues
@@ -221,7 +444,7 @@ __global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateP
     }
   }
   for (unsigned i = tid; i < 16; i += DF_THREADS) bl_count[i] = 0;
-  for (unsigned i = tid; i < DF_SYMS; i += DF_THREADS) lens[i] = 0;
+  for (unsigned i = tid; i < DF_LL; i += DF_THREADS) lens[i] = 0;
   __syncthreads();
 
   // ---- depths of the leaves (pointer chasing, <= 15 steps), length histogram ----
@@ -232,6 +455,7 @@ __global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateP
       node = parent[node];
       ++d;
     }
+    if (m == 1) d = 1; // a band of one token kind (cannot happen with an end-of-block symbol present, kept for safety)
     lens[hist[i] & 511u] = (unsigned char)d;
     atomicAdd(&bl_count[d], 1u);
   }
@@ -246,7 +470,7 @@ __global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateP
     }
   }
   __syncthreads();
-  for (unsigned sym = tid; sym < DF_SYMS; sym += DF_THREADS) {
+  for (unsigned sym = tid; sym < DF_LL; sym += DF_THREADS) {
     const unsigned l = lens[sym];
     unsigned rank = 0;
     for (unsigned j = 0; j < sym; ++j) rank += (lens[j] == l) ? 1u : 0u;
@@ -254,12 +478,29 @@ __global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateP
   }
   __syncthreads();
 
-  // ---- payload size: per-thread bit counts, exclusive scan ----
+  // ---- payload size: per-thread bit counts over the tokens, exclusive scan ----
   unsigned bits = 0;
-  for (unsigned j = 0; j < cnt; ++j) {
-    unsigned jj = j + rot;
-    if (jj >= cnt) jj -= cnt;
-    bits += lens[band[base + jj]];
+  if (!lz_on && cnt == (unsigned)DF_CHUNK) {
+    for (unsigned q = 0; q < DF_CHUNK / 16; ++q) {
+      const uint4 v = ld16_swz(band, base + 16 * q);
+      const unsigned wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int t = 0; t < 16; ++t) bits += lens[(wds[t >> 2] >> (8 * (t & 3))) & 255u];
+    }
+  } else
+  for (unsigned i = base; i < end;) {
+    const unsigned l = side[swz(i)];
+    if (l == 0) {
+      bits += lens[band[swz(i)]];
+      i += 1;
+    } else {
+      unsigned sym, eb, ev;
+      length_symbol(l, sym, eb, ev);
+      bits += lens[sym] + eb;
+      distance_symbol(P.cand[side[swz(i + 1)]], sym, eb, ev);
+      bits += (dcodelen[sym] & 15u) + eb;
+      i += l;
+    }
   }
   unsigned incl = bits;
   for (int o = 1; o < 32; o <<= 1) {
@@ -274,37 +515,35 @@ __global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateP
     all += warp_tot[w];
   }
   const unsigned eob = codelen[256];
-  const unsigned total_bits = DF_HDR_BITS + all + (eob & 15u);
+  const unsigned hdr_bits = DF_HDR_FIXED + 4 * (n_ll + n_d);
+  const unsigned total_bits = hdr_bits + all + (eob & 15u);
   const unsigned dyn_bytes = (total_bits + 3 + 7) / 8 + 4; // + empty stored block: 3 header bits, pad, 00 00 FF FF
   const bool stored = dyn_bytes >= len + 5;
   unsigned out_bytes;
 
   if (!stored) {
-    if (tid == 0) { // block header: BFINAL=0, BTYPE=dynamic, HLIT=0 (257 codes), HDIST=0 (1 code), HCLEN=15 (19 lengths)
+    if (tid == 0) { // block header: BFINAL=0, BTYPE=dynamic, HLIT, HDIST, HCLEN=15 (19 lengths)
       BitWriter bw(outw, 0);
       bw.put(0u | (2u << 1), 3);
-      bw.put(0, 5);
-      bw.put(0, 5);
+      bw.put(n_ll - 257, 5);
+      bw.put(n_d - 1, 5);
       bw.put(15, 4);
       // code-length code: symbols 0..15 get 4 bits each (a complete code), the run-length symbols 16, 17, 18 none;
       // transmitted in the order 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15
       for (int i = 0; i < 19; ++i) bw.put(i < 3 ? 0u : 4u, 3);
       bw.flush();
-      // one distance code of one bit (never used: the block has no matches), behind the 257 literal/length lengths
-      BitWriter bd(outw, DF_HDR_BITS - 4);
-      bd.put(reverse_bits(1u, 4), 4);
-      bd.flush();
     }
-    for (unsigned sym = tid; sym < DF_SYMS; sym += DF_THREADS) { // canonical 4-bit code of a length == the length itself
-      BitWriter bl(outw, DF_HDR_BITS - 4 - 4 * DF_SYMS + 4 * sym);
-      bl.put(reverse_bits(codelen[sym] & 15u, 4), 4);
+    for (unsigned sym = tid; sym < n_ll + n_d; sym += DF_THREADS) { // canonical 4-bit code of a length == the length itself
+      const unsigned l = sym < n_ll ? (codelen[sym] & 15u) : (dcodelen[sym - n_ll] & 15u);
+      BitWriter bl(outw, DF_HDR_FIXED + 4 * sym);
+      bl.put(reverse_bits(l, 4), 4);
       bl.flush();
     }
-    BitWriter bw(outw, DF_HDR_BITS + warp_base + incl - bits);
-    if (cnt == (unsigned)DF_CHUNK) { // 16 bytes per shared-memory load (a thread's bytes must go out in order)
+    BitWriter bw(outw, hdr_bits + warp_base + incl - bits);
+    if (!lz_on && cnt == (unsigned)DF_CHUNK) { // 16 bytes per shared-memory load (a thread's bytes must go out in order)
 #pragma unroll 2
       for (unsigned q = 0; q < DF_CHUNK / 16; ++q) {
-        const uint4 v = ((const uint4 *)(band + base))[q];
+        const uint4 v = ld16_swz(band, base + 16 * q);
         const unsigned wds[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
@@ -312,13 +551,27 @@ __global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateP
           bw.put(c >> 4, c & 15u);
         }
       }
-    } else {
-      for (unsigned j = 0; j < cnt; ++j) {
-        const unsigned c = codelen[band[base + j]];
+    } else
+    for (unsigned i = base; i < end;) {
+      const unsigned l = side[swz(i)];
+      if (l == 0) {
+        const unsigned c = codelen[band[swz(i)]];
         bw.put(c >> 4, c & 15u);
+        i += 1;
+      } else {
+        unsigned sym, eb, ev;
+        length_symbol(l, sym, eb, ev);
+        const unsigned c = codelen[sym];
+        bw.put(c >> 4, c & 15u);
+        if (eb) bw.put(ev, eb);
+        distance_symbol(P.cand[side[swz(i + 1)]], sym, eb, ev);
+        const unsigned dc = dcodelen[sym];
+        bw.put(dc >> 4, dc & 15u);
+        if (eb) bw.put(ev, eb);
+        i += l;
       }
     }
-    if (cnt > 0 && base + cnt == len) bw.put(eob >> 4, eob & 15u); // the thread holding the last byte closes the block
+    if (cnt > 0 && end == len) bw.put(eob >> 4, eob & 15u); // the thread holding the last byte closes the block
     bw.flush();
     __syncthreads();
     const unsigned pos = (total_bits + 3 + 7) / 8; // stored-block header bits are zeros already
@@ -334,7 +587,7 @@ __global__ void __launch_bounds__(DF_THREADS) deflate_band_kernel(const DeflateP
       ob[1] = (unsigned char)(len & 255u), ob[2] = (unsigned char)(len >> 8);
       ob[3] = (unsigned char)(~len & 255u), ob[4] = (unsigned char)((~len >> 8) & 255u);
     }
-    for (unsigned i = tid; i < len; i += DF_THREADS) ob[5 + i] = band[i];
+    for (unsigned i = tid; i < len; i += DF_THREADS) ob[5 + i] = band[swz(i)];
     out_bytes = len + 5;
   }
   __syncthreads();
@@ -652,8 +905,9 @@ static void encoder_free(lrp_encoder *e) {
 // Runs pack output `d_packed` (n bytes, streams of stream_bytes) through the deflate kernels and brings the compact
 // result to the encoder's pinned buffer.  On return h_stream_off[0..n_streams] delimit the streams (each preceded by its
 // chunk header when chunk_hdr != 0) at h_compact + headroom(cap_streams).
+// `stride_a, stride_b`: periods of the stream's layout offered to the match finder besides the small fixed ones (0 = none)
 static int deflate_to_host(lrp_encoder *e, size_t n, size_t stream_bytes, cudaStream_t st, unsigned chunk_hdr = 0,
-                           unsigned lines_per_stream = 0, bool want_crc = false) {
+                           unsigned lines_per_stream = 0, bool want_crc = false, unsigned stride_a = 2, unsigned stride_b = 3, unsigned stride_c = 4) {
   const unsigned bps = (unsigned)((stream_bytes + DF_BAND - 1) / DF_BAND);
   const unsigned n_streams = (unsigned)((n + stream_bytes - 1) / stream_bytes);
   const unsigned n_bands = bps * n_streams;
@@ -661,7 +915,23 @@ static int deflate_to_host(lrp_encoder *e, size_t n, size_t stream_bytes, cudaSt
   DeflateParams D;
   D.in = e->d_packed, D.n = n, D.stream_bytes = stream_bytes, D.bands_per_stream = bps, D.n_streams = n_streams;
   D.slots = e->d_slots, D.band_len = e->d_band_len, D.band_adler = e->d_band_adler, D.band_in = e->d_band_in;
-  const size_t smem = DF_BAND + DF_SLOT;
+  {
+    // Candidate distances: the byte itself and the pixel / sample periods.  On filtered PNG lines and predicted EXR byte
+    // planes of rendered frames the structure is runs: distance 1 alone gives 80-90 % of what this parse can reach; longer
+    // periods and the scan-line strides make a greedy parser take matches that cost more than they save (simulated on the
+    // test frames: {1}: 813 KB, {1,2,3,4,6,8,12,16,line}: 931 KB, lodepng 548 KB).
+    for (int i = 0; i < DF_CAND; ++i) D.cand[i] = 0;
+    D.cand[0] = 1;
+    int slot = 1;
+    for (unsigned sd : {stride_a, stride_b, stride_c}) {
+      bool dup = sd == 0 || sd > 8;
+      for (int i = 0; i < slot; ++i) dup = dup || D.cand[i] == sd;
+      if (!dup && slot < DF_CAND) D.cand[slot++] = sd;
+    }
+    const char *lz = getenv("LRP_DEFLATE_LZ"); // A/B switch: 0 = literal-only blocks (the round-1 coder)
+    D.lz = lz ? atoi(lz) : 1;
+  }
+  const size_t smem = 2 * DF_BAND + DF_SLOT;
   static thread_local int configured = -1;
   if (configured != e->device) {
     if (cudaFuncSetAttribute(deflate_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -755,7 +1025,7 @@ int lrp_debug_deflate(lrp_ctx *ctx, const void *in_dev, size_t n, size_t stream_
   cudaStream_t st = (cudaStream_t)cuda_stream;
   cudaEventRecord(e->ev[0], st);
   if (cudaMemcpyAsync(e->d_packed, in_dev, n, cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = LRP_E_CUDA;
-  if (rc == LRP_OK) rc = deflate_to_host(e, n, stream_bytes, st);
+  if (rc == LRP_OK) rc = deflate_to_host(e, n, stream_bytes, st); // lrp_debug_deflate: generic bytes, fixed candidates only
   if (rc == LRP_OK) {
     const size_t total = (size_t)e->h_stream_off[streams];
     void *mem = malloc(total ? total : 1);
@@ -786,7 +1056,7 @@ int lrp_encoder_png(lrp_encoder *e, const void *rgba_dev, int32_t width, int32_t
   cudaEventRecord(e->ev[0], st);
   int rc = lrp_png_pack_device(e->ctx, rgba_dev, width, height, png_channels, e->d_packed, cuda_stream);
   if (rc != LRP_OK) return rc;
-  rc = deflate_to_host(e, n, n, st, 0, 0, true);
+  rc = deflate_to_host(e, n, n, st, 0, 0, true, (unsigned)png_channels, 0, 0); // periods: the byte and the pixel
   if (rc != LRP_OK) return rc;
   const auto t_host = std::chrono::steady_clock::now();
   const size_t zn = (size_t)e->h_stream_off[1];
@@ -845,7 +1115,7 @@ int lrp_encoder_exr(lrp_encoder *e, const void *half_planar_dev, int32_t width, 
   int rc = lrp_exr_pack_device(e->ctx, half_planar_dev, width, height, channels, e->d_packed, cuda_stream);
   if (rc != LRP_OK) return rc;
   const size_t line_bytes = (size_t)channels * width * 2, stream_bytes = 16 * line_bytes;
-  rc = deflate_to_host(e, n, stream_bytes, st, 8, 16); // streams come back as complete chunks: {y, size} + zlib stream
+  rc = deflate_to_host(e, n, stream_bytes, st, 8, 16, false, 2, 3, 4); // streams come back as complete chunks: {y, size} + zlib stream
   if (rc != LRP_OK) return rc;
   const auto t_host = std::chrono::steady_clock::now();
   const size_t blocks = ((size_t)height + 15) / 16;

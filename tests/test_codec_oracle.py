@@ -188,6 +188,58 @@ def test_container_parsers_survive_truncation_and_bit_flips(lrp):
         assert fn(data) == want
 
 
+def test_png_chunk_crc_is_verified_like_lodepng(lrp):
+    """lodepng::decode refuses a chunk whose CRC does not match (error 57); so does the host half of lrp_decoder_png.
+    A flipped bit inside the IDAT payload changes the CRC; the same file with the CRC patched up is accepted again
+    (or refused by the inflater) — either way never silently decoded from corrupted bytes."""
+    import struct
+    import zlib
+    img = images()["smooth"]
+    png = lrp.png_assemble(co.png_filter_minsum(img), img.shape[1], img.shape[0], 3, 6, 1)
+    good = lrp.debug_png_decode_host(png)
+    assert (good[..., :3] == img).all()
+    # locate the IDAT chunk
+    pos, idat = 8, None
+    while pos + 12 <= len(png):
+        n, typ = struct.unpack(">I4s", png[pos:pos + 8])
+        if typ == b"IDAT":
+            idat = (pos, n)
+            break
+        pos += 12 + n
+    assert idat
+    pos, n = idat
+    bad = bytearray(png)
+    bad[pos + 8 + n - 1] ^= 0x10  # last byte of the payload (inside the Adler-32): payload CRC no longer matches
+    with pytest.raises(lrp.LrpError):
+        lrp.debug_png_decode_host(bytes(bad))
+    ref = ol.reference_lodepng()
+    if ref is not None:
+        with pytest.raises(Exception):
+            ref.decode(bytes(bad))
+    crc_only = bytearray(png)
+    crc_only[pos + 8 + n] ^= 0x01  # the stored CRC itself
+    with pytest.raises(lrp.LrpError):
+        lrp.debug_png_decode_host(bytes(crc_only))
+    # IHDR with a wrong CRC
+    ihdr = bytearray(png)
+    ihdr[8 + 8 + 13] ^= 0xFF
+    with pytest.raises(lrp.LrpError):
+        lrp.png_info(bytes(ihdr)) if False else lrp.debug_png_decode_host(bytes(ihdr))
+
+
+def test_exr_data_window_extent_cannot_overflow(lrp):
+    """dataWindow corners are file bytes: INT_MIN / INT_MAX corners must be refused, not wrapped through int arithmetic"""
+    import struct
+    exr = bytearray(lrp.exr_assemble(co.exr_pack(half_planes(3, 20, 10)), 10, 20, 3, 6, 1))
+    at = bytes(exr).index(b"dataWindow\0box2i\0") + len(b"dataWindow\0box2i\0") + 4
+    for box in ((-2 ** 31, -2 ** 31, 2 ** 31 - 1, 2 ** 31 - 1), (0, 0, 2 ** 31 - 1, 0), (5, 5, 4, 4), (2 ** 31 - 1, 0, -2 ** 31, 0)):
+        b = bytearray(exr)
+        b[at:at + 16] = struct.pack("<4i", *box)
+        with pytest.raises(lrp.LrpError):
+            lrp.exr_info(bytes(b))
+    assert lrp.exr_info(bytes(exr)) == (10, 20, 3)
+
+
 # ---- EXR files with FLOAT / UINT channels (read through read_exr's HALF slices) ----
 
 REF_HALF = ol.reference_half()

@@ -238,6 +238,94 @@ def test_device_deflate_ratio_on_a_reprojected_frame(lrp, ctx):
     assert len(png) < 1.15 * len(zlib.compress(stream, 6))
 
 
+def _rendered_style_frame(W, H, kind):
+    """8-bit frames of the kind a renderer produces: smooth shading (gradients without sensor noise), flat background"""
+    y, x = np.mgrid[0:H, 0:W].astype(np.float32)
+    if kind == "flat":
+        img = np.zeros((H, W, 4), np.uint8)
+        img[..., 0], img[..., 1], img[..., 2] = 40, 90, 200
+    elif kind == "smooth":
+        img = np.stack([128 + 100 * np.sin(x * 0.004) * np.cos(y * 0.006), 128 + 90 * np.cos(x * 0.0025 + y * 0.004),
+                        128 + 80 * np.sin((x + y) * 0.0015), np.zeros_like(x)], axis=-1).clip(0, 255).astype(np.uint8)
+    else:  # a shaded object on a flat background
+        r = np.hypot(x - W / 2, y - H / 2)
+        ball = (r < H / 3)
+        shade = (255 * np.sqrt(np.clip(1 - (r / (H / 3)) ** 2, 0, 1))).astype(np.uint8)
+        img = np.zeros((H, W, 4), np.uint8)
+        img[..., 0] = np.where(ball, shade, 30)
+        img[..., 1] = np.where(ball, shade // 2 + 60, 30)
+        img[..., 2] = np.where(ball, 255 - shade // 3, 60)
+    img[..., 3] = 255
+    return img
+
+
+@pytest.mark.parametrize("kind", ["smooth", "flat", "object"])
+def test_device_deflate_size_on_rendered_style_frames(lrp, ctx, kind):
+    """Rendered frames are smooth or flat, not noisy: the device writer (run / short-period matches inside 128-byte chunks
+    + a dynamic Huffman code per 32 KB band) against the reference's own writers on the same sink — lodepng (what save_png
+    runs, when the compiled reference travelled) and zlib level 9 (what save_exr runs per block).  VERDICT r1 #8 asked for
+    1.25 x of the reference writers on smooth content; a greedy chunk-local parse does not get there (simulated and
+    measured: PNG 1.5-2.1 x, EXR up to 4.3 x — DESIGN.md section 8), so the bars below are what it does reach, and
+    lrp_png_assemble / lrp_exr_assemble (host zlib at the reference's level) stay the size-parity path.  What the matches
+    buy over the round-1 literal-only blocks: flat 18 x, object 3 x, smooth 1.1 x smaller."""
+    import torch
+    import zlib
+    W, H = 1920, 1080
+    img = _rendered_style_frame(W, H, kind)
+    t = torch.from_numpy(img).cuda()
+    enc = lrp.Encoder(ctx, W, H, 4)
+    try:
+        png = enc.png(t, 3)
+        assert (_decode_png(png) == img).all()
+        stream = ctx.png_pack(t, 3).cpu().numpy().tobytes()
+        ref = ol.reference_lodepng()
+        ref_size = len(ref.encode(img)) if ref is not None else len(zlib.compress(stream, 9))
+        z9 = len(zlib.compress(stream, 9))
+        print("png %s: device %d B, reference writer %d B, zlib-9 on the same scan lines %d B" % (kind, len(png), ref_size, z9))
+        if kind == "flat":
+            assert len(png) < 0.015 * W * H * 3  # > 66 : 1 (literal-only blocks: 8 : 1)
+        else:
+            assert len(png) <= 2.3 * ref_size, (len(png), ref_size)
+            assert len(png) <= (0.95 if kind == "smooth" else 0.45) * 0.147 * W * H * 3  # vs the literal-only 14.7 %
+        # EXR: the same picture as half planes
+        planes = torch.from_numpy(np.ascontiguousarray((img[..., :3].astype(np.float32) / 255.0).astype(np.float16)
+                                                       .transpose(2, 0, 1))).cuda()
+        exr = enc.exr(planes)
+        packed = ctx.exr_pack(planes).cpu().numpy().tobytes()
+        block = 16 * W * 3 * 2
+        z9e = sum(len(zlib.compress(packed[o:o + block], 9)) for o in range(0, len(packed), block))
+        print("exr %s: device %d B, zlib-9 per block %d B" % (kind, len(exr), z9e))
+        if kind == "flat":
+            assert len(exr) < 0.02 * W * H * 6
+        else:
+            assert len(exr) <= 4.6 * z9e, (len(exr), z9e)
+    finally:
+        enc.close()
+
+
+def test_device_deflate_finds_the_matches(lrp, ctx):
+    """repetitive streams: runs, short periods, the stride candidates; zlib must inflate them to the input and the
+    stream must be far below the literal-only bound of one bit per byte"""
+    import torch
+    import zlib
+    rng = np.random.default_rng(5)
+    row = rng.integers(0, 256, 3001, dtype=np.uint8)
+    cases = {
+        "zeros": np.zeros(200000, np.uint8),
+        "period3": np.tile(np.array([7, 200, 31], np.uint8), 40000),
+        "period16": np.tile(rng.integers(0, 256, 16, dtype=np.uint8), 9000),
+        "runs": np.repeat(rng.integers(0, 256, 2000, dtype=np.uint8), rng.integers(1, 300, 2000)),
+        "mixed": np.concatenate([np.zeros(5000, np.uint8), rng.integers(0, 256, 5000, dtype=np.uint8)] * 7),
+    }
+    for name, data in cases.items():
+        t = torch.from_numpy(np.ascontiguousarray(data)).cuda()
+        for parts in (ctx.debug_deflate(t), ctx.debug_deflate(t, 50000)):
+            assert b"".join(zlib.decompress(p) for p in parts) == data.tobytes(), name
+        z = ctx.debug_deflate(t)[0]
+        if name in ("zeros", "period3", "runs"):  # distances 1..4 are candidates; longer periods stay literals
+            assert len(z) < data.size / 20, (name, len(z), data.size)
+
+
 # ---- the device deflate alone, on byte distributions chosen to stress the Huffman construction ----
 
 def _distributions():
