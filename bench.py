@@ -279,14 +279,15 @@ def device_leg(torch, lrp, ctx, name, interp, coords, variant, steps, barrier=No
     return {"us": round(us, 2), "gpix_per_s": round(W * H / us / 1e3, 2), "alg_gb_per_s": round(wl.algorithmic_bytes(name) / us / 1e3, 1)}
 
 
-def sched_leg(lrp, sched, jobs, n_out_pixels, reps, ctxs_stats=None):
-    """jobs through lrp_sched_submit / wait_all, then the same jobs copy-only -> dict"""
+def sched_leg(lrp, sched, jobs, n_out_pixels, reps, passes=1):
+    """jobs through lrp_sched_submit / wait_all (`passes` times: a pass ends with wait_all), then the same jobs copy-only -> dict"""
     def run():
         t0 = time.perf_counter()
-        for _ in range(reps):
-            for j in jobs:
-                sched.submit(j)
-        sched.wait_all()
+        for _ in range(passes):
+            for _ in range(reps):
+                for j in jobs:
+                    sched.submit(j)
+            sched.wait_all()
         return time.perf_counter() - t0
     run()  # warm-up: slot buffers, footprints, remap tables
     before = sched.stats()
@@ -296,7 +297,7 @@ def sched_leg(lrp, sched, jobs, n_out_pixels, reps, ctxs_stats=None):
     run()
     dt_copy = run()
     sched.copy_only(False)
-    n = reps * len(jobs)
+    n = passes * reps * len(jobs)
     return {"frames_per_s": round(n / dt, 2), "gpix_per_s": round(n * n_out_pixels / dt / 1e9, 3),
             "jobs": n, "jobs_per_device": [a - b for a, b in zip(after, before)],
             "copy_ceiling_frames_per_s": round(n / dt_copy, 2),
@@ -360,6 +361,13 @@ def run_sched_legs(lrp, world, params_c2, quick):
                 for k in range(6)]
         out["c5"] = sched_leg(lrp, sched, jobs, W * H, 2 if quick else 4)
         out["c5"]["note"] = "one 16384x8192 RGB half panorama in pinned memory, six rect(18,36) 4096x4096 views per pass"
+        # the same views with the source shared: one PCIe upload per pass, NVLink peer copies / reuse for the other views
+        jobs = [lrp.make_job(pano.ctypes.data, il, w, h, c, lrp.FMT_F16_PLANAR, sinks[k].ctypes.data, olens, W, H,
+                             lrp.FMT_F16_PLANAR, lrp.make_params(1, lrp.BICUBIC, lrp.rotation_from_degrees(*wl.C5_VIEWS[k]), None,
+                                                                 upload=lrp.UPLOAD_SHARED))
+                for k in range(6)]
+        out["c5_shared_source"] = sched_leg(lrp, sched, jobs, W * H, 1, passes=2 if quick else 4)
+        out["c5_shared_source"]["note"] = "lrp_upload SHARED: the panorama crosses PCIe once per pass of six views"
     finally:
         sched.close()
         for hnd in handles:
@@ -507,6 +515,19 @@ def run_gpu_arm(args, rank, world, local_rank):
                 us = t * 1e3 / launches
                 interp_legs[nm][cn] = {"us": round(us, 2), "gpix_per_s": round(N_OUT / us / 1e3, 2),
                                        "frac": round(algorithmic_bytes(nm) / us / 1e3 / measured_peak()[0], 4)}
+    supersampling = None
+    if world == 1 and not args.quick:  # --samples N: N x N coordinate chains and tap sets per pixel
+        supersampling = {}
+        for ns in (2, 3):
+            supersampling["ns%d" % ns] = {}
+            for cn, cm in (("fly", lrp.COORDS_FLY), ("auto", lrp.COORDS_AUTO)):
+                st = make_step(lrp.make_params(ns, interp, rot, None, coords=cm))
+                for _ in range(2):
+                    st()
+                t = timed(torch, st, 2, barrier)
+                us = t * 1e3 / (2 * B)
+                supersampling["ns%d" % ns][cn] = {"us": round(us, 1), "gpix_per_s": round(N_OUT / us / 1e3, 2),
+                                                  "subsamples_gs_per_s": round(ns * ns * N_OUT / us / 1e3, 2)}
     del srcs
     torch.cuda.empty_cache()
     if world == 1 and not args.quick:
@@ -582,7 +603,7 @@ def run_gpu_arm(args, rank, world, local_rank):
             "e2e_full_upload": {"value": sharding.whole_job_rate(world * full_steps * B * N_OUT, full_ms * 1e-3) / 1e9,
                                 "unit": "Gpix/s", "h2d_bytes_per_step": int(full_h2d_all), "steps": full_steps,
                                 "note": "the same leg with lrp_params.upload = FULL: the whole 134 MB source crosses PCIe per frame"},
-            "sched": sched, "interp_legs": interp_legs, "configs": configs,
+            "sched": sched, "interp_legs": interp_legs, "configs": configs, "supersampling": supersampling,
             "gpu_launches": int(launches_all), "clocks": clocks,
             "host_libm_fma": lrp.host_libm_uses_fma(),
         }

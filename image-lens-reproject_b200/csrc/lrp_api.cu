@@ -341,7 +341,7 @@ int prepare(const lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const
   if (!lens_supported(in->lens.type, p->extensions)) return LRP_E_UNSUPPORTED_INPUT_LENS;   // reference :395-397
   if (p->interpolation < 0 || p->interpolation > 2) return LRP_E_UNSUPPORTED_INTERP; // :364-366
   if (p->variant < LRP_VARIANT_AUTO || p->variant > LRP_VARIANT_TILED) return LRP_E_BAD_ARG;
-  if (p->upload < LRP_UPLOAD_AUTO || p->upload > LRP_UPLOAD_FULL) return LRP_E_BAD_ARG;
+  if (p->upload < LRP_UPLOAD_AUTO || p->upload > LRP_UPLOAD_SHARED) return LRP_E_BAD_ARG;
   if (p->coords < LRP_COORDS_AUTO || p->coords > LRP_COORDS_TABLE) return LRP_E_BAD_ARG;
   if (need_data) {
     if (!in->data || !out->data) return LRP_E_BAD_ARG;
@@ -776,6 +776,15 @@ struct Pool {
   int first_error = LRP_OK;
   bool stopping = false;
   bool copy_only = false; // lrp_sched_debug_copy_only: the same traffic without the kernel (the copy ceiling)
+  // LRP_UPLOAD_SHARED: device copies of host sources that several jobs read, per (host pointer, size)
+  struct SharedSrc {
+    std::vector<void *> d;          // per device of the pool
+    std::vector<cudaEvent_t> ready; // recorded behind the copy that fills d[i]
+  };
+  std::mutex shared_mu;
+  std::map<std::pair<const void *, size_t>, SharedSrc> shared;
+  bool peers_enabled = false;
+  std::atomic<uint64_t> peer_bytes{0};
 
   // ---- pixel jobs: enqueue on a slot's stream, no waiting ----
   static void CUDART_CB on_stream_done(void *p) {
@@ -802,10 +811,19 @@ struct Pool {
     Roi win;
     bool use_win = false;
     size_t h2d = 0;
-    int rc = upload_source(ctx, js->slot, &job.in, &job.out, &job.params, out_bytes, win, use_win, &h2d);
-    if (rc != LRP_OK) return rc;
     lrp_image din = job.in, dout = job.out;
-    din.data = js->slot.d_in;
+    int rc;
+    if (job.params.upload == LRP_UPLOAD_SHARED) {
+      void *d_src = nullptr;
+      rc = slot_reserve(js->slot, 0, out_bytes);
+      if (rc == LRP_OK) rc = shared_source(js, job.in.data, in_bytes, &d_src, &h2d);
+      if (rc != LRP_OK) return rc;
+      din.data = d_src;
+    } else {
+      rc = upload_source(ctx, js->slot, &job.in, &job.out, &job.params, out_bytes, win, use_win, &h2d);
+      if (rc != LRP_OK) return rc;
+      din.data = js->slot.d_in;
+    }
     dout.data = js->slot.d_out;
     if (!copy_only) {
       rc = launch_fused(ctx, &din, &dout, &job.params, nullptr, js->slot.stream, use_win ? &win : nullptr);
@@ -819,6 +837,77 @@ struct Pool {
     ctx->h2d_bytes += h2d;
     js->out_bytes = out_bytes;
     return LRP_OK;
+  }
+
+  // The device copy of a shared host source for the job on `js` (its stream waits for the copy): made from the host the
+  // first time any GPU needs it, from a GPU that already holds it (peer copy over NVLink) afterwards.
+  int shared_source(JobSlot *js, const void *host, size_t bytes, void **out, size_t *h2d) {
+    Engine *e = js->eng;
+    const int dev = e->dev_index;
+    std::lock_guard<std::mutex> lk(shared_mu);
+    if (!peers_enabled) { // once: direct peer access between every pair of the pool's GPUs (ignored where unsupported)
+      peers_enabled = true;
+      for (lrp_ctx *a : ctxs)
+        for (lrp_ctx *b : ctxs)
+          if (a->phys_device != b->phys_device) {
+            cudaSetDevice(a->phys_device);
+            cudaDeviceEnablePeerAccess(b->phys_device, 0);
+            cudaGetLastError();
+          }
+      cudaSetDevice(e->ctx->phys_device);
+    }
+    SharedSrc &S = shared[std::make_pair(host, bytes)];
+    if (S.d.empty()) {
+      S.d.assign(ctxs.size(), nullptr);
+      S.ready.assign(ctxs.size(), nullptr);
+    }
+    cudaStream_t st = js->slot.stream;
+    if (S.d[dev]) {
+      LRP_CUDA(cudaStreamWaitEvent(st, S.ready[dev], 0));
+      *out = S.d[dev];
+      return LRP_OK;
+    }
+    int from = -1;
+    for (size_t o = 0; o < S.d.size(); ++o)
+      if (S.d[o]) from = (int)o;
+    void *buf = nullptr;
+    cudaEvent_t ev = nullptr;
+    LRP_CUDA(cudaMalloc(&buf, bytes));
+    cudaError_t err = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (err == cudaSuccess) {
+      if (from >= 0) {
+        err = cudaStreamWaitEvent(st, S.ready[from], 0);
+        if (err == cudaSuccess)
+          err = cudaMemcpyPeerAsync(buf, e->ctx->phys_device, S.d[from], ctxs[from]->phys_device, bytes, st);
+        if (err == cudaSuccess) peer_bytes += bytes;
+      } else {
+        err = cudaMemcpyAsync(buf, host, bytes, cudaMemcpyHostToDevice, st);
+        if (err == cudaSuccess) *h2d = bytes;
+      }
+    }
+    if (err == cudaSuccess) err = cudaEventRecord(ev, st);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      cudaStreamSynchronize(st);
+      if (ev) cudaEventDestroy(ev);
+      cudaFree(buf);
+      return map_cuda(err);
+    }
+    S.d[dev] = buf;
+    S.ready[dev] = ev;
+    *out = buf;
+    return LRP_OK;
+  }
+  void drop_shared_sources() { // every job has completed
+    std::lock_guard<std::mutex> lk(shared_mu);
+    for (auto &kv : shared)
+      for (size_t i = 0; i < kv.second.d.size(); ++i)
+        if (kv.second.d[i]) {
+          cudaSetDevice(ctxs[i]->phys_device);
+          cudaFree(kv.second.d[i]);
+          cudaEventDestroy(kv.second.ready[i]);
+        }
+    shared.clear();
   }
 
   void finish(Engine *e, const Item &it, int rc) { // engine thread, `mu` not held
@@ -1075,11 +1164,15 @@ struct Pool {
   }
 
   int wait_all() {
-    std::unique_lock<std::mutex> lk(mu);
-    cv_done.wait(lk, [&] { return in_flight == 0; });
-    int rc = first_error;
-    first_error = LRP_OK;
-    done.clear();
+    int rc;
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv_done.wait(lk, [&] { return in_flight == 0; });
+      rc = first_error;
+      first_error = LRP_OK;
+      done.clear();
+    }
+    drop_shared_sources();
     return rc;
   }
 
@@ -1100,6 +1193,7 @@ struct Pool {
       delete e;
     }
     engines.clear();
+    drop_shared_sources();
     for (Worker *w : workers) {
       if (w->th.joinable()) w->th.join();
       cudaSetDevice(w->ctx->phys_device);

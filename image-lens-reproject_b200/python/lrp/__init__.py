@@ -23,7 +23,7 @@ RGB, RGBA, RGBZ, RGBAZ = range(4)
 NEAREST, BILINEAR, BICUBIC = range(3)
 FMT_F32, FMT_U8_RGBA, FMT_F16_PLANAR = range(3)
 VARIANT_AUTO, VARIANT_GATHER, VARIANT_STAGED, VARIANT_TILED = range(4)
-UPLOAD_AUTO, UPLOAD_FULL = range(2)
+UPLOAD_AUTO, UPLOAD_FULL, UPLOAD_SHARED = range(3)
 COORDS_AUTO, COORDS_FLY, COORDS_TABLE = range(3)
 EXT_FISHEYE_MODELS = 1
 

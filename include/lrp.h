@@ -147,7 +147,12 @@ typedef enum lrp_coords {
  * Results are bit-identical either way. */
 typedef enum lrp_upload {
   LRP_UPLOAD_AUTO = 0, /* the footprint's bounding box when it is clearly smaller than the image */
-  LRP_UPLOAD_FULL = 1  /* the whole source, as the reference's worker holds it                   */
+  LRP_UPLOAD_FULL = 1, /* the whole source, as the reference's worker holds it                   */
+  LRP_UPLOAD_SHARED = 2 /* lrp_submit / lrp_sched_submit: several jobs read this SAME host buffer (the six views of one
+                          panorama, BASELINE config #5) and it does not change before lrp_*_wait_all returns: the whole
+                          source crosses PCIe once, GPUs that need it later copy it from a GPU that holds it (NVLink
+                          peer copy), a GPU that holds it reuses it.  The copies are dropped by lrp_*_wait_all.  The
+                          synchronous drop-ins treat it as FULL. */
 } lrp_upload;
 
 /* Source-access strategies (north-star item 3); results are bit-identical.  Orthogonal to

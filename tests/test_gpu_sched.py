@@ -374,3 +374,33 @@ def test_file_jobs_wide_then_tall_and_unheld_handles(lrp):
             names, planes = co.exr_decode(data)
             got = co.exr_to_planes(names, planes, 3)
             assert (got == lin.astype(np.float16).transpose(2, 0, 1).view(np.uint16)).all()
+
+
+@pytest.mark.parametrize("fake", [0, 4])
+def test_shared_source_views_over_the_scheduler(lrp, monkeypatch, fake):
+    """BASELINE config #5's shape: several views of ONE host panorama (LRP_UPLOAD_SHARED: one PCIe upload, peer copies to
+    the other GPUs, reuse on a GPU that holds it); every view equals the oracle, twice in a row (the copies are dropped
+    by wait_all, so the second pass uploads again)."""
+    if fake:
+        monkeypatch.setenv("LRP_FAKE_GPUS", str(fake))
+    n = lrp.device_count()
+    w, h, W, H, c = 1024, 512, 256, 256, 3
+    rng = np.random.default_rng(9)
+    planes = np.ascontiguousarray((rng.random((c, h, w), dtype=np.float32) * 2).astype(np.float16).view(np.uint16))
+    src_f = ORC.half_planar_to_f32(planes)
+    views = ((0, 0, 0), (90, 0, 0), (180, 0, 0), (270, 0, 0), (0, 90, 0), (0, -90, 0))
+    il, olens = ol.erect(), ol.rect(18.0, 36.0, W, H)
+    want = [ORC.f32_to_half_planar(ORC.reproject(src_f, il, olens, W, H, 1, ol.BICUBIC, ORC.rotation_from_degrees(*v))) for v in views]
+    s = lrp.Scheduler(list(range(n)), streams_per_device=2)
+    for rep in range(2):
+        outs = [np.zeros((c, H, W), np.uint16) for _ in views]
+        for k, v in enumerate(views):
+            p = lrp.make_params(1, lrp.BICUBIC, ORC.rotation_from_degrees(*v), None, upload=lrp.UPLOAD_SHARED)
+            s.submit(lrp.make_job(planes.ctypes.data, lrp.lens_from(il), w, h, c, lrp.FMT_F16_PLANAR, outs[k].ctypes.data,
+                                  lrp.lens_from(olens), W, H, lrp.FMT_F16_PLANAR, p))
+        s.wait_all()
+        for k in range(len(views)):
+            same = (outs[k] == want[k]) | (((outs[k] & 0x7fff) > 0x7c00) & ((want[k] & 0x7fff) > 0x7c00))
+            assert same.all(), "pass %d view %d: %d differ" % (rep, k, (~same).sum())
+    assert sum(s.stats()) == 12
+    s.close()
