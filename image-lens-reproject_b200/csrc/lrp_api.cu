@@ -621,9 +621,12 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
     if (LaunchFn tf = get_tiled_launcher(coord, fc)) return map_cuda((cudaError_t)tf(K, stream));
   }
   if (variant == LRP_VARIANT_TILED) variant = LRP_VARIANT_STAGED; // formats / samplers the tiled kernel does not cover
-  const bool want_staged = (variant == LRP_VARIANT_STAGED) ||
-                           (variant == LRP_VARIANT_AUTO && p->interpolation == LRP_BICUBIC);
-  const bool staged = want_staged && p->num_samples == 1;
+  // Supersampled launches: the staged kernel keeps the sub-samples of a pixel in neighbouring lanes (ns^2 <= 32 lanes ->
+  // ns <= 5) and is bit-identical, but measured no faster than the gather kernel (c2, table coordinates, us per frame:
+  // ns 2: 553 vs 576, ns 3: 1615 vs 1244, ns 4: 2808 vs 2179 — its tiles shrink to 32 / ns^2 pixels per row), so AUTO
+  // gathers them; LRP_VARIANT_STAGED selects it explicitly.
+  const bool staged = (variant == LRP_VARIANT_STAGED && p->num_samples <= 5) ||
+                      (variant == LRP_VARIANT_AUTO && p->interpolation == LRP_BICUBIC && p->num_samples == 1);
   if (staged) K.nn_composite = 0; // the staged sampler keeps the float tail
   LaunchFn fn = get_launcher(coord, p->interpolation, fc, staged);
   if (!fn) return LRP_E_UNSUPPORTED_FORMAT;

@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
   __syncthreads(); // the only CTA-wide barrier
 
   const SrcViewT<false> S{P, lut_addr};
-  const bool separable = !TABLE && (P.ol.type == LENS_RECT || P.ol.type == LENS_ERECT);
+  const bool separable = !TABLE && (P.ol.type == LENS_RECT || P.ol.type == LENS_ERECT) && P.ns == 1;
   const bool out_rect = (P.ol.type == LENS_RECT);
   const float Wf = (float)P.W, Hf = (float)P.H;
   const float half_W = fmul(Wf, 0.5f), half_H = fmul(Hf, 0.5f);
@@ -436,10 +436,21 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
   const float off_hi = (INTERP == INTERP_NN) ? 0.5f : (INTERP == INTERP_BL) ? 1.0f : 2.0f;
   (void)NT;
 
-  const int tiles_x = (P.W + ST_TILE_W - 1) / ST_TILE_W, tiles_y = (P.H + ST_TILE_H - 1) / ST_TILE_H;
+  // Supersampled launches (num_samples = ns > 1, reference :294-341): the ns x ns sub-samples of a pixel sit in
+  // neighbouring lanes (lane = pixel * ns^2 + ssx * ns + ssy), a step is ONE row of 32 / ns^2 pixels, a tile 8 such rows.
+  // The coordinate slots, the bounding box, the plan and the staged records treat sub-samples like pixels — their
+  // footprints overlap almost completely, so one staged box serves all of them; the pixel's average is taken over its
+  // lanes in the reference's order (ssx outer, ssy inner) with shuffles.
+  const bool ss = P.ns > 1;
+  const int ns2 = P.ns * P.ns;
+  const int tile_w = ss ? 32 / ns2 : ST_TILE_W, tile_h = ss ? ST_STEPS : ST_TILE_H;
+  const int tiles_x = (P.W + tile_w - 1) / tile_w, tiles_y = (P.H + tile_h - 1) / tile_h;
   const int n_tiles = tiles_x * tiles_y;
   const int warps_total = gridDim.x * NW;
-  const int lx = lane & (ST_TILE_W - 1), ly = lane >> 4; // lane -> (column, row parity) of the 16 x 16 tile
+  // lane -> (column, row parity) of the 16 x 16 tile; supersampled: (pixel of the row, sub-sample)
+  const int lx = ss ? lane / ns2 : lane & (ST_TILE_W - 1), ly = ss ? 0 : lane >> 4;
+  const int sub = ss ? lane - lx * ns2 : 0, row_step = ss ? 1 : 2;
+  const bool lane_used = !ss || lx < tile_w;
 
   // Tiles are handed out dynamically (lrp_kernel.cuh, "tile scheduler"): the first round is static, every
   // further tile comes from the launch's global counter, so that no warp idles through a tail round
@@ -447,10 +458,10 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
   int tile = blockIdx.x * NW + wrp;
   while (tile < n_tiles) {
     const int ticket = take_ticket(P.sched, lane); // issued now, consumed after the tile: the atomic's latency is hidden
-    const int x0 = (tile % tiles_x) * ST_TILE_W, y0 = (tile / tiles_x) * ST_TILE_H;
+    const int x0 = (tile % tiles_x) * tile_w, y0 = (tile / tiles_x) * tile_h;
     const int x = x0 + lx;
-    const bool xvalid = x < P.W;
-    const int R = (min(ST_TILE_H, P.H - y0) + 1) >> 1; // steps: a step is two rows of 16 pixels
+    const bool xvalid = lane_used && x < P.W;
+    const int R = ss ? min(ST_STEPS, P.H - y0) : (min(ST_TILE_H, P.H - y0) + 1) >> 1; // steps: two rows of 16 pixels (ss: one row)
     const float cx = fsub(fadd((float)x, 0.5f), half_W); // :287; ns == 1: scx == cx exactly (:295)
 
     // separable parts of the output rays (rect / equirect output lenses, reference :155-157, :249-256):
@@ -491,17 +502,17 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
       float2 s[ST_STEPS];
 #pragma unroll
       for (int r = 0; r < ST_STEPS; ++r) {
-        const int y = y0 + 2 * r + ly;
+        const int y = y0 + row_step * r + ly;
         s[r] = make_float2(0.0f, 0.0f);
-        if (xvalid && y < P.H) s[r] = __ldg(P.remap + (size_t)y * (size_t)P.W + (size_t)x);
+        if (xvalid && y < P.H) s[r] = __ldg(P.remap + ((size_t)sub * (size_t)P.H + (size_t)y) * (size_t)P.W + (size_t)x);
       }
 #pragma unroll
       for (int r = 0; r < ST_STEPS; ++r) s_coord[r * 32 + lane] = s[r];
     }
     for (int r = 0; r < (TABLE ? 0 : R); ++r) {
-      const int y = y0 + 2 * r + ly;
+      const int y = y0 + row_step * r + ly;
       float sx = 0.0f, sy = 0.0f;
-      const float vy_row = __shfl_sync(0xffffffffu, row_vy, 2 * r + ly);
+      const float vy_row = __shfl_sync(0xffffffffu, row_vy, (2 * r + ly) & 31);
       if (xvalid && y < P.H) {
         float vx, vy, vz;
         if (separable) {
@@ -516,8 +527,9 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
           rotated_to_source<COORD>(P, vx, vy, vz, sx, sy);
         } else {
           const float cy = fsub(fadd((float)y, 0.5f), half_H); // :288
-          const float q = fdiv(fadd(0.0f, 1.0f), P.ss_den);
-          target_to_vec(P, fsub(fadd(cx, q), 0.5f), fsub(fadd(cy, q), 0.5f), vx, vy, vz);
+          const int ssx = sub / P.ns, ssy = sub - ssx * P.ns;   // :294, :297 (0, 0 when ns == 1)
+          const float qx = fdiv(fadd((float)ssx, 1.0f), P.ss_den), qy = fdiv(fadd((float)ssy, 1.0f), P.ss_den);
+          target_to_vec(P, fsub(fadd(cx, qx), 0.5f), fsub(fadd(cy, qy), 0.5f), vx, vy, vz); // :295, :298
           ray_to_source<COORD>(P, vx, vy, vz, sx, sy);
         }
       }
@@ -537,7 +549,7 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
         bool bad = false;
         if (xvalid) {
           for (int rr = start; rr < end; ++rr) {
-            if (y0 + 2 * rr + ly >= P.H) break;
+            if (y0 + row_step * rr + ly >= P.H) break;
             const float2 s = s_coord[rr * 32 + lane];
             // NaN / inf / |s| >= 2^30: x86 and CUDA float->int conversions differ there -> the block is gathered
             bad = bad || !((fabsf(s.x) < 1073741824.0f) && (fabsf(s.y) < 1073741824.0f));
@@ -571,20 +583,40 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
       const StageView V{s_stage, plan.eff.x0, plan.eff.y0, plan.pitch, plan.clamped,
                         fsub(1.0f, fmul(big, 1.1920929e-7f))};
       for (int rr = start; rr < end; ++rr) {
-        const int y = y0 + 2 * rr + ly;
-        if (!xvalid || y >= P.H) continue;
-        const float2 s = s_coord[rr * 32 + lane];
+        const int y = y0 + row_step * rr + ly;
+        const bool valid = xvalid && y < P.H;
+        if (!ss && !valid) continue;
+        if (ss && y >= P.H) break; // warp-uniform: a supersampled step is one row
         float v[C];
-        if (staged) {
-          staged_bicubic<WRAP, C, X2, NW>(P, V, s.x, s.y, v);
-        } else {
-          if (INTERP == INTERP_NN) sample_nearest<WRAP, FMT, C>(S, s.x, s.y, v);
-          else if (INTERP == INTERP_BL) sample_bilinear<WRAP, FMT, C>(S, s.x, s.y, v);
-          else sample_bicubic<WRAP, FMT, C, true>(S, s.x, s.y, v);
-        }
-        // ns == 1: acc = 0.0f + sample (:334-336; turns -0 into +0), then * 1.0f (:338-341; exact)
 #pragma unroll
-        for (int c = 0; c < C; ++c) v[c] = fadd(0.0f, v[c]);
+        for (int c = 0; c < C; ++c) v[c] = 0.0f;
+        if (valid) {
+          const float2 s = s_coord[rr * 32 + lane];
+          if (staged) {
+            staged_bicubic<WRAP, C, X2, NW>(P, V, s.x, s.y, v);
+          } else {
+            if (INTERP == INTERP_NN) sample_nearest<WRAP, FMT, C>(S, s.x, s.y, v);
+            else if (INTERP == INTERP_BL) sample_bilinear<WRAP, FMT, C>(S, s.x, s.y, v);
+            else sample_bicubic<WRAP, FMT, C, true>(S, s.x, s.y, v);
+          }
+        }
+        if (ss) { // acc += sample over the pixel's lanes, ssx outer / ssy inner (:334-336), then * 1 / ns^2 (:338-341)
+          float acc[C];
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[c] = 0.0f;
+          const int g0 = lx * ns2;
+          for (int k2 = 0; k2 < ns2; ++k2) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = fadd(acc[c], __shfl_sync(0xffffffffu, v[c], (g0 + k2) & 31));
+          }
+          if (!valid || sub != 0) continue; // the pixel's first lane stores
+#pragma unroll
+          for (int c = 0; c < C; ++c) v[c] = fmul(acc[c], P.normalize);
+        } else {
+          // ns == 1: acc = 0.0f + sample (:334-336; turns -0 into +0), then * 1.0f (:338-341; exact)
+#pragma unroll
+          for (int c = 0; c < C; ++c) v[c] = fadd(0.0f, v[c]);
+        }
         if (P.post) { // fused post_process, :421-437
 #pragma unroll
           for (int c = 0; c < (C < 3 ? C : 3); ++c) v[c] = post_process_value(v[c], P.exposure, P.r2);
@@ -610,7 +642,8 @@ int launch_reproject_staged(const KParams &P, void *stream) {
     if (e != cudaSuccess) return (int)e;
     configured_device = dev;
   }
-  const int tiles = ((P.W + ST_TILE_W - 1) / ST_TILE_W) * ((P.H + ST_TILE_H - 1) / ST_TILE_H);
+  const int tw = P.ns > 1 ? 32 / (P.ns * P.ns) : ST_TILE_W, th = P.ns > 1 ? ST_STEPS : ST_TILE_H;
+  const int tiles = ((P.W + tw - 1) / tw) * ((P.H + th - 1) / th);
   constexpr int NW = st_warps(INTERP, C);
   const int ctas_needed = (tiles + NW - 1) / NW;
   const int grid = ctas_needed < P.num_sms ? ctas_needed : P.num_sms;

@@ -353,3 +353,34 @@ def test_tiled_kernel_both_occupancies(lrp, ctas, monkeypatch):
                                            in_fmt=lrp.FMT_F16_PLANAR, out_fmt=lrp.FMT_F16_PLANAR, variant=lrp.VARIANT_TILED,
                                            coords=cm)
                 assert same_half(got16, want16).all(), "tiled f16 c%d %r: %d differ" % (c, (W, H, w, h), (~same_half(got16, want16)).sum())
+
+
+# ---- supersampling through the staged kernel (sub-samples of a pixel in neighbouring lanes) ---------------------------
+
+@pytest.mark.parametrize("ns", [2, 3, 4, 5, 6])
+def test_supersampling_staged_and_gathered(lrp, ns):
+    """--samples N: N x N sub-samples per pixel, accumulated ssx-outer / ssy-inner and scaled by 1 / N^2 (reference
+    src/reproject.cpp:294-341).  Staged (N <= 5: N^2 lanes per pixel) and gathered, on the fly and from the table, on
+    the three formats; sizes that leave partial tiles in both directions."""
+    rng = np.random.default_rng(ns)
+    for (W, H, w, h, il, olens, r) in (
+            (101, 37, 256, 128, ol.erect(), ol.rect(18.0, 36.0, 101, 37), rotd(30, 20, 10)),
+            (64, 50, 96, 96, ol.equidistant(math.pi), ol.erect(), None),
+            (45, 33, 80, 60, ol.rect(36.0, 36.0, 80, 60), ol.equidistant(2.5), rotd(0, 0, 45))):
+        rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        f4 = (rng.random((h, w, 4), dtype=np.float32) * 2.0).astype(np.float32)
+        f4[::7, ::5, 3] = 1e10
+        planes = ORC.f32_to_half_planar(f4)
+        want8 = ORC.png_encode(ORC.post_process(ORC.reproject(ORC.png_decode(rgba), il, olens, W, H, ns, ol.BICUBIC, r), 1.5, 4.0))
+        want16 = ORC.f32_to_half_planar(ORC.reproject(ORC.half_planar_to_f32(planes), il, olens, W, H, ns, ol.BICUBIC, r))
+        want32 = ORC.reproject(f4, il, olens, W, H, ns, ol.BICUBIC, r)
+        for v in (lrp.VARIANT_STAGED, lrp.VARIANT_GATHER):
+            for cm in (lrp.COORDS_FLY, lrp.COORDS_TABLE):
+                got8 = lrp.reproject_host(rgba, L(lrp, il), L(lrp, olens), W, H, ns, ol.BICUBIC, r, post=(1.5, 4.0),
+                                          in_fmt=lrp.FMT_U8_RGBA, out_fmt=lrp.FMT_U8_RGBA, variant=v, coords=cm)
+                assert (got8 == want8).all(), "ns %d u8 variant %d coords %d: %d differ" % (ns, v, cm, (got8 != want8).sum())
+                got16 = lrp.reproject_host(planes, L(lrp, il), L(lrp, olens), W, H, ns, ol.BICUBIC, r, in_fmt=lrp.FMT_F16_PLANAR,
+                                           out_fmt=lrp.FMT_F16_PLANAR, variant=v, coords=cm)
+                assert same_half(got16, want16).all(), "ns %d f16 variant %d coords %d" % (ns, v, cm)
+                got32 = lrp.reproject_host(f4, L(lrp, il), L(lrp, olens), W, H, ns, ol.BICUBIC, r, variant=v, coords=cm)
+                assert_same_f32(got32, want32, "ns %d f32 variant %d coords %d" % (ns, v, cm))
