@@ -611,7 +611,9 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
   // gathered through L1 (c2 nn 107 vs 179 us, bl 124 vs 139 us; c3 bl 137 vs 235 us)
   {
     const char *rp = getenv("LRP_REC_PAD"); // A/B switch: padded record rows in the staged kernel
-    K.rec_pad = rp ? atoi(rp) : 1;
+    K.rec_pad = rp ? atoi(rp) : 0; // measured neutral-to-slower (profiles/r2_staged_variants.txt): off
+    const char *sa = getenv("LRP_STAGE_ASYNC"); // A/B switch: cp.async staging (needs 4-byte aligned planes)
+    K.stage_async = (LRP_STAGED_ASYNC && sa && atoi(sa) != 0 && (in->format != LRP_FMT_F16_PLANAR || (((size_t)in->width * in->height) % 2 == 0 && ((size_t)in->data & 3) == 0))) ? 1 : 0;
   }
   {
     const char *tc = getenv("LRP_TL_CTAS"); // A/B switch: resident CTAs per SM of the tiled kernel
@@ -624,8 +626,8 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
   // Supersampled launches: the staged kernel keeps the sub-samples of a pixel in neighbouring lanes (ns^2 <= 32 lanes ->
   // ns <= 5) and is bit-identical, but measured no faster than the gather kernel (c2, table coordinates, us per frame:
   // ns 2: 553 vs 576, ns 3: 1615 vs 1244, ns 4: 2808 vs 2179 — its tiles shrink to 32 / ns^2 pixels per row), so AUTO
-  // gathers them; LRP_VARIANT_STAGED selects it explicitly.
-  const bool staged = (variant == LRP_VARIANT_STAGED && p->num_samples <= 5) ||
+  // gathers them; LRP_VARIANT_STAGED selects it explicitly in the A/B library (LRP_STAGED_SS, `make ab`).
+  const bool staged = (variant == LRP_VARIANT_STAGED && p->num_samples <= (LRP_STAGED_SS ? 5 : 1)) ||
                       (variant == LRP_VARIANT_AUTO && p->interpolation == LRP_BICUBIC && p->num_samples == 1);
   if (staged) K.nn_composite = 0; // the staged sampler keeps the float tail
   LaunchFn fn = get_launcher(coord, p->interpolation, fc, staged);
@@ -1218,7 +1220,7 @@ struct lrp_sched {
 
 extern "C" {
 
-const char *lrp_version(void) { return "lrp-b200 0.1 (sm_100a)"; }
+const char *lrp_version(void) { return (LRP_STAGED_SS || LRP_STAGED_ASYNC) ? "lrp-b200 0.2 (sm_100a, A/B build)" : "lrp-b200 0.2 (sm_100a)"; }
 
 const char *lrp_strerror(int s) {
   switch (s) {

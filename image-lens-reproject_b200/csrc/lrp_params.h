@@ -3,6 +3,16 @@
 #include <stddef.h>
 #include <stdint.h>
 
+// Experimental paths of the staged kernel, measured and NOT faster (profiles/r2_staged_variants.txt), compiled only into
+// the A/B library (`make ab` -> liblrp_ab.so): their mere presence costs the default kernel 10 % (136.6 -> 149.5 -> 155.8 us
+// per c2 frame with the supersampling / cp.async paths compiled in, never taken).
+#ifndef LRP_STAGED_SS
+#define LRP_STAGED_SS 0    // supersampled launches through the staged kernel (sub-samples of a pixel in neighbouring lanes)
+#endif
+#ifndef LRP_STAGED_ASYNC
+#define LRP_STAGED_ASYNC 0 // raw texels by cp.async (LDGSTS) into shared memory, records decoded from there
+#endif
+
 namespace lrp {
 
 enum : int { LENS_RECT = 0, LENS_EQUIDISTANT = 1, LENS_EQUISOLID = 2, LENS_STEREO = 3, LENS_ERECT = 4 };
@@ -62,6 +72,7 @@ struct KParams {
   int num_sms;                  // persistent grid size (SM count of the context's device)
   int stage_gain;               // staged kernel: issue slots per step (2 x 16 pixels) that staged taps save over gathered ones
   int *sched;                   // tile scheduler counters {tickets, retired warps} of this launch's stream, or nullptr
+  int stage_async;              // staged kernel: raw texels by cp.async into shared memory, records decoded from there
   int rec_pad;                  // staged kernel: pad the rows of staged records to a pitch of 4 (mod 8) records (bank groups)
   int tiled_ctas;               // tiled kernel: resident CTAs per SM (2 or 3), chosen by the host per format
   int fast_lens;                // input-lens divisors are normal numbers in [2^-20, 2^20]: unguarded divisions apply

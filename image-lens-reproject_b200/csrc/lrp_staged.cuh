@@ -60,12 +60,16 @@ constexpr int ST_FIXED_BYTES = 1088 + 1024 + 1024; // thresholds + 1 KB alignmen
 //   C == 4   one float4 (c0, c1, c2, c3)
 //   C == 5   float4 + float2 (c4, c4 of the next column)
 // NW = warps per CTA: a warp's staging area is its share of the dynamic shared memory
+template <int FMT> __host__ __device__ constexpr int raw_words(int c) { return FMT == FMT_U8 ? 1 : c; }
 template <int C, int NW> struct StageRec {
   static constexpr int STAGE_BYTES = (((ST_SMEM_BYTES - ST_FIXED_BYTES) / NW) - ST_COORD_BYTES) & ~15;
   static constexpr bool SPLIT = (C == 3);
   static constexpr int A_BYTES = SPLIT ? 8 : 16;
   static constexpr int B_BYTES = (C == 5 || SPLIT) ? 8 : 0;
   static constexpr int CAP = STAGE_BYTES / (A_BYTES + B_BYTES); // texels per warp
+  // asynchronous staging (P.stage_async): the raw texels land in shared memory first (cp.async, 4 bytes per texel and
+  // plane), the records are decoded from there
+  template <int FMT> __host__ __device__ static constexpr int cap_async() { return STAGE_BYTES / (A_BYTES + B_BYTES + 4 * raw_words<FMT>(C)); }
   static constexpr bool LONE = (C & 1) != 0; // odd channel count: the last channel travels as (value, value of the next column)
 };
 
@@ -131,6 +135,10 @@ template <int C> struct StageLoad<FMT_F32, C> {
       for (int c = 0; c < C; ++c) r.v[c] = __ldg(p + c);
     }
   }
+  static LRP_DEV void fetch_staged(const KParams &, unsigned, const unsigned *w, Raw &r) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) r.v[c] = __uint_as_float(w[c]);
+  }
   static LRP_DEV void decode(uint32_t, const Raw &r, float (&v)[C]) {
 #pragma unroll
     for (int c = 0; c < C; ++c) v[c] = r.v[c];
@@ -142,6 +150,7 @@ template <int C> struct StageLoad<FMT_U8, C> {
     static_assert(C == 3, "PNG sources decode to 3 channels");
     r.t = __ldg((const unsigned int *)byte_offset_rt(P.src, pix, 4u));
   }
+  static LRP_DEV void fetch_staged(const KParams &, unsigned, const unsigned *w, Raw &r) { r.t = w[0]; }
   static LRP_DEV void decode(uint32_t lut, const Raw &r, float (&v)[C]) {
     const uint32_t t = r.t;
     float r0, r1, r2; // powf(p / 255, 2.2) of src/image_formats.cpp:195-197 through the host-built table
@@ -158,6 +167,13 @@ template <int C> struct StageLoad<FMT_F16, C> {
 #pragma unroll
     for (int c = 0; c < C; ++c) r.v[c] = __ldg(p + (size_t)c * (size_t)P.src_plane);
   }
+  static LRP_DEV void fetch_staged(const KParams &P, unsigned pix, const unsigned *w, Raw &r) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) { // the aligned pair that holds the half: which one by bit 1 of its address
+      const size_t a = (size_t)P.src + ((size_t)pix + (size_t)c * (size_t)P.src_plane) * 2u;
+      r.v[c] = __ushort_as_half((unsigned short)((a & 2) ? (w[c] >> 16) : (w[c] & 0xFFFFu)));
+    }
+  }
   static LRP_DEV void decode(uint32_t, const Raw &r, float (&v)[C]) {
 #pragma unroll
     for (int c = 0; c < C; ++c) v[c] = __half2float(r.v[c]);
@@ -168,16 +184,41 @@ template <int C> struct StageLoad<FMT_F16, C> {
 // source wraps).  Record t = ty * bw + tx holds source texel (resolve_x(b.x0 + tx), b.y0 + ty).  Records are
 // dealt to the lanes in flat order (consecutive lanes = consecutive texels of a source row, whatever the box
 // width), U x 32 at a time with all the global loads of a round issued before the first decode.
+// `raw_area` != nullptr: asynchronous staging (north-star item 3: "stages each output tile's source footprint in shared
+// memory via TMA or cp.async") — pass 1 issues one cp.async (LDGSTS, 4 bytes) per texel and plane for the WHOLE box
+// without holding a register per load in flight, pass 2 decodes the records out of shared memory.  Texel t's words sit at
+// raw_area[t * RW ..]; a half is copied as the aligned 4-byte pair that holds it.  Measured against the register-staged
+// path in profiles/r2_stage_async_ab.txt.
 template <bool WRAP, int FMT, int C, int NW>
-LRP_DEV void stage_group(const KParams &P, uint32_t lut, unsigned char *stage, const BBox &b, unsigned bw, unsigned bh,
-                         unsigned pitch, int lane) {
+LRP_DEV void stage_group(const KParams &P, uint32_t lut, unsigned char *stage, unsigned char *recB_base, unsigned *raw_area,
+                         const BBox &b, unsigned bw, unsigned bh, unsigned pitch, int lane) {
   typedef StageRec<C, NW> Rec;
   constexpr unsigned STEP = Rec::LONE ? 31u : 32u; // odd C: lane k needs lane k+1's texel, so rounds overlap by one record
   constexpr int U = 4;
+  constexpr int RW = raw_words<FMT>(C);
   const unsigned n = bw * bh;
   const unsigned magic = 0xFFFFFFFFu / bw + 1u; // ceil(2^32 / bw): exact quotients t / bw for t < 2^16, bw <= 4096 (bw == 1: below)
   float4 *recA = (float4 *)stage;
-  float2 *recB = (float2 *)(stage + Rec::CAP * Rec::A_BYTES);
+  float2 *recB = (float2 *)(LRP_STAGED_ASYNC ? recB_base : stage + Rec::CAP * Rec::A_BYTES);
+  if (LRP_STAGED_ASYNC && raw_area != nullptr) {
+    const uint32_t raw_s = shared_addr(raw_area);
+    for (unsigned t = (unsigned)lane; t < n; t += 32u) {
+      const unsigned ty = (bw == 1u) ? t : __umulhi(t, magic);
+      const unsigned tx = t - ty * bw;
+      const int gx = resolve_x<WRAP>((int)((unsigned)b.x0 + tx), P.w);
+      const unsigned pix = ((unsigned)b.y0 + ty) * P.src_pitch + (unsigned)gx;
+#pragma unroll
+      for (int c = 0; c < RW; ++c) {
+        const char *g = byte_offset_rt(P.src, pix, P.src_px_bytes);
+        if (FMT == FMT_F16) g = (const char *)(((size_t)g + (size_t)c * (size_t)P.src_plane * 2u) & ~(size_t)3);
+        if (FMT == FMT_F32) g += 4 * c;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(raw_s + (t * RW + c) * 4u), "l"(g) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
   for (unsigned t0 = 0; t0 < n; t0 += U * STEP) {
     typename StageLoad<FMT, C>::Raw raw[U];
 #pragma unroll
@@ -187,7 +228,9 @@ LRP_DEV void stage_group(const KParams &P, uint32_t lut, unsigned char *stage, c
         const unsigned ty = (bw == 1u) ? t : __umulhi(t, magic);
         const unsigned tx = t - ty * bw;
         const int gx = resolve_x<WRAP>((int)((unsigned)b.x0 + tx), P.w);
-        StageLoad<FMT, C>::fetch(P, ((unsigned)b.y0 + ty) * P.src_pitch + (unsigned)gx, raw[u]);
+        const unsigned pix = ((unsigned)b.y0 + ty) * P.src_pitch + (unsigned)gx;
+        if (LRP_STAGED_ASYNC && raw_area != nullptr) StageLoad<FMT, C>::fetch_staged(P, pix, raw_area + t * RW, raw[u]);
+        else StageLoad<FMT, C>::fetch(P, pix, raw[u]);
       }
     }
 #pragma unroll
@@ -220,6 +263,7 @@ LRP_DEV void stage_group(const KParams &P, uint32_t lut, unsigned char *stage, c
 
 struct StageView {
   const unsigned char *stage; // this warp's records
+  const unsigned char *recB;  // the second record plane (odd channel counts)
   int bx0, by0;               // tap index of record (0, 0)
   unsigned bw;                // records per row (the plan's pitch)
   bool clamped;               // warp-uniform: resolve indices before addressing (border groups)
@@ -315,7 +359,8 @@ LRP_DEV void staged_bicubic(const KParams &P, const StageView &V, float sx, floa
   const bool regular = !V.clamped && (sx >= 1.0f) && (sy >= 1.0f) && (fx <= V.frac_max) && (fy <= V.frac_max);
   const ulonglong2 *recA = (const ulonglong2 *)V.stage;                  // C >= 4: float4 records
   const unsigned long long *recA64 = (const unsigned long long *)V.stage; // C == 3: (c0, c1) records
-  const unsigned long long *recB = (const unsigned long long *)(V.stage + Rec::CAP * Rec::A_BYTES); // odd C: lone channel
+  const unsigned long long *recB = // odd C: lone channel (a compile-time offset unless the A/B build moves it)
+      (const unsigned long long *)(LRP_STAGED_ASYNC ? V.recB : V.stage + Rec::CAP * Rec::A_BYTES);
   if (regular) { // consecutive records: row base + immediate offsets
     const unsigned t00 = (unsigned)(y1 - 1 - V.by0) * rowrec + (unsigned)(x1 - 1 - V.bx0);
 #pragma unroll
@@ -420,6 +465,11 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
   unsigned char *after_lut = smem_raw + (lut_addr - win0) + 1024u;
   float2 *s_coord = (float2 *)(after_lut + wrp * ST_COORD_BYTES);
   unsigned char *s_stage = after_lut + NW * ST_COORD_BYTES + wrp * Rec::STAGE_BYTES;
+  // record capacity of this warp's area: with asynchronous staging the raw texels take their share behind the records
+  const bool async = LRP_STAGED_ASYNC && P.stage_async;
+  const unsigned cap_rec = async ? (unsigned)Rec::template cap_async<FMT>() : (unsigned)Rec::CAP;
+  unsigned char *s_recB = s_stage + cap_rec * Rec::A_BYTES;
+  unsigned *s_raw = async ? (unsigned *)(s_stage + cap_rec * (Rec::A_BYTES + Rec::B_BYTES)) : nullptr;
 
   // ---- once per CTA: tables ----
   if (P.dst_fmt == FMT_U8 && tid <= 256) s_thr[tid] = (tid < 256) ? P.thr[tid] : __int_as_float(0x7f800000);
@@ -427,7 +477,7 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
   __syncthreads(); // the only CTA-wide barrier
 
   const SrcViewT<false> S{P, lut_addr};
-  const bool separable = !TABLE && (P.ol.type == LENS_RECT || P.ol.type == LENS_ERECT) && P.ns == 1;
+  const bool separable = !TABLE && (P.ol.type == LENS_RECT || P.ol.type == LENS_ERECT) && (!LRP_STAGED_SS || P.ns == 1);
   const bool out_rect = (P.ol.type == LENS_RECT);
   const float Wf = (float)P.W, Hf = (float)P.H;
   const float half_W = fmul(Wf, 0.5f), half_H = fmul(Hf, 0.5f);
@@ -441,7 +491,7 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
   // The coordinate slots, the bounding box, the plan and the staged records treat sub-samples like pixels — their
   // footprints overlap almost completely, so one staged box serves all of them; the pixel's average is taken over its
   // lanes in the reference's order (ssx outer, ssy inner) with shuffles.
-  const bool ss = P.ns > 1;
+  const bool ss = LRP_STAGED_SS && P.ns > 1;
   const int ns2 = P.ns * P.ns;
   const int tile_w = ss ? 32 / ns2 : ST_TILE_W, tile_h = ss ? ST_STEPS : ST_TILE_H;
   const int tiles_x = (P.W + tile_w - 1) / tile_w, tiles_y = (P.H + tile_h - 1) / tile_h;
@@ -567,20 +617,20 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
         const bool any_bad = __any_sync(0xffffffffu, bad);
         // worth it: the records fit, and staging them (about one issue slot per record) costs less than the
         // per-tap global loads + decodes it replaces (P.stage_gain issue slots per step, set by the host per format)
-        staged = plan_group<WRAP>(raw, P.w, P.h, Rec::CAP, plan, P.rec_pad) && !any_bad &&
+        staged = plan_group<WRAP>(raw, P.w, P.h, cap_rec, plan, P.rec_pad) && !any_bad &&
                  plan.bw * plan.bh <= (unsigned)(P.stage_gain * (end - start));
         if (staged || len == 1) break;
         len >>= 1;
       }
       const int end = min(start + len, R);
       if (staged) {
-        stage_group<WRAP, FMT, C, NW>(P, lut_addr, s_stage, plan.eff, plan.bw, plan.bh, plan.pitch, lane);
+        stage_group<WRAP, FMT, C, NW>(P, lut_addr, s_stage, s_recB, s_raw, plan.eff, plan.bw, plan.bh, plan.pitch, lane);
         __syncwarp();
       }
       // fraction bound of the sampler's consecutive-index shortcut: rounding error of s + 2.0f <= ulp / 2,
       // ulp(M) <= M * 2^-23; the bound leaves twice that
       const float big = (float)(max(plan.eff.x1, plan.eff.y1) + 4);
-      const StageView V{s_stage, plan.eff.x0, plan.eff.y0, plan.pitch, plan.clamped,
+      const StageView V{s_stage, s_recB, plan.eff.x0, plan.eff.y0, plan.pitch, plan.clamped,
                         fsub(1.0f, fmul(big, 1.1920929e-7f))};
       for (int rr = start; rr < end; ++rr) {
         const int y = y0 + row_step * rr + ly;

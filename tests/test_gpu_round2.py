@@ -362,6 +362,8 @@ def test_supersampling_staged_and_gathered(lrp, ns):
     """--samples N: N x N sub-samples per pixel, accumulated ssx-outer / ssy-inner and scaled by 1 / N^2 (reference
     src/reproject.cpp:294-341).  Staged (N <= 5: N^2 lanes per pixel) and gathered, on the fly and from the table, on
     the three formats; sizes that leave partial tiles in both directions."""
+    # (the staged kernel takes supersampled launches only in the A/B library, `make ab` + LRP_LIB: elsewhere
+    # LRP_VARIANT_STAGED falls back to the gather kernel for them, which this test then runs twice)
     rng = np.random.default_rng(ns)
     for (W, H, w, h, il, olens, r) in (
             (101, 37, 256, 128, ol.erect(), ol.rect(18.0, 36.0, 101, 37), rotd(30, 20, 10)),
