@@ -996,6 +996,7 @@ struct Pool {
     if (!j.in_file || j.in_size == 0 || j.out_width <= 0 || j.out_height <= 0) return LRP_E_BAD_ARG;
     int32_t iw = 0, ih = 0, ic = 3;
     int rc = j.in_kind == LRP_FILE_PNG ? lrp_png_info(j.in_file, j.in_size, &iw, &ih)
+             : j.in_kind == LRP_FILE_JPEG ? lrp_jpeg_info(j.in_file, j.in_size, &iw, &ih)
              : j.in_kind == LRP_FILE_EXR ? lrp_exr_info(j.in_file, j.in_size, &iw, &ih, &ic) : LRP_E_BAD_ARG;
     if (rc != LRP_OK) return rc;
     if (j.out_kind != LRP_FILE_PNG && j.out_kind != LRP_FILE_EXR) return LRP_E_BAD_ARG;
@@ -1024,10 +1025,12 @@ struct Pool {
         return rc;
       }
     }
-    const bool in_png = j.in_kind == LRP_FILE_PNG, out_png = j.out_kind == LRP_FILE_PNG;
+    const bool in_jpeg = j.in_kind == LRP_FILE_JPEG;
+    const bool in_png = j.in_kind == LRP_FILE_PNG || in_jpeg /* same RGBA8 source format */, out_png = j.out_kind == LRP_FILE_PNG;
     rc = slot_reserve(w->slot, in_png ? ipx * 4 : ipx * 2 * ic, out_png ? opx * 4 : opx * 2 * ic);
     if (rc != LRP_OK) return rc;
-    rc = in_png ? lrp_decoder_png(w->dec, j.in_file, j.in_size, w->slot.d_in, w->slot.stream)
+    rc = in_jpeg ? lrp_decoder_jpeg(w->dec, j.in_file, j.in_size, w->slot.d_in, w->slot.stream)
+         : in_png ? lrp_decoder_png(w->dec, j.in_file, j.in_size, w->slot.d_in, w->slot.stream)
                 : lrp_decoder_exr(w->dec, j.in_file, j.in_size, j.decode_threads > 0 || j.decode_threads == LRP_DECODE_ON_DEVICE ? j.decode_threads : 1, w->slot.d_in,
                                   w->slot.stream);
     if (rc != LRP_OK) return rc;

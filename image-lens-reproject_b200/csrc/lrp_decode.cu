@@ -24,6 +24,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <nvjpeg.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -599,6 +600,8 @@ struct lrp_decoder {
   int *h_status = nullptr, *d_status = nullptr;
   unsigned char *d_wide = nullptr; // 32-bit planes of the FLOAT / UINT channels of an EXR file, before their conversion to half
   std::vector<unsigned char> scratch;
+  nvjpegHandle_t jpeg = nullptr; // created by the first JPEG
+  nvjpegJpegState_t jpeg_state = nullptr;
 };
 
 // Files with FLOAT / UINT channels store up to twice the bytes per pixel the decoder was sized for (it is sized for what
@@ -691,6 +694,8 @@ int lrp_decoder_create(lrp_ctx *ctx, int32_t max_width, int32_t max_height, int3
 }
 
 int lrp_decoder_destroy(lrp_decoder *d) {
+  if (d && d->jpeg_state) nvjpegJpegStateDestroy(d->jpeg_state);
+  if (d && d->jpeg) nvjpegDestroy(d->jpeg);
   if (!d) return LRP_E_BAD_ARG;
   cudaSetDevice(d->device);
   cudaFreeHost(d->h_buf), cudaFreeHost(d->h_raw), cudaFreeHost(d->h_jobs), cudaFreeHost(d->h_status);
@@ -874,6 +879,83 @@ int lrp_decoder_png(lrp_decoder *d, const void *file, size_t n, void *out_rgba_d
   if (cudaMemcpyAsync(out_rgba_dev, d->h_buf, px * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
       cudaStreamSynchronize(st) != cudaSuccess)
     return LRP_E_CUDA;
+  return LRP_OK;
+}
+
+// ---- JPEG input: reproject::read_jpeg (reference src/image_formats.cpp:26-77) -----------------------------------
+// The reference decodes with the system libjpeg (scan lines of RGB bytes) and applies the same pow(p / 255, 2.2) as
+// read_png; here nvJPEG (the CUDA toolkit's decoder: Huffman on the host, IDCT + colour conversion on the device)
+// delivers the RGB bytes straight into device memory and the kernel's RGBA8 source format takes it from there.
+// PARITY UNPINNED: the reference names no libjpeg version (CMakeLists.txt:38 `find_package(JPEG)`), none is installed
+// here, and JPEG decoders differ in the last bits of the IDCT / colour conversion / chroma upsampling; the tests hold this
+// leg to a few LSB of libjpeg-turbo (Pillow) on the decoded bytes (measured: max 4, mean 0.5 on 4:4:4 files).  Grey-scale files come back as R = G = B (libjpeg would report one
+// channel, which the reference's RGB indexing then misreads).
+__global__ void rgb_to_rgba_kernel(const unsigned char *rgb, unsigned *rgba, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    rgba[i] = (unsigned)rgb[3 * i] | ((unsigned)rgb[3 * i + 1] << 8) | ((unsigned)rgb[3 * i + 2] << 16) | 0xFF000000u;
+}
+
+static int jpeg_ready(lrp_decoder *d) {
+  if (d->jpeg) return LRP_OK;
+  if (nvjpegCreateSimple(&d->jpeg) != NVJPEG_STATUS_SUCCESS) return LRP_E_CUDA;
+  if (nvjpegJpegStateCreate(d->jpeg, &d->jpeg_state) != NVJPEG_STATUS_SUCCESS) return LRP_E_CUDA;
+  return LRP_OK;
+}
+
+int lrp_jpeg_info(const void *file, size_t n, int32_t *width, int32_t *height) {
+  // SOF0..SOF2 marker scan: no decoder state needed (and no device)
+  const unsigned char *f = (const unsigned char *)file;
+  if (!f || !width || !height || n < 4 || f[0] != 0xFF || f[1] != 0xD8) return LRP_E_BAD_ARG;
+  size_t pos = 2;
+  while (pos + 4 <= n) {
+    if (f[pos] != 0xFF) return LRP_E_BAD_ARG;
+    const unsigned m = f[pos + 1];
+    if (m == 0xFF) { // fill byte
+      ++pos;
+      continue;
+    }
+    if (m == 0xD8 || m == 0x01 || (m >= 0xD0 && m <= 0xD7)) { // markers without a length
+      pos += 2;
+      continue;
+    }
+    const size_t len = ((size_t)f[pos + 2] << 8) | f[pos + 3];
+    if (len < 2 || pos + 2 + len > n) return LRP_E_BAD_ARG;
+    if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
+      if (len < 8) return LRP_E_BAD_ARG;
+      *height = (int32_t)(((unsigned)f[pos + 5] << 8) | f[pos + 6]);
+      *width = (int32_t)(((unsigned)f[pos + 7] << 8) | f[pos + 8]);
+      return (*width > 0 && *height > 0) ? LRP_OK : LRP_E_BAD_ARG;
+    }
+    if (m == 0xDA) break; // start of scan before any frame header
+    pos += 2 + len;
+  }
+  return LRP_E_UNSUPPORTED_FORMAT;
+}
+
+int lrp_decoder_jpeg(lrp_decoder *d, const void *file, size_t n, void *out_rgba_dev, void *cuda_stream) {
+  if (!d || !file || !out_rgba_dev) return LRP_E_BAD_ARG;
+  int32_t w = 0, h = 0;
+  int rc = lrp_jpeg_info(file, n, &w, &h);
+  if (rc != LRP_OK) return rc;
+  const size_t px = (size_t)w * h;
+  if (px * 4 > d->cap) return LRP_E_BAD_ARG;
+  if (cudaSetDevice(d->device) != cudaSuccess) return LRP_E_CUDA;
+  rc = jpeg_ready(d);
+  if (rc != LRP_OK) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  nvjpegImage_t img;
+  memset(&img, 0, sizeof(img));
+  img.channel[0] = d->d_buf; // interleaved RGB, 3 bytes per pixel (the staging buffer holds 4)
+  img.pitch[0] = (size_t)w * 3;
+  const nvjpegStatus_t js = nvjpegDecode(d->jpeg, d->jpeg_state, (const unsigned char *)file, n, NVJPEG_OUTPUT_RGBI, &img, st);
+  if (js != NVJPEG_STATUS_SUCCESS) {
+    cudaStreamSynchronize(st);
+    cudaGetLastError();
+    return (js == NVJPEG_STATUS_JPEG_NOT_SUPPORTED) ? LRP_E_UNSUPPORTED_FORMAT : LRP_E_BAD_ARG;
+  }
+  const unsigned grid = (unsigned)std::min<size_t>((px + 255) / 256, 148 * 16);
+  rgb_to_rgba_kernel<<<grid, 256, 0, st>>>(d->d_buf, (unsigned *)out_rgba_dev, px);
+  if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return LRP_E_CUDA; // d_buf is reused
   return LRP_OK;
 }
 

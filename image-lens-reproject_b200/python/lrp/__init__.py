@@ -59,7 +59,7 @@ class Job(C.Structure):
                 ("user", C.c_void_p)]
 
 
-FILE_PNG, FILE_EXR = 0, 1
+FILE_PNG, FILE_EXR, FILE_JPEG = 0, 1, 2
 FILE_DONE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t)
 
 
@@ -153,6 +153,8 @@ def lib():
         L.lrp_decoder_destroy.argtypes = [vp]
         L.lrp_decoder_exr.argtypes = [vp, C.c_char_p, C.c_size_t, i32, vp, vp]
         L.lrp_decoder_png.argtypes = [vp, C.c_char_p, C.c_size_t, vp, vp]
+        L.lrp_decoder_jpeg.argtypes = [vp, C.c_char_p, C.c_size_t, vp, vp]
+        L.lrp_jpeg_info.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(i32), C.POINTER(i32)]
         L.lrp_encoder_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
         L.lrp_encoder_destroy.argtypes = [vp]
         L.lrp_encoder_last_timing.argtypes = [vp, C.POINTER(C.c_double)]
@@ -527,6 +529,12 @@ def png_info(data):
     return w.value, h.value
 
 
+def jpeg_info(data):
+    w, h = C.c_int32(0), C.c_int32(0)
+    check(lib().lrp_jpeg_info(data, len(data), C.byref(w), C.byref(h)), "lrp_jpeg_info")
+    return w.value, h.value
+
+
 def debug_png_decode_host(data):
     """the host half of lrp_decoder_png (no device): bytes of a .png -> uint8 [H, W, 4] numpy array"""
     import numpy as np
@@ -555,6 +563,15 @@ class Decoder:
         out = torch.empty((c, h, w), dtype=torch.float16, device="cuda:%d" % self.ctx.device)
         check(lib().lrp_decoder_exr(self.h, data, len(data), threads, C.c_void_p(out.data_ptr()), self.ctx._stream(stream)),
               "lrp_decoder_exr")
+        return out
+
+    def jpeg(self, data, stream=None):
+        """-> torch.uint8 [H, W, 4] on the device (nvJPEG; alpha 255)"""
+        import torch
+        w, h = jpeg_info(data)
+        out = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda:%d" % self.ctx.device)
+        check(lib().lrp_decoder_jpeg(self.h, data, len(data), C.c_void_p(out.data_ptr()), self.ctx._stream(stream)),
+              "lrp_decoder_jpeg")
         return out
 
     def png(self, data, stream=None):

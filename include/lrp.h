@@ -377,6 +377,11 @@ int lrp_decoder_exr(lrp_decoder *dec, const void *file, size_t n, int32_t thread
                     void *cuda_stream);
 /* RGBA8 as lodepng::decode delivers it (the kernel reads it as LRP_FMT_U8_RGBA with channels = 3) */
 int lrp_decoder_png(lrp_decoder *dec, const void *file, size_t n, void *out_rgba_dev, void *cuda_stream);
+/* reproject::read_jpeg (src/image_formats.cpp:26-77): baseline / progressive JPEG -> RGBA8 (alpha 255) on the device through
+ * nvJPEG; the kernel applies the same gamma decode as for PNG sources.  PARITY UNPINNED: the reference links an unnamed system
+ * libjpeg, absent here; decoders differ in the last bits (measured against libjpeg-turbo: max 4 LSB, mean 0.5 on 4:4:4 files). */
+int lrp_jpeg_info(const void *file, size_t n, int32_t *width, int32_t *height);
+int lrp_decoder_jpeg(lrp_decoder *dec, const void *file, size_t n, void *out_rgba_dev, void *cuda_stream);
 
 /* ---- file jobs: one whole iteration of the reference's worker lambda (src/main.cpp:541-620): read_png / read_exr ->
  * reproject (+ post_process when params.apply_post) -> save_png / save_exr, from the bytes of the input file to the
@@ -384,7 +389,7 @@ int lrp_decoder_png(lrp_decoder *dec, const void *file, size_t n, void *out_rgba
  * Submitted to the multi-GPU scheduler like lrp_job; on_done runs on a library thread, file_bytes is valid only
  * during the call (write it out or copy it).  PNG input has 3 channels, EXR input 3..5 (R,G,B[,A][,Z]); the output
  * keeps the channel count, as the reference (output.channels = input.channels). */
-typedef enum lrp_file_kind { LRP_FILE_PNG = 0, LRP_FILE_EXR = 1 } lrp_file_kind;
+typedef enum lrp_file_kind { LRP_FILE_PNG = 0, LRP_FILE_EXR = 1, LRP_FILE_JPEG = 2 /* input only, as in the reference */ } lrp_file_kind;
 typedef void (*lrp_file_done_fn)(void *user, int status, const void *file_bytes, size_t file_size);
 typedef struct lrp_file_job {
   const void *in_file;    /* bytes of the input file; must stay valid until on_done */
