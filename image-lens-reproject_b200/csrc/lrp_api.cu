@@ -222,6 +222,7 @@ struct lrp_ctx {
   int device = 0;       // logical device index
   int phys_device = 0;  // CUDA ordinal (differs only under LRP_FAKE_GPUS)
   int num_sms = 148;
+  size_t l2_persist = 0; // bytes of L2 set aside for persisting accesses (the tables of a batch)
   float *d_lut = nullptr, *d_thr = nullptr;
   std::vector<cudaStream_t> streams;
   std::vector<Slot> slots; // for the synchronous host drop-ins
@@ -537,6 +538,13 @@ void remap_cache_clear(lrp_ctx *ctx) {
   ctx->remap_total = 0;
 }
 
+void set_l2_window(const lrp_ctx *ctx, KParams &K, const void *table, size_t bytes) {
+  if (!ctx->l2_persist || !table || !bytes) return;
+  K.l2_window = table;
+  K.l2_window_bytes = bytes;
+  K.l2_hit_ratio = bytes <= ctx->l2_persist ? 1.0f : (float)((double)ctx->l2_persist / (double)bytes);
+}
+
 // The whole per-sample function of an 8-bit source behind an 8-bit sink with one tap per pixel is a map from the
 // source byte to the sink byte:  encode_u8(post_process(0.0f + lut[p]) * 1.0f)  (reference src/image_formats.cpp:195-197,
 // src/reproject.cpp:334-341, 428-431, src/image_formats.cpp:156-158).  256 values, evaluated here with the host's own
@@ -598,6 +606,7 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
   if (!remap && (K.nn_composite || nn_copy) && K.w <= 65536 && K.h <= 65536) {
     if (const void *idx = acquire_remap(ctx, in, out, p, K, coord, REMAP_NN, stream)) {
       K.nn_index = (const unsigned *)idx;
+      set_l2_window(ctx, K, idx, (size_t)K.W * K.H * 4);
       return map_cuda((cudaError_t)launch_nn_table(K, fc, stream));
     }
   }
@@ -605,6 +614,7 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
   if (remap) {
     K.remap = (const float2 *)remap;
     coord = (coord == COORD_ERECT_WRAP) ? COORD_TABLE_WRAP : COORD_TABLE_CLAMP;
+    set_l2_window(ctx, K, remap, (size_t)K.W * K.H * K.ns * K.ns * 8);
   }
   // AUTO follows the measurements (profiles/r1_bench_configs_s6*.jsonl): footprint staging pays for the 16 taps of
   // bicubic on every config (c2 185 vs 209 us, c4t 249 vs 340 us); the 1 / 4 taps of nearest / bilinear are cheaper
@@ -1348,6 +1358,20 @@ int lrp_ctx_create(int device, int n_streams, lrp_ctx **out) {
   c->phys_device = phys;
   const HostTables &T = host_tables();
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, phys);
+  // Persisting L2 carve-out for the remap tables of a batch (launch_l2_window).  OFF by default: measured on c2 with 72 MB
+  // set aside, the bilinear / bicubic launches gain 8 % / 1 % (87.6 -> 80.1 us, 141.4 -> 139.4 us) but the
+  // nearest-neighbour permutation, the one kernel that is bandwidth-bound, halves its speed (17.5 -> 32 us) and ncu
+  // (--cache-control none) still sees the table come from HBM every frame (profiles/r2_l2_persist_ab.txt).
+  // LRP_L2_PERSIST_MB=<n> turns it on for A/B runs.
+  {
+    int max_persist = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, phys);
+    const char *e = getenv("LRP_L2_PERSIST_MB");
+    size_t want = e ? (size_t)atoll(e) << 20 : (size_t)0;
+    if (want > (size_t)max_persist) want = (size_t)max_persist;
+    if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) c->l2_persist = want;
+    cudaGetLastError();
+  }
   if (c->num_sms <= 0) c->num_sms = 148;
   cudaError_t e = cudaMalloc(&c->d_lut, sizeof(T.lut));
   if (e == cudaSuccess) e = cudaMalloc(&c->d_thr, sizeof(T.thr));

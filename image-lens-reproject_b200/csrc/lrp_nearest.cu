@@ -19,6 +19,8 @@
 //
 // Bound: HBM.  Bytes per pixel: 4 (index; L2-resident after the first frame) + 4 gathered (distinct texels only reach
 // DRAM) + 4 written.  No shared-memory staging: a tap is used by one pixel, or by neighbours of the same warp (L1).
+#include <stdlib.h>
+
 #include "lrp_kernel.cuh"
 
 namespace lrp {
@@ -84,7 +86,7 @@ LRP_DEV unsigned map_rgba(unsigned t, uint32_t tab_lane) {
 // Every warp-wide access covers 32 CONSECUTIVE output pixels: index loads and sink stores are one 128-byte line, and a
 // gather touches the one or two lines that hold the ~32 / magnification source texels of that run (a thread that owned 8
 // consecutive pixels instead spread each gather instruction over 256 pixels = a dozen lines: 13 us of L1 tag cycles on c2).
-template <bool IDENT>
+template <bool IDENT, int PER>
 __global__ void __launch_bounds__(NN_THREADS, 4) nn_table_u8_kernel(const __grid_constant__ KParams P) {
   __shared__ __align__(128) unsigned s_tab[IDENT ? 32 : 256 * 32];
   uint32_t tab_lane = 0;
@@ -101,20 +103,20 @@ __global__ void __launch_bounds__(NN_THREADS, 4) nn_table_u8_kernel(const __grid
   const unsigned long long keep = policy_evict_last(), stream = policy_evict_first();
   const unsigned lane = threadIdx.x & 31u, warp = (blockIdx.x * NN_THREADS + threadIdx.x) >> 5;
   const unsigned warps = (gridDim.x * NN_THREADS) >> 5;
-  constexpr unsigned CHUNK = 32 * NN_PER_THREAD;
+  constexpr unsigned CHUNK = 32 * PER;
 #pragma unroll 1
   for (unsigned base = warp * CHUNK; base < n; base += warps * CHUNK) {
-    unsigned e[NN_PER_THREAD], t[NN_PER_THREAD];
+    unsigned e[PER], t[PER];
 #pragma unroll
-    for (int k = 0; k < NN_PER_THREAD; ++k) {
+    for (int k = 0; k < PER; ++k) {
       const unsigned i = base + 32u * k + lane;
       e[k] = i < n ? ld_index(idx + i, keep) : 0u;
     }
 #pragma unroll
-    for (int k = 0; k < NN_PER_THREAD; ++k)
+    for (int k = 0; k < PER; ++k)
       t[k] = __ldg((const unsigned *)byte_offset_rt(src, (e[k] >> 16) * pitch + (e[k] & 0xFFFFu), 4u));
 #pragma unroll
-    for (int k = 0; k < NN_PER_THREAD; ++k) {
+    for (int k = 0; k < PER; ++k) {
       const unsigned i = base + 32u * k + lane;
       if (i < n) st_stream(dst + i, IDENT ? (t[k] | 0xFF000000u) : map_rgba(t[k], tab_lane), stream);
     }
@@ -199,20 +201,31 @@ int launch_nn_table(const KParams &P, int fc, void *stream) {
   if (ctas > persistent) ctas = persistent;
   const dim3 grid((unsigned)ctas), block(NN_THREADS);
   cudaStream_t st = (cudaStream_t)stream;
+  int rc = 0;
   switch (fc) {
-  case FC_U8_3:
-    if (P.ctab_identity) nn_table_u8_kernel<true><<<grid, block, 0, st>>>(P);
-    else nn_table_u8_kernel<false><<<grid, block, 0, st>>>(P);
+  case FC_U8_3: {
+    static const int per = [] { // A/B switch: pixels in flight per thread (4, 8 or 16)
+      const char *e = getenv("LRP_NN_PER");
+      return e ? atoi(e) : NN_PER_THREAD;
+    }();
+    if (P.ctab_identity) {
+      if (per == 4) rc = launch_l2_window(nn_table_u8_kernel<true, 4>, grid.x, block.x, 0, st, P);
+      else if (per == 16) rc = launch_l2_window(nn_table_u8_kernel<true, 16>, grid.x, block.x, 0, st, P);
+      else rc = launch_l2_window(nn_table_u8_kernel<true, 8>, grid.x, block.x, 0, st, P);
+    } else {
+      rc = launch_l2_window(nn_table_u8_kernel<false, 8>, grid.x, block.x, 0, st, P);
+    }
     break;
-  case FC_F16_3: nn_table_f16_kernel<3><<<grid, block, 0, st>>>(P); break;
-  case FC_F16_4: nn_table_f16_kernel<4><<<grid, block, 0, st>>>(P); break;
-  case FC_F16_5: nn_table_f16_kernel<5><<<grid, block, 0, st>>>(P); break;
-  case FC_F32_3: nn_table_f32_kernel<3><<<grid, block, 0, st>>>(P); break;
-  case FC_F32_4: nn_table_f32_kernel<4><<<grid, block, 0, st>>>(P); break;
-  case FC_F32_5: nn_table_f32_kernel<5><<<grid, block, 0, st>>>(P); break;
+  }
+  case FC_F16_3: rc = launch_l2_window(nn_table_f16_kernel<3>, grid.x, block.x, 0, st, P); break;
+  case FC_F16_4: rc = launch_l2_window(nn_table_f16_kernel<4>, grid.x, block.x, 0, st, P); break;
+  case FC_F16_5: rc = launch_l2_window(nn_table_f16_kernel<5>, grid.x, block.x, 0, st, P); break;
+  case FC_F32_3: rc = launch_l2_window(nn_table_f32_kernel<3>, grid.x, block.x, 0, st, P); break;
+  case FC_F32_4: rc = launch_l2_window(nn_table_f32_kernel<4>, grid.x, block.x, 0, st, P); break;
+  case FC_F32_5: rc = launch_l2_window(nn_table_f32_kernel<5>, grid.x, block.x, 0, st, P); break;
   default: return (int)cudaErrorInvalidValue;
   }
-  return (int)cudaGetLastError();
+  return rc;
 }
 
 } // namespace lrp

@@ -72,6 +72,9 @@ struct KParams {
   int num_sms;                  // persistent grid size (SM count of the context's device)
   int stage_gain;               // staged kernel: issue slots per step (2 x 16 pixels) that staged taps save over gathered ones
   int *sched;                   // tile scheduler counters {tickets, retired warps} of this launch's stream, or nullptr
+  const void *l2_window;        // table to keep resident in the persisting part of L2 across the launches of a batch
+  size_t l2_window_bytes;       // (0: none)
+  float l2_hit_ratio;           // share of the window that fits the persisting carve-out
   int stage_async;              // staged kernel: raw texels by cp.async into shared memory, records decoded from there
   int rec_pad;                  // staged kernel: pad the rows of staged records to a pitch of 4 (mod 8) records (bank groups)
   int tiled_ctas;               // tiled kernel: resident CTAs per SM (2 or 3), chosen by the host per format

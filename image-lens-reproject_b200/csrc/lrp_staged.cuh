@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
       for (int r = 0; r < ST_STEPS; ++r) {
         const int y = y0 + row_step * r + ly;
         s[r] = make_float2(0.0f, 0.0f);
-        if (xvalid && y < P.H) s[r] = __ldg(P.remap + ((size_t)sub * (size_t)P.H + (size_t)y) * (size_t)P.W + (size_t)x);
+        if (xvalid && y < P.H) s[r] = ld_table(P.remap + ((size_t)sub * (size_t)P.H + (size_t)y) * (size_t)P.W + (size_t)x);
       }
 #pragma unroll
       for (int r = 0; r < ST_STEPS; ++r) s_coord[r * 32 + lane] = s[r];
@@ -697,8 +697,7 @@ int launch_reproject_staged(const KParams &P, void *stream) {
   constexpr int NW = st_warps(INTERP, C);
   const int ctas_needed = (tiles + NW - 1) / NW;
   const int grid = ctas_needed < P.num_sms ? ctas_needed : P.num_sms;
-  kern<<<grid, NW * 32, ST_SMEM_BYTES, (cudaStream_t)stream>>>(P);
-  return (int)cudaGetLastError();
+  return launch_l2_window(kern, (unsigned)grid, NW * 32, ST_SMEM_BYTES, stream, P);
 }
 
 } // namespace lrp

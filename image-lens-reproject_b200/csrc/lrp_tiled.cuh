@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(TL_THREADS, NCTA) reproject_tiled_kernel(const
 #pragma unroll
       for (int r = 0; r < TL_ROWS; ++r) {
         float2 s = make_float2(0.0f, 0.0f);
-        if (xvalid && yw + r < P.H) s = __ldg(P.remap + (size_t)(yw + r) * (size_t)P.W + (size_t)x);
+        if (xvalid && yw + r < P.H) s = ld_table(P.remap + (size_t)(yw + r) * (size_t)P.W + (size_t)x);
         sx[r] = s.x;
         sy[r] = s.y;
       }
@@ -480,8 +480,7 @@ int launch_reproject_tiled_n(const KParams &P, void *stream) {
   const int tiles = ((P.W + TL_W - 1) / TL_W) * ((P.H + TL_H - 1) / TL_H);
   const int persistent = P.num_sms * NCTA;
   const int grid = tiles < persistent ? tiles : persistent;
-  kern<<<grid, TL_THREADS, tl_smem_bytes(NCTA), (cudaStream_t)stream>>>(P);
-  return (int)cudaGetLastError();
+  return launch_l2_window(kern, (unsigned)grid, TL_THREADS, tl_smem_bytes(NCTA), stream, P);
 }
 
 template <int COORD, int FMT, int C>
