@@ -67,11 +67,13 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(interp):
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+def recorded_traffic(interp, table):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (cold caches): the entry of the
+    kernel that actually ran (coordinates from the context's remap table, or on the fly)."""
     p = os.path.join(ROOT, "profiles", "ncu_summary.json")
     try:
-        return json.load(open(p))["c2"][interp]["dram_bytes_per_launch"]
+        d = json.load(open(p))["c2"]
+        return d[interp + "_table" if table and interp + "_table" in d else interp]["dram_bytes_per_launch"]
     except Exception:
         return None
 
@@ -587,7 +589,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                                    "one run of the reference shares one geometry across its images)",
                     "remap_tables_held": remap_tables[0], "remap_table_bytes": remap_tables[1]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": recorded_traffic(args.interp), "peak_source": peak_src,
+                         "traffic": recorded_traffic(args.interp, table_used), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": balg, "us_per_launch": per_launch_s * 1e6, "kernel": kname},
             "coords_legs": {"fly": leg(fly_ms), "table": leg(table_ms),
                             "note": "the timed steps again with lrp_params.coords forced; table = +8 B (nearest: +4 B) per "

@@ -53,10 +53,11 @@ constexpr int ST_COORD_BYTES = ST_STEPS * 32 * 8;
 constexpr int ST_SMEM_BYTES = 232448;     // 227 KB: the opt-in maximum of dynamic shared memory per CTA
 constexpr int ST_FIXED_BYTES = 1088 + 1024 + 1024; // thresholds + 1 KB alignment slack + gamma table
 
-// staging records (shared-memory wavefronts bound this kernel: profiles/r2_c2_bc_table_staged_wavefronts.txt):
+// staging records (per-instruction wavefronts: profiles/r2_c2_bc_table_staged_wavefronts.txt):
 //   C == 3   two planes of 8-byte records: A = (c0, c1), B = (c2, c2 of the next column) — every load is a 64-bit load of
-//            densely packed records (2.1 wavefronts per warp; the former float4 record cost 5.45 per 128-bit load and
-//            4.27 per 64-bit load of half a record, 78 -> 50 wavefronts per 32 pixels)
+//            densely packed records.  Measured 3.38 wavefronts per warp-wide LDS.64 (ideal 2.0; the former float4 record
+//            cost 5.45 per LDS.128 and 4.27 per LDS.64 of half a record): the total per 32 pixels did not move (108 vs 104,
+//            24 loads instead of 16) and neither did c2 (140 vs 138 us), but the half formats gained (c5e 335 -> 307 us).
 //   C == 4   one float4 (c0, c1, c2, c3)
 //   C == 5   float4 + float2 (c4, c4 of the next column)
 // NW = warps per CTA: a warp's staging area is its share of the dynamic shared memory
