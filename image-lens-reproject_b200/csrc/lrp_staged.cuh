@@ -89,10 +89,11 @@ struct GroupPlan {
   unsigned pitch; // records per staged row: bw, padded to 4 (mod 8) when P.rec_pad — see below
   bool clamped;
 };
-// Shared-memory bank groups: a record is 16 bytes, a quarter-warp (8 lanes) is served per wavefront of a 128-bit load when
-// its records fall into 8 different 16-byte bank groups, i.e. have different indices mod 8.  The 8 pixels of a quarter
-// touch 3-4 consecutive records of one source row and, when the mapping is rotated, as many of the next row: with a row
-// pitch of 4 (mod 8) the two runs land in disjoint residues whatever the box width is (measured: profiles/r2_*pad*).
+// Shared-memory banks and the row pitch of the records (3-channel layout: 8-byte records, a half-warp = 16 pixels of one
+// output row per wavefront of a 64-bit load): the 16 pixels touch ~6 consecutive records of one source row and, when the
+// mapping is rotated, as many of the next row; with a pitch of 8 (mod 16) records the two runs fall into disjoint bank
+// pairs whatever the box width is.  Measured (profiles/r2_staged_variants.txt): c2 141.3 -> 135.3 us, c3 275 -> 270,
+// c5e 307 -> 303; the float4 records of 4-5 channels do not gain (c4t 186 -> 192) and keep pitch = width.
 template <bool WRAP> LRP_DEV bool plan_group(const BBox &raw, int w, int h, unsigned cap, GroupPlan &g, int rec_pad = 0) {
   // out-of-image tests on the RAW box (unsigned compare: negative indices are huge)
   const bool cut_y = ((unsigned)raw.y0 >= (unsigned)h) || ((unsigned)raw.y1 >= (unsigned)h);
@@ -110,7 +111,10 @@ template <bool WRAP> LRP_DEV bool plan_group(const BBox &raw, int w, int h, unsi
   g.clamped = cut_x || cut_y;
   g.bw = (unsigned)g.eff.x1 - (unsigned)g.eff.x0 + 1u;
   g.bh = (unsigned)g.eff.y1 - (unsigned)g.eff.y0 + 1u;
-  g.pitch = rec_pad ? (((g.bw + 3u) & ~7u) + 4u) : g.bw;
+  // rec_pad 1: pitch = 4 (mod 8) records (the float4-record theory); 2: pitch = 8 (mod 16) — 8-byte records: a half-warp's
+  // two source rows of ~6 records each then fall into disjoint bank pairs
+  g.pitch = rec_pad == 2 ? (((g.bw + 7u) & ~15u) + 8u) : rec_pad == 1 ? (((g.bw + 3u) & ~7u) + 4u) : g.bw;
+  if (g.pitch * g.bh > cap) g.pitch = g.bw; // padding must never cost a block its place in shared memory
   return ok && g.bw <= 4096u && g.bh <= 4096u && g.pitch * g.bh <= cap;
 }
 
@@ -618,7 +622,7 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
         const bool any_bad = __any_sync(0xffffffffu, bad);
         // worth it: the records fit, and staging them (about one issue slot per record) costs less than the
         // per-tap global loads + decodes it replaces (P.stage_gain issue slots per step, set by the host per format)
-        staged = plan_group<WRAP>(raw, P.w, P.h, cap_rec, plan, P.rec_pad) && !any_bad &&
+        staged = plan_group<WRAP>(raw, P.w, P.h, cap_rec, plan, Rec::SPLIT ? P.rec_pad : 0) && !any_bad &&
                  plan.bw * plan.bh <= (unsigned)(P.stage_gain * (end - start));
         if (staged || len == 1) break;
         len >>= 1;
