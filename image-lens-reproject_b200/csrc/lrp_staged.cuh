@@ -354,14 +354,22 @@ LRP_DEV void staged_bicubic(const KParams &P, const StageView &V, float sx, floa
   // gives sx - x1 >= w.)  Only the pixels that fail the test — the truncation kink at index 0, border groups —
   // evaluate the four truncations per axis of the reference (:114-127).
   const int x1 = __float2int_rz(sx), y1 = __float2int_rz(sy); // staged pixels have |s| < 2^30: cvt.rzi == cvttss2si
-  const float fx = clamp01_std(fsub(sx, (float)resolve_x<WRAP>(x1, P.w))); // :130 (post-wrap/clamp x1)
-  const float fy = clamp01_std(fsub(sy, (float)clampi(y1, P.h)));     // :131
+  // Fractions (:130-131: s - float(resolved middle index), clamped to [0, 1]).  Common case first: in a block that the
+  // image border does not cut every tap row / column is inside the image, so the resolved middle index IS the raw one
+  // (a wrapping source may still hold x1 outside [0, w): tested), s - trunc(s) is exact and lies in [0, 1) for s >= 1 —
+  // no resolve, no clamp.  Everything else takes the literal form.
+  float fx = fsub(sx, (float)x1), fy = fsub(sy, (float)y1);
 
   // taps as packed pairs: P0[xi][yi] = (c0, c1), P1[xi][yi] = (c2, c3) for C >= 4,
   // lone channel (odd C): L[h][yi] = (value at column 2h, value at column 2h + 1)
   f2 P0[4][4], P1[4][4], L[2][4];
   const unsigned rowrec = V.bw;
-  const bool regular = !V.clamped && (sx >= 1.0f) && (sy >= 1.0f) && (fx <= V.frac_max) && (fy <= V.frac_max);
+  const bool regular = !V.clamped && (sx >= 1.0f) && (sy >= 1.0f) && (fx <= V.frac_max) && (fy <= V.frac_max) &&
+                       (!WRAP || (unsigned)x1 < (unsigned)P.w);
+  if (!regular) {
+    fx = clamp01_std(fsub(sx, (float)resolve_x<WRAP>(x1, P.w))); // :130 (post-wrap/clamp x1)
+    fy = clamp01_std(fsub(sy, (float)clampi(y1, P.h)));     // :131
+  }
   const ulonglong2 *recA = (const ulonglong2 *)V.stage;                  // C >= 4: float4 records
   const unsigned long long *recA64 = (const unsigned long long *)V.stage; // C == 3: (c0, c1) records
   const unsigned long long *recB = // odd C: lone channel (a compile-time offset unless the A/B build moves it)

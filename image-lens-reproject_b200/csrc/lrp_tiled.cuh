@@ -210,12 +210,13 @@ LRP_DEV void tiled_bicubic(const KParams &P, const TileView &V, float sx, float 
   constexpr int RB = TileRec<C>::BYTES;
   // see staged_bicubic: a sufficient test for "tap indices are x1-1 .. x1+2 and y1-1 .. y1+2" on the middle index alone
   const int x1 = __float2int_rz(sx), y1 = __float2int_rz(sy);
-  const float fx = clamp01_std(fsub(sx, (float)resolve_x<WRAP>(x1, P.w))); // :130 (post-wrap/clamp x1)
-  const float fy = clamp01_std(fsub(sy, (float)clampi(y1, P.h)));     // :131
-  const bool regular = !V.clamped && (sx >= 1.0f) && (sy >= 1.0f) && (fx <= V.frac_max) && (fy <= V.frac_max);
+  const float fx = fsub(sx, (float)x1), fy = fsub(sy, (float)y1); // exact, in [0, 1): see staged_bicubic
+  const bool regular = !V.clamped && (sx >= 1.0f) && (sy >= 1.0f) && (fx <= V.frac_max) && (fy <= V.frac_max) &&
+                       (!WRAP || (unsigned)x1 < (unsigned)P.w);
   if (!regular) {
     float o[C];
-    tiled_bicubic_taps<WRAP, C>(P, V, sx, sy, fx, fy, o);
+    tiled_bicubic_taps<WRAP, C>(P, V, sx, sy, clamp01_std(fsub(sx, (float)resolve_x<WRAP>(x1, P.w))), // :130
+                                clamp01_std(fsub(sy, (float)clampi(y1, P.h))), o);                    // :131
 #pragma unroll
     for (int c = 0; c < C; ++c) out[c] = o[c];
     return;
