@@ -621,7 +621,8 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
   // gathered through L1 (c2 nn 107 vs 179 us, bl 124 vs 139 us; c3 bl 137 vs 235 us)
   {
     const char *rp = getenv("LRP_REC_PAD"); // A/B switch: padded record rows in the staged kernel
-    K.rec_pad = rp ? atoi(rp) : 2; // 8-byte records at a pitch of 8 (mod 16): measured -4 % on c2 (profiles/r2_staged_variants.txt)
+    K.rec_pad = rp ? atoi(rp) : 17; // 8-byte records at a row pitch of 1 (mod 16): the best of the 16 residues, -7 % on c2
+                                     // (profiles/r2_staged_variants.txt; 16 + r selects residue r, 0 = no padding)
     const char *sa = getenv("LRP_STAGE_ASYNC"); // A/B switch: cp.async staging (needs 4-byte aligned planes)
     K.stage_async = (LRP_STAGED_ASYNC && sa && atoi(sa) != 0 && (in->format != LRP_FMT_F16_PLANAR || (((size_t)in->width * in->height) % 2 == 0 && ((size_t)in->data & 3) == 0))) ? 1 : 0;
   }

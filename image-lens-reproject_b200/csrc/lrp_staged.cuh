@@ -89,11 +89,12 @@ struct GroupPlan {
   unsigned pitch; // records per staged row: bw, padded to 4 (mod 8) when P.rec_pad — see below
   bool clamped;
 };
-// Shared-memory banks and the row pitch of the records (3-channel layout: 8-byte records, a half-warp = 16 pixels of one
-// output row per wavefront of a 64-bit load): the 16 pixels touch ~6 consecutive records of one source row and, when the
-// mapping is rotated, as many of the next row; with a pitch of 8 (mod 16) records the two runs fall into disjoint bank
-// pairs whatever the box width is.  Measured (profiles/r2_staged_variants.txt): c2 141.3 -> 135.3 us, c3 275 -> 270,
-// c5e 307 -> 303; the float4 records of 4-5 channels do not gain (c4t 186 -> 192) and keep pitch = width.
+// Shared-memory banks and the row pitch of the records (3-channel layout: 8-byte records).  The pixels of a warp touch a few
+// consecutive records of one or two source rows per tap; which bank pairs the second row falls into is a matter of the
+// pitch.  Measured over all 16 residues of the pitch mod 16 (profiles/r2_staged_variants.txt, c2 table coordinates):
+// 1 (mod 16) is the best (129.8 us; unpadded 139.7; 8: 133.7; 12-15: 146-155), so rows are padded to the next such
+// pitch whenever the padded box still fits the warp's staging area.  The float4 records of 4-5 channels do not gain
+// (c4t 186 -> 192 us) and keep pitch = width.
 template <bool WRAP> LRP_DEV bool plan_group(const BBox &raw, int w, int h, unsigned cap, GroupPlan &g, int rec_pad = 0) {
   // out-of-image tests on the RAW box (unsigned compare: negative indices are huge)
   const bool cut_y = ((unsigned)raw.y0 >= (unsigned)h) || ((unsigned)raw.y1 >= (unsigned)h);
@@ -111,9 +112,9 @@ template <bool WRAP> LRP_DEV bool plan_group(const BBox &raw, int w, int h, unsi
   g.clamped = cut_x || cut_y;
   g.bw = (unsigned)g.eff.x1 - (unsigned)g.eff.x0 + 1u;
   g.bh = (unsigned)g.eff.y1 - (unsigned)g.eff.y0 + 1u;
-  // rec_pad 1: pitch = 4 (mod 8) records (the float4-record theory); 2: pitch = 8 (mod 16) — 8-byte records: a half-warp's
-  // two source rows of ~6 records each then fall into disjoint bank pairs
-  g.pitch = rec_pad == 2 ? (((g.bw + 7u) & ~15u) + 8u) : rec_pad == 1 ? (((g.bw + 3u) & ~7u) + 4u) : g.bw;
+  // (rec_pad 1 / 2: the earlier 4 (mod 8) / 8 (mod 16) experiments, kept for A/B runs)
+  g.pitch = rec_pad >= 16 ? g.bw + (((unsigned)(rec_pad - 16) - g.bw) & 15u) /* the next pitch = rec_pad - 16 (mod 16) */
+            : rec_pad == 2 ? (((g.bw + 7u) & ~15u) + 8u) : rec_pad == 1 ? (((g.bw + 3u) & ~7u) + 4u) : g.bw;
   if (g.pitch * g.bh > cap) g.pitch = g.bw; // padding must never cost a block its place in shared memory
   return ok && g.bw <= 4096u && g.bh <= 4096u && g.pitch * g.bh <= cap;
 }
@@ -199,7 +200,10 @@ LRP_DEV void stage_group(const KParams &P, uint32_t lut, unsigned char *stage, u
                          const BBox &b, unsigned bw, unsigned bh, unsigned pitch, int lane) {
   typedef StageRec<C, NW> Rec;
   constexpr unsigned STEP = Rec::LONE ? 31u : 32u; // odd C: lane k needs lane k+1's texel, so rounds overlap by one record
-  constexpr int U = 4;
+#ifndef LRP_STAGE_U
+#define LRP_STAGE_U 4
+#endif
+  constexpr int U = LRP_STAGE_U; // texels per lane and round, their global loads all in flight before the first decode
   constexpr int RW = raw_words<FMT>(C);
   const unsigned n = bw * bh;
   const unsigned magic = 0xFFFFFFFFu / bw + 1u; // ceil(2^32 / bw): exact quotients t / bw for t < 2^16, bw <= 4096 (bw == 1: below)

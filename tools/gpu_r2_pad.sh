@@ -1,9 +1,9 @@
 #!/bin/bash
-for pad in 2 0; do
+for pad in 17 2 0; do
   LRP_REC_PAD=$pad timeout 300 python bench.py --steps 20 --quick --no-cpu-baseline --no-sched --e2e-steps 1 2>/dev/null | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('pad $pad c2 fly', d['coords_legs']['fly']['us_per_launch'], 'table', d['coords_legs']['table']['us_per_launch'])"
-  LRP_REC_PAD=$pad timeout 600 python tools/bench_configs.py --configs c1t,c3,c4t,c5e,c5p --variants staged --coords table 2>/dev/null | python -c "
+  LRP_REC_PAD=$pad timeout 600 python tools/bench_configs.py --configs c1t,c3,c5e,c5p --variants staged --coords table 2>/dev/null | python -c "
 import json,sys
 for l in sys.stdin:
     d=json.loads(l); print(' ', d['config'], d['coords'], d['us_per_frame'])"
