@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(NN_THREADS, 4) nn_table_u8_kernel(const __grid
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
       const unsigned i = base + 32u * k + lane;
-      e[k] = i < n ? ld_index(idx + i, keep) : 0u;
+      e[k] = ld_index(idx + (i < n ? i : n - 1u), keep); // lanes beyond the image repeat its last pixel: texel (0, 0) may lie
+                                                        // outside an uploaded region of interest
     }
 #pragma unroll
     for (int k = 0; k < PER; ++k)
@@ -147,7 +148,8 @@ template <int C> __global__ void __launch_bounds__(NN_THREADS, 4) nn_table_f16_k
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
       const unsigned i = base + 32u * k + lane;
-      e[k] = i < n ? ld_index(idx + i, keep) : 0u;
+      e[k] = ld_index(idx + (i < n ? i : n - 1u), keep); // lanes beyond the image repeat its last pixel: texel (0, 0) may lie
+                                                        // outside an uploaded region of interest
     }
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
