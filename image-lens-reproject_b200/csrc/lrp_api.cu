@@ -495,10 +495,15 @@ const void *acquire_remap(lrp_ctx *ctx, const lrp_image *in, const lrp_image *ou
     ctx->remap_total -= victim->second.bytes;
     ctx->remap_cache.erase(victim);
   }
+  // stream-ordered allocation from the device's pool (its release threshold is raised at context creation): no
+  // device-wide synchronisation in the middle of a batch, which cudaMalloc would be
   void *tab = nullptr;
-  if (cudaMalloc(&tab, bytes) != cudaSuccess) {
+  if (cudaMallocAsync(&tab, bytes, stream) != cudaSuccess) {
     cudaGetLastError();
-    return nullptr;
+    if (cudaMalloc(&tab, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
   }
   cudaEvent_t ev = nullptr;
   KParams B = K;
@@ -1359,6 +1364,14 @@ int lrp_ctx_create(int device, int n_streams, lrp_ctx **out) {
   c->phys_device = phys;
   const HostTables &T = host_tables();
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, phys);
+  { // remap tables come from the device's stream-ordered pool: keep what it has freed instead of returning it to the driver
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, phys) == cudaSuccess && pool) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   // Persisting L2 carve-out for the remap tables of a batch (launch_l2_window).  OFF by default: measured on c2 with 72 MB
   // set aside, the bilinear / bicubic launches gain 8 % / 1 % (87.6 -> 80.1 us, 141.4 -> 139.4 us) but the
   // nearest-neighbour permutation, the one kernel that is bandwidth-bound, halves its speed (17.5 -> 32 us) and ncu
