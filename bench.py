@@ -604,7 +604,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                          "algorithmic_bytes_per_launch": balg, "us_per_launch": per_launch_s * 1e6, "kernel": kname},
             "coords_legs": {"fly": leg(fly_ms), "table": leg(table_ms),
                             "note": "the timed steps again with lrp_params.coords forced; table = +8 B (nearest: +4 B) per "
-                                    "output pixel of reads, kept in L2 across frames"},
+                                    "output pixel of HBM reads every frame (ncu: the table does not stay in L2 between frames)"},
             "e2e": {"value": e2e_value, "unit": "Gpix/s", "h2d_bytes_per_step": int(h2d_all),
                     "d2h_bytes_per_step": int(d2h_all), "steps": e2e_steps, "warmup": 3, "matches_device_path": e2e_ok,
                     "api": "lrp_submit/lrp_wait_all (C ABI, pinned host buffers, %d jobs in flight per GPU, one engine "
