@@ -337,7 +337,7 @@ int prepare(const lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const
   // pixel indices are 32-bit on the device (the reference's own index arithmetic is `int`)
   if ((uint64_t)in->width * (uint64_t)in->height >= (1ull << 31)) return LRP_E_BAD_ARG;
   if ((uint64_t)out->width * (uint64_t)out->height >= (1ull << 31)) return LRP_E_BAD_ARG;
-  if (p->extensions & ~LRP_EXT_FISHEYE_MODELS) return LRP_E_BAD_ARG;
+  if (p->extensions & ~(LRP_EXT_FISHEYE_MODELS | LRP_EXT_FOV_MASK)) return LRP_E_BAD_ARG;
   if (!lens_supported(out->lens.type, p->extensions)) return LRP_E_UNSUPPORTED_OUTPUT_LENS; // reference :415-417
   if (!lens_supported(in->lens.type, p->extensions)) return LRP_E_UNSUPPORTED_INPUT_LENS;   // reference :395-397
   if (p->interpolation < 0 || p->interpolation > 2) return LRP_E_UNSUPPORTED_INTERP; // :364-366
@@ -385,6 +385,12 @@ int prepare(const lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const
   K.thr = ctx->d_thr;
   K.neg_zero2 = 0x8000000080000000ull;
   K.num_sms = ctx->num_sms;
+  if (p->extensions & LRP_EXT_FOV_MASK) { // extension lenses only, fov > 0 only (lrp.h)
+    auto ext = [](const LensP &l) { return (l.type == LENS_EQUISOLID || l.type == LENS_STEREO) && l.p1 > 0.0f; };
+    K.fov_mask = (ext(K.ol) ? 1 : 0) | (ext(K.il) ? 2 : 0);
+    K.ol_half_fov = 0.5f * K.ol.p1;
+    K.il_half_fov = 0.5f * K.il.p1;
+  }
   K.src_pitch = (unsigned)in->width;
   K.src_px_bytes = in->format == LRP_FMT_F32 ? 4u * (unsigned)in->channels : in->format == LRP_FMT_U8_RGBA ? 4u : 2u;
   { // lrp_fastlibm.cuh: the unguarded divisions need sane divisors (any real lens has them)
@@ -440,6 +446,7 @@ std::string geometry_key(const lrp_image *in, const lrp_image *out, const lrp_pa
   put(&out->width, 4);
   put(&out->height, 4);
   put(&p->num_samples, 4);
+  put(&p->extensions, 4); // the field-of-view mask changes tables and footprints
   if (with_sampler) put(&p->interpolation, 4);
   const int32_t hr = p->has_rotation ? 1 : 0;
   put(&hr, 4);
@@ -461,6 +468,7 @@ const void *acquire_remap(lrp_ctx *ctx, const lrp_image *in, const lrp_image *ou
   if (const char *e = getenv("LRP_COORDS")) { // A/B switch for unmodified callers: fly | table | auto
     if (mode == LRP_COORDS_AUTO) mode = e[0] == 'f' ? LRP_COORDS_FLY : e[0] == 't' ? LRP_COORDS_TABLE : LRP_COORDS_AUTO;
   }
+  if (K.fov_mask) mode = LRP_COORDS_TABLE; // the mask lives in the table (coords_kernel), whatever the caller prefers
   if (mode == LRP_COORDS_FLY) return nullptr;
   const size_t px = (size_t)K.W * (size_t)K.H;
   const size_t bytes = kind == REMAP_NN ? px * 4 : px * (size_t)K.ns * (size_t)K.ns * 8;
@@ -602,7 +610,8 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
   // ---- nearest, one sample per pixel, codec-native 8-bit in and out: the byte-map path (lrp_nearest.cu) ----
   const bool nn1 = p->interpolation == LRP_NEAREST && p->num_samples == 1 && variant != LRP_VARIANT_STAGED && variant != LRP_VARIANT_TILED;
   const char *no_nn = getenv("LRP_NO_NN_FAST"); // A/B switch: nearest through the generic float tail
-  const bool nn_fast = nn1 && !(no_nn && no_nn[0] == '1');
+  if (K.fov_mask) variant = LRP_VARIANT_GATHER; // masked samples are skipped by the gather kernel's table mode only
+  const bool nn_fast = nn1 && !(no_nn && no_nn[0] == '1') && !K.fov_mask;
   if (nn_fast && in->format == LRP_FMT_U8_RGBA && out->format == LRP_FMT_U8_RGBA) {
     build_composite_table(host_tables(), K, K.ctab, &K.ctab_identity);
     K.nn_composite = 1;
@@ -616,6 +625,7 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
     }
   }
   if (!remap) remap = acquire_remap(ctx, in, out, p, K, coord, REMAP_F2, stream);
+  if (K.fov_mask && !remap) return LRP_E_OOM; // no table, no mask: never fall back to unmasked output
   if (remap) {
     K.remap = (const float2 *)remap;
     coord = (coord == COORD_ERECT_WRAP) ? COORD_TABLE_WRAP : COORD_TABLE_CLAMP;
@@ -684,6 +694,7 @@ int source_footprint(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, co
   r.x1 = ctx->h_bbox[1];
   r.y0 = ctx->h_bbox[2];
   r.y1 = ctx->h_bbox[3];
+  if (K.fov_mask && r.x0 > r.x1) r.x0 = r.x1 = r.y0 = r.y1 = 0; // every sub-sample masked: no texel is read
   // resolved indices are inside the image by construction; anything else is a bug, not a region
   if (r.x0 < 0 || r.y0 < 0 || r.x1 >= in->width || r.y1 >= in->height || r.x0 > r.x1 || r.y0 > r.y1) return LRP_E_CUDA;
   if (ctx->fp_cache.size() > 4096) ctx->fp_cache.clear();

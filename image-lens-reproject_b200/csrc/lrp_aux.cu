@@ -46,6 +46,7 @@ __device__ void footprint_pixel(const KParams &P, int coord, int x, int y, const
       const float scy = fsub(fadd(cy, fdiv(fadd((float)ssy, 1.0f), P.ss_den)), 0.5f);
       float sx, sy;
       source_coord_rt(P, coord, scx, scy, sx, sy);
+      if (P.fov_mask && coord_masked(sx)) continue; // a masked sub-sample touches no texel
       int xs[N], ys[N];
       tap_indices<WRAP, N>(sx, sy, off, P.w, P.h, xs, ys);
 #pragma unroll

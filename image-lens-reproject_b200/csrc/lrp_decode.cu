@@ -35,6 +35,7 @@
 
 #include "../../include/lrp.h"
 #include "lrp_inflate.cuh"
+#include "lrp_inflate_fast.h"
 #include "lrp_exr_blocks.h"
 
 extern "C" int lrp_ctx_phys_device_(const lrp_ctx *ctx); // lrp_api.cu
@@ -165,6 +166,23 @@ __global__ void __launch_bounds__(UNPACK_WARPS * 32) exr_unpack_kernel(const Exr
     base_lo += __shfl_sync(0xffffffffu, il, 31);
     base_hi += __shfl_sync(0xffffffffu, ih, 31);
   }
+}
+
+// A whole zlib stream -> exactly `want` bytes, Adler-32 checked: the host inflate of PNG IDAT streams and EXR ZIP blocks
+// (lrp_inflate_fast.h: 1.3-2x zlib 1.3's inflate on filtered scan lines; LRP_INFLATE_ZLIB=1 is the A/B switch back).
+static bool inflate_exact(unsigned char *dst, size_t want, const unsigned char *src, size_t n) {
+  static const bool use_zlib = [] {
+    const char *e = getenv("LRP_INFLATE_ZLIB");
+    return e && e[0] == '1';
+  }();
+  if (use_zlib) {
+    uLongf got = (uLongf)want;
+    return uncompress(dst, &got, src, (uLong)n) == Z_OK && got == want;
+  }
+  static thread_local fastinf::Tables T;
+  uint32_t stored = 0;
+  if (fastinf::inflate_zlib(src, n, dst, want, T, &stored) != fastinf::OK) return false;
+  return fastinf::adler32_fast(dst, want) == stored;
 }
 
 // ---- EXR: the zlib streams of the blocks inflated on the device (lrp_inflate.cuh) -----------------------------
@@ -797,8 +815,7 @@ int lrp_decoder_exr(lrp_decoder *d, const void *file, size_t n, int32_t threads,
       }
       d->h_raw[b] = 0;
     } else {
-      uLongf got = (uLongf)raw_n;
-      if (uncompress(dst, &got, f + off + 8, (uLong)hdr[1]) != Z_OK || got != raw_n) {
+      if (!inflate_exact(dst, raw_n, f + off + 8, (size_t)hdr[1])) {
         status = LRP_E_BAD_ARG;
         return;
       }
@@ -854,8 +871,7 @@ int lrp_decoder_png(lrp_decoder *d, const void *file, size_t n, void *out_rgba_d
   if ((I.ctype == 2 || I.ctype == 6) && I.depth == 8 && !I.interlace && trns.empty() && (row + 1) * I.h <= d->cap && !(host_only && host_only[0] == '1')) {
     // RGB / RGBA: inflate straight into pinned memory, upload the FILTERED scan lines (3 or 4 bytes per pixel), reconstruct
     // them on the device (png_unfilter_kernel) directly into the caller's RGBA8 buffer
-    uLongf got = (uLongf)((row + 1) * I.h);
-    if (uncompress(d->h_buf, &got, idat.data(), (uLong)idat.size()) != Z_OK || got != (row + 1) * I.h) return LRP_E_BAD_ARG;
+    if (!inflate_exact(d->h_buf, (row + 1) * I.h, idat.data(), idat.size())) return LRP_E_BAD_ARG;
     for (uint32_t y = 0; y < I.h; ++y)
       if (d->h_buf[(size_t)y * (row + 1)] > 4) return LRP_E_BAD_ARG; // filter type
     if (cudaSetDevice(d->device) != cudaSuccess) return LRP_E_CUDA;
@@ -869,9 +885,7 @@ int lrp_decoder_png(lrp_decoder *d, const void *file, size_t n, void *out_rgba_d
     return LRP_OK;
   }
   d->scratch.resize(png_stream_bytes(I));
-  uLongf got = (uLongf)d->scratch.size();
-  if (uncompress(d->scratch.data(), &got, idat.data(), (uLong)idat.size()) != Z_OK || got != d->scratch.size())
-    return LRP_E_BAD_ARG;
+  if (!inflate_exact(d->scratch.data(), d->scratch.size(), idat.data(), idat.size())) return LRP_E_BAD_ARG;
   rc = png_decode_host(I, d->scratch, plte, trns, d->h_buf);
   if (rc != LRP_OK) return rc;
   if (cudaSetDevice(d->device) != cudaSuccess) return LRP_E_CUDA;
@@ -969,8 +983,7 @@ int lrp_debug_png_decode_host(const void *file, size_t n, void *out_rgba_host, s
   if (rc != LRP_OK) return rc;
   if ((size_t)I.w * I.h * 4 != out_bytes) return LRP_E_BAD_ARG;
   std::vector<unsigned char> stream(png_stream_bytes(I));
-  uLongf got = (uLongf)stream.size();
-  if (uncompress(stream.data(), &got, idat.data(), (uLong)idat.size()) != Z_OK || got != stream.size()) return LRP_E_BAD_ARG;
+  if (!inflate_exact(stream.data(), stream.size(), idat.data(), idat.size())) return LRP_E_BAD_ARG;
   return png_decode_host(I, stream, plte, trns, (unsigned char *)out_rgba_host);
 }
 

@@ -198,13 +198,48 @@ LRP_DEV void source_coord(const KParams &P, float scx, float scy, float &sx, flo
   ray_to_source<COORD>(P, vx, vy, vz, sx, sy);
 }
 
-// runtime dispatch over the input-lens projection (the wrap variants only differ in the sampler)
+// Extension (LRP_EXT_FOV_MASK, specified by oracle/lrp_oracle.c fov_masked): is this sub-sample outside the field of
+// view of an extension lens?  The output side repeats target_to_vec's theta, the input side vec_to_source_full's
+// atan2f of the rotated ray — the same operations on the same inputs, so the same floats.
+constexpr unsigned MASKED_COORD = 0x7fc0ca5eu; // both components of a masked sub-sample's table entry (a quiet NaN
+                                               // no device or host operation produces)
+LRP_DEV bool coord_masked(float sx) { return __float_as_uint(sx) == MASKED_COORD; }
+static __device__ __noinline__ bool fov_masked(const KParams &P, float scx, float scy) {
+  if (P.fov_mask & 1) {
+    float r_px = fsqrt(fadd(fmul(scx, scx), fmul(scy, scy)));
+    float r_mm = fmul(fdiv(r_px, (float)P.W), P.ol.sw);
+    float half = fdiv(r_mm, fmul(2.0f, P.ol.p0));
+    float theta = fmul(2.0f, (P.ol.type == LENS_EQUISOLID) ? dev_asinf(half) : dev_atanf(half));
+    if (!(theta <= P.ol_half_fov)) return true;
+  }
+  if (P.fov_mask & 2) {
+    float vx, vy, vz;
+    target_to_vec(P, scx, scy, vx, vy, vz);
+    if (P.has_rot) { // :303-311
+      const float *R = P.R;
+      float nx = fadd(fadd(fmul(R[0], vx), fmul(R[1], vy)), fmul(R[2], vz));
+      float ny = fadd(fadd(fmul(R[3], vx), fmul(R[4], vy)), fmul(R[5], vz));
+      float nz = fadd(fadd(fmul(R[6], vx), fmul(R[7], vy)), fmul(R[8], vz));
+      vx = nx;
+      vy = ny;
+      vz = nz;
+    }
+    float rho = fsqrt(fadd(fmul(vx, vx), fmul(vy, vy)));
+    float theta = dev_atan2f(rho, -vz);
+    if (!(theta <= P.il_half_fov)) return true;
+  }
+  return false;
+}
+
+// runtime dispatch over the input-lens projection (the wrap variants only differ in the sampler); the one place
+// where the field-of-view mask of the extension lenses enters (tables, footprints, debug coordinates)
 LRP_DEV void source_coord_rt(const KParams &P, int coord, float scx, float scy, float &sx, float &sy) {
   if (coord == COORD_RECT) source_coord<COORD_RECT>(P, scx, scy, sx, sy);
   else if (coord == COORD_EQUIDISTANT) source_coord<COORD_EQUIDISTANT>(P, scx, scy, sx, sy);
   else if (coord == COORD_EQUISOLID) source_coord<COORD_EQUISOLID>(P, scx, scy, sx, sy);
   else if (coord == COORD_STEREO) source_coord<COORD_STEREO>(P, scx, scy, sx, sy);
   else source_coord<COORD_ERECT_CLAMP>(P, scx, scy, sx, sy);
+  if (P.fov_mask && fov_masked(P, scx, scy)) sx = sy = __uint_as_float(MASKED_COORD);
 }
 
 // The remap table is re-read by every frame of a batch while sources and sinks stream through once: its loads carry an
@@ -669,7 +704,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) reproject_kernel(const __grid_con
             continue; // ns == 1: the pixel is done (the tail below is skipped)
           }
           float smp[C];
-          if (INTERP == INTERP_NN) sample_nearest<WRAP, FMT, C>(S, sx, sy, smp);
+          if (TABLE && P.fov_mask && coord_masked(sx)) { // extension: outside the lens's field of view -> 0, no load
+#pragma unroll
+            for (int c = 0; c < C; ++c) smp[c] = 0.0f;
+          } else if (INTERP == INTERP_NN) sample_nearest<WRAP, FMT, C>(S, sx, sy, smp);
           else if (INTERP == INTERP_BL) sample_bilinear<WRAP, FMT, C>(S, sx, sy, smp);
           else sample_bicubic<WRAP, FMT, C, PACKED>(S, sx, sy, smp);
 #pragma unroll

@@ -83,6 +83,10 @@ struct KParams {
   // build_composite_table); ctab_identity: the map is the identity (no post-process), the texel is copied
   int nn_composite, ctab_identity;
   unsigned char ctab[256];
+  // extension, LRP_EXT_FOV_MASK: bit 0 = the output lens masks, bit 1 = the input lens masks; half_fov = 0.5f * fov.
+  // Masked launches always read their coordinates from a table (coords_kernel writes MASKED_COORD for masked samples)
+  int fov_mask;
+  float ol_half_fov, il_half_fov;
   const unsigned *nn_index;     // nearest tap per output pixel, resolved: x | y << 16  (lrp_nearest.cu)
   unsigned *nn_index_out;       // nn_index_kernel output
 };

@@ -26,6 +26,7 @@ VARIANT_AUTO, VARIANT_GATHER, VARIANT_STAGED, VARIANT_TILED = range(4)
 UPLOAD_AUTO, UPLOAD_FULL, UPLOAD_SHARED = range(3)
 COORDS_AUTO, COORDS_FLY, COORDS_TABLE = range(3)
 EXT_FISHEYE_MODELS = 1
+EXT_FOV_MASK = 2
 
 
 class LrpError(RuntimeError):

@@ -135,10 +135,23 @@ typedef enum lrp_coords {
  *             s = sinf(theta)/r_px; ray = (s*cx, s*cy, -cosf(theta))
  *     input   rho = sqrt(x^2+y^2); theta = atan2f(rho, -z); t = sinf(theta/2) | sinf(theta/2)/cosf(theta/2);
  *             r_px = (2f*t)/sw*w; (cx, cy) = (x/rho*r_px, y/rho*r_px)
- *   Both lens types use the fisheye_equisolid payload (focal_length, fov); fov is carried, not applied (the
+ *   Both lens types use the fisheye_equisolid payload (focal_length, fov); fov is applied only with LRP_EXT_FOV_MASK (the
  *   reference never masks by field of view).  Without the bit both types return LRP_E_UNSUPPORTED_*_LENS
  *   exactly as the reference exit(1)s. */
 #define LRP_EXT_FISHEYE_MODELS 1
+/* LRP_EXT_FOV_MASK  (with LRP_EXT_FISHEYE_MODELS) applies the `fov` of the extension lenses: a sub-sample contributes 0
+ *   to every channel, instead of a source sample, when
+ *     the OUTPUT lens is an extension lens with fov > 0 and its theta (above) does not satisfy theta <= 0.5f*fov
+ *       (the NaN theta outside the equisolid image circle is masked), or
+ *     the INPUT lens is an extension lens with fov > 0 and the rotated ray's theta = atan2f(rho, -z) does not
+ *       satisfy theta <= 0.5f*fov;
+ *   normalisation, post_process and the sink's quantiser then run as usual (a fully masked pixel is 0 in every
+ *   channel it has; an RGBA8 sink of a 3-channel image keeps alpha 255).  Masked launches always read their
+ *   coordinates from the context's table (lrp_coords is overridden), where a masked sub-sample is the quiet NaN
+ *   0x7fc0ca5e in both components — lrp_debug_coords and lrp_build_remap show it — and masked samples are excluded
+ *   from lrp_source_footprint.  The reference never masks; without the bit nothing changes.  Specified, like the
+ *   models, by oracle/lrp_oracle.c (fov_masked). */
+#define LRP_EXT_FOV_MASK 2
 
 /* What lrp_reproject_host / lrp_submit / lrp_sched_submit upload of a host source.  The texels a
  * launch can touch depend on the geometry only (lenses, sizes, rotation, sampler) — for the 8K

@@ -253,17 +253,47 @@ static int loops_horizontally(const orc_lens *in_lens) {
   return fabs((double)long_range - (2 * M_PI)) < (double)1e-5f;
 }
 
-/* 0 (default): exactly the reference's lens support; 1: the equisolid / stereographic extension too */
+/* 0 (default): exactly the reference's lens support; bit 0: the equisolid / stereographic extension too;
+ * bit 1: their optional field-of-view mask (below) */
 static int g_extensions = 0;
 void orc_set_extensions(int on) { g_extensions = on; }
 static int lens_supported(int t) {
   if (t == L_RECT || t == L_EQUIDISTANT || t == L_ERECT) return 1;
-  return g_extensions && (t == L_EQUISOLID || t == L_STEREO);
+  return (g_extensions & 1) && (t == L_EQUISOLID || t == L_STEREO);
+}
+
+/* ---- extension: optional field-of-view mask (the reference never masks, SURVEY fact 0.3c, and
+ * carries the equisolid `fov` without using it, src/config.hpp:24-27).  With bit 1 of the extensions set, a
+ * sub-sample is MASKED — it contributes 0.0f to every channel instead of a source sample — when
+ *   the OUTPUT lens is an extension lens with fov > 0 and its off-axis angle theta (as target_to_vec computes it)
+ *     does not satisfy theta <= 0.5f * fov  (a NaN theta, outside the equisolid image circle, is masked), or
+ *   the INPUT lens is an extension lens with fov > 0 and the rotated ray's angle atan2f(rho, -z) (as
+ *     vec_to_source computes it) does not satisfy theta <= 0.5f * fov.
+ * Coordinates of a masked sub-sample are reported as the quiet NaN 0x7fc0ca5e in both components.
+ * PARITY UNPINNED, like the lens models themselves: this file is the specification. ---- */
+#define ORC_MASKED_BITS 0x7fc0ca5eu
+static int is_ext_lens(int t) { return t == L_EQUISOLID || t == L_STEREO; }
+static int fov_masked(const orc_lens *ol, float W, const orc_lens *il, float scx, float scy, float vx, float vy,
+                      float vz) {
+  if (!(g_extensions & 2)) return 0;
+  if (is_ext_lens(ol->type) && ol->p[1] > 0.0f) {
+    float r_px = sqrtf(scx * scx + scy * scy);
+    float r_mm = r_px / W * ol->sensor_width;
+    float half = r_mm / (2.0f * ol->p[0]);
+    float theta = 2.0f * (ol->type == L_EQUISOLID ? asinf(half) : atanf(half));
+    if (!(theta <= 0.5f * ol->p[1])) return 1;
+  }
+  if (is_ext_lens(il->type) && il->p[1] > 0.0f) {
+    float rho = sqrtf(vx * vx + vy * vy);
+    float theta = atan2f(rho, -vz);
+    if (!(theta <= 0.5f * il->p[1])) return 1;
+  }
+  return 0;
 }
 
 /* one sub-sample's coordinate chain, reference :301-324 */
-static void chain(const orc_lens *ol, int W, int H, const orc_lens *il, int w, int h,
-                  const float *rm, float scx, float scy, float *v, float *sx, float *sy) {
+static int chain(const orc_lens *ol, int W, int H, const orc_lens *il, int w, int h,
+                 const float *rm, float scx, float scy, float *v, float *sx, float *sy) {
   float vx = 0.0f, vy = 0.0f, vz = 0.0f;
   target_to_vec(ol, (float)W, (float)H, scx, scy, &vx, &vy, &vz);
   if (v) { v[0] = vx; v[1] = vy; v[2] = vz; }
@@ -277,6 +307,13 @@ static void chain(const orc_lens *ol, int W, int H, const orc_lens *il, int w, i
   vec_to_source(il, (float)w, (float)h, vx, vy, vz, &cx, &cy);
   *sx = (cx - 0.5f) + w * 0.5f; /* :323 */
   *sy = (cy - 0.5f) + h * 0.5f; /* :324 */
+  if (fov_masked(ol, (float)W, il, scx, scy, vx, vy, vz)) { /* extension; returns 1: the sub-sample is masked */
+    uint32_t m = ORC_MASKED_BITS;
+    memcpy(sx, &m, 4);
+    memcpy(sy, &m, 4);
+    return 1;
+  }
+  return 0;
 }
 
 int orc_coords(const orc_lens *ol, int W, int H, const orc_lens *il, int w, int h, const float *rm,
@@ -318,8 +355,11 @@ int orc_reproject(const orc_lens *il, int w, int h, int c, const float *in_data,
         for (int ssy = 0; ssy < ns; ++ssy) {
           float scy = cy + (ssy + 1.0f) / (ns + 1.0f) - 0.5f; /* :298 */
           float sx, sy;
-          chain(ol, W, H, il, w, h, rm, scx, scy, NULL, &sx, &sy);
-          sample_any(interpolation, loop, w, h, c, in_data, sx, sy, smp);
+          if (chain(ol, W, H, il, w, h, rm, scx, scy, NULL, &sx, &sy)) {
+            for (int k = 0; k < c; ++k) smp[k] = 0.0f; /* extension: masked sub-sample */
+          } else {
+            sample_any(interpolation, loop, w, h, c, in_data, sx, sy, smp);
+          }
           for (int k = 0; k < c; ++k) acc[k] += smp[k]; /* :334-336 */
         }
       }
@@ -464,7 +504,7 @@ int64_t orc_footprint(const orc_lens *il, int w, int h, const orc_lens *ol, int 
         float scx = cx + (ssx + 1.0f) / (ns + 1.0f) - 0.5f;
         for (int ssy = 0; ssy < ns; ++ssy) {
           float scy = cy + (ssy + 1.0f) / (ns + 1.0f) - 0.5f, sx, sy;
-          chain(ol, W, H, il, w, h, rm, scx, scy, NULL, &sx, &sy);
+          if (chain(ol, W, H, il, w, h, rm, scx, scy, NULL, &sx, &sy)) continue; /* masked: no texel touched */
           if (sx != sx || sy != sy) nans++;
           int xs[4], ys[4], nx, ny;
           if (interpolation == 0) {

@@ -215,3 +215,179 @@ def test_gpu_refused_without_the_extension_bit(lrp):
     with pytest.raises(lrp.LrpError) as e:
         lrp.reproject_host(src, lrp.lens_from(st), lrp.lens_from(ol.rect(18, 36, 8, 8)), 8, 8)
     assert e.value.status == lrp.E_UNSUPPORTED_INPUT_LENS
+
+
+# ---- the optional field-of-view mask (LRP_EXT_FOV_MASK) --------------------------------------------------------
+# Specified by oracle/lrp_oracle.c (fov_masked): PARITY UNPINNED like the models.  Checked: the oracle against a float64
+# model of the two angle tests, masked sub-samples contribute exactly 0, unmasked pixels are untouched, nothing changes
+# without the bit [CPU]; the CUDA path is bit-identical to the oracle [GPU].
+
+@pytest.fixture
+def ext_mask():
+    ORC.set_extensions(3)
+    yield
+    ORC.set_extensions(0)
+
+
+MASK_LENS = {
+    "equisolid_120": lambda W, H: ol.equisolid(12.5, 36.0, math.radians(120), W, H),
+    "stereo_100": lambda W, H: ol.stereographic(9.0, 36.0, math.radians(100), W, H),
+    "equisolid_nofov": lambda W, H: ol.equisolid(12.5, 36.0, 0.0, W, H),  # fov <= 0: this lens never masks
+}
+MASK_PAIRS = [("equisolid_120", "erect"), ("rect", "stereo_100"), ("equisolid_120", "stereo_100"),
+              ("stereo_100", "equisolid_120"), ("erect", "equisolid_120"), ("equisolid_nofov", "stereo_100")]
+MASKED_BITS = 0x7FC0CA5E
+
+
+def mask64(olens, W, H, ilens, w, h, R):
+    """float64 model -> (masked, margin): margin = distance of the deciding angle from its threshold"""
+    xs = (np.arange(W) + 0.5) - W * 0.5
+    ys = (np.arange(H) + 0.5) - H * 0.5
+    cx, cy = np.meshgrid(xs, ys)
+    masked = np.zeros((H, W), bool)
+    margin = np.full((H, W), np.inf)
+    ext_t = (ol.EQUISOLID, ol.STEREOGRAPHIC)
+    with np.errstate(invalid="ignore"):
+        if olens.type in ext_t and olens.p[1] > 0:
+            half = np.hypot(cx, cy) / W * olens.sensor_width / (2 * olens.p[0])
+            th = 2 * (np.arcsin(half) if olens.type == ol.EQUISOLID else np.arctan(half))
+            masked |= ~(th <= 0.5 * olens.p[1])
+            margin = np.minimum(margin, np.where(np.isnan(th), np.inf, np.abs(th - 0.5 * olens.p[1])))
+        if ilens.type in ext_t and ilens.p[1] > 0:
+            v = ray64(olens, W, H, cx, cy) if olens.type in ext_t + (ol.RECT,) else None
+            if v is None:  # erect output
+                lon = (cx / W + 0.5) * (olens.p[3] - olens.p[2]) + olens.p[2]
+                lat = (cy / H + 0.5) * (olens.p[1] - olens.p[0]) + olens.p[0]
+                v = np.stack([np.sin(lon), np.sin(lat), -np.cos(lon)])
+            if R is not None:
+                v = np.tensordot(np.asarray(R, np.float64).reshape(3, 3), v, axes=1)
+            th = np.arctan2(np.hypot(v[0], v[1]), -v[2])
+            masked |= ~(th <= 0.5 * ilens.p[1])
+            margin = np.minimum(margin, np.where(np.isnan(th), np.inf, np.abs(th - 0.5 * ilens.p[1])))
+    return masked, margin
+
+
+@pytest.mark.parametrize("o,i", MASK_PAIRS)
+def test_mask_definition_against_float64_model(ext_mask, o, i):
+    lenses = dict(FISH, **OTHER, **MASK_LENS)
+    W, H, w, h = 200, 120, 160, 100
+    cuts = False
+    for r in (None, rotm(30, 20, 10), rotm(0, 90, 0)):
+        got = ORC.coords_image(lenses[o](W, H), W, H, lenses[i](w, h), w, h, r)
+        g = (ol.bits(got[..., 0]) == MASKED_BITS) & (ol.bits(got[..., 1]) == MASKED_BITS)
+        want, margin = mask64(lenses[o](W, H), W, H, lenses[i](w, h), w, h, r)
+        sure = margin > 1e-4  # float32 vs float64 may disagree within a few ulps of the threshold
+        assert (g[sure] == want[sure]).all(), "%s<-%s: %d pixels" % (o, i, (g[sure] != want[sure]).sum())
+        cuts = cuts or (g.any() and not g.all())
+    assert cuts  # some rotation really cuts the image (others may keep or mask all of it)
+
+
+@pytest.mark.parametrize("o,i", MASK_PAIRS)
+def test_masked_subsamples_contribute_zero(o, i):
+    lenses = dict(FISH, **OTHER, **MASK_LENS)
+    W, H, w, h = 60, 40, 50, 36
+    src = ol.noise(h, w, 4, seed=3) + 0.25
+    r = rotm(30, 20, 10)
+    for interp in (ol.NEAREST, ol.BICUBIC):
+        ORC.set_extensions(1)
+        plain = ORC.reproject(src, lenses[i](w, h), lenses[o](W, H), W, H, 1, interp, r)
+        plain2 = ORC.reproject(src, lenses[i](w, h), lenses[o](W, H), W, H, 2, interp, r)
+        ORC.set_extensions(3)
+        try:
+            got = ORC.reproject(src, lenses[i](w, h), lenses[o](W, H), W, H, 1, interp, r)
+            got2 = ORC.reproject(src, lenses[i](w, h), lenses[o](W, H), W, H, 2, interp, r)
+            c = ORC.coords_image(lenses[o](W, H), W, H, lenses[i](w, h), w, h, r)
+        finally:
+            ORC.set_extensions(0)
+        m = ol.bits(c[..., 0]) == MASKED_BITS
+        assert (got[m] == 0).all()                                   # masked pixels: exactly 0 in every channel
+        assert bits_same(got[~m], plain[~m]).all()                   # the others: untouched
+        # supersampled: a pixel is the sum of its unmasked sub-samples / ns^2 -> between 0 and the unmasked value
+        edge = ~bits_same(got2, plain2).all(axis=-1)
+        assert (np.abs(got2[edge]) <= np.abs(plain2[edge]) + 1e-6).all() or interp == ol.BICUBIC
+
+
+def test_mask_bit_alone_changes_nothing_for_reference_lenses():
+    W, H, w, h = 40, 30, 64, 32
+    src = ol.noise(h, w, 3, seed=8)
+    plain = ORC.reproject(src, ol.erect(), ol.rect(18, 36, W, H), W, H, 1, ol.BICUBIC, rotm(30, 20, 10))
+    ORC.set_extensions(3)
+    try:
+        got = ORC.reproject(src, ol.erect(), ol.rect(18, 36, W, H), W, H, 1, ol.BICUBIC, rotm(30, 20, 10))
+    finally:
+        ORC.set_extensions(0)
+    assert bits_same(got, plain).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("o,i", MASK_PAIRS)
+def test_gpu_mask_coordinates_and_pixels_bit_exact(lrp, ext_mask, o, i):
+    lenses = dict(FISH, **OTHER, **MASK_LENS)
+    EXT = lrp.EXT_FISHEYE_MODELS | lrp.EXT_FOV_MASK
+    W, H, w, h = 150, 96, 120, 80
+    ctx = lrp.Context(0, 1)
+    for r in (None, rotm(30, 20, 10), rotm(0, 90, 0)):
+        p = lrp.make_params(1, lrp.BICUBIC, r, ext=EXT)
+        got = ctx.debug_coords(lrp.lens_from(lenses[i](w, h)), w, h, lrp.lens_from(lenses[o](W, H)), W, H, p).cpu().numpy()
+        want = ORC.coords_image(lenses[o](W, H), W, H, lenses[i](w, h), w, h, r)
+        assert (ol.bits(got) == ol.bits(want))[ol.bits(want) == MASKED_BITS].all()
+        assert bits_same(got, want).all(), "%s<-%s: %d coordinates differ" % (o, i, (~bits_same(got, want)).sum())
+    ctx.close()
+    r = rotm(30, 20, 10)
+    for c in (3, 4):
+        src = ol.noise(h, w, c, seed=40 + c) + 0.125
+        for interp in (ol.NEAREST, ol.BILINEAR, ol.BICUBIC):
+            for ns in (1, 2):
+                for coords in (lrp.COORDS_AUTO, lrp.COORDS_FLY):  # FLY is overridden: the mask lives in the table
+                    want = ORC.reproject(src, lenses[i](w, h), lenses[o](W, H), W, H, ns, interp, r)
+                    got = lrp.reproject_host(src, lrp.lens_from(lenses[i](w, h)), lrp.lens_from(lenses[o](W, H)), W, H, ns,
+                                             interp, r, ext=EXT, coords=coords)
+                    same = bits_same(got, want)
+                    assert same.all(), "%s<-%s c%d interp %d ns %d: %d differ" % (o, i, c, interp, ns, (~same).sum())
+
+
+@pytest.mark.gpu
+def test_gpu_mask_codec_formats_and_footprint(lrp, ext_mask):
+    """RGBA8 and planar-half sources / sinks (the nearest byte map and the staged kernel must step aside), host buffers
+    with the footprint upload: masked samples are not part of the footprint."""
+    EXT = lrp.EXT_FISHEYE_MODELS | lrp.EXT_FOV_MASK
+    W, H, w, h = 256, 144, 512, 256
+    il, olens = ol.erect(), ol.equisolid(12.5, 36.0, math.radians(100), W, H)
+    rng = np.random.default_rng(12)
+    rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    r = rotm(10, 5, 0)
+    for interp in (ol.NEAREST, ol.BICUBIC):
+        want = ORC.png_encode(ORC.reproject(ORC.png_decode(rgba), il, olens, W, H, 1, interp, r))
+        got = lrp.reproject_host(rgba, lrp.lens_from(il), lrp.lens_from(olens), W, H, 1, interp, r,
+                                 in_fmt=lrp.FMT_U8_RGBA, out_fmt=lrp.FMT_U8_RGBA, ext=EXT)
+        assert (got == want).all(), "u8 interp %d: %d differ" % (interp, (got != want).sum())
+        assert (got[0, 0, :3] == 0).all() and got[0, 0, 3] == 255  # the corner is outside 100 degrees
+    f4 = ol.noise(h, w, 4, seed=9) + 0.5
+    planes = ORC.f32_to_half_planar(f4)
+    want16 = ORC.f32_to_half_planar(ORC.reproject(ORC.half_planar_to_f32(planes), il, olens, W, H, 1, ol.NEAREST, r))
+    got16 = lrp.reproject_host(planes, lrp.lens_from(il), lrp.lens_from(olens), W, H, 1, ol.NEAREST, r,
+                               in_fmt=lrp.FMT_F16_PLANAR, out_fmt=lrp.FMT_F16_PLANAR, ext=EXT)
+    assert (got16 == want16).all()
+    # the footprint of the masked launch is inside the unmasked one, and smaller
+    ctx = lrp.Context(0, 1)
+    pm = lrp.make_params(1, lrp.BICUBIC, r, ext=EXT)
+    pu = lrp.make_params(1, lrp.BICUBIC, r, ext=lrp.EXT_FISHEYE_MODELS)
+    fm = ctx.source_footprint(lrp.lens_from(il), w, h, lrp.lens_from(olens), W, H, pm)
+    fu = ctx.source_footprint(lrp.lens_from(il), w, h, lrp.lens_from(olens), W, H, pu)
+    ctx.close()
+    assert fm[0] >= fu[0] and fm[1] <= fu[1] and fm[2] >= fu[2] and fm[3] <= fu[3]
+    assert (fm[1] - fm[0]) * (fm[3] - fm[2]) < (fu[1] - fu[0]) * (fu[3] - fu[2])
+
+
+@pytest.mark.gpu
+def test_gpu_mask_bit_needs_nothing_else(lrp):
+    """the bit without an extension lens (or with fov <= 0) is a no-op; unknown bits are refused"""
+    W, H, w, h = 64, 48, 128, 64
+    src = ol.noise(h, w, 3, seed=2)
+    a = lrp.reproject_host(src, lrp.lens_from(ol.erect()), lrp.lens_from(ol.rect(18, 36, W, H)), W, H, 1, ol.BICUBIC, None)
+    b = lrp.reproject_host(src, lrp.lens_from(ol.erect()), lrp.lens_from(ol.rect(18, 36, W, H)), W, H, 1, ol.BICUBIC, None,
+                           ext=lrp.EXT_FISHEYE_MODELS | lrp.EXT_FOV_MASK)
+    assert bits_same(a, b).all()
+    with pytest.raises(lrp.LrpError) as e:
+        lrp.reproject_host(src, lrp.lens_from(ol.erect()), lrp.lens_from(ol.rect(18, 36, W, H)), W, H, 1, ol.BICUBIC, None, ext=4)
+    assert e.value.status == lrp.E_BAD_ARG

@@ -35,3 +35,11 @@ def test_exr_rle_and_pxr24_block_expanders_under_sanitizers(tmp_path):
     """csrc/lrp_exr_blocks.h: round trips against encoders written from the format descriptions, and 5500 corrupted /
     truncated blocks with output buffers of exactly the expected size (any overflow is an ASan abort)"""
     assert _build_and_run(tmp_path, "exr_blocks_host_test", []).startswith("OK cases 96")
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="no host compiler")
+def test_fast_host_inflate_against_zlib_under_sanitizers(tmp_path):
+    """csrc/lrp_inflate_fast.h (PNG IDAT / EXR ZIP blocks on the host: two-literal table entries, 64-bit refills, AVX2
+    Adler-32): 4900 streams of every level / strategy / window size inflate to the input, 140 000 corrupted or truncated
+    ones are rejected or are flips zlib accepts with the same bytes; input and output are exact-size heap blocks"""
+    assert _build_and_run(tmp_path, "inflate_fast_host_test", ["-lz"]).startswith("OK streams 4900")
