@@ -814,6 +814,9 @@ struct Pool {
     std::vector<cudaEvent_t> ready; // recorded behind the copy that fills d[i]
   };
   std::mutex shared_mu;
+  // device buffers of completed shared sources, kept for the next batch (a batch of panoramas re-uses one size): a
+  // cudaMalloc / cudaFree of 0.8 GB per pass costs more than the upload it serves and synchronises the device
+  std::vector<std::pair<void *, size_t>> shared_spare; // [device of the pool] -> (buffer, bytes)
   std::map<std::pair<const void *, size_t>, SharedSrc> shared;
   bool peers_enabled = false;
   std::atomic<uint64_t> peer_bytes{0};
@@ -904,7 +907,13 @@ struct Pool {
       if (S.d[o]) from = (int)o;
     void *buf = nullptr;
     cudaEvent_t ev = nullptr;
-    LRP_CUDA(cudaMalloc(&buf, bytes));
+    if (shared_spare.size() != ctxs.size()) shared_spare.assign(ctxs.size(), std::make_pair((void *)nullptr, (size_t)0));
+    if (shared_spare[dev].first && shared_spare[dev].second >= bytes) { // the previous batch's buffer (its jobs completed)
+      buf = shared_spare[dev].first;
+      shared_spare[dev] = std::make_pair((void *)nullptr, (size_t)0);
+    } else {
+      LRP_CUDA(cudaMalloc(&buf, bytes));
+    }
     cudaError_t err = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (err == cudaSuccess) {
       if (from >= 0) {
@@ -930,16 +939,30 @@ struct Pool {
     *out = buf;
     return LRP_OK;
   }
-  void drop_shared_sources() { // every job has completed
+  void drop_shared_sources(bool destroy = false) { // every job has completed
     std::lock_guard<std::mutex> lk(shared_mu);
+    if (shared_spare.size() != ctxs.size()) shared_spare.assign(ctxs.size(), std::make_pair((void *)nullptr, (size_t)0));
     for (auto &kv : shared)
       for (size_t i = 0; i < kv.second.d.size(); ++i)
         if (kv.second.d[i]) {
           cudaSetDevice(ctxs[i]->phys_device);
-          cudaFree(kv.second.d[i]);
           cudaEventDestroy(kv.second.ready[i]);
+          const size_t bytes = kv.first.second;
+          if (!destroy && bytes > shared_spare[i].second) { // keep the largest per device for the next batch
+            if (shared_spare[i].first) cudaFree(shared_spare[i].first);
+            shared_spare[i] = std::make_pair(kv.second.d[i], bytes);
+          } else {
+            cudaFree(kv.second.d[i]);
+          }
         }
     shared.clear();
+    if (destroy)
+      for (size_t i = 0; i < shared_spare.size(); ++i)
+        if (shared_spare[i].first) {
+          cudaSetDevice(ctxs[i]->phys_device);
+          cudaFree(shared_spare[i].first);
+          shared_spare[i] = std::make_pair((void *)nullptr, (size_t)0);
+        }
   }
 
   void finish(Engine *e, const Item &it, int rc) { // engine thread, `mu` not held
@@ -1228,7 +1251,7 @@ struct Pool {
       delete e;
     }
     engines.clear();
-    drop_shared_sources();
+    drop_shared_sources(true);
     for (Worker *w : workers) {
       if (w->th.joinable()) w->th.join();
       cudaSetDevice(w->ctx->phys_device);
