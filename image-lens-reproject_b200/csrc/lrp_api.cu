@@ -35,6 +35,8 @@ LRP_DECL(6, 0) LRP_DECL(6, 1) LRP_DECL(6, 2) LRP_DECL(7, 0) LRP_DECL(7, 1) LRP_D
 #define LRP_DECL(c) LaunchFn get_staged_launcher_c##c##_i2(int fc);
 LRP_DECL(0) LRP_DECL(1) LRP_DECL(2) LRP_DECL(3) LRP_DECL(4) LRP_DECL(5)
 #undef LRP_DECL
+LaunchFn get_staged_blocks_launcher_c3_i2(int fc);
+LaunchFn get_staged_blocks_launcher_c5_i2(int fc);
 #define LRP_DECL(c) LaunchFn get_tiled_launcher_c##c(int fc);
 LRP_DECL(0) LRP_DECL(1) LRP_DECL(2) LRP_DECL(3) LRP_DECL(4) LRP_DECL(5)
 #undef LRP_DECL
@@ -53,8 +55,10 @@ static LaunchFn get_tiled_launcher(int coord, int fc) {
   return (coord >= 0 && coord < 6) ? table[coord](fc) : nullptr;
 }
 
-static LaunchFn get_launcher(int coord, int interp, int fc, bool staged) {
+static LaunchFn get_launcher(int coord, int interp, int fc, bool staged, bool blocks = false) {
   typedef LaunchFn (*Getter)(int);
+  if (staged && blocks && interp == INTERP_BC && coord == COORD_ERECT_WRAP) return get_staged_blocks_launcher_c3_i2(fc);
+  if (staged && blocks && interp == INTERP_BC && coord == COORD_TABLE_WRAP) return get_staged_blocks_launcher_c5_i2(fc);
   // footprint staging: bicubic on the reference's lenses and the table modes (the extension lenses always take the
   // guarded projections and the 1 / 4 taps of nearest / bilinear are cheaper gathered: both run the gather kernel)
   static const Getter staged_table[6] = {get_staged_launcher_c0_i2, get_staged_launcher_c1_i2, get_staged_launcher_c2_i2,
@@ -581,6 +585,8 @@ void build_composite_table(const HostTables &T, const KParams &K, unsigned char 
   *identity = ident ? 1 : 0;
 }
 
+int source_footprint(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const lrp_params *p, Roi &roi);
+
 // `win` (host-buffer paths): in->data holds only the texels of that region of the source, rows of win->width()
 // texels (planes of width x height for planar formats).  The kernels keep addressing texel (x, y) of the whole
 // image: the source pointer is moved to where texel (0, 0) would be and the row pitch becomes the region's width.
@@ -656,7 +662,21 @@ int launch_fused(lrp_ctx *ctx, const lrp_image *in, const lrp_image *out, const 
   const bool staged = (variant == LRP_VARIANT_STAGED && p->num_samples <= (LRP_STAGED_SS ? 5 : 1)) ||
                       (variant == LRP_VARIANT_AUTO && p->interpolation == LRP_BICUBIC && p->num_samples == 1);
   if (staged) K.nn_composite = 0; // the staged sampler keeps the float tail
-  LaunchFn fn = get_launcher(coord, p->interpolation, fc, staged);
+  // Half-warp shape of the staged kernel (lrp_staged.cuh, BLOCKS): rows of 16 pixels unless the view crosses a pole of a
+  // wrapping panorama — its footprint then spans the whole width of the source, the tap boxes of 16-pixel strips no longer
+  // fit the staging area and 4 x 4 blocks keep the pieces compact (c5 pole view 634 -> 490 us; every view that does not
+  // cross a pole is faster in rows).  The footprint is cached per geometry (one 0.7 ms kernel the first time).
+  bool blocks = false;
+  if (staged && (coord == COORD_ERECT_WRAP || coord == COORD_TABLE_WRAP)) {
+    const char *fb = getenv("LRP_ST_BLOCKS"); // A/B switch: 0 / 1 force the shape
+    if (fb && (fb[0] == '0' || fb[0] == '1')) blocks = fb[0] == '1';
+    else {
+      Roi fp;
+      blocks = source_footprint(ctx, in, out, p, fp) == LRP_OK && fp.x0 == 0 && fp.x1 == in->width - 1;
+    }
+    if (blocks) K.rec_pad = 20; // 4 (mod 16): distinct banks for the taps of a 4 x 4 half-warp (tools/dev/bank_model.py)
+  }
+  LaunchFn fn = get_launcher(coord, p->interpolation, fc, staged, blocks);
   if (!fn) return LRP_E_UNSUPPORTED_FORMAT;
   return map_cuda((cudaError_t)fn(K, stream));
 }

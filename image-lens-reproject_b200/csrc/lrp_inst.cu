@@ -17,8 +17,12 @@
 
 #define LRP_CAT2(a, b, c, d) a##b##c##d
 #define LRP_CAT(a, b, c, d) LRP_CAT2(a, b, c, d)
-#ifdef LRP_STAGED
+#if defined(LRP_STAGED) && defined(LRP_STAGED_BLOCKS)
+#define LRP_GETTER LRP_CAT(get_staged_blocks_launcher_c, LRP_COORD, _i, LRP_INTERP)
+#define LRP_BLOCKS true
+#elif defined(LRP_STAGED)
 #define LRP_GETTER LRP_CAT(get_staged_launcher_c, LRP_COORD, _i, LRP_INTERP)
+#define LRP_BLOCKS false
 #else
 #define LRP_GETTER LRP_CAT(get_launcher_c, LRP_COORD, _i, LRP_INTERP)
 #endif
@@ -26,16 +30,17 @@
 namespace lrp {
 
 #ifdef LRP_STAGED
-// the footprint-staging variant (lrp_staged.cuh); num_samples == 1 only
+// the footprint-staging variant (lrp_staged.cuh); num_samples == 1 only.  -DLRP_STAGED_BLOCKS: 4 x 4-pixel half-warps
+// (the wrapping coordinate modes only: views that cross a pole of the panorama)
 LaunchFn LRP_GETTER(int fc) {
   switch (fc) {
-  case FC_F32_3: return &launch_reproject_staged<LRP_COORD, LRP_INTERP, FMT_F32, 3>;
-  case FC_F32_4: return &launch_reproject_staged<LRP_COORD, LRP_INTERP, FMT_F32, 4>;
-  case FC_F32_5: return &launch_reproject_staged<LRP_COORD, LRP_INTERP, FMT_F32, 5>;
-  case FC_U8_3: return &launch_reproject_staged<LRP_COORD, LRP_INTERP, FMT_U8, 3>;
-  case FC_F16_3: return &launch_reproject_staged<LRP_COORD, LRP_INTERP, FMT_F16, 3>;
-  case FC_F16_4: return &launch_reproject_staged<LRP_COORD, LRP_INTERP, FMT_F16, 4>;
-  case FC_F16_5: return &launch_reproject_staged<LRP_COORD, LRP_INTERP, FMT_F16, 5>;
+  case FC_F32_3: return &launch_reproject_staged<LRP_COORD, LRP_INTERP, FMT_F32, 3, LRP_BLOCKS>;
+  case FC_F32_4: return &launch_reproject_staged<LRP_COORD, LRP_INTERP, FMT_F32, 4, LRP_BLOCKS>;
+  case FC_F32_5: return &launch_reproject_staged<LRP_COORD, LRP_INTERP, FMT_F32, 5, LRP_BLOCKS>;
+  case FC_U8_3: return &launch_reproject_staged<LRP_COORD, LRP_INTERP, FMT_U8, 3, LRP_BLOCKS>;
+  case FC_F16_3: return &launch_reproject_staged<LRP_COORD, LRP_INTERP, FMT_F16, 3, LRP_BLOCKS>;
+  case FC_F16_4: return &launch_reproject_staged<LRP_COORD, LRP_INTERP, FMT_F16, 4, LRP_BLOCKS>;
+  case FC_F16_5: return &launch_reproject_staged<LRP_COORD, LRP_INTERP, FMT_F16, 5, LRP_BLOCKS>;
   default: return nullptr;
   }
 }

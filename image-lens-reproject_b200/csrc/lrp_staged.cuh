@@ -464,7 +464,13 @@ LRP_DEV void staged_bicubic(const KParams &P, const StageView &V, float sx, floa
 //   next 1 KB boundary .. + 1 KB         gamma table, plain                         (FMT_U8)
 //   + NW x 2 KB                          per-warp source coordinates of the tile    float2[8][32]
 //   + NW x Rec::STAGE_BYTES              per-warp staging records
-template <int COORD, int INTERP, int FMT, int C>
+// BLOCKS: which pixels a half-warp samples together.  false: 16 consecutive pixels of one output row (a step = two rows of
+// 16); true: a 4 x 4 block (a step = two blocks side by side, 8 x 4 pixels).  Rows give 64-byte store / table segments and
+// are the faster shape whenever a tile's footprint fits the staging area as a whole (c2 130 vs 132 us); blocks keep the
+// pieces of a SPLIT tile compact — near the poles of a panorama a 16-pixel strip maps to an arc as wide as the source, an
+// 8 x 4 block to a patch (c5 pole view 648 -> 490 us, equator view 312 -> 300; profiles/r2_staged_variants.txt item 14).
+// The host instantiates both for the wrapping modes and picks per launch (lrp_api.cu: launch_fused).
+template <int COORD, int INTERP, int FMT, int C, bool BLOCKS = false>
 __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_kernel(const __grid_constant__ KParams P) {
   static_assert(INTERP == INTERP_BC, "the 1 / 4 taps of nearest / bilinear are cheaper gathered through L1 (measured, round 1)");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -518,6 +524,12 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
   const int lx = ss ? lane / ns2 : lane & (ST_TILE_W - 1), ly = ss ? 0 : lane >> 4;
   const int sub = ss ? lane - lx * ns2 : 0, row_step = ss ? 1 : 2;
   const bool lane_used = !ss || lx < tile_w;
+  // block mapping (ns == 1): step r = the 4 x 4 blocks 2r and 2r + 1 of the tile (row-major, four per row), one per
+  // half-warp; a lane then meets two columns (even / odd steps, 8 apart) and four rows of the tile
+  constexpr bool MAP = BLOCKS && !LRP_STAGED_SS;
+  const int mq = lane & 15, mhw = lane >> 4;
+  auto PX = [&](int r) { return MAP ? 4 * ((2 * r + mhw) & 3) + (mq & 3) : lx; };        // column of the tile at step r
+  auto PY = [&](int r) { return MAP ? 4 * (r >> 1) + (mq >> 2) : row_step * r + ly; };   // row of the tile at step r
 
   // Tiles are handed out dynamically (lrp_kernel.cuh, "tile scheduler"): the first round is static, every
   // further tile comes from the launch's global counter, so that no warp idles through a tail round
@@ -527,40 +539,55 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
     const int ticket = take_ticket(P.sched, lane); // issued now, consumed after the tile: the atomic's latency is hidden
     const int x0 = (tile % tiles_x) * tile_w, y0 = (tile / tiles_x) * tile_h;
     const int x = x0 + lx;
-    const bool xvalid = lane_used && x < P.W;
-    const int R = ss ? min(ST_STEPS, P.H - y0) : (min(ST_TILE_H, P.H - y0) + 1) >> 1; // steps: two rows of 16 pixels (ss: one row)
+    const bool xvalid = MAP || (lane_used && x < P.W); // block mapping: the column depends on the step, tested there
+    const int R = ss    ? min(ST_STEPS, P.H - y0)
+                  : MAP ? 2 * ((min(ST_TILE_H, P.H - y0) + 3) >> 2)
+                        : (min(ST_TILE_H, P.H - y0) + 1) >> 1; // steps: two rows of 16 pixels (ss: one row; MAP: two 4 x 4 blocks)
     const float cx = fsub(fadd((float)x, 0.5f), half_W); // :287; ns == 1: scx == cx exactly (:295)
 
     // separable parts of the output rays (rect / equirect output lenses, reference :155-157, :249-256):
     // every lane holds its column's part; lane k (k < 16) computes the row part of row y0 + k
-    float col_vx = 0.0f, col_vz = -1.0f, row_vy = 0.0f;
-    if (separable) {
-      const float q = fdiv(fadd(0.0f, 1.0f), P.ss_den);
-      const float scx = fsub(fadd(cx, q), 0.5f);
-      const float cyl = fsub(fadd((float)(y0 + lx), 0.5f), half_H);
-      const float scyl = fsub(fadd(cyl, q), 0.5f);
-      if (out_rect) {
-        col_vx = fdiv(fmul(fdiv(scx, Wf), P.ol.sw), P.ol.p0);
-        row_vy = fdiv(fmul(fdiv(scyl, Hf), P.ol.sh), P.ol.p0);
-      } else {
-        const float lon = fadd(fmul(fadd(fdiv(scx, Wf), 0.5f), fsub(P.ol.p3, P.ol.p2)), P.ol.p2);
-        const float lat = fadd(fmul(fadd(fdiv(scyl, Hf), 0.5f), fsub(P.ol.p1, P.ol.p0)), P.ol.p0);
-        float sn, cs;
-        dev_sincosf(lon, P.use_fma != 0, &sn, &cs);
-        col_vx = sn;
-        col_vz = -cs;
-        dev_sincosf(lat, P.use_fma != 0, &row_vy, nullptr); // not scaled by cos(lat): reference quirk
-      }
-    }
-
+    // (block mapping: a lane meets two columns, PX(0) on even and PX(1) on odd steps — both column parts are kept)
+    constexpr int NCOL = MAP ? 2 : 1;
+    float col_vx[NCOL], col_vz[NCOL], row_vy = 0.0f;
     // rotation :303-311 with the column-only products hoisted out of the row loop (same products, same sums):
     //   n_i = (R[3i] * vx + R[3i+1] * vy) + R[3i+2] * vz,   vx and vz depend on the column only
-    float rvx[3] = {0.0f, 0.0f, 0.0f}, rvz[3] = {0.0f, 0.0f, 0.0f};
-    if (separable && P.has_rot) {
+    float rvx[NCOL][3], rvz[NCOL][3];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        rvx[i] = fmul(P.R[3 * i], col_vx);
-        rvz[i] = fmul(P.R[3 * i + 2], col_vz);
+    for (int k = 0; k < NCOL; ++k) {
+      col_vx[k] = 0.0f, col_vz[k] = -1.0f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) rvx[k][i] = rvz[k][i] = 0.0f;
+    }
+    if (separable) {
+      const float q = fdiv(fadd(0.0f, 1.0f), P.ss_den);
+      const float cyl = fsub(fadd((float)(y0 + lx), 0.5f), half_H);
+      const float scyl = fsub(fadd(cyl, q), 0.5f);
+      if (out_rect) row_vy = fdiv(fmul(fdiv(scyl, Hf), P.ol.sh), P.ol.p0);
+      else {
+        const float lat = fadd(fmul(fadd(fdiv(scyl, Hf), 0.5f), fsub(P.ol.p1, P.ol.p0)), P.ol.p0);
+        dev_sincosf(lat, P.use_fma != 0, &row_vy, nullptr); // not scaled by cos(lat): reference quirk
+      }
+#pragma unroll
+      for (int k = 0; k < NCOL; ++k) {
+        const float cxk = MAP ? fsub(fadd((float)(x0 + PX(k)), 0.5f), half_W) : cx;
+        const float scx = fsub(fadd(cxk, q), 0.5f);
+        if (out_rect) {
+          col_vx[k] = fdiv(fmul(fdiv(scx, Wf), P.ol.sw), P.ol.p0);
+        } else {
+          const float lon = fadd(fmul(fadd(fdiv(scx, Wf), 0.5f), fsub(P.ol.p3, P.ol.p2)), P.ol.p2);
+          float sn, cs;
+          dev_sincosf(lon, P.use_fma != 0, &sn, &cs);
+          col_vx[k] = sn;
+          col_vz[k] = -cs;
+        }
+        if (P.has_rot) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            rvx[k][i] = fmul(P.R[3 * i], col_vx[k]);
+            rvz[k][i] = fmul(P.R[3 * i + 2], col_vz[k]);
+          }
+        }
       }
     }
 
@@ -569,34 +596,36 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
       float2 s[ST_STEPS];
 #pragma unroll
       for (int r = 0; r < ST_STEPS; ++r) {
-        const int y = y0 + row_step * r + ly;
+        const int y = y0 + PY(r), xr = MAP ? x0 + PX(r) : x;
         s[r] = make_float2(0.0f, 0.0f);
-        if (xvalid && y < P.H) s[r] = ld_table(P.remap + ((size_t)sub * (size_t)P.H + (size_t)y) * (size_t)P.W + (size_t)x);
+        if (xvalid && xr < P.W && y < P.H) s[r] = ld_table(P.remap + ((size_t)sub * (size_t)P.H + (size_t)y) * (size_t)P.W + (size_t)xr);
       }
 #pragma unroll
       for (int r = 0; r < ST_STEPS; ++r) s_coord[r * 32 + lane] = s[r];
     }
     for (int r = 0; r < (TABLE ? 0 : R); ++r) {
-      const int y = y0 + row_step * r + ly;
+      const int y = y0 + PY(r), xr = MAP ? x0 + PX(r) : x;
       float sx = 0.0f, sy = 0.0f;
-      const float vy_row = __shfl_sync(0xffffffffu, row_vy, (2 * r + ly) & 31);
-      if (xvalid && y < P.H) {
+      const float vy_row = __shfl_sync(0xffffffffu, row_vy, PY(r) & 31);
+      if (xvalid && xr < P.W && y < P.H) {
         float vx, vy, vz;
         if (separable) {
-          vx = col_vx;
-          vz = col_vz;
+          const bool odd = MAP && (r & 1); // selects, not indexing: the arrays stay in registers
+          vx = odd ? col_vx[NCOL - 1] : col_vx[0];
+          vz = odd ? col_vz[NCOL - 1] : col_vz[0];
           vy = vy_row;
           if (P.has_rot) {
-            vx = fadd(fadd(rvx[0], fmul(P.R[1], vy_row)), rvz[0]);
-            vy = fadd(fadd(rvx[1], fmul(P.R[4], vy_row)), rvz[1]);
-            vz = fadd(fadd(rvx[2], fmul(P.R[7], vy_row)), rvz[2]);
+            vx = fadd(fadd(odd ? rvx[NCOL - 1][0] : rvx[0][0], fmul(P.R[1], vy_row)), odd ? rvz[NCOL - 1][0] : rvz[0][0]);
+            vy = fadd(fadd(odd ? rvx[NCOL - 1][1] : rvx[0][1], fmul(P.R[4], vy_row)), odd ? rvz[NCOL - 1][1] : rvz[0][1]);
+            vz = fadd(fadd(odd ? rvx[NCOL - 1][2] : rvx[0][2], fmul(P.R[7], vy_row)), odd ? rvz[NCOL - 1][2] : rvz[0][2]);
           }
           rotated_to_source<COORD>(P, vx, vy, vz, sx, sy);
         } else {
           const float cy = fsub(fadd((float)y, 0.5f), half_H); // :288
+          const float cxr = MAP ? fsub(fadd((float)xr, 0.5f), half_W) : cx;
           const int ssx = sub / P.ns, ssy = sub - ssx * P.ns;   // :294, :297 (0, 0 when ns == 1)
           const float qx = fdiv(fadd((float)ssx, 1.0f), P.ss_den), qy = fdiv(fadd((float)ssy, 1.0f), P.ss_den);
-          target_to_vec(P, fsub(fadd(cx, qx), 0.5f), fsub(fadd(cy, qy), 0.5f), vx, vy, vz); // :295, :298
+          target_to_vec(P, fsub(fadd(cxr, qx), 0.5f), fsub(fadd(cy, qy), 0.5f), vx, vy, vz); // :295, :298
           ray_to_source<COORD>(P, vx, vy, vz, sx, sy);
         }
       }
@@ -616,7 +645,10 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
         bool bad = false;
         if (xvalid) {
           for (int rr = start; rr < end; ++rr) {
-            if (y0 + row_step * rr + ly >= P.H) break;
+            if (MAP ? (x0 + PX(rr) >= P.W || y0 + PY(rr) >= P.H) : (y0 + row_step * rr + ly >= P.H)) {
+              if (MAP) continue;
+              break;
+            }
             const float2 s = s_coord[rr * 32 + lane];
             // NaN / inf / |s| >= 2^30: x86 and CUDA float->int conversions differ there -> the block is gathered
             bad = bad || !((fabsf(s.x) < 1073741824.0f) && (fabsf(s.y) < 1073741824.0f));
@@ -650,8 +682,8 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
       const StageView V{s_stage, s_recB, plan.eff.x0, plan.eff.y0, plan.pitch, plan.clamped,
                         fsub(1.0f, fmul(big, 1.1920929e-7f))};
       for (int rr = start; rr < end; ++rr) {
-        const int y = y0 + row_step * rr + ly;
-        const bool valid = xvalid && y < P.H;
+        const int y = y0 + PY(rr), xs = MAP ? x0 + PX(rr) : x;
+        const bool valid = xvalid && xs < P.W && y < P.H;
         if (!ss && !valid) continue;
         if (ss && y >= P.H) break; // warp-uniform: a supersampled step is one row
         float v[C];
@@ -688,7 +720,7 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
 #pragma unroll
           for (int c = 0; c < (C < 3 ? C : 3); ++c) v[c] = post_process_value(v[c], P.exposure, P.r2);
         }
-        store_pixel<C>(P, s_thr, x, y, v);
+        store_pixel<C>(P, s_thr, xs, y, v);
       }
       __syncwarp(); // the records may be overwritten by the next block
       start = end;
@@ -698,9 +730,9 @@ __global__ void __launch_bounds__(st_warps(INTERP, C) * 32, 1) reproject_staged_
   retire_warp(P.sched, lane, warps_total);
 }
 
-template <int COORD, int INTERP, int FMT, int C>
+template <int COORD, int INTERP, int FMT, int C, bool BLOCKS = false>
 int launch_reproject_staged(const KParams &P, void *stream) {
-  auto kern = reproject_staged_kernel<COORD, INTERP, FMT, C>;
+  auto kern = reproject_staged_kernel<COORD, INTERP, FMT, C, BLOCKS>;
   static thread_local int configured_device = -1;
   int dev = 0;
   cudaGetDevice(&dev);

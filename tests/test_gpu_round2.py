@@ -386,3 +386,38 @@ def test_supersampling_staged_and_gathered(lrp, ns):
                 assert same_half(got16, want16).all(), "ns %d f16 variant %d coords %d" % (ns, v, cm)
                 got32 = lrp.reproject_host(f4, L(lrp, il), L(lrp, olens), W, H, ns, ol.BICUBIC, r, variant=v, coords=cm)
                 assert_same_f32(got32, want32, "ns %d f32 variant %d coords %d" % (ns, v, cm))
+
+
+# ---- half-warp shape of the staged kernel: rows of 16 pixels / 4 x 4 blocks (pole-crossing views) -----------------------
+
+@pytest.mark.parametrize("blocks", ["0", "1"])
+def test_staged_half_warp_shapes_bit_exact(lrp, blocks, monkeypatch):
+    """both shapes on wrapping panoramas of every format / channel count, ragged sizes, on-the-fly and table coordinates,
+    views across the seam and across both poles (LRP_ST_BLOCKS forces the shape; AUTO picks blocks for views whose
+    footprint spans the whole width)"""
+    monkeypatch.setenv("LRP_ST_BLOCKS", blocks)
+    w, h = 700, 350
+    il = ol.erect()
+    for (W, H) in ((203, 131), (64, 48)):
+        olens = ol.rect(18.0, 36.0, W, H)
+        for c in (3, 4, 5):
+            src = ol.noise(h, w, c, seed=60 + c)
+            for r in (rotd(30, 20, 10), rotd(179, 0, 0), rotd(0, 90, 0), rotd(10, -85, 40)):
+                want = ORC.reproject(src, il, olens, W, H, 1, ol.BICUBIC, r)
+                for cm in (lrp.COORDS_FLY, lrp.COORDS_TABLE):
+                    got = lrp.reproject_host(src, L(lrp, il), L(lrp, olens), W, H, 1, ol.BICUBIC, r, variant=lrp.VARIANT_STAGED, coords=cm)
+                    assert ol.same_bits(got, want), "f32 c%d %dx%d blocks %s coords %d" % (c, W, H, blocks, cm)
+        # codec-native formats
+        rng = np.random.default_rng(77)
+        rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        planes = (rng.random((3, h, w), dtype=np.float32) * 2).astype(np.float16).view(np.uint16)
+        for r in (rotd(30, 20, 10), rotd(0, -90, 0)):
+            want8 = ORC.png_encode(ORC.reproject(ORC.png_decode(rgba), il, olens, W, H, 1, ol.BICUBIC, r))
+            want16 = ORC.f32_to_half_planar(ORC.reproject(ORC.half_planar_to_f32(planes), il, olens, W, H, 1, ol.BICUBIC, r))
+            for cm in (lrp.COORDS_FLY, lrp.COORDS_TABLE):
+                got8 = lrp.reproject_host(rgba, L(lrp, il), L(lrp, olens), W, H, 1, ol.BICUBIC, r, in_fmt=lrp.FMT_U8_RGBA,
+                                          out_fmt=lrp.FMT_U8_RGBA, variant=lrp.VARIANT_STAGED, coords=cm)
+                assert (got8 == want8).all(), "u8 %dx%d blocks %s coords %d" % (W, H, blocks, cm)
+                got16 = lrp.reproject_host(planes, L(lrp, il), L(lrp, olens), W, H, 1, ol.BICUBIC, r, in_fmt=lrp.FMT_F16_PLANAR,
+                                           out_fmt=lrp.FMT_F16_PLANAR, variant=lrp.VARIANT_STAGED, coords=cm)
+                assert same_half(got16, want16).all(), "f16 %dx%d blocks %s coords %d" % (W, H, blocks, cm)
