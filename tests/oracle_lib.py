@@ -169,10 +169,12 @@ class _Checker:
         return out
 
     def reproject_mt(self, src, in_lens, out_lens, W, H, ns, interp, rot, apply_post, exposure,
-                     reinhard, n_images, n_threads):
+                     reinhard, n_images, n_threads, mark_idle=False):
         src = np.ascontiguousarray(src, dtype=np.float32)
         h, w, c = src.shape
-        out = np.empty((n_threads, H, W, c), dtype=np.float32)
+        # images are handed out dynamically: a thread that finds the queue empty before it starts writes nothing
+        # (mark_idle: its buffer then reads NaN instead of whatever the allocation held)
+        out = (np.full if mark_idle else np.empty)((n_threads, H, W, c), *((np.nan,) if mark_idle else ()), dtype=np.float32)
         r = None if rot is None else np.ascontiguousarray(rot, dtype=np.float32)
         self._f("reproject_mt")(C.byref(in_lens), w, h, c, self._ptr(src), C.byref(out_lens), W, H,
                                 self._ptr(out), ns, interp, self._ptr(r), int(apply_post),

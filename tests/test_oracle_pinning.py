@@ -210,9 +210,14 @@ def test_mt_wrapper_equals_single():
     one = REF.post_process(one, 1.5, 4.0)
     for chk in (ORC, REF):
         many = chk.reproject_mt(src, ol.erect(), ol.rect(18, 36, W, H), W, H, 1, ol.BICUBIC, r, True,
-                                1.5, 4.0, 6, 3)
+                                1.5, 4.0, 6, 3, mark_idle=True)
+        worked = 0
         for t in range(3):
+            if np.isnan(many[t]).all():  # images are handed out dynamically: this thread found the queue already empty
+                continue
+            worked += 1
             assert ol.same_bits(many[t], one)
+        assert worked >= 1
 
 
 # ---- 3. golden fixtures ---------------------------------------------------------------------
