@@ -437,7 +437,19 @@ struct PngInfo {
 
 static uint32_t be32(const unsigned char *p) { return ((uint32_t)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3]; }
 
-static int png_parse(const unsigned char *f, size_t n, PngInfo &I, std::vector<unsigned char> &idat,
+// The IDAT payload: a view into the file when it is ONE chunk (what lodepng and this library's encoder write: no copy of
+// tens of megabytes per frame), the chunks joined otherwise.
+struct IdatView {
+  const unsigned char *p = nullptr;
+  size_t n = 0;
+  int chunks = 0;
+  std::vector<unsigned char> joined;
+  const unsigned char *data() const { return chunks > 1 ? joined.data() : p; }
+  size_t size() const { return chunks > 1 ? joined.size() : n; }
+  bool empty() const { return size() == 0; }
+};
+
+static int png_parse(const unsigned char *f, size_t n, PngInfo &I, IdatView &idat,
                      std::vector<unsigned char> &plte, std::vector<unsigned char> &trns) {
   static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
   if (!f || n < 8 + 25 || memcmp(f, sig, 8) != 0) return LRP_E_BAD_ARG;
@@ -464,7 +476,12 @@ static int png_parse(const unsigned char *f, size_t n, PngInfo &I, std::vector<u
       if ((uint64_t)I.w * (uint64_t)I.h >= (1ull << 31)) return LRP_E_BAD_ARG; // pixel indices are 32-bit on the device
       have_ihdr = true;
     } else if (!memcmp(type, "IDAT", 4)) {
-      idat.insert(idat.end(), data, data + len);
+      if (idat.chunks == 0) idat.p = data, idat.n = len;
+      else {
+        if (idat.chunks == 1) idat.joined.assign(idat.p, idat.p + idat.n);
+        idat.joined.insert(idat.joined.end(), data, data + len);
+      }
+      idat.chunks++;
     } else if (!memcmp(type, "PLTE", 4)) {
       plte.assign(data, data + len);
     } else if (!memcmp(type, "tRNS", 4)) {
@@ -673,7 +690,8 @@ int lrp_exr_info(const void *file, size_t n, int32_t *width, int32_t *height, in
 
 int lrp_png_info(const void *file, size_t n, int32_t *width, int32_t *height) {
   PngInfo I;
-  std::vector<unsigned char> idat, plte, trns;
+  IdatView idat;
+  std::vector<unsigned char> plte, trns;
   const int rc = png_parse((const unsigned char *)file, n, I, idat, plte, trns);
   if (rc != LRP_OK) return rc;
   if (width) *width = (int32_t)I.w;
@@ -862,7 +880,8 @@ int lrp_decoder_exr(lrp_decoder *d, const void *file, size_t n, int32_t threads,
 int lrp_decoder_png(lrp_decoder *d, const void *file, size_t n, void *out_rgba_dev, void *cuda_stream) {
   if (!d || !file || !out_rgba_dev) return LRP_E_BAD_ARG;
   PngInfo I;
-  std::vector<unsigned char> idat, plte, trns;
+  IdatView idat;
+  std::vector<unsigned char> plte, trns;
   int rc = png_parse((const unsigned char *)file, n, I, idat, plte, trns);
   if (rc != LRP_OK) return rc;
   const size_t row = (size_t)I.w * I.channels, px = (size_t)I.w * I.h;
@@ -978,7 +997,8 @@ int lrp_decoder_jpeg(lrp_decoder *d, const void *file, size_t n, void *out_rgba_
 int lrp_debug_png_decode_host(const void *file, size_t n, void *out_rgba_host, size_t out_bytes) {
   if (!file || !out_rgba_host) return LRP_E_BAD_ARG;
   PngInfo I;
-  std::vector<unsigned char> idat, plte, trns;
+  IdatView idat;
+  std::vector<unsigned char> plte, trns;
   const int rc = png_parse((const unsigned char *)file, n, I, idat, plte, trns);
   if (rc != LRP_OK) return rc;
   if ((size_t)I.w * I.h * 4 != out_bytes) return LRP_E_BAD_ARG;
