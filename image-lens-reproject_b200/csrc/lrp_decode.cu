@@ -461,7 +461,10 @@ static int png_parse(const unsigned char *f, size_t n, PngInfo &I, IdatView &ida
     const unsigned char *type = f + pos + 4, *data = f + pos + 8;
     // lodepng verifies every chunk's CRC (ignore_crc = 0, lib/lodepng/lodepng.cpp: error 57): a corrupted file the
     // reference refuses is refused here too
-    if ((uint32_t)crc32(0L, type, 4 + len) != be32(data + len)) return LRP_E_BAD_ARG;
+    if (fastinf::crc32_fast(0u, type, 4 + (size_t)len, [](uint32_t c, const unsigned char *q, size_t m) {
+          return (uint32_t)crc32(c, q, (uInt)m);
+        }) != be32(data + len))
+      return LRP_E_BAD_ARG;
     if (!memcmp(type, "IHDR", 4)) {
       if (len != 13) return LRP_E_BAD_ARG;
       I.w = be32(data), I.h = be32(data + 4), I.depth = data[8], I.ctype = data[9];

