@@ -6,7 +6,8 @@
 //   * a 12-bit first-level table for the literal / length code and an 8-bit one for the distance code, entries hold
 //     the decoded base value, the number of extra bits and the code length; longer codes go through second-level tables,
 //   * first-level entries that hold TWO literals when both codes fit the 12-bit index (one dependent look-up, two
-//     output bytes), up to three look-ups per refill, matches copied in 8-byte steps (runs of distance 1 as a fill),
+//     output bytes), up to three look-ups per refill, the NEXT symbol's entry looked up before the current symbol's bytes are
+//     written (the table load overlaps a match's copy), matches copied in 8-byte steps (runs of distance 1 as a fill),
 //   * a fast loop while >= 16 input bytes and >= 280 output bytes remain, the same decoder with per-step bounds for
 //     the tails — a corrupted or truncated stream is an error, never an out-of-bounds access (tests/test_inflate.py
 //     runs it under AddressSanitizer + UBSan against zlib).
@@ -247,61 +248,79 @@ static int inflate_raw(const unsigned char *in, size_t in_n, unsigned char *out,
       if (in_end - ip >= 16 && out_end - op >= 280) {
         const unsigned char *const ip_fast = in_end - 16;
         unsigned char *const op_fast = out_end - 280;
-        while (ip <= ip_fast && op <= op_fast) {
-          buf |= load64(ip) << cnt;
-          ip += (63 - cnt) >> 3;
-          cnt |= 56;
-          uint32_t e = ll[buf & ((1u << LL_BITS) - 1)];
+        // The entry of the NEXT symbol is looked up before the bytes of the current one are written (a match's copy, the
+        // literals' stores), so the table load's latency overlaps them; `e` is always the unconsumed entry at the current
+        // bit position, looked up with at least 15 valid bits (a refill only adds bits above them).
+        buf |= load64(ip) << cnt;
+        ip += (63 - cnt) >> 3;
+        cnt |= 56;
+        uint32_t e = ll[buf & ((1u << LL_BITS) - 1)];
+        for (;;) {
           if (e & F_SUB) e = ll[(e >> 16) + ((buf >> LL_BITS) & ((1u << ((e >> 8) & 15u)) - 1))];
           buf >>= (e & 255u), cnt -= (int)(e & 255u);
           if (e & F_LIT) { // one or two literals per entry: both bytes are stored, the pointer moves by the count
             uint16_t v = (uint16_t)(e >> 16);
+            const uint32_t n1 = 1 + ((e >> 8) & 1u);
+            e = ll[buf & ((1u << LL_BITS) - 1)]; // >= 41 valid bits
             memcpy(op, &v, 2);
-            op += 1 + ((e >> 8) & 1u);
-            e = ll[buf & ((1u << LL_BITS) - 1)];
-            if ((e & (F_LIT | F_SUB)) != F_LIT) continue;
-            buf >>= (e & 255u), cnt -= (int)(e & 255u);
-            v = (uint16_t)(e >> 16);
-            memcpy(op, &v, 2);
-            op += 1 + ((e >> 8) & 1u);
-            e = ll[buf & ((1u << LL_BITS) - 1)];
-            if ((e & (F_LIT | F_SUB)) != F_LIT) continue;
-            buf >>= (e & 255u), cnt -= (int)(e & 255u);
-            v = (uint16_t)(e >> 16);
-            memcpy(op, &v, 2);
-            op += 1 + ((e >> 8) & 1u);
-            continue;
-          }
-          if (e & (F_EOB | F_INV)) {
-            if (e & F_INV) return E_DATA;
-            done = true;
-            break;
-          }
-          const uint32_t xl = (e >> 8) & 15u;
-          const uint32_t length = (e >> 16) + (uint32_t)(buf & ((1u << xl) - 1));
-          buf >>= xl, cnt -= (int)xl;
-          uint32_t d = dt[buf & ((1u << D_BITS) - 1)];
-          if (d & F_SUB) d = dt[(d >> 16) + ((buf >> D_BITS) & ((1u << ((d >> 8) & 15u)) - 1))];
-          if (d & F_INV) return E_DATA;
-          buf >>= (d & 255u), cnt -= (int)(d & 255u);
-          const uint32_t xd = (d >> 8) & 15u;
-          const uint32_t dist = (d >> 16) + (uint32_t)(buf & ((1u << xd) - 1));
-          buf >>= xd, cnt -= (int)xd;
-          if (dist > (size_t)(op - out)) return E_DATA;
-          const unsigned char *src = op - dist;
-          unsigned char *const end = op + length;
-          if (dist >= 8) {
-            do {
-              memcpy(op, src, 8);
-              op += 8, src += 8;
-            } while (op < end);
-          } else if (dist == 1) {
-            memset(op, *src, length);
+            op += n1;
+            if ((e & (F_LIT | F_SUB)) == F_LIT) {
+              buf >>= (e & 255u), cnt -= (int)(e & 255u);
+              v = (uint16_t)(e >> 16);
+              const uint32_t n2 = 1 + ((e >> 8) & 1u);
+              e = ll[buf & ((1u << LL_BITS) - 1)]; // >= 29 valid bits
+              memcpy(op, &v, 2);
+              op += n2;
+              if ((e & (F_LIT | F_SUB)) == F_LIT) {
+                buf >>= (e & 255u), cnt -= (int)(e & 255u);
+                v = (uint16_t)(e >> 16);
+                const uint32_t n3 = 1 + ((e >> 8) & 1u);
+                e = ll[buf & ((1u << LL_BITS) - 1)]; // >= 17 valid bits: enough for any code (15)
+                memcpy(op, &v, 2);
+                op += n3;
+              }
+            }
           } else {
-            do *op++ = *src++;
-            while (op < end);
+            if (e & (F_EOB | F_INV)) {
+              if (e & F_INV) return E_DATA;
+              done = true;
+              break;
+            }
+            const uint32_t xl = (e >> 8) & 15u;
+            const uint32_t length = (e >> 16) + (uint32_t)(buf & ((1u << xl) - 1));
+            buf >>= xl, cnt -= (int)xl;
+            uint32_t d = dt[buf & ((1u << D_BITS) - 1)];
+            if (d & F_SUB) d = dt[(d >> 16) + ((buf >> D_BITS) & ((1u << ((d >> 8) & 15u)) - 1))];
+            if (d & F_INV) return E_DATA;
+            buf >>= (d & 255u), cnt -= (int)(d & 255u);
+            const uint32_t xd = (d >> 8) & 15u;
+            const uint32_t dist = (d >> 16) + (uint32_t)(buf & ((1u << xd) - 1));
+            buf >>= xd, cnt -= (int)xd;
+            if (dist > (size_t)(op - out)) return E_DATA;
+            // (the loop's entry condition left 16 input bytes, the refill at its top took at most 7: 8 more can be read)
+            buf |= load64(ip) << cnt;
+            ip += (63 - cnt) >> 3;
+            cnt |= 56;
+            e = ll[buf & ((1u << LL_BITS) - 1)];
+            const unsigned char *src = op - dist;
+            unsigned char *const end = op + length;
+            if (dist >= 8) {
+              do {
+                memcpy(op, src, 8);
+                op += 8, src += 8;
+              } while (op < end);
+            } else if (dist == 1) {
+              memset(op, *src, length);
+            } else {
+              do *op++ = *src++;
+              while (op < end);
+            }
+            op = end;
           }
-          op = end;
+          if (!(ip <= ip_fast && op <= op_fast)) break; // `e` stays unconsumed: the careful loop looks it up again
+          buf |= load64(ip) << cnt;
+          ip += (63 - cnt) >> 3;
+          cnt |= 56;
         }
       }
       // hand the bit position back to the careful reader (bits above `cnt` were only looked ahead, never consumed)
